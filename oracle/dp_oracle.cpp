@@ -10,6 +10,9 @@
 
 namespace orc {
 
+CellHook g_cellHook = nullptr;
+GridHook g_gridHook = nullptr;
+
 namespace {
 
 enum ColProp { INITIAL, INNER, FINAL };           // align/dp_meta_info.h:60-65
@@ -321,8 +324,10 @@ struct DPRun {
 
     // ------------------------------------------------------------------ cell / track
     // align/dp_algorithm_impl.h:279-311 and seeds/banded_chain_alignment_impl.h:405-560
+    long hookRow = 0;  // matrix row of the cell being computed (debug hook only)
     void computeCell(ColProp cp, ColLoc cl, CellT ct, uint8_t hv, uint8_t vv) {
         Cell& a = col[sAct];
+        if (g_cellHook) g_cellHook((int)coordH(), (int)hookRow, tpos, tLeap, (int)cp, (int)cl, (int)ct, (int)dimV);
         if (p.algo == ALGO_CHAIN) {
             uint8_t tv;
             if (cp == INITIAL) {
@@ -344,14 +349,17 @@ struct DPRun {
     // align/dp_algorithm_impl.h:330-396
     void computeTrack(ColProp cp, ColLoc cl, uint8_t hv, uint8_t vFirst, long vBegin, long vEnd) {
         goNext(cp, cl, FIRST);
+        hookRow = (cl == FULL || cl == TOP) ? 0 : vBegin;
         computeCell(cp, cl, FIRST, hv, vFirst);
         long it = vBegin;
         long itEnd = vEnd - 1;
         for (; it != itEnd; ++it) {
             goNext(cp, cl, INNERC);
+            hookRow = it + 1;
             computeCell(cp, cl, INNERC, hv, p.V[it]);
         }
         goNext(cp, cl, LAST);
+        hookRow = it + 1;
         computeCell(cp, cl, LAST, hv, p.V[it]);
     }
 
@@ -382,12 +390,14 @@ struct DPRun {
 
         if (hBegin == nH - 1) {  // :545-558
             goNext(INITIAL, TOP, FIRST);
+            hookRow = 0;
             computeCell(INITIAL, TOP, FIRST, p.H[hBegin], p.V[0]);
             extraScout(globalTrack(FINAL, TOP, FIRST));
             return;
         }
         if (hEndBottom == 0) {  // :559-573
             goNext(INITIAL, BOTTOM, FIRST);
+            hookRow = vBegin;
             computeCell(INITIAL, BOTTOM, FIRST, p.H[0], p.V[vBegin]);
             extraScout(globalTrack(INITIAL, BOTTOM, LAST));
             return;
@@ -430,11 +440,13 @@ struct DPRun {
         }
         if (h < nH - 1) {  // Case 1 :692-706
             goNext(INNER, BOTTOM, FIRST);
+            hookRow = vBegin + 1;
             computeCell(INNER, BOTTOM, FIRST, p.H[h], p.V[vBegin]);
             extraScout(globalTrack(INNER, BOTTOM, LAST));
         } else if (h == nH - 1) {  // Case 2 :707-
             if (up == nH - nV) {
                 goNext(FINAL, BOTTOM, FIRST);
+                hookRow = vBegin + 1;
                 computeCell(FINAL, BOTTOM, FIRST, p.H[h], p.V[vBegin]);
                 extraScout(globalTrack(FINAL, BOTTOM, LAST));
             } else {
@@ -633,6 +645,7 @@ void countCells(CellCounter* cc, const DPRun& r) {
 
 // _computeAlignment for the default (global) profile.  Returns score; throws BadScore.
 int runGlobal(const DPProblem& prob, Trace& out, CellCounter* cc) {
+    if (g_gridHook) g_gridHook(3, prob.nH, prob.nV, prob.banded ? 1 : 0, prob.lower, prob.upper, prob.st ? (long)prob.st->hNext : 0, prob.st ? (long)prob.st->vNext : 0);
     DPRun r(prob);
     if (!r.validSettings()) return INT_MIN;  // :1543-1544 — no traceback, no throw
     r.initNavigators();
@@ -654,6 +667,7 @@ int runGlobal(const DPProblem& prob, Trace& out, CellCounter* cc) {
 // _computeAlignment for BandedChainAlignment_ profiles: fills, then one traceback per
 // tied maximum (seeds/banded_chain_alignment_traceback.h:357-388).
 int runChainGrid(const DPProblem& prob, std::vector<Trace>& localTraces, CellCounter* cc) {
+    if (g_gridHook) g_gridHook((int)prob.loc, prob.nH, prob.nV, prob.banded ? 1 : 0, prob.lower, prob.upper, (long)prob.st->hNext, (long)prob.st->vNext);
     DPRun r(prob);
     if (!r.validSettings()) return INT_MIN;
     r.initNavigators();

@@ -93,6 +93,14 @@ struct CellCounter {
     long long grids = 0;
 };
 
+// Debug hook (unit tests of the product's geometry helpers): called for every computed cell
+// with the navigator state of the literal emulation.
+typedef void (*CellHook)(int col, int row, long tpos, long tLeap, int cp, int cl, int ct, int dimV);
+extern CellHook g_cellHook;
+// Called once per sub-DP: kind (0 initial, 1 inner, 2 final, 3 default-scout global), dims, band, next-grid origin.
+typedef void (*GridHook)(int kind, long nH, long nV, int banded, long lo, long up, long hNext, long vNext);
+extern GridHook g_gridHook;
+
 // One DP problem (one call of _computeAlignment, align/dp_algorithm_impl.h:1513-1604).
 struct DPProblem {
     const uint8_t* H;

@@ -1,0 +1,582 @@
+// extern "C" surface of libunicycler_b200.so (declared in include/unicycler_b200.h).
+// Host orchestration only: parsing, seeding, planning, formatting.  All DP runs on the GPU engine;
+// if the engine cannot be created the calls fail loudly (no CPU fallback).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/unicycler_b200.h"
+#include "engine.hpp"
+#include "host_align.hpp"
+#include "seeding.hpp"
+
+using namespace ub200;
+
+typedef std::unordered_map<std::string, std::string> SeqMap;  // include/ref_seqs.h:18
+
+namespace {
+
+int g_device = -1;
+std::mutex g_engineMu;
+std::unique_ptr<Engine> g_engine;
+
+Engine& engine() {
+    std::lock_guard<std::mutex> lock(g_engineMu);
+    if (!g_engine) {
+        int dev = g_device;
+        if (dev < 0) {
+            const char* e = getenv("UNICYCLER_B200_DEVICE");
+            if (e) dev = atoi(e);
+        }
+        g_engine.reset(new Engine(dev));
+    }
+    return *g_engine;
+}
+
+[[noreturn]] void fatal(const std::string& msg) {
+    fprintf(stderr, "unicycler_b200: fatal: %s\n", msg.c_str());
+    fflush(stderr);
+    abort();
+}
+
+char* dupString(const std::string& s) {  // cppStringToCString, src/string_functions.cpp:19-24
+    char* p = (char*)malloc(s.size() + 1);
+    memcpy(p, s.data(), s.size());
+    p[s.size()] = '\0';
+    return p;
+}
+
+long long nowMs() {
+    return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+}
+
+std::vector<std::string> splitString(const std::string& in, char delim) {  // src/string_functions.cpp:37-49
+    std::vector<std::string> result;
+    if (in.empty()) return result;
+    std::stringstream ss(in);
+    while (ss.good()) {
+        std::string sub;
+        getline(ss, sub, delim);
+        result.push_back(sub);
+    }
+    return result;
+}
+
+// ------------------------------------------------------------------ global / path
+struct PairJob {
+    std::vector<uint8_t> H, V;
+    Job job;
+    bool planned = false;
+    long long startMs = 0;
+};
+
+void buildPairJob(PairJob& pj, const char* s1, const char* s2, const Scoring& sc, bool useBanding, int bandSize,
+                  bool path) {
+    pj.startMs = nowMs();
+    toDna5(s1, strlen(s1), pj.H);
+    toDna5(s2, strlen(s2), pj.V);
+    long lenH = (long)pj.H.size(), lenV = (long)pj.V.size();
+    long lo = -bandSize, up = bandSize;
+    long diff = lenV - lenH;
+    if (!path) {  // src/global_align.cpp:55-66
+        if (diff > 0) lo -= diff;
+        else if (diff < 0) up -= diff;
+    } else {  // src/path_align.cpp:58-63
+        if (diff < 0) up -= diff;
+    }
+    Job& j = pj.job;
+    j.H = pj.H.data(); j.lenH = (int32_t)lenH;
+    j.V = pj.V.data(); j.lenV = (int32_t)lenV;
+    j.match = sc.match; j.mismatch = sc.mismatch; j.gapOpen = sc.gapOpen; j.gapExtend = sc.gapExtend;
+    j.freeFirstRow = j.freeFirstCol = j.freeLastRow = 0;
+    j.freeLastCol = path ? 1 : 0;  // AlignConfig<false,false,true,false>
+    j.complete = 0;                // SingleTrace (AlignConfig2 default, seqan/align/dp_profile.h:335-336)
+    pj.planned = planGlobal(lenH, lenV, useBanding, lo, up, false, false, false, path, j.grids);
+}
+
+std::string finishPairJob(PairJob& pj, const Scoring& sc, bool path) {
+    if (!pj.planned) return "";  // see DESIGN.md: empty inputs / band width < 3 are undefined in the reference
+    const JobResult& r = pj.job.result;
+    if (r.status == JOB_BAD_SCORE) return "";  // catch (...) -> return 0 (global_align.cpp:69-82)
+    if (r.status != JOB_OK) fatal("DP job failed with status " + std::to_string(r.status));
+    if (path && r.score < -1000000) return "";  // path_align.cpp:84-85
+    const std::vector<Seg>& trace = r.gridTraces[0][0];
+    AlignmentRecord rec;
+    scoreAlignment(trace, false, pj.H.data(), (long)pj.H.size(), pj.V.data(), (long)pj.V.size(), 0, true, true, !path,
+                   sc, rec);
+    return fullString(rec, "s1", "s2", nowMs() - pj.startMs);
+}
+
+// ------------------------------------------------------------------ chain jobs
+struct ChainJob {
+    std::vector<uint8_t> H, V;
+    std::string readName, refName;
+    int refOffset = 0;
+    Job job;
+    bool planned = false;
+    long long startMs = 0;
+};
+
+void buildChainJob(ChainJob& cj, const char* readSeq, size_t readLen, const char* refSeq, size_t refLen,
+                   const std::vector<ChainSeed>& chain, const Scoring& sc, int bandSize) {
+    cj.startMs = nowMs();
+    toDna5(readSeq, readLen, cj.H);
+    toDna5(refSeq, refLen, cj.V);
+    Job& j = cj.job;
+    j.H = cj.H.data(); j.lenH = (int32_t)cj.H.size();
+    j.V = cj.V.data(); j.lenV = (int32_t)cj.V.size();
+    j.match = sc.match; j.mismatch = sc.mismatch; j.gapOpen = sc.gapOpen; j.gapExtend = sc.gapExtend;
+    j.freeFirstRow = j.freeFirstCol = j.freeLastRow = j.freeLastCol = 1;  // AlignConfig<true,true,true,true>
+    j.complete = 1;  // CompleteTrace (seeds/banded_chain_alignment_profile.h:200-204)
+    cj.planned = planChain(chain, (long)cj.H.size(), (long)cj.V.size(), bandSize, j.grids);
+}
+
+// returns false when the reference produces no alignment (exception swallowed at semi_global_align.cpp:311)
+bool finishChainJob(ChainJob& cj, const Scoring& sc, std::string& out) {
+    if (!cj.planned) fatal("seed chain geometry outside the supported range (reference behaviour undefined)");
+    const JobResult& r = cj.job.result;
+    if (r.status == JOB_BAD_SCORE) return false;
+    if (r.status != JOB_OK) fatal("chain DP job failed with status " + std::to_string(r.status));
+    std::vector<Seg> trace;
+    bool empty = true;
+    glueChain(cj.job.grids, r, trace, empty);
+    AlignmentRecord rec;
+    scoreAlignment(trace, empty, cj.H.data(), (long)cj.H.size(), cj.V.data(), (long)cj.V.size(), cj.refOffset, false,
+                   false, false, sc, rec);
+    out = fullString(rec, cj.readName, cj.refName, nowMs() - cj.startMs);
+    return true;
+}
+
+// ------------------------------------------------------------------ semi-global (one read)
+struct ReadWork {
+    std::string readName, posSeq, negSeq, console;
+    std::vector<std::unique_ptr<ChainJob> > jobs;  // in the reference's output order
+};
+
+// src/semi_global_align.cpp:608-639
+std::pair<int, int> getRefRange(int refStart, int refEnd, int refLen, int readStart, int readEnd, int readLen,
+                                bool posStrand) {
+    int halfReadLen = 1 + readLen / 2;
+    int before = readStart, after = readLen - readEnd;
+    if (!posStrand) std::swap(before, after);
+    int ns = std::max(0, refStart - before - halfReadLen);
+    int ne = std::min(refLen, refEnd + after + halfReadLen);
+    return std::make_pair(ns, ne);
+}
+std::vector<std::pair<int, int> > simplifyRanges(std::vector<std::pair<int, int> > ranges) {
+    std::sort(ranges.begin(), ranges.end());
+    std::vector<std::pair<int, int> > out;
+    std::pair<int, int> cur = ranges[0];
+    for (size_t i = 1; i < ranges.size(); ++i) {
+        if (cur.second >= ranges[i].first) cur.second = std::max(cur.second, ranges[i].second);
+        else { out.push_back(cur); cur = ranges[i]; }
+    }
+    out.push_back(cur);
+    return out;
+}
+
+// Host part of semiGlobalAlignment (semi_global_align.cpp:24-142): produces the chain jobs.
+void prepareRead(ReadWork& w, const char* readNameC, const char* readSeqC, int verbosity, const char* hitsC,
+                 SeqMap* refSeqs, const Scoring& sc, int sensitivityLevel) {
+    typedef std::unordered_map<std::string, std::vector<std::pair<int, int> > > RefRangeMap;
+    SensitivityParams sp = sensitivityParams(sensitivityLevel);
+    w.readName = readNameC;
+    w.posSeq = readSeqC;
+    const int readLength = (int)w.posSeq.size();
+    std::vector<std::string> hits = splitString(hitsC, ';');
+    if (verbosity > 2) {
+        w.console += "minimap alignments:\n";
+        for (const std::string& h : hits) w.console += "    " + h + "\n";
+    }
+    RefRangeMap refRanges;
+    for (const std::string& hit : hits) {
+        std::vector<std::string> p = splitString(hit, ',');
+        int readStart = std::stoi(p[0]), readEnd = std::stoi(p[1]);
+        char strand = p[2][0];
+        std::string refName = p[3];
+        int refStart = std::stoi(p[4]), refEnd = std::stoi(p[5]);
+        const std::string& refSeq = refSeqs->at(refName);
+        std::pair<int, int> r = getRefRange(refStart, refEnd, (int)refSeq.size(), readStart, readEnd, readLength, strand == '+');
+        refRanges[refName + strand].push_back(r);
+    }
+    RefRangeMap simplified;
+    for (const auto& r : refRanges) simplified[r.first] = simplifyRanges(r.second);
+    if (verbosity > 2) {
+        w.console += "Reference ranges:\n";
+        for (const auto& r : simplified)
+            for (const auto& rr : r.second)
+                w.console += "    " + r.first + ": " + std::to_string(rr.first) + " - " + std::to_string(rr.second) + "\n";
+    }
+    KmerPosMap posKmers, negKmers;
+    bool havePos = false, haveNeg = false;
+    for (const auto& r : simplified) {
+        std::string refName = r.first;
+        char strand = refName.back();
+        refName.pop_back();
+        const std::string& refSeq = refSeqs->at(refName);
+        const std::string* readSeq;
+        const KmerPosMap* kmers;
+        if (strand == '+') {
+            if (!havePos) { buildKmerPositions(w.posSeq, sp.kSize, posKmers); havePos = true; }
+            readSeq = &w.posSeq; kmers = &posKmers;
+        } else {
+            if (!haveNeg) { w.negSeq = reverseComplement(w.posSeq); buildKmerPositions(w.negSeq, sp.kSize, negKmers); haveNeg = true; }
+            readSeq = &w.negSeq; kmers = &negKmers;
+        }
+        for (const auto& range : r.second) {
+            const int refStart = range.first, refEnd = range.second;
+            std::string trimmed = refSeq.substr((size_t)refStart, (size_t)(refEnd - refStart));
+            RangeSeeds rs;
+            seedRange(*readSeq, *kmers, trimmed, sp, verbosity, refName, refStart, refEnd, rs);
+            w.console += rs.console;
+            for (const auto& chain : rs.chains) {
+                std::unique_ptr<ChainJob> cj(new ChainJob());
+                cj->readName = w.readName + strand;
+                cj->refName = refName;
+                cj->refOffset = refStart;
+                buildChainJob(*cj, readSeq->data(), readSeq->size(), trimmed.data(), trimmed.size(), chain, sc, sp.bandSize);
+                w.jobs.push_back(std::move(cj));
+            }
+        }
+    }
+}
+
+std::string finishRead(ReadWork& w, const Scoring& sc) {
+    std::string ret;
+    for (auto& cj : w.jobs) {
+        std::string s;
+        if (finishChainJob(*cj, sc, s)) ret += s + ";";
+    }
+    ret += w.console;
+    return ret;
+}
+
+// ------------------------------------------------------------------ forwarding of out-of-scope symbols
+void* forwardSym(const char* name) {
+    static void* handle = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!handle) {
+        const char* path = getenv("UNICYCLER_B200_FORWARD_LIB");
+        if (!path) fatal(std::string(name) + " is outside the accelerated path; set UNICYCLER_B200_FORWARD_LIB to the stock cpp_functions.so");
+        handle = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+        if (!handle) fatal(std::string("cannot dlopen ") + path + ": " + dlerror());
+    }
+    void* sym = dlsym(handle, name);
+    if (!sym) fatal(std::string("symbol not found in forward library: ") + name);
+    return sym;
+}
+
+// device-resident bench state
+struct ChainBench {
+    std::vector<std::unique_ptr<ChainJob> > jobs;
+    std::vector<Job*> ptrs;
+    Scoring sc;
+} g_bench;
+
+}  // namespace
+
+extern "C" {
+
+const char* ub200_version(void) { return "unicycler_b200 0.1 (reference ABI: Unicycler 0.5.1)"; }
+
+int ub200_setDevice(int device) {
+    std::lock_guard<std::mutex> lock(g_engineMu);
+    if (g_engine && g_engine->device() != device) g_engine.reset();
+    g_device = device;
+    return 0;
+}
+
+void freeCString(char* p) { free(p); }
+
+void* newRefSeqs(void) { return new SeqMap(); }
+void addRefSeq(void* h, char* name, char* seq) { ((SeqMap*)h)->emplace(name, seq); }
+void deleteRefSeqs(void* h) { delete (SeqMap*)h; }
+
+static char* pairAlignment(char* s1, char* s2, int m, int mm, int go, int ge, bool useBanding, int bandSize, bool path) {
+    Scoring sc{m, mm, go, ge};
+    PairJob pj;
+    buildPairJob(pj, s1, s2, sc, useBanding, bandSize, path);
+    if (pj.planned) {
+        std::vector<Job*> jobs{&pj.job};
+        engine().run(jobs);
+    }
+    return dupString(finishPairJob(pj, sc, path));
+}
+
+char* fullyGlobalAlignment(char* s1, char* s2, int m, int mm, int go, int ge, bool useBanding, int bandSize) {
+    return pairAlignment(s1, s2, m, mm, go, ge, useBanding, bandSize, false);
+}
+
+char* pathAlignment(char* s1, char* s2, int m, int mm, int go, int ge, bool useBanding, int bandSize) {
+    return pairAlignment(s1, s2, m, mm, go, ge, useBanding, bandSize, true);
+}
+
+int ub200_globalAlignmentBatch(int n, const char* const* s1, const char* const* s2, int mode, int m, int mm, int go,
+                               int ge, bool useBanding, int bandSize, char** results) {
+    Scoring sc{m, mm, go, ge};
+    const bool path = mode == 1;
+    std::vector<std::unique_ptr<PairJob> > pjs((size_t)n);
+    std::vector<Job*> jobs;
+    for (int i = 0; i < n; ++i) {
+        pjs[(size_t)i].reset(new PairJob());
+        buildPairJob(*pjs[(size_t)i], s1[i], s2[i], sc, useBanding, bandSize, path);
+        if (pjs[(size_t)i]->planned) jobs.push_back(&pjs[(size_t)i]->job);
+    }
+    engine().run(jobs);
+    for (int i = 0; i < n; ++i) results[i] = dupString(finishPairJob(*pjs[(size_t)i], sc, path));
+    return 0;
+}
+
+char* getRandomSequenceAlignmentScores(int seqLength, int n, int m, int mm, int go, int ge) {
+    // src/random_alignments.cpp:30-52: n unbanded global alignments of uniform random ACGT pairs
+    Scoring sc{m, mm, go, ge};
+    std::mt19937 gen;
+    const char* seedEnv = getenv("UNICYCLER_B200_SEED");
+    if (seedEnv) gen.seed((unsigned)strtoul(seedEnv, nullptr, 10));
+    else { std::random_device rd; gen.seed(rd()); }
+    std::uniform_int_distribution<int> dist(0, 3);
+    static const char bases[4] = {'A', 'C', 'G', 'T'};
+    std::vector<double> scores;
+    // batches bounded by trace memory: ~2^31 cells per batch
+    const long long cellsPerPair = (long long)(seqLength + 1) * (seqLength + 1);
+    long long perBatch = std::max(1LL, std::min<long long>(n, (1LL << 32) / std::max(1LL, cellsPerPair)));
+    perBatch = std::min(perBatch, 65536LL);
+    std::string a((size_t)seqLength, 'A'), b((size_t)seqLength, 'A');
+    for (long long done = 0; done < n; done += perBatch) {
+        long long cnt = std::min<long long>(perBatch, n - done);
+        std::vector<std::unique_ptr<PairJob> > pjs((size_t)cnt);
+        std::vector<Job*> jobs;
+        for (long long i = 0; i < cnt; ++i) {
+            for (int k = 0; k < seqLength; ++k) a[(size_t)k] = bases[dist(gen)];
+            for (int k = 0; k < seqLength; ++k) b[(size_t)k] = bases[dist(gen)];
+            pjs[(size_t)i].reset(new PairJob());
+            buildPairJob(*pjs[(size_t)i], a.c_str(), b.c_str(), sc, false, 0, false);
+            if (pjs[(size_t)i]->planned) jobs.push_back(&pjs[(size_t)i]->job);
+        }
+        engine().run(jobs);
+        for (long long i = 0; i < cnt; ++i) {
+            PairJob& pj = *pjs[(size_t)i];
+            if (!pj.planned || pj.job.result.status != JOB_OK) continue;  // "if (alignment != 0)"
+            AlignmentRecord rec;
+            scoreAlignment(pj.job.result.gridTraces[0][0], false, pj.H.data(), (long)pj.H.size(), pj.V.data(),
+                           (long)pj.V.size(), 0, true, true, true, sc, rec);
+            scores.push_back(rec.scaledScore);
+        }
+    }
+    double mean = 0.0, sd = 0.0;  // getMeanAndStDev :187-202 (population sd)
+    if (!scores.empty()) {
+        for (double v : scores) mean += v;
+        mean /= (double)scores.size();
+        double dev = 0.0;
+        for (double v : scores) dev += (v - mean) * (v - mean);
+        sd = sqrt(dev / (double)scores.size());
+    }
+    return dupString(std::to_string(mean) + "," + std::to_string(sd));
+}
+
+static void seedsFromArray(const int64_t* seeds, int nSeeds, std::vector<ChainSeed>& chain) {
+    chain.resize((size_t)nSeeds);
+    for (int i = 0; i < nSeeds; ++i)
+        chain[(size_t)i] = ChainSeed{(long)seeds[6 * i], (long)seeds[6 * i + 1], (long)seeds[6 * i + 2],
+                                     (long)seeds[6 * i + 3], (long)seeds[6 * i + 4], (long)seeds[6 * i + 5]};
+}
+
+char* ub200_chainAlignment(const char* readSeq, const char* refSeq, const int64_t* seeds, int nSeeds, int m, int mm,
+                           int go, int ge, int bandSize, const char* readName, const char* refName, int refOffset) {
+    Scoring sc{m, mm, go, ge};
+    std::vector<ChainSeed> chain;
+    seedsFromArray(seeds, nSeeds, chain);
+    ChainJob cj;
+    cj.readName = readName; cj.refName = refName; cj.refOffset = refOffset;
+    buildChainJob(cj, readSeq, strlen(readSeq), refSeq, strlen(refSeq), chain, sc, bandSize);
+    if (!cj.planned) return dupString("!ERROR:unsupported seed chain geometry");
+    std::vector<Job*> jobs{&cj.job};
+    engine().run(jobs);
+    std::string out;
+    if (!finishChainJob(cj, sc, out)) out = "";
+    return dupString(out);
+}
+
+static int buildChainBatch(int n, const char* const* readSeqs, const char* const* refSeqs, const int64_t* seeds,
+                           const int64_t* seedOffsets, const Scoring& sc, int bandSize, const char* const* readNames,
+                           const char* const* refNames, const int* refOffsets,
+                           std::vector<std::unique_ptr<ChainJob> >& cjs, std::vector<Job*>& jobs) {
+    cjs.resize((size_t)n);
+    jobs.clear();
+    for (int i = 0; i < n; ++i) {
+        std::vector<ChainSeed> chain;
+        seedsFromArray(seeds + 6 * seedOffsets[i], (int)(seedOffsets[i + 1] - seedOffsets[i]), chain);
+        cjs[(size_t)i].reset(new ChainJob());
+        ChainJob& cj = *cjs[(size_t)i];
+        cj.readName = readNames ? readNames[i] : "read+";
+        cj.refName = refNames ? refNames[i] : "ref";
+        cj.refOffset = refOffsets ? refOffsets[i] : 0;
+        buildChainJob(cj, readSeqs[i], strlen(readSeqs[i]), refSeqs[i], strlen(refSeqs[i]), chain, sc, bandSize);
+        if (!cj.planned) return -1;
+        jobs.push_back(&cj.job);
+    }
+    return 0;
+}
+
+int ub200_chainAlignmentBatch(int n, const char* const* readSeqs, const char* const* refSeqs, const int64_t* seeds,
+                              const int64_t* seedOffsets, int m, int mm, int go, int ge, int bandSize,
+                              const char* const* readNames, const char* const* refNames, const int* refOffsets,
+                              char** results) {
+    Scoring sc{m, mm, go, ge};
+    std::vector<std::unique_ptr<ChainJob> > cjs;
+    std::vector<Job*> jobs;
+    if (buildChainBatch(n, readSeqs, refSeqs, seeds, seedOffsets, sc, bandSize, readNames, refNames, refOffsets, cjs, jobs))
+        return -1;
+    engine().run(jobs);
+    for (int i = 0; i < n; ++i) {
+        std::string out;
+        if (!finishChainJob(*cjs[(size_t)i], sc, out)) out = "";
+        results[i] = dupString(out);
+    }
+    return 0;
+}
+
+int ub200_chainBenchPrepare(int n, const char* const* readSeqs, const char* const* refSeqs, const int64_t* seeds,
+                            const int64_t* seedOffsets, int m, int mm, int go, int ge, int bandSize) {
+    g_bench.sc = Scoring{m, mm, go, ge};
+    if (buildChainBatch(n, readSeqs, refSeqs, seeds, seedOffsets, g_bench.sc, bandSize, nullptr, nullptr, nullptr,
+                        g_bench.jobs, g_bench.ptrs))
+        return -1;
+    engine().upload(g_bench.ptrs);
+    return 0;
+}
+
+double ub200_chainBenchRun(void) {
+    Engine& e = engine();
+    e.launch();
+    // kernel time is read back in finish(); here we only synchronise via a cheap stats fetch
+    return 0.0;
+}
+
+int ub200_chainBenchFinish(char** results) {
+    Engine& e = engine();
+    e.fetch(g_bench.ptrs);
+    for (size_t i = 0; i < g_bench.jobs.size(); ++i) {
+        std::string out;
+        if (!finishChainJob(*g_bench.jobs[i], g_bench.sc, out)) out = "";
+        if (results) results[i] = dupString(out);
+    }
+    return 0;
+}
+
+char* semiGlobalAlignment(char* readName, char* readSeq, int verbosity, char* hits, void* refSeqs, int m, int mm,
+                          int go, int ge, double, bool, int sensitivityLevel) {
+    Scoring sc{m, mm, go, ge};
+    ReadWork w;
+    prepareRead(w, readName, readSeq, verbosity, hits, (SeqMap*)refSeqs, sc, sensitivityLevel);
+    std::vector<Job*> jobs;
+    for (auto& cj : w.jobs) jobs.push_back(&cj->job);
+    engine().run(jobs);
+    return dupString(finishRead(w, sc));
+}
+
+int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const char* const* readSeqs,
+                                   const char* const* hits, void* refSeqs, int m, int mm, int go, int ge,
+                                   int sensitivityLevel, char** results) {
+    Scoring sc{m, mm, go, ge};
+    std::vector<std::unique_ptr<ReadWork> > works((size_t)n);
+    std::vector<Job*> jobs;
+    for (int i = 0; i < n; ++i) {
+        works[(size_t)i].reset(new ReadWork());
+        prepareRead(*works[(size_t)i], readNames[i], readSeqs[i], 0, hits[i], (SeqMap*)refSeqs, sc, sensitivityLevel);
+        for (auto& cj : works[(size_t)i]->jobs) jobs.push_back(&cj->job);
+    }
+    engine().run(jobs);
+    for (int i = 0; i < n; ++i) results[i] = dupString(finishRead(*works[(size_t)i], sc));
+    return 0;
+}
+
+char* ub200_seedChains(const char* readSeq, const char* trimmedRefSeq, int sensitivityLevel) {
+    SensitivityParams sp = sensitivityParams(sensitivityLevel);
+    std::string read(readSeq), ref(trimmedRefSeq);
+    KmerPosMap kmers;
+    buildKmerPositions(read, sp.kSize, kmers);
+    RangeSeeds rs;
+    seedRange(read, kmers, ref, sp, 0, "ref", 0, (int)ref.size(), rs);
+    std::string out = std::to_string(rs.chains.size()) + ";";
+    for (const auto& chain : rs.chains) {
+        out += std::to_string(chain.size()) + ":";
+        for (size_t i = 0; i < chain.size(); ++i) {
+            const ChainSeed& s = chain[i];
+            if (i) out += "|";
+            out += std::to_string(s.beginH) + "," + std::to_string(s.beginV) + "," + std::to_string(s.endH) + "," +
+                   std::to_string(s.endV) + "," + std::to_string(s.lowerDiag) + "," + std::to_string(s.upperDiag);
+        }
+        out += ";";
+    }
+    return dupString(out);
+}
+
+double ub200_intPeakOpsPerSec(void) { return measureIntPeak(engine().device()); }
+
+void ub200_lastStats(int64_t* cells, double* kernelMs, int64_t* launches, double* h2dMs, double* d2hMs) {
+    EngineStats s = engine().lastStats();
+    if (cells) *cells = s.cells;
+    if (kernelMs) *kernelMs = s.kernelMs;
+    if (launches) *launches = s.launches;
+    if (h2dMs) *h2dMs = s.h2dMs;
+    if (d2hMs) *d2hMs = s.d2hMs;
+}
+
+// ---- forwarders for the symbols outside the hot path (cpp_wrappers.py:61-74,180-357)
+char* semiGlobalAlignmentExhaustive(char* a, char* b, int c, int d, int e, int f) {
+    typedef char* (*F)(char*, char*, int, int, int, int);
+    return ((F)forwardSym("semiGlobalAlignmentExhaustive"))(a, b, c, d, e, f);
+}
+char* startAlignment(char* a, char* b, int c, int d, int e, int f) {
+    typedef char* (*F)(char*, char*, int, int, int, int);
+    return ((F)forwardSym("startAlignment"))(a, b, c, d, e, f);
+}
+char* endAlignment(char* a, char* b, int c, int d, int e, int f) {
+    typedef char* (*F)(char*, char*, int, int, int, int);
+    return ((F)forwardSym("endAlignment"))(a, b, c, d, e, f);
+}
+char* overlapAlignment(char* a, char* b, int c, int d, int e, int f, int g) {
+    typedef char* (*F)(char*, char*, int, int, int, int, int);
+    return ((F)forwardSym("overlapAlignment"))(a, b, c, d, e, f, g);
+}
+char* multipleSequenceAlignment(char** a, char** b, unsigned long c, unsigned int d, int e, int f, int g, int h) {
+    typedef char* (*F)(char**, char**, unsigned long, unsigned int, int, int, int, int);
+    return ((F)forwardSym("multipleSequenceAlignment"))(a, b, c, d, e, f, g, h);
+}
+char* minimapAlignReads(char* a, char* b, int c, int d, int e) {
+    typedef char* (*F)(char*, char*, int, int, int);
+    return ((F)forwardSym("minimapAlignReads"))(a, b, c, d, e);
+}
+char* minimapAlignReadsWithSettings(char* a, char* b, int c, bool d, int e, int f, float g, int h, int i, int j, int k) {
+    typedef char* (*F)(char*, char*, int, bool, int, int, float, int, int, int, int);
+    return ((F)forwardSym("minimapAlignReadsWithSettings"))(a, b, c, d, e, f, g, h, i, j, k);
+}
+void miniasmAssembly(char* a, char* b, char* c, int d) {
+    typedef void (*F)(char*, char*, char*, int);
+    ((F)forwardSym("miniasmAssembly"))(a, b, c, d);
+}
+char* getRandomSequenceAlignmentErrorRates(int a, int b, int c, int d, int e, int f) {
+    typedef char* (*F)(int, int, int, int, int, int);
+    return ((F)forwardSym("getRandomSequenceAlignmentErrorRates"))(a, b, c, d, e, f);
+}
+char* simulateDepths(int* a, int b, int c, int d, int e) {
+    typedef char* (*F)(int*, int, int, int, int);
+    return ((F)forwardSym("simulateDepths"))(a, b, c, d, e);
+}
+
+}  // extern "C"

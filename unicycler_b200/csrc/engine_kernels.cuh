@@ -1,0 +1,444 @@
+// Device side of the B200 DP engine (sm_100a).  See engine.hpp for the job model.
+//
+// Execution model
+//   * persistent CTAs (NWARPS warps) pull jobs from an atomic queue; a job's grids run
+//     back to back inside the CTA because grid k+1 is initialised from the traceback of
+//     grid k (seeds/banded_chain_alignment_traceback.h:296-330).
+//   * fill: the matrix is cut into horizontal strips of SH = 32*R rows.  Inside a strip
+//     lane t owns R consecutive rows and walks the columns one step behind lane t-1
+//     (anti-diagonal wavefront, cell hand-off with __shfl_up); strips are pipelined over
+//     the CTA's warps, `lag` 32-column chunks apart, with one __syncthreads per chunk
+//     phase; the row between two strips travels through an L2-resident buffer.
+//   * trace: one byte per cell (the reference's TraceBitMap_ value), written as one 16-byte
+//     store per lane and step into a skewed, fully coalesced layout:
+//        addr(i,j) = stripBase[s] + ((j - jlo(s) + t)*32 + t)*R + r,
+//        s=(i-1)/SH, t=((i-1)%SH)/R, r=(i-1)%R.
+//   * tracking + traceback: warp 0 finds the tied maxima over the tracked cells and walks
+//     the trace exactly like SeqAn's TracebackCoordinator_, in SeqAn's storage coordinates
+//     (dpgeom.hpp maps them to matrix coordinates).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "dpgeom.hpp"
+#include "engine.hpp"
+
+namespace ub200 {
+
+constexpr int R = 16;
+constexpr int SH = 32 * R;
+constexpr int NWARPS = 8;
+constexpr int NTHREADS = NWARPS * 32;
+constexpr unsigned FULLMASK = 0xffffffffu;
+
+struct DCell {
+    int s, h, v;
+};
+
+struct JobDev {
+    long long hOff, vOff;
+    int lenH, lenV;
+    int match, mismatch, gapOpen, gapExtend;
+    int fe;  // bit0 firstRow, bit1 firstCol, bit2 lastRow, bit3 lastCol
+    int complete;
+    int gridBegin, gridCount;
+    long long outOff;
+    int outCap;
+    int pad;
+};
+
+struct JobOut {
+    int status, score, outLen, pad;
+};
+
+struct ScratchLayout {  // byte offsets inside one CTA's scratch block
+    long long trace, stripBase, bnd, initRow, initCol, hInitNext, vInitNext, box, lastRow, lastCol, cand, planted,
+        colTab, total;
+    int bndStride, maxCand, maxPlanted, maxColTab;
+    long long maxBox;
+    int maxCapH, maxCapV, maxNH, maxNV;
+    long long maxTrace;
+    int maxStrips, pad;
+};
+
+struct KParams {
+    const JobDev* jobs;
+    const GridDesc* grids;
+    const uint8_t* seq;
+    int* out;
+    JobOut* jobOut;
+    const int* order;  // job processing order (largest first)
+    int nJobs;
+    int* queue;
+    uint8_t* scratch;
+    long long scratchStride;
+    ScratchLayout lay;
+};
+
+struct PlantedCell {
+    int i1, i2;
+    DCell c;
+};
+
+// Everything a grid needs, built once per grid by thread 0 (shared memory).
+struct GridCtx {
+    GridGeom g;
+    int kind, h0, v0, hNext, vNext, capNextH, capNextV;
+    int match, mismatch, go, ge, fe, complete, affine;
+    const uint8_t* seqH;
+    const uint8_t* seqV;
+    // scratch pointers
+    uint8_t* trace;
+    long long* stripBase;
+    int2* bnd;
+    DCell *initRow, *initCol, *hInitNext, *vInitNext, *box, *lastRow, *lastCol;
+    int* cand;
+    PlantedCell* planted;
+    ColInfo* colTab;
+    // strips / schedule
+    int NS, P, lag, totalPhases, bndStride;
+    int colZeroMax;
+    // capture
+    int capEdges;  // 1: last row + last column; 0: box
+    int boxRow0, boxH, boxW;
+    // limits
+    int maxCand, maxPlanted, maxColTab;
+    long long maxBox, maxTrace;
+};
+
+__device__ __forceinline__ int stripJlo(const GridGeom& g, int s) {
+    return g.banded ? imax(1, s * SH + 1 + g.lo) : 1;
+}
+__device__ __forceinline__ int stripJhi(const GridGeom& g, int s) {
+    if (!g.banded) return g.nH;
+    int r1 = imin(g.nV, (s + 1) * SH);
+    return imin(g.nH, r1 + g.up);
+}
+__device__ __forceinline__ int stripChunks(const GridGeom& g, int s) {
+    int ncols = stripJhi(g, s) - stripJlo(g, s) + 1;
+    return ncols > 0 ? (ncols + 62) / 32 : 0;
+}
+
+__device__ __forceinline__ size_t traceAddr(const GridCtx& G, int i, int j) {
+    int s = (i - 1) / SH;
+    int rem = (i - 1) - s * SH;
+    int t = rem / R, r = rem - t * R;
+    int k = j - stripJlo(G.g, s) + t;
+    return (size_t)G.stripBase[s] + ((size_t)k * 32 + t) * R + r;
+}
+
+// ---------------------------------------------------------------------------------------
+// cell recurrences (seqan/align/dp_formula_affine.h:459-636, dp_formula_linear.h:150-291)
+// mode: 0 = RecursionDirectionAll, 1 = UpperDiagonal, 2 = LowerDiagonal, 3 = outside the band
+// ---------------------------------------------------------------------------------------
+template <bool AFF, bool CT>
+__device__ __forceinline__ uint32_t cellUpdate(int& s, int& h, int& v, int sl, int hl, int su, int vu, int sd,
+                                               int sub, int go, int ge, int mode) {
+    uint32_t tv;
+    if (AFF) {
+        int a = hl + ge, b = sl + go;
+        int c = vu + ge, e = su + go;
+        uint32_t tvH, tvV, tvM;
+        if (mode == 1) { v = NEG_INF; tvV = 0; }
+        else { v = max(c, e); tvV = (c < e) ? T_VO : ((CT && c == e) ? (T_V | T_VO) : T_V); }
+        if (mode == 2) { h = NEG_INF; tvH = 0; }
+        else { h = max(a, b); tvH = (a < b) ? T_HO : ((CT && a == b) ? (T_H | T_HO) : T_H); }
+        int m;
+        if (mode == 1) { m = h; tvM = T_MH; }
+        else if (mode == 2) { m = v; tvM = T_MV; }
+        else { m = max(v, h); tvM = (v < h) ? T_MH : ((CT && v == h) ? (T_MV | T_MH) : T_MV); }
+        int d = sd + sub;
+        uint32_t gap = tvH | tvV;
+        if (!CT) {
+            if (m <= d) { s = d; tv = T_D | gap; }
+            else { s = m; tv = gap | tvM; }
+        } else {
+            if (m < d) { s = d; tv = T_D | gap; }
+            else if (m == d) { s = m; tv = gap | T_D | tvM; }
+            else { s = m; tv = gap | tvM; }
+        }
+    } else {
+        int x = sd + sub;
+        tv = T_D;
+        if (mode != 1) {  // vertical
+            int t = su + ge;
+            if (x < t) { x = t; tv = T_V | T_MV; }
+            else if (CT && x == t) tv |= (T_V | T_MV);
+        }
+        if (mode != 2) {  // horizontal
+            int t = sl + ge;
+            if (x < t) { x = t; tv = T_H | T_MH; }
+            else if (CT && x == t) tv |= (T_H | T_MH);
+        }
+        s = x; h = NEG_INF; v = NEG_INF;
+    }
+    if (mode == 3) { s = NEG_INF; h = NEG_INF; v = NEG_INF; tv = 0; }
+    return tv;
+}
+
+// S and V-matrix value of the cell just above strip s in column j (j >= 1)
+template <bool BANDED>
+__device__ __forceinline__ void upBoundary(const GridCtx& G, int s, int j, int& bS, int& bV) {
+    int rowAbove = s * SH;
+    if (BANDED) {
+        int d = j - rowAbove;
+        if (d < G.g.lo || d > G.g.up) { bS = NEG_INF; bV = NEG_INF; return; }
+    }
+    if (s == 0) {
+        DCell c = G.initRow[j];
+        bS = c.s; bV = c.v;
+    } else {
+        int2 b = __ldcg(&G.bnd[(size_t)((s - 1) & 1) * G.bndStride + j]);
+        bS = b.x; bV = b.y;
+    }
+}
+
+template <bool AFF, bool CT, bool BANDED, bool CAP>
+__device__ __forceinline__ void stripSteps(const GridCtx& G, int s, int c, int lane, int jlo, int jhi, int i0,
+                                           int (&Sl)[R], int (&Hl)[R], const uint32_t (&vcw)[R / 4], int& prevUpS, int& pubS,
+                                           int& pubV, int& curHc, int bS, int bV, int hcN, bool writeBnd) {
+    const int match = G.match, mismatch = G.mismatch, go = G.go, ge = G.ge;
+    const int nV = G.g.nV, nH = G.g.nH, lo = G.g.lo, up = G.g.up;
+    uint8_t* tbase = G.trace + (size_t)G.stripBase[s];
+#pragma unroll 1
+    for (int kk = 0; kk < 32; ++kk) {
+        const int k = 32 * c + kk;
+        int inS = __shfl_up_sync(FULLMASK, pubS, 1);
+        int inV = __shfl_up_sync(FULLMASK, pubV, 1);
+        int inHc = __shfl_up_sync(FULLMASK, curHc, 1);
+        int l0S = __shfl_sync(FULLMASK, bS, kk);
+        int l0V = __shfl_sync(FULLMASK, bV, kk);
+        int l0Hc = __shfl_sync(FULLMASK, hcN, kk);
+        if (lane == 0) { inS = l0S; inV = l0V; inHc = l0Hc; }
+        curHc = inHc;
+        const int j = jlo + k - lane;
+        const bool act = (k >= lane) && (j <= jhi);
+        if (act) {
+            int Sd = prevUpS, Su = inS, Vu = inV;
+            uint32_t tw[4] = {0u, 0u, 0u, 0u};
+            // per-byte equality of this lane's 16 vertical codes with the column's horizontal code
+            const uint32_t hc4 = (uint32_t)curHc * 0x01010101u;
+            uint32_t eq[R / 4];
+#pragma unroll
+            for (int w4 = 0; w4 < R / 4; ++w4) eq[w4] = __vcmpeq4(vcw[w4], hc4);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = i0 + r;
+                int mode = 0;
+                if (BANDED) {
+                    int d = j - i;
+                    mode = (d < lo || d > up) ? 3 : (d == up ? 1 : (d == lo ? 2 : 0));
+                }
+                int sub = (eq[r >> 2] & (1u << (8 * (r & 3)))) ? match : mismatch;
+                int ns, nh, nv;
+                uint32_t tv = cellUpdate<AFF, CT>(ns, nh, nv, Sl[r], Hl[r], Su, Vu, Sd, sub, go, ge, mode);
+                Sd = Sl[r];
+                Sl[r] = ns; Hl[r] = nh; Su = ns; Vu = nv;
+                tw[r >> 2] |= tv << (8 * (r & 3));
+                if (CAP) {
+                    if (G.capEdges) {
+                        if (i == nV) G.lastRow[j] = DCell{ns, nh, nv};
+                        if (j == nH && i <= nV) G.lastCol[i] = DCell{ns, nh, nv};
+                    } else if (j >= G.hNext && i >= G.boxRow0 && i <= nV && mode != 3) {
+                        G.box[(size_t)(j - G.hNext) * G.boxH + (i - G.boxRow0)] = DCell{ns, nh, nv};
+                    }
+                }
+            }
+            prevUpS = inS;
+            pubS = Su; pubV = Vu;
+            *reinterpret_cast<uint4*>(tbase + ((size_t)k * 32 + lane) * R) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+            if (writeBnd && lane == 31) __stcg(&G.bnd[(size_t)(s & 1) * G.bndStride + j], make_int2(Su, Vu));
+        }
+    }
+}
+
+template <bool AFF, bool CT, bool BANDED>
+__device__ __noinline__ void fillGrid(const GridCtx& G) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int Sl[R], Hl[R];
+    uint32_t vcw[R / 4];
+    int prevUpS = NEG_INF, pubS = NEG_INF, pubV = NEG_INF, curHc = 0;
+    int jlo = 1, jhi = 0, i0 = 1, nch = 0;
+    const GridGeom& g = G.g;
+#pragma unroll 1
+    for (int p = 0; p < G.totalPhases; ++p) {
+        int t = p - warp * G.lag;
+        if (t >= 0) {
+            int q = t / G.P;
+            int c = t - q * G.P;
+            int s = warp + NWARPS * q;
+            if (s < G.NS) {
+                if (c == 0) {  // strip start: load this lane's rows
+                    jlo = stripJlo(g, s);
+                    jhi = stripJhi(g, s);
+                    nch = stripChunks(g, s);
+                    i0 = s * SH + lane * R + 1;
+#pragma unroll
+                    for (int w4 = 0; w4 < R / 4; ++w4) vcw[w4] = 0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        int i = i0 + r;
+                        uint32_t code = (i <= g.nV) ? (uint32_t)G.seqV[i - 1] : 255u;
+                        vcw[r >> 2] |= code << (8 * (r & 3));
+                        if (jlo == 1 && i <= G.colZeroMax) { DCell ic = G.initCol[i]; Sl[r] = ic.s; Hl[r] = ic.h; }
+                        else { Sl[r] = NEG_INF; Hl[r] = NEG_INF; }
+                    }
+                    if (jlo == 1) prevUpS = (i0 - 1 <= G.colZeroMax) ? G.initCol[i0 - 1].s : NEG_INF;
+                    else {
+                        prevUpS = NEG_INF;
+                        if (lane == 0) { int bS, bV; upBoundary<BANDED>(G, s, jlo - 1, bS, bV); prevUpS = bS; }
+                    }
+                    pubS = NEG_INF; pubV = NEG_INF; curHc = 0;
+                }
+                if (c < nch) {
+                    int jj = jlo + 32 * c + lane;
+                    int bS = NEG_INF, bV = NEG_INF, hcN = 0;
+                    if (jj <= jhi) { hcN = G.seqH[jj - 1]; upBoundary<BANDED>(G, s, jj, bS, bV); }
+                    bool writeBnd = (s + 1 < G.NS);
+                    bool cap;
+                    int jmaxChunk = jlo + 32 * c + 31;  // largest column any lane touches in this chunk
+                    if (G.capEdges) cap = ((s + 1) * SH >= g.nV) || (jmaxChunk >= g.nH);
+                    else cap = (jmaxChunk >= G.hNext) && ((s + 1) * SH >= G.boxRow0);
+                    if (cap)
+                        stripSteps<AFF, CT, BANDED, true>(G, s, c, lane, jlo, jhi, i0, Sl, Hl, vcw, prevUpS, pubS, pubV,
+                                                          curHc, bS, bV, hcN, writeBnd);
+                    else
+                        stripSteps<AFF, CT, BANDED, false>(G, s, c, lane, jlo, jhi, i0, Sl, Hl, vcw, prevUpS, pubS, pubV,
+                                                           curHc, bS, bV, hcN, writeBnd);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// traceback (seqan/align/dp_traceback_impl.h, seeds/banded_chain_alignment_traceback.h)
+// in SeqAn storage coordinates (col, cv); lane 0 of warp 0 only.
+// ---------------------------------------------------------------------------------------
+struct Coord {
+    int currCol, currRow, endCol, endRow, bp1, bp2;
+    bool inBandFlag;
+    __device__ __forceinline__ bool reachedEnd() const { return currCol <= endCol || currRow <= endRow; }
+    __device__ __forceinline__ bool isInBand() const {
+        if (!inBandFlag) return false;
+        return currCol > bp1 || currCol <= bp2;
+    }
+};
+
+struct OutStream {
+    int* buf;
+    int cap, len;
+    bool overflow;
+    int h0, v0;
+    __device__ __forceinline__ void put(int x) {
+        if (len < cap) buf[len] = x;
+        else overflow = true;
+        ++len;
+    }
+};
+
+struct TraceWalker {
+    const GridCtx& G;
+    OutStream& out;
+    int pc, pv;       // navigator position: column, storage row
+    int nSegs;        // segments emitted for the current trace
+    bool emitOn;
+    bool bad;         // undefined trace value (reference: endless loop / assert)
+
+    __device__ TraceWalker(const GridCtx& g, OutStream& o) : G(g), out(o), pc(0), pv(0), nSegs(0), emitOn(true), bad(false) {}
+
+    __device__ __forceinline__ uint32_t tvHere() const {
+        int i = pv - storageOffset(G.g, pc);
+        if (i <= 0 || pc <= 0 || i > G.g.nV || pc > G.g.nH) return 0;
+        return G.trace[traceAddr(G, i, pc)];
+    }
+    __device__ Coord makeCoord(int endCol, int endRow) const {  // dp_traceback_impl.h:121-141
+        Coord c;
+        c.currCol = pc; c.currRow = pv; c.endCol = endCol; c.endRow = endRow; c.bp1 = 0; c.bp2 = 0;
+        c.inBandFlag = false;
+        if (G.g.banded) {
+            if (c.currCol > G.g.up) c.currRow += c.currCol - G.g.up;
+            if (c.endCol > G.g.up) c.endRow += c.endCol - G.g.up;
+            c.bp1 = imin(G.g.nH, imax(0, G.g.up));
+            c.bp2 = imin(G.g.nH, imax(0, G.g.nV + G.g.lo));
+            int mb = imin(c.bp1, c.bp2);
+            if (c.currCol < mb) c.currRow -= mb - c.currCol;
+            c.inBandFlag = true;
+        }
+        return c;
+    }
+    __device__ __forceinline__ void record(int h, int v, int len, uint32_t tv) {  // dp_trace_segment.h:319-337
+        if (len == 0) return;
+        int dir;
+        if (tv & T_D) dir = T_D;
+        else if (tv & T_V) dir = T_V;
+        else if (tv & T_H) dir = T_H;
+        else return;
+        if (!emitOn) return;
+        out.put(h + out.h0); out.put(v + out.v0); out.put(len); out.put(dir);
+        ++nSegs;
+    }
+    __device__ __forceinline__ void moveH(const Coord& c) { if (c.isInBand()) { --pc; ++pv; } else --pc; }
+    __device__ __forceinline__ void moveD(const Coord& c) { if (c.isInBand()) { --pc; } else { --pc; --pv; } }
+    __device__ __forceinline__ void moveV() { --pv; }
+
+    __device__ void doTraceback(uint32_t& tv, uint32_t& last, int& frag, Coord& c) {  // dp_traceback_impl.h:335-431
+        const bool aff = G.affine;
+        if (tv & T_D) {
+            if (!(last & T_D)) { record(c.currCol, c.currRow, frag, last); last = T_D; frag = 0; }
+            moveD(c); tv = tvHere(); --c.currCol; --c.currRow; ++frag;
+        } else if ((tv & T_MV) && (tv & T_V)) {
+            if (!(last & T_V)) { record(c.currCol, c.currRow, frag, last); last = T_V; frag = 0; }
+            if (aff) {
+                while ((!(tv & T_VO) || (tv & T_V)) && c.currRow != 1) { moveV(); tv = tvHere(); --c.currRow; ++frag; }
+                moveV(); tv = tvHere(); --c.currRow; ++frag;
+            } else { moveV(); tv = tvHere(); --c.currRow; ++frag; }
+        } else if ((tv & T_MV) && (tv & T_VO)) {
+            if (!(last & T_V)) { record(c.currCol, c.currRow, frag, last); last = T_V; frag = 0; }
+            moveV(); tv = tvHere(); --c.currRow; ++frag;
+        } else if ((tv & T_MH) && (tv & T_H)) {
+            if (!(last & T_H)) { record(c.currCol, c.currRow, frag, last); last = T_H; frag = 0; }
+            if (aff) {
+                while ((!(tv & T_HO) || (tv & T_H)) && c.currCol != 1) { moveH(c); tv = tvHere(); --c.currCol; ++frag; }
+                moveH(c); tv = tvHere(); --c.currCol; ++frag;
+            } else { moveH(c); tv = tvHere(); --c.currCol; ++frag; }
+        } else if ((tv & T_MH) && (tv & T_HO)) {
+            if (!(last & T_H)) { record(c.currCol, c.currRow, frag, last); last = T_H; frag = 0; }
+            moveH(c); tv = tvHere(); --c.currCol; ++frag;
+        } else {
+            if (tv != T_NONE) { bad = true; tv = T_NONE; }
+        }
+    }
+    __device__ static uint32_t initialDirection(uint32_t& tv, bool prefer) {  // dp_traceback_impl.h:433-461
+        if (prefer) {
+            if (tv & T_MV) { tv &= (T_V | T_VO | T_MV); return T_V; }
+            if (tv & T_MH) { tv &= (T_H | T_HO | T_MH); return T_H; }
+            return T_D;
+        }
+        if (tv & T_D) return T_D;
+        if (tv & (T_V | T_MV)) return T_V;
+        if (tv & (T_H | T_MH)) return T_H;
+        return T_NONE;
+    }
+    // generic _computeTraceback (dp_traceback_impl.h:463-526); tvOverride >= 0 replaces the
+    // start cell's trace value (the SingleTrace _correctTraceValue patch, dp_algorithm_impl.h:1354-1370)
+    __device__ void generic(bool prefer, bool head, bool tail, int tvOverride) {
+        uint32_t tv = tvOverride >= 0 ? (uint32_t)tvOverride : tvHere();
+        uint32_t last = initialDirection(tv, prefer);
+        Coord c = makeCoord(0, 0);
+        const int nH = G.g.nH, nV = G.g.nV;
+        if (tail) {
+            if (c.currRow != nV) record(nH, c.currRow, nV - c.currRow, T_V);
+            if (c.currCol != nH) record(c.currCol, c.currRow, nH - c.currCol, T_H);
+        }
+        int frag = 0;
+        while (!c.reachedEnd() && tv != T_NONE) doTraceback(tv, last, frag, c);
+        record(c.currCol, c.currRow, frag, last);
+        if (head) {
+            if (c.currRow != 0) record(0, 0, c.currRow, T_V);
+            if (c.currCol != 0) record(0, 0, c.currCol, T_H);
+        }
+    }
+};
+
+}  // namespace ub200

@@ -1,0 +1,648 @@
+// Host seeding stage (see seeding.hpp).  Restates unicycler/src/semi_global_align.cpp:197-291,350-605,739-803,
+// the L1 kd-tree radius search of nanoflann 1.2.3 (include/nanoflann.hpp:1043-1256) and SeqAn's seed merge
+// and sparse global chaining (seqan/seeds/seeds_seed_set_unordered.h:248-361, seeds_combination.h:102-197,
+// seeds_global_chaining.h:102-280).  The container types, hash and iteration orders are the reference's
+// on purpose: several decisions sum doubles in container order.
+#include "seeding.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <set>
+#include <unordered_set>
+
+namespace ub200 {
+
+// include/settings.h
+static const int LINE_TRACING_START_POINT_SEARCH_RADIUS = 100;
+static const double TRACE_LINE_COLLECTION_DISTANCE = 20.0;
+static const int TRACE_LINE_STEP_DISTANCE = 500;
+static const int TRACE_LINE_MUTATION_SIZE = 5;
+static const double MAX_POINTS_SCORE = 10000.0;
+static const double MAX_SLOPE_SCORE = 1.0;
+static const double MIN_ACCEPTABLE_LINE_SEGMENT_SLOPE = 0.5;
+static const long long MAX_BANDED_ALIGNMENT_GAP_AREA = 100000000LL;
+static const double SCORE_DISTANCE_FROM_DIAGONAL = 5.0;
+
+SensitivityParams sensitivityParams(int level) {
+    SensitivityParams p{10, 25, 2, 4};
+    if (level == 1) p = SensitivityParams{10, 50, 2, 8};
+    else if (level == 2) p = SensitivityParams{9, 75, 3, 12};
+    else if (level == 3) p = SensitivityParams{8, 100, 4, 16};
+    return p;
+}
+
+void buildKmerPositions(const std::string& sequence, int kSize, KmerPosMap& out) {
+    out.clear();
+    int kCount = (int)sequence.size() - kSize + 1;
+    for (int i = 0; i < kCount; ++i) out[sequence.substr((size_t)i, (size_t)kSize)].push_back(i);
+}
+
+std::string reverseComplement(const std::string& s) {
+    std::string rc;
+    rc.reserve(s.size());
+    for (size_t k = s.size(); k > 0; --k) {
+        switch (s[k - 1]) {
+        case 'A': rc.push_back('T'); break;
+        case 'T': rc.push_back('A'); break;
+        case 'G': rc.push_back('C'); break;
+        case 'C': rc.push_back('G'); break;
+        case 'R': rc.push_back('Y'); break;
+        case 'Y': rc.push_back('R'); break;
+        case 'S': rc.push_back('S'); break;
+        case 'W': rc.push_back('W'); break;
+        case 'K': rc.push_back('M'); break;
+        case 'M': rc.push_back('K'); break;
+        case 'B': rc.push_back('V'); break;
+        case 'D': rc.push_back('H'); break;
+        case 'H': rc.push_back('D'); break;
+        case 'V': rc.push_back('B'); break;
+        case 'N': rc.push_back('N'); break;
+        case '.': rc.push_back('.'); break;
+        case '-': rc.push_back('-'); break;
+        case '?': rc.push_back('?'); break;
+        case '*': rc.push_back('*'); break;
+        default: break;  // any other character is dropped, like the reference
+        }
+    }
+    return rc;
+}
+
+namespace {
+
+struct Point {
+    int x, y;
+    Point() : x(0), y(0) {}
+    Point(int px, int py) : x(px), y(py) {}
+    bool operator==(const Point& o) const { return x == o.x && y == o.y; }
+    bool operator<(const Point& o) const { return x == o.x ? y < o.y : x < o.x; }
+};
+struct PointHash {  // include/semi_global_align.h:79-86
+    size_t operator()(const Point& p) const { return (std::hash<int>()(p.x) ^ (std::hash<int>()(p.y) << 1)) >> 1; }
+};
+typedef std::unordered_set<Point, PointHash> PointSet;
+typedef std::vector<Point> PointVector;
+
+// ------------------------------------------------------------------ kd-tree (nanoflann algorithm, int L1 metric)
+class KdTree {
+public:
+    explicit KdTree(const PointVector& pts) : pts_(pts), root_(-1) {}
+
+    void build() {
+        const size_t n = pts_.size();
+        vind_.resize(n);
+        for (size_t i = 0; i < n; ++i) vind_[i] = i;
+        nodes_.clear();
+        root_ = -1;
+        if (n == 0) return;
+        for (int d = 0; d < 2; ++d) rootBox_[d].low = rootBox_[d].high = coord(0, d);
+        for (size_t k = 1; k < n; ++k)
+            for (int d = 0; d < 2; ++d) {
+                if (coord(k, d) < rootBox_[d].low) rootBox_[d].low = coord(k, d);
+                if (coord(k, d) > rootBox_[d].high) rootBox_[d].high = coord(k, d);
+            }
+        Interval box[2] = {rootBox_[0], rootBox_[1]};
+        root_ = divide(0, n, box);
+        rootBox_[0] = box[0];
+        rootBox_[1] = box[1];
+    }
+
+    // radiusSearch with SearchParams() defaults: eps = 0, sorted by distance (unstable std::sort)
+    void radiusSearch(const int q[2], int radius, std::vector<std::pair<size_t, int> >& out) const {
+        out.clear();
+        if (pts_.empty() || root_ < 0) return;
+        int dists[2] = {0, 0};
+        int distsq = 0;
+        for (int d = 0; d < 2; ++d) {
+            if (q[d] < rootBox_[d].low) { dists[d] = std::abs(q[d] - rootBox_[d].low); distsq += dists[d]; }
+            if (q[d] > rootBox_[d].high) { dists[d] = std::abs(q[d] - rootBox_[d].high); distsq += dists[d]; }
+        }
+        search(out, q, radius, root_, distsq, dists, 1.0f);
+        std::sort(out.begin(), out.end(),
+                  [](const std::pair<size_t, int>& a, const std::pair<size_t, int>& b) { return a.second < b.second; });
+    }
+
+private:
+    struct Interval { int low, high; };
+    struct Node {
+        bool leaf;
+        size_t left, right;
+        int divfeat, divlow, divhigh;
+        int child1, child2;
+    };
+    const PointVector& pts_;
+    std::vector<size_t> vind_;
+    std::vector<Node> nodes_;
+    int root_;
+    Interval rootBox_[2];
+    static const size_t kLeafMax = 10;  // KDTreeSingleIndexAdaptorParams(10), semi_global_align.cpp:217
+
+    int coord(size_t idx, int d) const { return d == 0 ? pts_[idx].x : pts_[idx].y; }
+
+    int divide(size_t left, size_t right, Interval box[2]) {
+        int id = (int)nodes_.size();
+        nodes_.push_back(Node());
+        if (right - left <= kLeafMax) {
+            Node nd;
+            nd.leaf = true; nd.left = left; nd.right = right; nd.child1 = nd.child2 = -1;
+            nd.divfeat = nd.divlow = nd.divhigh = 0;
+            for (int d = 0; d < 2; ++d) box[d].low = box[d].high = coord(vind_[left], d);
+            for (size_t k = left + 1; k < right; ++k)
+                for (int d = 0; d < 2; ++d) {
+                    if (box[d].low > coord(vind_[k], d)) box[d].low = coord(vind_[k], d);
+                    if (box[d].high < coord(vind_[k], d)) box[d].high = coord(vind_[k], d);
+                }
+            nodes_[(size_t)id] = nd;
+        } else {
+            size_t idx;
+            int cutfeat, cutval;
+            middleSplit(&vind_[0] + left, right - left, idx, cutfeat, cutval, box);
+            Interval lbox[2] = {box[0], box[1]};
+            lbox[cutfeat].high = cutval;
+            int c1 = divide(left, left + idx, lbox);
+            Interval rbox[2] = {box[0], box[1]};
+            rbox[cutfeat].low = cutval;
+            int c2 = divide(left + idx, right, rbox);
+            Node nd;
+            nd.leaf = false; nd.left = nd.right = 0;
+            nd.divfeat = cutfeat; nd.divlow = lbox[cutfeat].high; nd.divhigh = rbox[cutfeat].low;
+            nd.child1 = c1; nd.child2 = c2;
+            for (int d = 0; d < 2; ++d) {
+                box[d].low = std::min(lbox[d].low, rbox[d].low);
+                box[d].high = std::max(lbox[d].high, rbox[d].high);
+            }
+            nodes_[(size_t)id] = nd;
+        }
+        return id;
+    }
+
+    void minMax(const size_t* ind, size_t count, int d, int& mn, int& mx) const {
+        mn = mx = coord(ind[0], d);
+        for (size_t i = 1; i < count; ++i) {
+            int v = coord(ind[i], d);
+            if (v < mn) mn = v;
+            if (v > mx) mx = v;
+        }
+    }
+
+    // With integer element/distance types the EPS of the original is static_cast<int>(0.00001) == 0, so the
+    // "span > (1-EPS)*max_span" test never holds and the cut dimension stays 0 (nanoflann.hpp:1113-1131).
+    void middleSplit(size_t* ind, size_t count, size_t& index, int& cutfeat, int& cutval, const Interval box[2]) {
+        const int EPS = static_cast<int>(0.00001);
+        int maxSpan = box[0].high - box[0].low;
+        for (int d = 1; d < 2; ++d) {
+            int span = box[d].high - box[d].low;
+            if (span > maxSpan) maxSpan = span;
+        }
+        int maxSpread = -1;
+        cutfeat = 0;
+        for (int d = 0; d < 2; ++d) {
+            int span = box[d].high - box[d].low;
+            if (span > (1 - EPS) * maxSpan) {
+                int mn, mx;
+                minMax(ind, count, d, mn, mx);
+                int spread = mx - mn;
+                if (spread > maxSpread) { cutfeat = d; maxSpread = spread; }
+            }
+        }
+        int splitVal = (box[cutfeat].low + box[cutfeat].high) / 2;
+        int mn, mx;
+        minMax(ind, count, cutfeat, mn, mx);
+        if (splitVal < mn) cutval = mn;
+        else if (splitVal > mx) cutval = mx;
+        else cutval = splitVal;
+        size_t lim1, lim2;
+        planeSplit(ind, count, cutfeat, cutval, lim1, lim2);
+        if (lim1 > count / 2) index = lim1;
+        else if (lim2 < count / 2) index = lim2;
+        else index = count / 2;
+    }
+
+    void planeSplit(size_t* ind, size_t count, int cutfeat, int cutval, size_t& lim1, size_t& lim2) {
+        size_t left = 0, right = count - 1;
+        for (;;) {
+            while (left <= right && coord(ind[left], cutfeat) < cutval) ++left;
+            while (right && left <= right && coord(ind[right], cutfeat) >= cutval) --right;
+            if (left > right || !right) break;
+            std::swap(ind[left], ind[right]);
+            ++left;
+            --right;
+        }
+        lim1 = left;
+        right = count - 1;
+        for (;;) {
+            while (left <= right && coord(ind[left], cutfeat) <= cutval) ++left;
+            while (right && left <= right && coord(ind[right], cutfeat) > cutval) --right;
+            if (left > right || !right) break;
+            std::swap(ind[left], ind[right]);
+            ++left;
+            --right;
+        }
+        lim2 = left;
+    }
+
+    void search(std::vector<std::pair<size_t, int> >& out, const int q[2], int radius, int nodeId, int mindistsq,
+                int dists[2], float epsError) const {
+        const Node& nd = nodes_[(size_t)nodeId];
+        if (nd.leaf) {
+            for (size_t i = nd.left; i < nd.right; ++i) {
+                size_t index = vind_[i];
+                int dist = std::abs(q[0] - pts_[index].x) + std::abs(q[1] - pts_[index].y);
+                if (dist < radius) out.push_back(std::make_pair(index, dist));
+            }
+            return;
+        }
+        int idx = nd.divfeat;
+        int val = q[idx];
+        int diff1 = val - nd.divlow, diff2 = val - nd.divhigh;
+        int best, other, cutDist;
+        if (diff1 + diff2 < 0) { best = nd.child1; other = nd.child2; cutDist = std::abs(val - nd.divhigh); }
+        else { best = nd.child2; other = nd.child1; cutDist = std::abs(val - nd.divlow); }
+        search(out, q, radius, best, mindistsq, dists, epsError);
+        int dst = dists[idx];
+        mindistsq = mindistsq + cutDist - dst;
+        dists[idx] = cutDist;
+        if (mindistsq * epsError <= radius) search(out, q, radius, other, mindistsq, dists, epsError);
+        dists[idx] = dst;
+    }
+};
+
+// ------------------------------------------------------------------ line tracing (semi_global_align.cpp:350-605,739-803)
+struct Cloud {
+    PointVector pts;
+    KdTree tree;
+    Cloud() : tree(pts) {}
+};
+
+void fillCloud(Cloud& cloud, const PointVector& common, const PointSet& used) {
+    cloud.pts.clear();
+    for (const Point& p : common)
+        if (used.find(p) == used.end()) cloud.pts.push_back(p);
+    cloud.tree.build();
+}
+
+PointVector radiusSearchAroundPoint(Point point, int radius, const Cloud& cloud) {
+    PointVector out;
+    std::vector<std::pair<size_t, int> > matches;
+    const int q[2] = {point.x, point.y};
+    cloud.tree.radiusSearch(q, radius, matches);
+    for (const auto& m : matches) out.push_back(cloud.pts[m.first]);
+    return out;
+}
+
+double getSlope(const Point& p1, const Point& p2) {
+    int xDiff = p1.x - p2.x, yDiff = p1.y - p2.y;
+    double slope = 0.0;
+    if (xDiff != 0) slope = double(yDiff) / double(xDiff);
+    if (xDiff == 0 && yDiff == 0) slope = 1.0;
+    return slope;
+}
+
+double distanceToLineSegment(Point p, Point l1, Point l2) {
+    double A = p.x - l1.x, B = p.y - l1.y, C = l2.x - l1.x, D = l2.y - l1.y;
+    double dot = A * C + B * D;
+    double lenSq = C * C + D * D;
+    double param = -1;
+    if (lenSq != 0) param = dot / lenSq;
+    double xx, yy;
+    if (param < 0) { xx = l1.x; yy = l1.y; }
+    else if (param > 1) { xx = l2.x; yy = l2.y; }
+    else { xx = l1.x + param * C; yy = l1.y + param * D; }
+    double dx = p.x - xx, dy = p.y - yy;
+    return sqrt(dx * dx + dy * dy);
+}
+
+double scoreLineSegment(Point p1, Point p2, const PointSet& pointsNearLine) {
+    double slope = getSlope(p1, p2);
+    if (slope > 1.0) slope = 1.0 / slope;
+    double slopeScore = (MAX_SLOPE_SCORE / (1.0 - MIN_ACCEPTABLE_LINE_SEGMENT_SLOPE)) * (slope - MIN_ACCEPTABLE_LINE_SEGMENT_SLOPE);
+    double maxScorePerPoint = MAX_POINTS_SCORE / TRACE_LINE_STEP_DISTANCE;
+    double pointDistanceScore = 0.0;
+    for (const Point& p : pointsNearLine) {
+        double dist = distanceToLineSegment(p, p1, p2);
+        pointDistanceScore += maxScorePerPoint / (dist + 1.0);
+    }
+    return slopeScore + pointDistanceScore;
+}
+
+Point shiftUp(Point p, int steps) { p.x -= steps; p.y += steps; return p; }
+Point shiftDown(Point p, int steps) { p.x += steps; p.y -= steps; return p; }
+
+Point mutateLineToBestFitPoints(Point p1, Point p2, const Cloud& cloud, PointSet& pointsNearLine, bool leftRectangle) {
+    int radius = int(TRACE_LINE_STEP_DISTANCE * 1.1);
+    PointVector nearP1 = radiusSearchAroundPoint(p1, radius, cloud);
+    PointVector nearP2 = radiusSearchAroundPoint(p2, radius, cloud);
+    pointsNearLine.insert(nearP1.begin(), nearP1.end());
+    pointsNearLine.insert(nearP2.begin(), nearP2.end());
+    if (leftRectangle) return p2;
+    Point p2Up = shiftUp(p2, TRACE_LINE_MUTATION_SIZE), p2Down = shiftDown(p2, TRACE_LINE_MUTATION_SIZE);
+    double unmutated = scoreLineSegment(p1, p2, pointsNearLine);
+    double up = scoreLineSegment(p1, p2Up, pointsNearLine);
+    double down = scoreLineSegment(p1, p2Down, pointsNearLine);
+    while (true) {
+        if (unmutated >= up && unmutated >= down) break;
+        else if (up > unmutated) {
+            p2Down = p2; down = unmutated;
+            p2 = p2Up; unmutated = up;
+            p2Up = shiftUp(p2, TRACE_LINE_MUTATION_SIZE);
+            up = scoreLineSegment(p1, p2Up, pointsNearLine);
+        } else if (down > unmutated) {
+            p2Up = p2; up = unmutated;
+            p2 = p2Down; unmutated = down;
+            p2Down = shiftDown(p2, TRACE_LINE_MUTATION_SIZE);
+            down = scoreLineSegment(p1, p2Down, pointsNearLine);
+        }
+    }
+    return p2;
+}
+
+double getPointDensityScore(int radius, Point p, const Cloud& cloud) {
+    PointVector neighbours = radiusSearchAroundPoint(p, radius, cloud);
+    double a = 1.0 / SCORE_DISTANCE_FROM_DIAGONAL;
+    double score = 0.0;
+    for (const Point& n : neighbours) {
+        int xDiff = n.x - p.x, yDiff = n.y - p.y;
+        score += ((1.0 + a) / (abs(xDiff - yDiff) + 1.0)) - a;
+    }
+    return score;
+}
+
+Point getHighestDensityPoint(int radius, const Cloud& cloud) {
+    Point best = cloud.pts[0];
+    double bestScore = 0.0;
+    for (const Point& p : cloud.pts) {
+        double s = getPointDensityScore(radius, p, cloud);
+        if (s > bestScore) { bestScore = s; best = p; }
+    }
+    return best;
+}
+
+double variance(std::vector<double>& v) {
+    double sum = std::accumulate(v.begin(), v.end(), 0.0);
+    double mean = sum / v.size();
+    std::vector<double> diff(v.size());
+    std::transform(v.begin(), v.end(), diff.begin(), [mean](double x) { return x - mean; });
+    double sqSum = std::inner_product(diff.begin(), diff.end(), diff.begin(), 0.0);
+    return sqSum / v.size();
+}
+
+double getWorstSlope(PointVector traceDots) {
+    double worst = 1.0;
+    std::sort(traceDots.begin(), traceDots.end());
+    for (size_t i = 0; i + 1 < traceDots.size(); ++i) {
+        double slope = getSlope(traceDots[i], traceDots[i + 1]);
+        if (slope > 1) slope = 1.0 / slope;
+        if (slope < worst) worst = slope;
+    }
+    return worst;
+}
+
+double scorePointSet(const PointSet& pointSet, const PointVector& traceDots, bool& failedLine) {
+    if (pointSet.size() == 1) return 0.0;
+    double pointCount = double(pointSet.size());
+    double worstSlopeScore = getWorstSlope(traceDots) * 0.9 + 0.1;
+    std::vector<double> xPlusY;
+    double mn = std::numeric_limits<int>::max(), mx = std::numeric_limits<int>::min();
+    xPlusY.reserve(pointSet.size());
+    for (const Point& p : pointSet) {
+        double sum = p.x + p.y;
+        xPlusY.push_back(sum);
+        if (sum > mx) mx = sum;
+        if (sum < mn) mn = sum;
+    }
+    double uniformVariance = (mx - mn) * (mx - mn) / 12.0;
+    double varianceScore = variance(xPlusY) / uniformVariance;
+    if (varianceScore > 1.0) varianceScore = 1.0 / varianceScore;
+    failedLine = (worstSlopeScore * varianceScore) < 0.8;
+    return pointCount * worstSlopeScore * varianceScore;
+}
+
+PointSet lineTracing(const PointVector& common, PointSet& usedPoints, const Cloud& cloud, int readLen, int refLen,
+                     int lineNum, int verbosity, std::string& console, bool& failedLine, double& pointSetScore) {
+    Cloud startCloud;
+    fillCloud(startCloud, common, usedPoints);
+    Point startPoint = getHighestDensityPoint(LINE_TRACING_START_POINT_SEARCH_RADIUS, startCloud);
+    Point p = startPoint;
+    PointVector traceDots;
+    traceDots.push_back(p);
+    PointVector nearby = radiusSearchAroundPoint(p, (int)TRACE_LINE_COLLECTION_DISTANCE, cloud);
+    PointSet pointSet(nearby.begin(), nearby.end());
+    const int directions[2] = {1, -1};
+    for (int direction : directions) {
+        p = startPoint;
+        const int maxX = readLen, maxY = refLen;
+        while (true) {
+            int step = direction * TRACE_LINE_STEP_DISTANCE;
+            Point previousP = p;
+            Point newP(p.x + step, p.y + step);
+            bool left = false;
+            if (direction == 1 && (newP.x > maxX || newP.y > maxY)) left = true;
+            if (direction == -1 && (newP.x < 0 || newP.y < 0)) left = true;
+            PointSet pointsNearLine;
+            p = mutateLineToBestFitPoints(previousP, newP, cloud, pointsNearLine, left);
+            traceDots.push_back(p);
+            for (const Point& q : pointsNearLine)  // addPointsNearLine :506-512
+                if (distanceToLineSegment(q, previousP, p) <= TRACE_LINE_COLLECTION_DISTANCE) pointSet.insert(q);
+            if (left) break;
+        }
+    }
+    pointSetScore = scorePointSet(pointSet, traceDots, failedLine);
+    if (verbosity > 2) {
+        console += "    line " + std::to_string(lineNum + 1) + ": " + std::to_string(pointSet.size()) + " points, " +
+                   "score=" + std::to_string(pointSetScore) + " (" + (failedLine ? "bad" : "good") + ")\n";
+    }
+    for (const Point& q : pointSet) usedPoints.insert(q);
+    return pointSet;
+}
+
+// ------------------------------------------------------------------ seeds (SeqAn Seed<Simple>, Unordered SeedSet)
+struct LessBeginDiagonal {
+    bool operator()(const ChainSeed& a, const ChainSeed& b) const { return (a.beginH - a.beginV) < (b.beginH - b.beginV); }
+};
+typedef std::multiset<ChainSeed, LessBeginDiagonal> SeedMultiSet;
+
+// seeds_combination.h:102-124 (Merge): b right of / overlapping a, diagonals at most maxDiag apart
+bool combineable(const ChainSeed& a, const ChainSeed& b, unsigned maxDiag) {
+    if (b.beginH < a.beginH || b.beginV < a.beginV) return false;
+    if (b.beginH > a.endH || b.beginV > a.endV) return false;
+    long d = (a.endH - a.endV) - (b.beginH - b.beginV);
+    if ((unsigned)std::labs(d) > maxDiag) return false;
+    return true;
+}
+
+void mergeInto(ChainSeed& seed, const ChainSeed& other) {  // seeds_combination.h:186-197
+    seed.beginH = std::min(seed.beginH, other.beginH);
+    seed.beginV = std::min(seed.beginV, other.beginV);
+    seed.endH = std::max(seed.endH, other.endH);
+    seed.endV = std::max(seed.endV, other.endV);
+    seed.lowerDiag = std::min(seed.lowerDiag, other.lowerDiag);
+    seed.upperDiag = std::max(seed.upperDiag, other.upperDiag);
+}
+
+bool addSeedMerge(SeedMultiSet& set, const ChainSeed& seed, unsigned maxDiag) {  // seed_set_unordered.h:248-343
+    for (SeedMultiSet::iterator it = set.begin(); it != set.end(); ++it) {
+        if (combineable(*it, seed, maxDiag)) {
+            ChainSeed left = *it;
+            mergeInto(left, seed);
+            set.erase(it);
+            set.insert(left);
+            return true;
+        } else if (combineable(seed, *it, maxDiag)) {
+            ChainSeed left = seed;
+            mergeInto(left, *it);
+            set.erase(it);
+            set.insert(left);
+            return true;
+        }
+    }
+    return false;
+}
+
+// seeds_global_chaining.h:102-280 (Gusfield sparse chaining, maximising the summed seed sizes)
+void chainSeedsGlobally(std::vector<ChainSeed>& target, const SeedMultiSet& seedSet) {
+    typedef unsigned long TPos;
+    std::vector<ChainSeed> seeds(seedSet.begin(), seedSet.end());
+    struct IntervalPoint {
+        TPos pos; bool isBegin; unsigned idx;
+        bool operator<(const IntervalPoint& o) const {
+            if (pos < o.pos) return true;
+            if (pos == o.pos && isBegin < o.isBegin) return true;
+            if (pos == o.pos && isBegin == o.isBegin && idx < o.idx) return true;
+            return false;
+        }
+    };
+    struct Solution {
+        TPos endV; TPos quality; unsigned idx;
+        bool operator<(const Solution& o) const {
+            if (endV < o.endV) return true;
+            if (endV == o.endV && quality < o.quality) return true;
+            if (endV == o.endV && quality == o.quality && idx < o.idx) return true;
+            return false;
+        }
+    };
+    const unsigned NONE = std::numeric_limits<unsigned>::max();
+    std::vector<IntervalPoint> points;
+    std::map<unsigned, TPos> quality;
+    std::map<unsigned, unsigned> predecessor;
+    for (unsigned i = 0; i < seeds.size(); ++i) {
+        quality[i] = (TPos)std::max(seeds[i].endH - seeds[i].beginH, seeds[i].endV - seeds[i].beginV);
+        predecessor[i] = NONE;
+        points.push_back(IntervalPoint{(TPos)seeds[i].beginH, true, i});
+        points.push_back(IntervalPoint{(TPos)seeds[i].endH, false, i});
+    }
+    std::sort(points.begin(), points.end());
+    std::multiset<Solution> sols;
+    for (const IntervalPoint& pt : points) {
+        const ChainSeed& seedK = seeds[pt.idx];
+        if (pt.isBegin) {
+            Solution ref{(TPos)seedK.beginV, std::numeric_limits<TPos>::max(), NONE};
+            std::multiset<Solution>::iterator itJ = sols.upper_bound(ref);
+            if (itJ == sols.begin()) {
+                if (sols.size() > 0 && sols.rbegin()->endV <= (TPos)seedK.beginV) { itJ = sols.end(); --itJ; }
+                else continue;
+            } else
+                --itJ;
+            quality[pt.idx] += itJ->quality;
+            predecessor[pt.idx] = itJ->idx;
+        } else {
+            Solution ref{(TPos)seedK.endV, 0, NONE};
+            std::multiset<Solution>::iterator itSol = sols.upper_bound(ref);
+            if (itSol == sols.end()) {
+                sols.insert(Solution{(TPos)seedK.endV, quality[pt.idx], pt.idx});
+            } else {
+                const ChainSeed& seedJ = seeds[itSol->idx];
+                if (seedJ.endV > seedK.endV || (seedJ.endV == seedK.endV && quality[pt.idx] > itSol->quality))
+                    sols.insert(Solution{(TPos)seedK.endV, quality[pt.idx], pt.idx});
+            }
+            std::multiset<Solution>::iterator itDel = sols.upper_bound(ref);
+            while (itDel != sols.end()) {
+                std::multiset<Solution>::iterator ptr = itDel;
+                ++itDel;
+                if (quality[pt.idx] > ptr->quality) sols.erase(ptr);
+            }
+        }
+    }
+    target.clear();
+    if (sols.empty()) return;
+    unsigned next = sols.rbegin()->idx;
+    while (next != NONE) {
+        target.push_back(seeds[next]);
+        next = predecessor[next];
+    }
+    std::reverse(target.begin(), target.end());
+}
+
+long long maxSeedChainGapArea(const std::vector<ChainSeed>& chain, int readLen, int refLen) {  // :321-347
+    int prevH = 0, prevV = 0;
+    long long maxArea = 0;
+    const int n = (int)chain.size();
+    for (int i = 0; i <= n; ++i) {
+        int hPos = (i == n) ? readLen : (int)chain[(size_t)i].beginH;
+        int vPos = (i == n) ? refLen : (int)chain[(size_t)i].beginV;
+        long long area = (long long)(hPos - prevH) * (long long)(vPos - prevV);
+        if (area > maxArea) maxArea = area;
+        if (i < n) { prevH = (int)chain[(size_t)i].endH; prevV = (int)chain[(size_t)i].endV; }
+    }
+    return maxArea;
+}
+
+}  // namespace
+
+void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const std::string& trimmedRefSeq,
+               const SensitivityParams& sp, int verbosity, const std::string& refName, int refStart, int refEnd,
+               RangeSeeds& out) {
+    out.chains.clear();
+    const int kSize = sp.kSize;
+    const int readLen = (int)readSeq.size(), refLen = (int)trimmedRefSeq.size();
+    if (verbosity > 2)
+        out.console += "Range: " + refName + ": " + std::to_string(refStart) + " - " + std::to_string(refEnd) + "\n";
+    // common k-mers :197-207
+    PointVector common;
+    const int maxI = refLen - kSize + 1;
+    std::string kmer;
+    for (int i = 0; i < maxI; ++i) {
+        kmer.assign(trimmedRefSeq, (size_t)i, (size_t)kSize);
+        KmerPosMap::const_iterator it = readKmers.find(kmer);
+        if (it != readKmers.end())
+            for (int pos : it->second) common.push_back(Point(pos, i));
+    }
+    if (verbosity > 2)
+        out.console += "    common " + std::to_string(kSize) + "-mers: " + std::to_string(common.size()) + "\n";
+    if (common.empty()) return;  // the reference dereferences an empty vector here (undefined); no alignment
+    PointSet usedPoints;
+    Cloud cloud;
+    fillCloud(cloud, common, usedPoints);
+    std::vector<PointSet> goodPointSets;
+    double bestPointScore = 0.0;
+    for (int lineNum = 0; lineNum < sp.maxLineTraceCount; ++lineNum) {
+        bool failedLine = false;
+        double pointSetScore = 0.0;
+        PointSet pointSet = lineTracing(common, usedPoints, cloud, readLen, refLen, lineNum, verbosity, out.console,
+                                        failedLine, pointSetScore);
+        if (pointSetScore > bestPointScore) bestPointScore = pointSetScore;
+        if (!failedLine) goodPointSets.push_back(pointSet);
+        else if (pointSetScore == bestPointScore) goodPointSets.push_back(pointSet);
+        if (!failedLine && lineNum >= sp.minLineTraceCount - 1) break;
+        if (usedPoints.size() >= common.size()) break;
+    }
+    for (const PointSet& good : goodPointSets) {
+        PointVector pts;
+        pts.reserve(good.size());
+        for (const Point& p : good) pts.push_back(p);
+        std::sort(pts.begin(), pts.end());
+        SeedMultiSet seedSet;
+        for (const Point& p : pts) {
+            ChainSeed s{(long)p.x, (long)p.y, (long)p.x + kSize, (long)p.y + kSize, (long)p.x - (long)p.y, (long)p.x - (long)p.y};
+            if (!addSeedMerge(seedSet, s, 2)) seedSet.insert(s);
+        }
+        std::vector<ChainSeed> chain;
+        chainSeedsGlobally(chain, seedSet);
+        if (chain.empty()) return;
+        if (maxSeedChainGapArea(chain, readLen, refLen) > MAX_BANDED_ALIGNMENT_GAP_AREA) return;
+        out.chains.push_back(chain);
+    }
+}
+
+}  // namespace ub200

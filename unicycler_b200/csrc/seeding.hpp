@@ -1,0 +1,38 @@
+// Host seeding stage of semiGlobalAlignment (unicycler/src/semi_global_align.cpp:156-291 and helpers):
+// common k-mers -> kd-tree line tracing -> seed merge -> sparse global chaining.  0.6 % of the
+// reference's runtime and floating-point / container-order sensitive, so it stays on the host and keeps
+// the reference's container types and iteration orders (SURVEY.md §7 hard part 4).
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "host_align.hpp"
+
+namespace ub200 {
+
+typedef std::unordered_map<std::string, std::vector<int> > KmerPosMap;  // include/kmers.h:26
+
+struct SensitivityParams {  // include/settings.h:17-42
+    int kSize, bandSize, minLineTraceCount, maxLineTraceCount;
+};
+SensitivityParams sensitivityParams(int level);
+
+// KmerPositions::addPositions (src/kmers.cpp:51-65)
+void buildKmerPositions(const std::string& sequence, int kSize, KmerPosMap& out);
+
+struct RangeSeeds {
+    std::vector<std::vector<ChainSeed> > chains;  // one per accepted point set, in the reference's order
+    std::string console;                          // verbosity > 2 text
+};
+
+// Everything alignReadToReferenceRange does before bandedChainAlignment (semi_global_align.cpp:197-291).
+// The returned chains stop at the first point set whose chain is empty or whose gap area exceeds
+// MAX_BANDED_ALIGNMENT_GAP_AREA, like the early returns at :286-291.
+void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const std::string& trimmedRefSeq,
+               const SensitivityParams& sp, int verbosity, const std::string& refName, int refStart, int refEnd,
+               RangeSeeds& out);
+
+std::string reverseComplement(const std::string& s);  // src/string_functions.cpp:52-79
+
+}  // namespace ub200

@@ -1,0 +1,256 @@
+"""ctypes bindings of libunicycler_b200.so mirroring unicycler/cpp_wrappers.py (reference file:line cited per
+function).  Strings returned by the library are malloc()ed there and released through freeCString, exactly
+like cpp_wrappers.c_string_to_python_string (cpp_wrappers.py:126-133)."""
+import ctypes
+import os
+from ctypes import c_bool, c_char_p, c_double, c_int, c_int64, c_void_p, POINTER
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libunicycler_b200.so')
+_LIB = None
+
+
+def load_library():
+    """Loads the shared library (cpp_wrappers.py:23-28).  Raises if it has not been built: the product has no
+    pure-Python or CPU path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError('libunicycler_b200.so not found at %s — run `python -c "import __graft_entry__ as g; '
+                          'g.build()"` or `make -C unicycler_b200/csrc`' % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.semiGlobalAlignment.argtypes = [c_char_p, c_char_p, c_int, c_char_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_double, c_bool, c_int]
+    L.semiGlobalAlignment.restype = c_void_p
+    for name in ('fullyGlobalAlignment', 'pathAlignment'):
+        f = getattr(L, name)
+        f.argtypes = [c_char_p, c_char_p, c_int, c_int, c_int, c_int, c_bool, c_int]
+        f.restype = c_void_p
+    L.getRandomSequenceAlignmentScores.argtypes = [c_int] * 6
+    L.getRandomSequenceAlignmentScores.restype = c_void_p
+    L.newRefSeqs.argtypes = []
+    L.newRefSeqs.restype = c_void_p
+    L.addRefSeq.argtypes = [c_void_p, c_char_p, c_char_p]
+    L.addRefSeq.restype = None
+    L.deleteRefSeqs.argtypes = [c_void_p]
+    L.deleteRefSeqs.restype = None
+    L.freeCString.argtypes = [c_void_p]
+    L.freeCString.restype = None
+    L.ub200_globalAlignmentBatch.argtypes = [c_int, POINTER(c_char_p), POINTER(c_char_p), c_int, c_int, c_int, c_int,
+                                             c_int, c_bool, c_int, POINTER(c_void_p)]
+    L.ub200_globalAlignmentBatch.restype = c_int
+    L.ub200_chainAlignment.argtypes = [c_char_p, c_char_p, POINTER(c_int64), c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_char_p, c_char_p, c_int]
+    L.ub200_chainAlignment.restype = c_void_p
+    L.ub200_chainAlignmentBatch.argtypes = [c_int, POINTER(c_char_p), POINTER(c_char_p), POINTER(c_int64),
+                                            POINTER(c_int64), c_int, c_int, c_int, c_int, c_int, POINTER(c_char_p),
+                                            POINTER(c_char_p), POINTER(c_int), POINTER(c_void_p)]
+    L.ub200_chainAlignmentBatch.restype = c_int
+    L.ub200_semiGlobalAlignmentBatch.argtypes = [c_int, POINTER(c_char_p), POINTER(c_char_p), POINTER(c_char_p),
+                                                 c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]
+    L.ub200_semiGlobalAlignmentBatch.restype = c_int
+    L.ub200_seedChains.argtypes = [c_char_p, c_char_p, c_int]
+    L.ub200_seedChains.restype = c_void_p
+    L.ub200_lastStats.argtypes = [POINTER(c_int64), POINTER(c_double), POINTER(c_int64), POINTER(c_double),
+                                  POINTER(c_double)]
+    L.ub200_lastStats.restype = None
+    L.ub200_chainBenchPrepare.argtypes = [c_int, POINTER(c_char_p), POINTER(c_char_p), POINTER(c_int64),
+                                          POINTER(c_int64), c_int, c_int, c_int, c_int, c_int]
+    L.ub200_chainBenchPrepare.restype = c_int
+    L.ub200_chainBenchRun.argtypes = []
+    L.ub200_chainBenchRun.restype = c_double
+    L.ub200_chainBenchFinish.argtypes = [POINTER(c_void_p)]
+    L.ub200_chainBenchFinish.restype = c_int
+    L.ub200_setDevice.argtypes = [c_int]
+    L.ub200_setDevice.restype = c_int
+    L.ub200_intPeakOpsPerSec.argtypes = []
+    L.ub200_intPeakOpsPerSec.restype = c_double
+    L.ub200_version.argtypes = []
+    L.ub200_version.restype = c_char_p
+    _LIB = L
+    return L
+
+
+def _to_str(ptr):
+    s = ctypes.cast(ptr, c_char_p).value.decode()
+    load_library().freeCString(ptr)
+    return s
+
+
+def _cstrs(items):
+    arr = (c_char_p * len(items))()
+    arr[:] = [x.encode() if isinstance(x, str) else x for x in items]
+    return arr
+
+
+# ---- reference-compatible wrappers -------------------------------------------------------------------------------
+
+def semi_global_alignment(read_name, read_sequence, verbosity, minimap_alignments_str, ref_seqs_ptr, match_score,
+                          mismatch_score, gap_open_score, gap_extend_score, low_score_threshold, keep_bad,
+                          sensitivity_level):
+    """cpp_wrappers.py:47-55"""
+    ptr = load_library().semiGlobalAlignment(read_name.encode(), read_sequence.encode(), verbosity,
+                                             minimap_alignments_str.encode(), ref_seqs_ptr, match_score,
+                                             mismatch_score, gap_open_score, gap_extend_score, low_score_threshold,
+                                             keep_bad, sensitivity_level)
+    return _to_str(ptr)
+
+
+def fully_global_alignment(sequence_1, sequence_2, scoring_scheme, use_banding, band_size):
+    """cpp_wrappers.py:90-95; scoring_scheme = (match, mismatch, gap_open, gap_extend) or an object with those
+    attributes (alignment.AlignmentScoringScheme)."""
+    m, mm, go, ge = _scheme(scoring_scheme)
+    return _to_str(load_library().fullyGlobalAlignment(sequence_1.encode(), sequence_2.encode(), m, mm, go, ge,
+                                                       use_banding, band_size))
+
+
+def path_alignment(partial_seq, full_seq, scoring_scheme, use_banding, band_size):
+    """cpp_wrappers.py:112-117"""
+    m, mm, go, ge = _scheme(scoring_scheme)
+    return _to_str(load_library().pathAlignment(partial_seq.encode(), full_seq.encode(), m, mm, go, ge, use_banding,
+                                                band_size))
+
+
+def get_random_sequence_alignment_mean_and_std_dev(seq_length, count, scoring_scheme):
+    """cpp_wrappers.py:169-175"""
+    m, mm, go, ge = _scheme(scoring_scheme)
+    parts = _to_str(load_library().getRandomSequenceAlignmentScores(seq_length, count, m, mm, go, ge)).split(',')
+    return float(parts[0]), float(parts[1])
+
+
+def new_ref_seqs():
+    return load_library().newRefSeqs()
+
+
+def add_ref_seq(ref_seqs_ptr, name, sequence):
+    load_library().addRefSeq(ref_seqs_ptr, name.encode(), sequence.encode())
+
+
+def delete_ref_seqs(ref_seqs_ptr):
+    load_library().deleteRefSeqs(ref_seqs_ptr)
+
+
+def _scheme(s):
+    if isinstance(s, (tuple, list)):
+        return tuple(int(x) for x in s)
+    return s.match, s.mismatch, s.gap_open, s.gap_extend
+
+
+# ---- additive batch API --------------------------------------------------------------------------------------------
+
+def _global_batch(mode, seqs_1, seqs_2, scoring_scheme, use_banding, band_size):
+    m, mm, go, ge = _scheme(scoring_scheme)
+    n = len(seqs_1)
+    out = (c_void_p * n)()
+    rc = load_library().ub200_globalAlignmentBatch(n, _cstrs(seqs_1), _cstrs(seqs_2), mode, m, mm, go, ge, use_banding,
+                                                   band_size, out)
+    if rc != 0:
+        raise RuntimeError('ub200_globalAlignmentBatch failed: %d' % rc)
+    return [_to_str(p) for p in out]
+
+
+def fully_global_alignment_batch(seqs_1, seqs_2, scoring_scheme, use_banding, band_size):
+    return _global_batch(0, seqs_1, seqs_2, scoring_scheme, use_banding, band_size)
+
+
+def path_alignment_batch(seqs_1, seqs_2, scoring_scheme, use_banding, band_size):
+    return _global_batch(1, seqs_1, seqs_2, scoring_scheme, use_banding, band_size)
+
+
+def _seed_array(seeds):
+    flat = [int(x) for s in seeds for x in s]
+    return (c_int64 * max(1, len(flat)))(*flat)
+
+
+def chain_alignment(read_seq, trimmed_ref_seq, seeds, scoring_scheme, band_size, read_name, ref_name, ref_offset):
+    m, mm, go, ge = _scheme(scoring_scheme)
+    return _to_str(load_library().ub200_chainAlignment(read_seq.encode(), trimmed_ref_seq.encode(), _seed_array(seeds),
+                                                       len(seeds), m, mm, go, ge, band_size, read_name.encode(),
+                                                       ref_name.encode(), ref_offset))
+
+
+def _chain_args(jobs):
+    """jobs: list of dicts with readSeq, refSeq, seeds[, readName, refName, refOffset]."""
+    n = len(jobs)
+    flat, offs = [], [0]
+    for j in jobs:
+        for s in j['seeds']:
+            flat.extend(int(x) for x in s)
+        offs.append(offs[-1] + len(j['seeds']))
+    seeds = (c_int64 * max(1, len(flat)))(*flat)
+    offsets = (c_int64 * (n + 1))(*offs)
+    return n, _cstrs([j['readSeq'] for j in jobs]), _cstrs([j['refSeq'] for j in jobs]), seeds, offsets
+
+
+def chain_alignment_batch(jobs, scoring_scheme, band_size):
+    m, mm, go, ge = _scheme(scoring_scheme)
+    n, reads, refs, seeds, offsets = _chain_args(jobs)
+    names = _cstrs([j.get('readName', 'read+') for j in jobs])
+    rnames = _cstrs([j.get('refName', 'ref') for j in jobs])
+    roffs = (c_int * n)(*[int(j.get('refOffset', 0)) for j in jobs])
+    out = (c_void_p * n)()
+    rc = load_library().ub200_chainAlignmentBatch(n, reads, refs, seeds, offsets, m, mm, go, ge, band_size, names,
+                                                  rnames, roffs, out)
+    if rc != 0:
+        raise RuntimeError('ub200_chainAlignmentBatch failed: %d' % rc)
+    return [_to_str(p) for p in out]
+
+
+def semi_global_alignment_batch(read_names, read_seqs, hit_strs, ref_seqs_ptr, scoring_scheme, sensitivity_level=0):
+    m, mm, go, ge = _scheme(scoring_scheme)
+    n = len(read_names)
+    out = (c_void_p * n)()
+    rc = load_library().ub200_semiGlobalAlignmentBatch(n, _cstrs(read_names), _cstrs(read_seqs), _cstrs(hit_strs),
+                                                       ref_seqs_ptr, m, mm, go, ge, sensitivity_level, out)
+    if rc != 0:
+        raise RuntimeError('ub200_semiGlobalAlignmentBatch failed: %d' % rc)
+    return [_to_str(p) for p in out]
+
+
+def seed_chains(read_seq, trimmed_ref_seq, sensitivity_level=0):
+    """Host seeding stage only -> list of chains, each a list of [beginH, beginV, endH, endV, lowerDiag, upperDiag]."""
+    out = _to_str(load_library().ub200_seedChains(read_seq.encode(), trimmed_ref_seq.encode(), sensitivity_level))
+    parts = out.split(';')
+    chains = []
+    for c in parts[1:1 + int(parts[0])]:
+        body = c.split(':', 1)[1]
+        chains.append([[int(x) for x in s.split(',')] for s in body.split('|')] if body else [])
+    return chains
+
+
+def last_stats():
+    cells, launches = c_int64(), c_int64()
+    kms, h2d, d2h = c_double(), c_double(), c_double()
+    load_library().ub200_lastStats(ctypes.byref(cells), ctypes.byref(kms), ctypes.byref(launches), ctypes.byref(h2d),
+                                   ctypes.byref(d2h))
+    return dict(cells=cells.value, kernel_ms=kms.value, launches=launches.value, h2d_ms=h2d.value, d2h_ms=d2h.value)
+
+
+def set_device(device):
+    return load_library().ub200_setDevice(int(device))
+
+
+def int_peak_ops_per_sec():
+    return load_library().ub200_intPeakOpsPerSec()
+
+
+class ChainBench(object):
+    """Device-resident benchmark harness for the banded-chain path: inputs are uploaded and planned once;
+    run() launches the DP kernel on the resident inputs; finish() fetches and formats the results."""
+
+    def __init__(self, jobs, scoring_scheme, band_size):
+        m, mm, go, ge = _scheme(scoring_scheme)
+        self.n, reads, refs, seeds, offsets = _chain_args(jobs)
+        self._keep = (reads, refs, seeds, offsets)
+        rc = load_library().ub200_chainBenchPrepare(self.n, reads, refs, seeds, offsets, m, mm, go, ge, band_size)
+        if rc != 0:
+            raise RuntimeError('ub200_chainBenchPrepare failed: %d' % rc)
+
+    def run(self):
+        load_library().ub200_chainBenchRun()
+
+    def finish(self, want_results=True):
+        out = (c_void_p * self.n)()
+        load_library().ub200_chainBenchFinish(out)
+        res = [_to_str(p) for p in out]
+        return res if want_results else None
