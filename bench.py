@@ -1,0 +1,351 @@
+#!/usr/bin/env python3
+"""Benchmark of the long-read alignment hot path (BASELINE.json metric: GCUPS / reads per second).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): sample_data/long_reads_low_depth (30 long reads, 261,649 bp) aligned
+semi-globally to sample_data/reference.fasta (3 replicons), scheme 3,-6,-5,-2, sensitivity 0 — 171
+bandedChainAlignment jobs, 23,019 sub-DPs, 8.222e9 DP cells (reference cell definition).
+The inputs (reads, references, the reference minimap's hit strings) are the committed fixture
+tests/golden/semiglobal_sample.json.gz.  One "step" aligns the whole read set once.
+
+  value  GCUPS with inputs resident in HBM: K back-to-back launches of the DP kernel, CUDA events on the
+         launching stream (weak scaling: every rank aligns one copy of the read set; cells of all ranks ÷ max time).
+  e2e    the same metric through the reference-facing C ABI with HOST buffers (semiGlobalAlignment batch call:
+         host seeding + planning, H2D, kernel, D2H, trace gluing, CIGAR formatting [+ result all-gather for N>1]).
+  --impl reference  times the UNMODIFIED reference C++ library (oracle/_ref, built from /root/reference by
+         oracle/Makefile.ref) on the host cores on a bounded sample of the same reads (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+
+SCHEME = (3, -6, -5, -2)
+OPS_PER_CELL_AFFINE = 17  # algorithmic int32 ops per affine cell update
+WORKLOAD = ('sample_data long_reads_low_depth (30 reads) vs reference.fasta (3 replicons): semi-global, '
+            'scheme 3,-6,-5,-2, sensitivity 0; 171 banded-chain alignments, 23019 sub-DPs')
+
+
+def load_workload():
+    from oracle_lib import golden_chain_jobs, load_golden
+    d = load_golden('semiglobal_sample.json.gz')
+    jobs = golden_chain_jobs(d)
+    reads = [r for r in d['reads'] if r[0] in d['expected']]
+    return d, jobs, reads
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(suffix='.csv')
+        q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(',')]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, p[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            os.remove(self.path)
+        except Exception:
+            pass
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(smax) if smax else None),
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return None
+
+
+def cpu_reference_run(reads, refs, threads, expected=None):
+    """Unmodified reference library on the host cores (Python threads; ctypes releases the GIL, exactly how
+    unicycler_align.py:203-225 drives it).  Returns wall seconds."""
+    from multiprocessing.dummy import Pool as ThreadPool
+    from oracle_lib import REF_LIB, mask_semi_global
+    from refdriver import AbiLib
+    lib = AbiLib(REF_LIB)
+    h = lib.new_refs(refs)
+
+    def one(r):
+        return lib.semi_global(r[0], r[1], r[2], h, SCHEME)
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        outs = [one(r) for r in reads]
+    else:
+        pool = ThreadPool(threads)
+        outs = pool.map(one, reads)
+        pool.close()
+    dt = time.perf_counter() - t0
+    lib.delete_refs(h)
+    if expected is not None:
+        for r, o in zip(reads, outs):
+            assert mask_semi_global(o) == expected[r[0]], 'reference library output differs from the golden fixture'
+    return dt
+
+
+def cpu_port_run(jobs, threads):
+    """Fallback when oracle/_ref did not travel: the oracle port (scalar C++) on the chain jobs."""
+    from multiprocessing.dummy import Pool as ThreadPool
+    from oracle_lib import Oracle
+    orc = Oracle()
+
+    def one(j):
+        return orc.chain(j['readSeq'], j['refSeq'], j['seeds'], SCHEME, j['band'], j['readName'], j['refName'], j['refOffset'])
+
+    t0 = time.perf_counter()
+    pool = ThreadPool(threads)
+    pool.map(one, jobs)
+    pool.close()
+    return time.perf_counter() - t0
+
+
+def bounded_sample(reads, jobs, cells_per_job, budget_cells):
+    """First reads (file order) whose summed DP cells stay within budget_cells (at least one read)."""
+    per_read = {}
+    for j, c in zip(jobs, cells_per_job):
+        per_read[j['readName'][:-1]] = per_read.get(j['readName'][:-1], 0) + c
+    chosen, total = [], 0
+    for r in sorted(reads, key=lambda r: per_read.get(r[0], 0)):
+        c = per_read.get(r[0], 0)
+        if chosen and total + c > budget_cells:
+            break
+        chosen.append(r)
+        total += c
+    return chosen, total
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    import unicycler_b200 as ub
+    from oracle_lib import REF_LIB
+    d, jobs, reads = load_workload()
+    cells_per_job = [ub.chain_cells(len(j['readSeq']), len(j['refSeq']), j['seeds'], j['band'])[0] for j in jobs]
+    threads = os.cpu_count() or 1
+    # ~0.04 GCUPS per thread: keep one step around 10-20 s
+    budget = int(0.04e9 * min(threads, 30) * 12)
+    sample, cells = bounded_sample(reads, jobs, cells_per_job, budget)
+    use_threads = max(1, min(threads, len(sample)))
+    kind = 'reference' if os.path.isfile(REF_LIB) else 'port'
+    names = set(r[0] for r in sample)
+    sample_jobs = [j for j in jobs if j['readName'][:-1] in names]
+
+    def step():
+        if kind == 'reference':
+            return cpu_reference_run(sample, d['refs'], use_threads)
+        return cpu_port_run(sample_jobs, use_threads)
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    times = [step() for _ in range(args.steps)]
+    dt = sum(times) / len(times)
+    gcups = cells / dt / 1e9
+    line = dict(metric='GCUPS (DP cell updates per second, semi-global long-read alignment)', value=gcups, unit='GCUPS',
+                impl='reference', n_gpus=args.gpus, steps=args.steps, warmup=min(args.warmup, 1),
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='int32',
+                data='sample_data fixture (tests/golden/semiglobal_sample.json.gz)',
+                config=dict(workload=WORKLOAD, sample='%d of %d reads (smallest first), %.3g DP cells per step' %
+                            (len(sample), len(reads), cells)),
+                reads_per_s=len(sample) / dt,
+                cpu_baseline=dict(value=gcups, unit='GCUPS', cores=use_threads, kind=kind,
+                                  sample='%d of %d reads, %.3g cells' % (len(sample), len(reads), cells)),
+                e2e=dict(value=gcups, unit='GCUPS', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import unicycler_b200 as ub
+    from oracle_lib import mask_semi_global
+    from unicycler_b200 import sharding
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product has no CPU path')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    ub.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist_mod.init_process_group('nccl', rank=rank, world_size=world, device_id=device)
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    d, jobs, reads = load_workload()
+    # reference set: replicated on every GPU; rank 0 broadcasts it once over NCCL (setup, not timed)
+    refs = d['refs'] if rank == 0 or dist is None else None
+    if dist is not None:
+        refs = sharding.broadcast_references(refs, dist, device)
+    cells_per_job = [ub.chain_cells(len(j['readSeq']), len(j['refSeq']), j['seeds'], j['band'])[0] for j in jobs]
+    cells_per_rank = sum(cells_per_job)
+
+    # ---------------- device-resident arm (value): K launches of the DP kernel on resident inputs
+    bench = ub.ChainBench(jobs, SCHEME, jobs[0]['band'])
+    tb = ub.transfer_bytes()
+    for _ in range(args.warmup):
+        bench.run_steps(1)
+    # parity gate on the very data that is timed
+    res = bench.finish(True)
+    from oracle_lib import mask_ms
+    bad = sum(1 for j, g in zip(jobs, res) if mask_ms(g) != j['result'])
+    if bad:
+        raise SystemExit('parity failure: %d of %d alignments differ from the reference golden output' % (bad, len(jobs)))
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    total_ms = bench.run_steps(args.steps)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    ms_per_step = max_over_ranks(total_ms / args.steps)
+    gcups = world * cells_per_rank / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------- end-to-end arm through the C ABI with host buffers
+    h = ub.new_ref_seqs()
+    for name, seq in refs:
+        ub.add_ref_seq(h, name, seq)
+    names = [r[0] for r in reads]
+    seqs = [r[1] for r in reads]
+    hits = [r[2] for r in reads]
+
+    def e2e_step():
+        out = ub.semi_global_alignment_batch(names, seqs, hits, h, SCHEME, 0)
+        if dist is not None:
+            out = sharding.all_gather_strings(out, dist, device)
+        return out
+
+    for _ in range(min(args.warmup, 2)):
+        out = e2e_step()
+    bad = sum(1 for r, o in zip(reads, out[:len(reads)]) if mask_semi_global(o) != d['expected'][r[0]])
+    if bad:
+        raise SystemExit('e2e parity failure: %d reads differ from the reference golden output' % bad)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    e2e_gcups = world * cells_per_rank / e2e_s / 1e9
+    tb2 = ub.transfer_bytes()
+    clocks = sampler.stop() if sampler else None
+    ub.delete_ref_seqs(h)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        hbm_peak = peaks['hbm_gbs'] if peaks else 6650.0
+        int_peak = ub.int_peak_ops_per_sec()
+        kernel_s = ms_per_step * 1e-3
+        achieved_gbs = cells_per_rank * 1.0 / kernel_s / 1e9  # algorithmic 1 B of trace per DP cell
+        line = dict(
+            metric='GCUPS (DP cell updates per second, semi-global long-read alignment)', value=gcups, unit='GCUPS',
+            n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
+            scaling='weak', vs_baseline=None, dtype='int32',
+            data='sample_data fixture (tests/golden/semiglobal_sample.json.gz); every rank aligns one copy',
+            config=dict(workload=WORKLOAD, cells_per_gpu_per_step=cells_per_rank, jobs_per_gpu=len(jobs),
+                        reads_per_gpu=len(reads), resident_ctas=tb['ctas'],
+                        l2='per-step trace working set %.2f GB >> 126 MB L2 (no explicit flush needed)' % (tb['trace_bytes'] / 1e9),
+                        parallelism='reads sharded over %d GPU(s); replicated reference; no data-path collective' % world),
+            reads_per_s=world * len(reads) / kernel_s,
+            wall_ms_timed_region=wall_ms,
+            gpu_launches=args.steps,
+            e2e=dict(value=e2e_gcups, unit='GCUPS', h2d_bytes_per_step=tb2['h2d_bytes'], d2h_bytes_per_step=tb2['d2h_bytes'],
+                     ms_per_step=e2e_s * 1e3, reads_per_s=world * len(reads) / e2e_s,
+                     path='ub200_semiGlobalAlignmentBatch (host strings in, result strings out)'),
+            roofline=dict(bound='hbm', achieved=achieved_gbs, peak=hbm_peak, unit='GB/s', frac=achieved_gbs / hbm_peak,
+                          traffic=None, kernel='dpJobKernel', bytes_per_cell=1,
+                          peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
+                          note='integer max-plus kernel: the binding roofline is int_roofline, HBM trace traffic is secondary'),
+            int_roofline=dict(achieved_ops_per_s=cells_per_rank * OPS_PER_CELL_AFFINE / kernel_s, peak_ops_per_s=int_peak,
+                              frac=cells_per_rank * OPS_PER_CELL_AFFINE / kernel_s / int_peak if int_peak else None,
+                              ops_per_cell=OPS_PER_CELL_AFFINE, peak_source='ub200_intPeakOpsPerSec microbenchmark (IADD3/VIMNMX/IMAD mix, all SMs)'),
+            clocks=clocks)
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle_lib import REF_LIB
+            threads = os.cpu_count() or 1
+            budget = int(0.04e9 * min(threads, 30) * 12)
+            sample, cells = bounded_sample(reads, jobs, cells_per_job, budget)
+            use_threads = max(1, min(threads, len(sample)))
+            if os.path.isfile(REF_LIB):
+                dt = cpu_reference_run(sample, d['refs'], use_threads, d['expected'])
+                kind = 'reference'
+            else:
+                nm = set(r[0] for r in sample)
+                dt = cpu_port_run([j for j in jobs if j['readName'][:-1] in nm], use_threads)
+                kind = 'port'
+            line['cpu_baseline'] = dict(value=cells / dt / 1e9, unit='GCUPS', cores=use_threads, kind=kind,
+                                        sample='%d of %d reads (smallest first), %.3g DP cells, %.1f s' %
+                                        (len(sample), len(reads), cells, dt))
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -106,6 +106,12 @@ int ub200_chainBenchPrepare(int n, const char* const* readSeqs, const char* cons
                             int gapOpenScore, int gapExtensionScore, int bandSize);
 double ub200_chainBenchRun(void);
 int ub200_chainBenchFinish(char** results);
+/* `steps` back-to-back launches on the resident inputs; returns their total CUDA-event time in ms. */
+double ub200_chainBenchRunSteps(int steps);
+/* Bytes moved by the last run (host->device, device->host), trace bytes written per launch, resident CTAs. */
+void ub200_lastTransferBytes(int64_t* h2d, int64_t* d2h, int64_t* traceBytes, int* ctas);
+/* Reference DP-cell count and sub-DP count of one banded-chain alignment; planner only. */
+int64_t ub200_chainCells(int readLen, int refLen, const int64_t* seeds, int nSeeds, int bandSize, int* nGrids);
 
 /* Selects the CUDA device for this process' engine (before first use).  Returns 0 on success. */
 int ub200_setDevice(int device);

@@ -467,6 +467,31 @@ double ub200_chainBenchRun(void) {
     return 0.0;
 }
 
+double ub200_chainBenchRunSteps(int steps) { return engine().launchTimed(steps); }
+
+void ub200_lastTransferBytes(int64_t* h2d, int64_t* d2h, int64_t* traceBytes, int* ctas) {
+    EngineStats s = engine().lastStats();
+    if (h2d) *h2d = s.h2dBytes;
+    if (d2h) *d2h = s.d2hBytes;
+    if (traceBytes) *traceBytes = s.traceBytes;
+    if (ctas) *ctas = s.ctas;
+}
+
+// Reference DP-cell count of one banded-chain alignment (planner only; needs no GPU).
+int64_t ub200_chainCells(int readLen, int refLen, const int64_t* seeds, int nSeeds, int bandSize, int* nGrids) {
+    std::vector<ChainSeed> chain;
+    chain.resize((size_t)nSeeds);
+    for (int i = 0; i < nSeeds; ++i)
+        chain[(size_t)i] = ChainSeed{(long)seeds[6 * i], (long)seeds[6 * i + 1], (long)seeds[6 * i + 2],
+                                     (long)seeds[6 * i + 3], (long)seeds[6 * i + 4], (long)seeds[6 * i + 5]};
+    std::vector<GridDesc> grids;
+    if (!planChain(chain, readLen, refLen, bandSize, grids)) return -1;
+    int64_t cells = 0;
+    for (const GridDesc& g : grids) cells += referenceCells(g);
+    if (nGrids) *nGrids = (int)grids.size();
+    return cells;
+}
+
 int ub200_chainBenchFinish(char** results) {
     Engine& e = engine();
     e.fetch(g_bench.ptrs);

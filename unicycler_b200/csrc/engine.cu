@@ -428,7 +428,7 @@ __device__ __forceinline__ void fillDispatch(const GridCtx& G) {
     else fillGrid<AFF, CT, false>(G);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) dpJobKernel(KParams P) {
+__global__ void __launch_bounds__(NTHREADS, 1) dpJobKernel(KParams P) {
     __shared__ GridCtx G;
     __shared__ TrackResult TR;
     __shared__ int sJob, sStatus, sNPlanted, sOutLen, sScore;
@@ -442,20 +442,28 @@ __global__ void __launch_bounds__(NTHREADS, 2) dpJobKernel(KParams P) {
         const int jobIdx = P.order[q];
         const JobDev jb = P.jobs[jobIdx];
         if (tid == 0) { sStatus = JOB_OK; sNPlanted = 0; sOutLen = 0; sScore = 0; }
+        long long prof[6] = {0, 0, 0, 0, 0, 0};
+        long long tJob0 = clock64();
         __syncthreads();
         for (int gi = 0; gi < jb.gridCount; ++gi) {
             const GridDesc gd = P.grids[jb.gridBegin + gi];
+            long long c0 = clock64();
             if (tid == 0) setupGrid(G, P, jb, gd, scratch);
             __syncthreads();
+            long long c1 = clock64();
             initGrid(G, gd, sNPlanted);
+            long long c2 = clock64();
             // fill
             if (G.affine) { if (G.complete) fillDispatch<true, true>(G); else fillDispatch<true, false>(G); }
             else { if (G.complete) fillDispatch<false, true>(G); else fillDispatch<false, false>(G); }
             __syncthreads();
+            long long c3 = clock64();
+            long long c4 = c3;
             // tracking + traceback: warp 0
             if (tid < 32) {
                 if (gd.kind == GRID_GLOBAL) trackGlobal(G, TR);
                 else trackChain(G, TR);
+                c4 = clock64();
                 if (tid == 0) {
                     OutStream out;
                     out.buf = P.out + jb.outOff; out.cap = jb.outCap; out.len = sOutLen; out.overflow = false;
@@ -498,11 +506,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) dpJobKernel(KParams P) {
                 }
             }
             __syncthreads();
+            long long c5 = clock64();
+            prof[0] += c1 - c0; prof[1] += c2 - c1; prof[2] += c3 - c2; prof[3] += c4 - c3; prof[4] += c5 - c4;
             if (sStatus != JOB_OK) break;
         }
         if (tid == 0) {
             JobOut jo;
             jo.status = sStatus; jo.score = sScore; jo.outLen = sOutLen; jo.pad = 0;
+            prof[5] = clock64() - tJob0;
+            for (int k = 0; k < 6; ++k) jo.prof[k] = prof[k];
             P.jobOut[jobIdx] = jo;
         }
         __syncthreads();
@@ -530,6 +542,8 @@ static long long hostTraceBytes(const GridDesc& gd, int& nStrips) {
     for (int s = 0; s < nStrips; ++s) total += hostStripChunks(g, s) * 32LL * 32 * R;
     return total;
 }
+
+static const int CTAS_PER_SM = 1;
 
 struct Engine::Impl {
     int device = 0;
@@ -708,7 +722,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     size_t fixed = nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + I.seqBytes + I.outInts * 4 + (64u << 20);
     size_t budget = (freeB + I.capScratch > fixed) ? (size_t)((freeB + I.capScratch - fixed) * 0.9) : 0;
     long long byMem = (long long)(budget / (size_t)L.total);
-    int nCtas = (int)std::min<long long>(std::min<long long>((long long)nJobs, 2LL * I.numSMs), std::max<long long>(byMem, 0));
+    int nCtas = (int)std::min<long long>(std::min<long long>((long long)nJobs, (long long)CTAS_PER_SM * I.numSMs), std::max<long long>(byMem, 0));
     if (nCtas < 1) throw std::runtime_error("unicycler_b200: not enough device memory for one DP scratch arena");
     I.nCtas = nCtas;
     I.growDev(I.dJobs, I.capJobs, nJobs * sizeof(JobDev));
@@ -732,6 +746,10 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.lay = L;
     I.stats = EngineStats();
     I.stats.cells = totalCells;
+    I.stats.h2dBytes = (int64_t)(I.seqBytes + nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + nJobs * sizeof(int));
+    I.stats.ctas = nCtas;
+    I.stats.traceBytes = 0;
+    for (const GridDesc& gd : I.gridsAll) { int ns = 0; I.stats.traceBytes += hostTraceBytes(gd, ns); }
 }
 
 void Engine::launch() {
@@ -744,6 +762,34 @@ void Engine::launch() {
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventRecord(I.ev[3], I.stream));
     I.stats.launches += 1;
+}
+
+double Engine::launchTimed(int steps) {
+    Impl& I = *impl_;
+    CUDA_CHECK(cudaSetDevice(I.device));
+    if (I.kp.nJobs == 0 || steps <= 0) return 0.0;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaStreamSynchronize(I.stream));
+    CUDA_CHECK(cudaEventRecord(e0, I.stream));
+    for (int k = 0; k < steps; ++k) {
+        CUDA_CHECK(cudaMemsetAsync(I.dQueue, 0, sizeof(int), I.stream));
+        dpJobKernel<<<I.nCtas, NTHREADS, 0, I.stream>>>(I.kp);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(e1, I.stream));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    I.stats.launches += steps;
+    I.stats.kernelMs = ms / steps;
+    // leave ev[2]/ev[3] consistent for fetch()
+    CUDA_CHECK(cudaEventRecord(I.ev[2], I.stream));
+    CUDA_CHECK(cudaEventRecord(I.ev[3], I.stream));
+    return ms;
 }
 
 void Engine::fetch(std::vector<Job*>& jobs) {
@@ -767,9 +813,17 @@ void Engine::fetch(std::vector<Job*>& jobs) {
     CUDA_CHECK(cudaEventRecord(I.ev[5], I.stream));
     CUDA_CHECK(cudaStreamSynchronize(I.stream));
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, I.ev[2], I.ev[3]) == cudaSuccess) I.stats.kernelMs = ms;
+    if (cudaEventElapsedTime(&ms, I.ev[2], I.ev[3]) == cudaSuccess && ms > 0.0005f) I.stats.kernelMs = ms;
     if (cudaEventElapsedTime(&ms, I.ev[0], I.ev[1]) == cudaSuccess) I.stats.h2dMs = ms;
     if (cudaEventElapsedTime(&ms, I.ev[4], I.ev[5]) == cudaSuccess) I.stats.d2hMs = ms;
+    if (getenv("UNICYCLER_B200_PROFILE")) {
+        long long tot[6] = {0, 0, 0, 0, 0, 0}, mx = 0;
+        for (size_t k = 0; k < nJobs; ++k) { for (int q = 0; q < 6; ++q) tot[q] += I.jobOut[k].prof[q]; mx = std::max(mx, I.jobOut[k].prof[5]); }
+        fprintf(stderr, "[ub200 profile] jobs=%zu ctas=%d cycles: setup=%lld init=%lld fill=%lld track=%lld traceback=%lld total=%lld maxjob=%lld\n",
+                nJobs, I.nCtas, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], mx);
+    }
+    I.stats.d2hBytes = (int64_t)(nJobs * sizeof(JobOut));
+    for (size_t k = 0; k < nJobs; ++k) I.stats.d2hBytes += 4LL * std::max(0, std::min(I.jobOut[k].outLen, I.jobsDev[k].outCap));
     for (size_t k = 0; k < nJobs; ++k) {
         Job& j = *jobs[k];
         const JobDev& d = I.jobsDev[k];

@@ -86,6 +86,8 @@ struct EngineStats {
     int64_t cells = 0;
     int64_t launches = 0;
     int64_t traceBytes = 0;      // bytes of trace written (algorithmic 1 B/cell incl. padding)
+    int64_t h2dBytes = 0, d2hBytes = 0;
+    int ctas = 0;
 };
 
 // Reference cell count of one grid (seqan/align/dp_algorithm_impl.h:1547-1560).
@@ -105,6 +107,8 @@ public:
     // inputs already in HBM; fetch() copies results back.
     void upload(std::vector<Job*>& jobs);
     void launch();
+    // launches `steps` times back to back; returns the CUDA-event time of all launches in ms
+    double launchTimed(int steps);
     void fetch(std::vector<Job*>& jobs);
 
 private:

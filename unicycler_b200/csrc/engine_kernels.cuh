@@ -24,9 +24,9 @@
 
 namespace ub200 {
 
-constexpr int R = 16;
+constexpr int R = 8;
 constexpr int SH = 32 * R;
-constexpr int NWARPS = 8;
+constexpr int NWARPS = 16;
 constexpr int NTHREADS = NWARPS * 32;
 constexpr unsigned FULLMASK = 0xffffffffu;
 
@@ -48,6 +48,7 @@ struct JobDev {
 
 struct JobOut {
     int status, score, outLen, pad;
+    long long prof[6];  // cycles: setup, init, fill, track, traceback, total (thread 0)
 };
 
 struct ScratchLayout {  // byte offsets inside one CTA's scratch block
@@ -130,48 +131,64 @@ __device__ __forceinline__ size_t traceAddr(const GridCtx& G, int i, int j) {
 // cell recurrences (seqan/align/dp_formula_affine.h:459-636, dp_formula_linear.h:150-291)
 // mode: 0 = RecursionDirectionAll, 1 = UpperDiagonal, 2 = LowerDiagonal, 3 = outside the band
 // ---------------------------------------------------------------------------------------
-template <bool AFF, bool CT>
+template <bool AFF, bool CT, bool BANDED>
 __device__ __forceinline__ uint32_t cellUpdate(int& s, int& h, int& v, int sl, int hl, int su, int vu, int sd,
                                                int sub, int go, int ge, int mode) {
+    // Branch-free formulation.  The only loop-carried chain inside a lane is su -> e -> v -> s (3 ops);
+    // everything else depends on the previous column only.
     uint32_t tv;
     if (AFF) {
-        int a = hl + ge, b = sl + go;
-        int c = vu + ge, e = su + go;
-        uint32_t tvH, tvV, tvM;
-        if (mode == 1) { v = NEG_INF; tvV = 0; }
-        else { v = max(c, e); tvV = (c < e) ? T_VO : ((CT && c == e) ? (T_V | T_VO) : T_V); }
-        if (mode == 2) { h = NEG_INF; tvH = 0; }
-        else { h = max(a, b); tvH = (a < b) ? T_HO : ((CT && a == b) ? (T_H | T_HO) : T_H); }
-        int m;
-        if (mode == 1) { m = h; tvM = T_MH; }
-        else if (mode == 2) { m = v; tvM = T_MV; }
-        else { m = max(v, h); tvM = (v < h) ? T_MH : ((CT && v == h) ? (T_MV | T_MH) : T_MV); }
-        int d = sd + sub;
-        uint32_t gap = tvH | tvV;
-        if (!CT) {
-            if (m <= d) { s = d; tv = T_D | gap; }
-            else { s = m; tv = gap | tvM; }
+        const int a = hl + ge, b = sl + go;
+        const int c = vu + ge, e = su + go;
+        const int d = sd + sub;
+        int hh = max(a, b);
+        int vv = max(c, e);
+        uint32_t tvH, tvV;
+        if (CT) {
+            tvH = ((a >= b) ? (uint32_t)T_H : 0u) | ((a <= b) ? (uint32_t)T_HO : 0u);
+            tvV = ((c >= e) ? (uint32_t)T_V : 0u) | ((c <= e) ? (uint32_t)T_VO : 0u);
         } else {
-            if (m < d) { s = d; tv = T_D | gap; }
-            else if (m == d) { s = m; tv = gap | T_D | tvM; }
-            else { s = m; tv = gap | tvM; }
+            tvH = (a < b) ? (uint32_t)T_HO : (uint32_t)T_H;
+            tvV = (c < e) ? (uint32_t)T_VO : (uint32_t)T_V;
         }
+        if (BANDED) {
+            const bool top = (mode == 1), bot = (mode == 2);
+            vv = top ? NEG_INF : vv; tvV = top ? 0u : tvV;
+            hh = bot ? NEG_INF : hh; tvH = bot ? 0u : tvH;
+        }
+        const int m = max(vv, hh);
+        uint32_t tvM;
+        if (CT) tvM = ((vv >= hh) ? (uint32_t)T_MV : 0u) | ((vv <= hh) ? (uint32_t)T_MH : 0u);
+        else tvM = (vv < hh) ? (uint32_t)T_MH : (uint32_t)T_MV;
+        if (BANDED) {
+            tvM = (mode == 1) ? (uint32_t)T_MH : tvM;
+            tvM = (mode == 2) ? (uint32_t)T_MV : tvM;
+        }
+        const uint32_t gap = tvH | tvV;
+        s = max(m, d);
+        if (CT) tv = gap | ((m <= d) ? (uint32_t)T_D : 0u) | ((m >= d) ? tvM : 0u);
+        else tv = gap | ((m <= d) ? (uint32_t)T_D : tvM);
+        h = hh; v = vv;
     } else {
-        int x = sd + sub;
-        tv = T_D;
-        if (mode != 1) {  // vertical
-            int t = su + ge;
-            if (x < t) { x = t; tv = T_V | T_MV; }
-            else if (CT && x == t) tv |= (T_V | T_MV);
+        const int x0 = sd + sub;
+        int tV = su + ge, tH = sl + ge;
+        if (BANDED) {
+            tV = (mode == 1) ? INT32_MIN : tV;   // UpperDiagonal: no vertical candidate
+            tH = (mode == 2) ? INT32_MIN : tH;   // LowerDiagonal: no horizontal candidate
         }
-        if (mode != 2) {  // horizontal
-            int t = sl + ge;
-            if (x < t) { x = t; tv = T_H | T_MH; }
-            else if (CT && x == t) tv |= (T_H | T_MH);
-        }
-        s = x; h = NEG_INF; v = NEG_INF;
+        const int x1 = max(x0, tV);
+        const int x2 = max(x1, tH);
+        uint32_t t1;
+        if (CT) t1 = ((x0 >= tV) ? (uint32_t)T_D : 0u) | ((x0 <= tV) ? (uint32_t)(T_V | T_MV) : 0u);
+        else t1 = (x0 < tV) ? (uint32_t)(T_V | T_MV) : (uint32_t)T_D;
+        if (CT) tv = ((x1 >= tH) ? t1 : 0u) | ((x1 <= tH) ? (uint32_t)(T_H | T_MH) : 0u);
+        else tv = (x1 < tH) ? (uint32_t)(T_H | T_MH) : t1;
+        s = x2; h = NEG_INF; v = NEG_INF;
     }
-    if (mode == 3) { s = NEG_INF; h = NEG_INF; v = NEG_INF; tv = 0; }
+    if (BANDED) {
+        const bool outside = (mode == 3);
+        s = outside ? NEG_INF : s; h = outside ? NEG_INF : h; v = outside ? NEG_INF : v; tv = outside ? 0u : tv;
+    }
     return tv;
 }
 
@@ -214,7 +231,9 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, int s, int c, int l
         const bool act = (k >= lane) && (j <= jhi);
         if (act) {
             int Sd = prevUpS, Su = inS, Vu = inV;
-            uint32_t tw[4] = {0u, 0u, 0u, 0u};
+            uint32_t tw[R / 4];
+#pragma unroll
+            for (int w4 = 0; w4 < R / 4; ++w4) tw[w4] = 0u;
             // per-byte equality of this lane's 16 vertical codes with the column's horizontal code
             const uint32_t hc4 = (uint32_t)curHc * 0x01010101u;
             uint32_t eq[R / 4];
@@ -230,7 +249,7 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, int s, int c, int l
                 }
                 int sub = (eq[r >> 2] & (1u << (8 * (r & 3)))) ? match : mismatch;
                 int ns, nh, nv;
-                uint32_t tv = cellUpdate<AFF, CT>(ns, nh, nv, Sl[r], Hl[r], Su, Vu, Sd, sub, go, ge, mode);
+                uint32_t tv = cellUpdate<AFF, CT, BANDED>(ns, nh, nv, Sl[r], Hl[r], Su, Vu, Sd, sub, go, ge, mode);
                 Sd = Sl[r];
                 Sl[r] = ns; Hl[r] = nh; Su = ns; Vu = nv;
                 tw[r >> 2] |= tv << (8 * (r & 3));
@@ -245,7 +264,8 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, int s, int c, int l
             }
             prevUpS = inS;
             pubS = Su; pubV = Vu;
-            *reinterpret_cast<uint4*>(tbase + ((size_t)k * 32 + lane) * R) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+            static_assert(R == 8, "trace store assumes 8 rows per lane");
+            *reinterpret_cast<uint2*>(tbase + ((size_t)k * 32 + lane) * R) = make_uint2(tw[0], tw[1]);
             if (writeBnd && lane == 31) __stcg(&G.bnd[(size_t)(s & 1) * G.bndStride + j], make_int2(Su, Vu));
         }
     }

@@ -61,6 +61,12 @@ def load_library():
     L.ub200_chainBenchRun.restype = c_double
     L.ub200_chainBenchFinish.argtypes = [POINTER(c_void_p)]
     L.ub200_chainBenchFinish.restype = c_int
+    L.ub200_chainBenchRunSteps.argtypes = [c_int]
+    L.ub200_chainBenchRunSteps.restype = c_double
+    L.ub200_lastTransferBytes.argtypes = [POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]
+    L.ub200_lastTransferBytes.restype = None
+    L.ub200_chainCells.argtypes = [c_int, c_int, POINTER(c_int64), c_int, c_int, POINTER(c_int)]
+    L.ub200_chainCells.restype = c_int64
     L.ub200_setDevice.argtypes = [c_int]
     L.ub200_setDevice.restype = c_int
     L.ub200_intPeakOpsPerSec.argtypes = []
@@ -226,6 +232,19 @@ def last_stats():
     return dict(cells=cells.value, kernel_ms=kms.value, launches=launches.value, h2d_ms=h2d.value, d2h_ms=d2h.value)
 
 
+def transfer_bytes():
+    h2d, d2h, tb, ctas = c_int64(), c_int64(), c_int64(), c_int()
+    load_library().ub200_lastTransferBytes(ctypes.byref(h2d), ctypes.byref(d2h), ctypes.byref(tb), ctypes.byref(ctas))
+    return dict(h2d_bytes=h2d.value, d2h_bytes=d2h.value, trace_bytes=tb.value, ctas=ctas.value)
+
+
+def chain_cells(read_len, ref_len, seeds, band_size):
+    """(reference DP cells, sub-DP count) of one banded-chain alignment; host planner only (no GPU)."""
+    n = c_int()
+    cells = load_library().ub200_chainCells(read_len, ref_len, _seed_array(seeds), len(seeds), band_size, ctypes.byref(n))
+    return cells, n.value
+
+
 def set_device(device):
     return load_library().ub200_setDevice(int(device))
 
@@ -248,6 +267,10 @@ class ChainBench(object):
 
     def run(self):
         load_library().ub200_chainBenchRun()
+
+    def run_steps(self, steps):
+        """`steps` back-to-back launches; returns total CUDA-event milliseconds."""
+        return load_library().ub200_chainBenchRunSteps(int(steps))
 
     def finish(self, want_results=True):
         out = (c_void_p * self.n)()
