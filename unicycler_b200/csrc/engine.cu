@@ -145,84 +145,78 @@ struct TrackResult {
     DCell maxCell;
 };
 
-// Order-preserving "all tied maxima" update over one batch of <= 32 tracked cells (warp 0).
-__device__ __forceinline__ void scoutBatch(const GridCtx& G, bool tracked, int score, int tpos, int lane, int& curMax,
-                                           int& nCand, bool& overflow) {
-    int sc = tracked ? score : INT32_MIN;
-    int m = sc;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULLMASK, m, o));
-    unsigned anyTracked = __ballot_sync(FULLMASK, tracked);
-    if (!anyTracked) return;
-    // seeds/banded_chain_alignment_scout.h:256-268: ">=" keeps ties, ">" restarts the list
-    if (m > curMax) { curMax = m; nCand = 0; }
-    if (m == curMax) {
-        unsigned mask = __ballot_sync(FULLMASK, tracked && sc == curMax);
-        int idx = nCand + __popc(mask & ((1u << lane) - 1));
-        if (tracked && sc == curMax) {
-            if (idx < G.maxCand) G.cand[idx] = tpos;
-            else overflow = true;
-        }
-        nCand += __popc(mask);
-    }
-}
+struct TrackShared {
+    int maxScore;
+    int count;
+    int ub;
+    int nCols;
+};
 
-// Tracking pass for banded-chain grids: stores the next grid's init row/column and collects
-// every tied maximum in visiting order (warp 0, all lanes).
-__device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res) {
-    const int lane = threadIdx.x & 31;
+// Tracked-cell enumeration shared by both passes of the chain tracking.  Calls f(i, j, cv, opts) for
+// every cell of the grid that _determineTrackingOptions flags (seeds/banded_chain_alignment_impl.h:282-377),
+// distributing cells over all threads of the CTA.
+template <typename F>
+__device__ __forceinline__ void forEachFlaggedCell(const GridCtx& G, int nColTab, F f) {
+    const int tid = threadIdx.x;
     const GridGeom& g = G.g;
     const bool chainFinal = (G.kind == GRID_CHAIN_FINAL);
     const bool feLastRow = G.fe & 4, feLastCol = G.fe & 8;
-    int curMax = NEG_INF;  // default-constructed _maxScore
-    int nCand = 0;
-    bool overflow = false, ub = false;
-    // NOTE: a tracked cell equal to NEG_INF is appended by the reference (== branch); harmless because
-    // such a grid fails the -1000000 check.  We start from NEG_INF - 1 to keep ">=" semantics simple.
-    curMax = NEG_INF - 1;
-
     if (G.capEdges) {
-        // unbanded final matrix (hNext = vNext = 0): last row of every column, then the last column
+        // unbanded final matrix, hNext = vNext = 0: last row of columns 0..nH-1, then the last column
         const int nH = g.nH, nV = g.nV;
-        for (int base = 0; base < nH; base += 32) {
-            int j = base + lane;
-            bool tr = (j < nH) && feLastRow;
-            DCell c = DCell{NEG_INF, NEG_INF, NEG_INF};
-            if (j < nH) c = (j == 0) ? G.initCol[nV] : G.lastRow[j];
-            scoutBatch(G, tr, c.s, j * g.dimV + nV, lane, curMax, nCand, overflow);
-        }
-        for (int base = 0; base <= nV; base += 32) {
-            int i = base + lane;
-            bool tr = (i <= nV) && (i == nV || feLastCol);
-            DCell c = DCell{NEG_INF, NEG_INF, NEG_INF};
-            if (i <= nV) c = (i == 0) ? G.initRow[nH] : G.lastCol[i];
-            scoutBatch(G, tr, c.s, nH * g.dimV + i, lane, curMax, nCand, overflow);
+        const int total = nH + nV + 1;
+        for (int idx = tid; idx < total; idx += NTHREADS) {
+            TrackOpts o;
+            o.storeCol = o.storeRow = false;
+            int i, j;
+            if (idx < nH) { i = nV; j = idx; o.lastRow = feLastRow; o.lastCol = false; }
+            else { i = idx - nH; j = nH; o.lastCol = (i == nV) || feLastCol; o.lastRow = (i == nV); }
+            if (o.lastRow || o.lastCol) f(i, j, i, o);
         }
     } else if (!g.banded) {
         const int nH = g.nH, nV = g.nV;
-        for (int j = G.hNext; j <= nH; ++j) {
-            int cp = (j == 0) ? CP_INITIAL : (j == nH ? CP_FINAL : CP_INNER);
-            for (int base = G.boxRow0; base <= nV; base += 32) {
-                int i = base + lane;
-                bool valid = i <= nV;
-                bool tr = false;
-                DCell c = DCell{NEG_INF, NEG_INF, NEG_INF};
-                if (valid) {
-                    c = cellAtBox(G, i, j);
-                    int ct = (i == 0) ? CT_FIRST : (i == nV ? CT_LAST : CT_INNER);
-                    TrackOpts o = chainTrackingOptions(j, i, 1, cp, CL_FULL, ct, G.hNext, G.vNext, chainFinal,
-                                                       feLastRow, feLastCol);
-                    if (o.storeCol) { int k = i - G.vNext; if (k >= 0 && k < G.capNextV) G.vInitNext[k] = c; else ub = true; }
-                    if (o.storeRow) { int k = j - G.hNext; if (k >= 0 && k < G.capNextH) G.hInitNext[k] = c; else ub = true; }
-                    tr = o.lastCol || o.lastRow;
-                }
-                scoutBatch(G, tr, c.s, j * g.dimV + i, lane, curMax, nCand, overflow);
-            }
+        const int bw = G.boxW, bh = G.boxH;
+        for (int idx = tid; idx < bw * bh; idx += NTHREADS) {
+            const int j = G.hNext + idx / bh;
+            const int i = G.boxRow0 + idx % bh;
+            const int cp = (j == 0) ? CP_INITIAL : (j == nH ? CP_FINAL : CP_INNER);
+            const int ct = (i == 0) ? CT_FIRST : (i == nV ? CT_LAST : CT_INNER);
+            TrackOpts o = chainTrackingOptions(j, i, 1, cp, CL_FULL, ct, G.hNext, G.vNext, chainFinal, feLastRow, feLastCol);
+            if (o.lastRow || o.lastCol || o.storeCol || o.storeRow) f(i, j, i, o);
         }
     } else {
-        // banded anchor: literal column walk (lane 0), then lane-parallel evaluation
-        __shared__ int sNCols;
-        if (lane == 0) {
+        for (int ccol = 0; ccol < nColTab; ++ccol) {
+            const ColInfo ci = G.colTab[ccol];
+            for (int c = tid; c < ci.nCells; c += NTHREADS) {
+                const int i = ci.rowTop + c;
+                const int cv = ci.cvFirst + c;
+                const int ct = (c == 0) ? CT_FIRST : (c == ci.nCells - 1 ? CT_LAST : CT_INNER);
+                const int leap = (ct == CT_LAST) ? ci.tLeapLast : ci.tLeap;
+                TrackOpts o = chainTrackingOptions(ci.j, cv, leap, ci.cp, ci.cl, ct, G.hNext, G.vNext, chainFinal,
+                                                   feLastRow, feLastCol);
+                if (o.lastRow || o.lastCol || o.storeCol || o.storeRow) f(i, ci.j, cv, o);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ DCell trackedCell(const GridCtx& G, int i, int j) {
+    if (j == 0) return G.initCol[i];
+    if (i == 0) return G.initRow[j];
+    if (G.capEdges) return (i == G.g.nV) ? G.lastRow[j] : G.lastCol[i];
+    return G.box[(size_t)(j - G.hNext) * G.boxH + (i - G.boxRow0)];
+}
+
+// Tracking pass for banded-chain grids (all threads): stores the next grid's init row/column, finds
+// the maximum over the tracked cells and collects every tied maximum in visiting order
+// (seeds/banded_chain_alignment_scout.h:230-270).  Visiting order == ascending host position.
+__device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res, TrackShared& TS) {
+    const int tid = threadIdx.x;
+    const GridGeom& g = G.g;
+    if (tid == 0) {
+        TS.maxScore = INT32_MIN; TS.count = 0; TS.ub = 0; TS.nCols = 0;
+        if (!G.capEdges && g.banded) {
+            // literal column walk of _computeBandedAlignment for the columns right of the next grid's origin
             BandWalker w;
             w.init(g);
             ColInfo ci;
@@ -233,112 +227,101 @@ __device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res) {
                     ++n;
                 }
             }
-            sNCols = n;
-        }
-        __syncwarp();
-        int nCols = sNCols;
-        if (nCols > G.maxColTab) { ub = true; nCols = G.maxColTab; }
-        for (int ccol = 0; ccol < nCols; ++ccol) {
-            ColInfo ci = G.colTab[ccol];
-            for (int base = 0; base < ci.nCells; base += 32) {
-                int c = base + lane;
-                bool valid = c < ci.nCells;
-                bool tr = false;
-                DCell cell = DCell{NEG_INF, NEG_INF, NEG_INF};
-                int cv = ci.cvFirst + c;
-                if (valid) {
-                    int i = ci.rowTop + c;
-                    cell = cellAtBox(G, i, ci.j);
-                    int ct = (c == 0) ? CT_FIRST : (c == ci.nCells - 1 ? CT_LAST : CT_INNER);
-                    int leap = (ct == CT_LAST) ? ci.tLeapLast : ci.tLeap;
-                    TrackOpts o = chainTrackingOptions(ci.j, cv, leap, ci.cp, ci.cl, ct, G.hNext, G.vNext, chainFinal,
-                                                       feLastRow, feLastCol);
-                    if (o.storeCol) { int k = cv - G.vNext; if (k >= 0 && k < G.capNextV) G.vInitNext[k] = cell; else ub = true; }
-                    if (o.storeRow) { int k = ci.j - G.hNext; if (k >= 0 && k < G.capNextH) G.hInitNext[k] = cell; else ub = true; }
-                    tr = o.lastCol || o.lastRow;
-                }
-                scoutBatch(G, tr, cell.s, ci.j * g.dimV + cv, lane, curMax, nCand, overflow);
-            }
+            if (n > G.maxColTab) { TS.ub = 1; n = G.maxColTab; }
+            TS.nCols = n;
         }
     }
-    unsigned anyUb = __ballot_sync(FULLMASK, ub);
-    unsigned anyOv = __ballot_sync(FULLMASK, overflow);
-    if (lane == 0) {
-        res.maxScore = (nCand == 0) ? NEG_INF : curMax;
-        res.nCand = nCand;
-        res.status = anyUb ? JOB_REF_UB : (anyOv ? JOB_REF_UB : JOB_OK);
+    __syncthreads();
+    const int nCols = TS.nCols;
+    const int dimV = g.dimV;
+    // pass 1: init stores + maximum
+    forEachFlaggedCell(G, nCols, [&](int i, int j, int cv, const TrackOpts& o) {
+        const DCell c = trackedCell(G, i, j);
+        if (o.storeCol) { int k = cv - G.vNext; if (k >= 0 && k < G.capNextV) G.vInitNext[k] = c; else TS.ub = 1; }
+        if (o.storeRow) { int k = j - G.hNext; if (k >= 0 && k < G.capNextH) G.hInitNext[k] = c; else TS.ub = 1; }
+        if (o.lastCol || o.lastRow) atomicMax(&TS.maxScore, c.s);
+    });
+    __syncthreads();
+    const int best = TS.maxScore;
+    // pass 2: every tracked cell that reaches the maximum
+    forEachFlaggedCell(G, nCols, [&](int i, int j, int cv, const TrackOpts& o) {
+        if (!(o.lastCol || o.lastRow)) return;
+        const DCell c = trackedCell(G, i, j);
+        if (c.s == best) {
+            int k = atomicAdd(&TS.count, 1);
+            if (k < G.maxCand) G.cand[k] = j * dimV + cv;
+        }
+    });
+    __syncthreads();
+    if (tid == 0) {
+        int n = TS.count;
+        if (n > G.maxCand) { TS.ub = 1; n = G.maxCand; }
+        for (int a = 1; a < n; ++a) {  // insertion sort: candidates are few
+            int x = G.cand[a], b = a - 1;
+            while (b >= 0 && G.cand[b] > x) { G.cand[b + 1] = G.cand[b]; --b; }
+            G.cand[b + 1] = x;
+        }
+        res.maxScore = (n == 0) ? NEG_INF : best;
+        res.nCand = n;
+        res.status = TS.ub ? JOB_REF_UB : JOB_OK;
     }
-    __syncwarp();
+    __syncthreads();
 }
 
-// Tracking for the default scout (GRID_GLOBAL): first maximum in column-major visiting order
-// with strict ">" (seqan/align/dp_scout.h:163-179) over the cells dp_meta_info.h marks tracked.
-__device__ __noinline__ void trackGlobal(const GridCtx& G, TrackResult& res) {
-    const int lane = threadIdx.x & 31;
+// Tracking for the default scout (GRID_GLOBAL): first maximum in column-major visiting order with
+// strict ">" (seqan/align/dp_scout.h:163-179) over the cells dp_meta_info.h marks tracked: the last-row
+// cells when the last row is free, then the band cells of the final column (all of them when the last
+// column is free, otherwise only the corner).  All threads.
+__device__ __noinline__ void trackGlobal(const GridCtx& G, TrackResult& res, TrackShared& TS) {
+    const int tid = threadIdx.x;
     const GridGeom& g = G.g;
     const bool feLastRow = G.fe & 4, feLastCol = G.fe & 8;
     const int nH = g.nH, nV = g.nV;
-    int best = NEG_INF, bestPos = -1;
-    DCell bestCell = DCell{NEG_INF, NEG_INF, NEG_INF};
-    // last-row cells of columns < nH (only when the last row is free)
-    if (feLastRow) {
-        for (int base = 0; base < nH; base += 32) {
-            int j = base + lane;
-            bool tr = (j < nH) && (!g.banded || (j - nV >= g.lo && j - nV <= g.up));
-            DCell c = DCell{NEG_INF, NEG_INF, NEG_INF};
-            if (tr) c = (j == 0) ? G.initCol[nV] : G.lastRow[j];
-            int sc = tr ? c.s : INT32_MIN;
-            int m = sc;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULLMASK, m, o));
-            if (m > best) {
-                unsigned mask = __ballot_sync(FULLMASK, tr && sc == m);
-                int src = __ffs(mask) - 1;
-                best = m;
-                bestPos = __shfl_sync(FULLMASK, j * g.dimV + nV + storageOffset(g, j), src);
-                bestCell.s = __shfl_sync(FULLMASK, c.s, src);
-                bestCell.h = __shfl_sync(FULLMASK, c.h, src);
-                bestCell.v = __shfl_sync(FULLMASK, c.v, src);
-            }
-        }
+    const int top = colTop(g, nH), bot = colBottom(g, nH);
+    const int nRowCells = feLastRow ? nH : 0;
+    const int total = nRowCells + (bot - top + 1);
+    if (tid == 0) { TS.maxScore = INT32_MIN; TS.count = INT32_MAX; TS.ub = 0; }
+    __syncthreads();
+    auto cellOf = [&](int idx, int& i, int& j, bool& tracked) {
+        if (idx < nRowCells) { i = nV; j = idx; tracked = !g.banded || (j - nV >= g.lo && j - nV <= g.up); }
+        else { i = top + (idx - nRowCells); j = nH; tracked = feLastCol || i == nV; }
+    };
+    for (int idx = tid; idx < total; idx += NTHREADS) {
+        int i, j; bool tr;
+        cellOf(idx, i, j, tr);
+        if (tr) atomicMax(&TS.maxScore, trackedCell(G, i, j).s);
     }
-    // final column: every band row if the last column is free, else only the corner
-    {
-        int top = colTop(g, nH), bot = colBottom(g, nH);
-        for (int base = top; base <= bot; base += 32) {
-            int i = base + lane;
-            bool tr = (i <= bot) && (feLastCol || i == nV);
-            DCell c = DCell{NEG_INF, NEG_INF, NEG_INF};
-            if (tr) c = (i == 0) ? G.initRow[nH] : G.lastCol[i];
-            int sc = tr ? c.s : INT32_MIN;
-            int m = sc;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULLMASK, m, o));
-            if (m > best) {
-                unsigned mask = __ballot_sync(FULLMASK, tr && sc == m);
-                int src = __ffs(mask) - 1;
-                best = m;
-                bestPos = __shfl_sync(FULLMASK, nH * g.dimV + i + storageOffset(g, nH), src);
-                bestCell.s = __shfl_sync(FULLMASK, c.s, src);
-                bestCell.h = __shfl_sync(FULLMASK, c.h, src);
-                bestCell.v = __shfl_sync(FULLMASK, c.v, src);
-            }
-        }
+    __syncthreads();
+    const int best = TS.maxScore;
+    for (int idx = tid; idx < total; idx += NTHREADS) {
+        int i, j; bool tr;
+        cellOf(idx, i, j, tr);
+        if (tr && trackedCell(G, i, j).s == best) atomicMin(&TS.count, idx);  // first in visiting order
     }
-    if (lane == 0) {
-        res.maxScore = best;
-        res.nCand = bestPos >= 0 ? 1 : 0;
-        if (bestPos >= 0) G.cand[0] = bestPos;
-        res.maxCell = bestCell;
+    __syncthreads();
+    if (tid == 0) {
+        if (TS.count == INT32_MAX || best <= NEG_INF) {
+            // default scout starts from a default (-inf) cell with strict '>': nothing tracked above -inf
+            res.maxScore = NEG_INF; res.nCand = 0;
+        } else {
+            int i, j; bool tr;
+            cellOf(TS.count, i, j, tr);
+            res.maxScore = best;
+            res.nCand = 1;
+            res.maxCell = trackedCell(G, i, j);
+            G.cand[0] = j * g.dimV + i + storageOffset(g, j);
+        }
         res.status = JOB_OK;
     }
-    __syncwarp();
+    __syncthreads();
 }
 
-// One candidate of a banded-chain grid (seeds/banded_chain_alignment_traceback.h:233-355).  Lane 0.
-__device__ __noinline__ void chainTracebackOne(const GridCtx& G, OutStream& out, int startPos, int& nPlanted, int& nTraces,
-                                  int& status) {
-    TraceWalker w(G, out);
+// One candidate of a banded-chain grid (seeds/banded_chain_alignment_traceback.h:233-355).
+// Warp-uniform: every lane of warp 0 executes it; lane 0 writes.
+__device__ __noinline__ void chainTracebackOne(const GridCtx& G, OutStream& out, uint8_t* win, int startPos,
+                                               int& nPlanted, int& nTraces, int& status) {
+    const int lane = threadIdx.x & 31;
+    TraceWalker w(G, out, win);
     const bool affine = G.affine;
     const bool prefer = affine && G.kind == GRID_CHAIN_FINAL;
     w.pc = startPos / G.g.dimV;
@@ -359,17 +342,17 @@ __device__ __noinline__ void chainTracebackOne(const GridCtx& G, OutStream& out,
         w.emitOn = false;
         while (!c.reachedEnd() && tv != T_NONE) w.doTraceback(tv, last, frag, c);
         w.emitOn = true;
-        int hInit = c.currCol - c.endCol;
-        int vInit = c.currRow - c.endRow;
+        const int hInit = c.currCol - c.endCol;
+        const int vInit = c.currRow - c.endRow;
         bool inserted = false;
         DCell* cellPtr = nullptr;
         int i1, i2;
         if (vInit <= 0) {
-            if (hInit < 0 || hInit >= G.capNextH) { status = JOB_REF_UB; }
+            if (hInit < 0 || hInit >= G.capNextH) status = JOB_REF_UB;
             else cellPtr = &G.hInitNext[hInit];
             i1 = hInit; i2 = 0;
         } else {
-            if (vInit >= G.capNextV) { status = JOB_REF_UB; }
+            if (vInit >= G.capNextV) status = JOB_REF_UB;
             else cellPtr = &G.vInitNext[vInit];
             i1 = 0; i2 = vInit;
         }
@@ -380,7 +363,8 @@ __device__ __noinline__ void chainTracebackOne(const GridCtx& G, OutStream& out,
                 else if (last & T_V) cell.h = NEG_INF;
                 else cell.v = NEG_INF;
             }
-            *cellPtr = cell;
+            __syncwarp();
+            if (lane == 0) *cellPtr = cell;
             // std::set<Triple<unsigned, unsigned, DPCell>>::insert: same position => equivalent
             // unless one cell is component-wise smaller (dp_cell_affine.h:113-118)
             bool dup = false;
@@ -396,9 +380,13 @@ __device__ __noinline__ void chainTracebackOne(const GridCtx& G, OutStream& out,
                 }
             }
             if (!dup) {
-                if (nPlanted < G.maxPlanted) { G.planted[nPlanted] = PlantedCell{i1, i2, cell}; ++nPlanted; inserted = true; }
-                else status = JOB_REF_UB;
+                if (nPlanted < G.maxPlanted) {
+                    if (lane == 0) G.planted[nPlanted] = PlantedCell{i1, i2, cell};
+                    ++nPlanted;
+                    inserted = true;
+                } else status = JOB_REF_UB;
             }
+            __syncwarp();
         }
         if (inserted) {
             if (vInit < 0) w.record(c.currCol, c.currRow, -vInit, last);
@@ -417,7 +405,7 @@ __device__ __noinline__ void chainTracebackOne(const GridCtx& G, OutStream& out,
     if (w.nSegs == 0) {
         out.len = headerPos;  // empty target: not appended (traceback.h:383-385)
     } else {
-        if (headerPos < out.cap) out.buf[headerPos] = w.nSegs;
+        out.patch(headerPos, w.nSegs);
         ++nTraces;
     }
 }
@@ -431,6 +419,8 @@ __device__ __forceinline__ void fillDispatch(const GridCtx& G) {
 __global__ void __launch_bounds__(NTHREADS, 1) dpJobKernel(KParams P) {
     __shared__ GridCtx G;
     __shared__ TrackResult TR;
+    __shared__ TrackShared TS;
+    __shared__ __align__(16) uint8_t sWin[WIN * WIN];
     __shared__ int sJob, sStatus, sNPlanted, sOutLen, sScore;
     uint8_t* scratch = P.scratch + (size_t)blockIdx.x * P.scratchStride;
     const int tid = threadIdx.x;
@@ -458,52 +448,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpJobKernel(KParams P) {
             else { if (G.complete) fillDispatch<false, true>(G); else fillDispatch<false, false>(G); }
             __syncthreads();
             long long c3 = clock64();
-            long long c4 = c3;
-            // tracking + traceback: warp 0
+            // tracking: all threads
+            if (gd.kind == GRID_GLOBAL) trackGlobal(G, TR, TS);
+            else trackChain(G, TR, TS);
+            long long c4 = clock64();
+            // traceback: warp 0, warp-uniform
             if (tid < 32) {
-                if (gd.kind == GRID_GLOBAL) trackGlobal(G, TR);
-                else trackChain(G, TR);
-                c4 = clock64();
-                if (tid == 0) {
-                    OutStream out;
-                    out.buf = P.out + jb.outOff; out.cap = jb.outCap; out.len = sOutLen; out.overflow = false;
-                    out.h0 = gd.h0; out.v0 = gd.v0;
-                    int status = TR.status;
-                    sScore = TR.maxScore;
-                    if (status == JOB_OK && TR.maxScore < -1000000) status = JOB_BAD_SCORE;  // the RRW throw
-                    if (status == JOB_OK) {
-                        out.put(gi);
-                        int cntPos = out.len;
-                        out.put(0);
-                        int nTraces = 0;
-                        if (gd.kind == GRID_GLOBAL) {
-                            TraceWalker w(G, out);
-                            int pos = G.cand[0];
-                            w.pc = pos / G.g.dimV; w.pv = pos % G.g.dimV;
-                            int hdr = out.len; out.put(0);
-                            int tvOverride = -1;
-                            if (!G.complete && G.affine) {  // _correctTraceValue
-                                uint32_t t = w.tvHere();
-                                if (TR.maxCell.v == TR.maxCell.s) { t &= ~(uint32_t)T_D; t |= T_MV; }
-                                else if (TR.maxCell.h == TR.maxCell.s) { t &= ~(uint32_t)T_D; t |= T_MH; }
-                                tvOverride = (int)t;
-                            }
-                            w.generic(G.affine, true, true, tvOverride);
-                            if (w.bad) status = JOB_REF_UB;
-                            if (hdr < out.cap) out.buf[hdr] = w.nSegs;
-                            nTraces = 1;
-                        } else {
-                            int nPlanted = 0;  // _nextInitializationCells.clear()
-                            for (int k = 0; k < TR.nCand && status == JOB_OK; ++k)
-                                chainTracebackOne(G, out, G.cand[k], nPlanted, nTraces, status);
-                            sNPlanted = nPlanted;
+                OutStream out;
+                out.buf = P.out + jb.outOff; out.cap = jb.outCap; out.len = sOutLen; out.overflow = false;
+                out.h0 = gd.h0; out.v0 = gd.v0; out.lane = tid;
+                int status = TR.status;
+                const int maxScore = TR.maxScore;
+                if (status == JOB_OK && maxScore < -1000000) status = JOB_BAD_SCORE;  // the RRW throw
+                int nPlanted = 0;  // _nextInitializationCells.clear()
+                if (status == JOB_OK) {
+                    out.put(gi);
+                    const int cntPos = out.len;
+                    out.put(0);
+                    int nTraces = 0;
+                    if (gd.kind == GRID_GLOBAL) {
+                        TraceWalker w(G, out, sWin);
+                        const int pos = G.cand[0];
+                        w.pc = pos / G.g.dimV; w.pv = pos % G.g.dimV;
+                        const int hdr = out.len; out.put(0);
+                        int tvOverride = -1;
+                        if (!G.complete && G.affine) {  // _correctTraceValue
+                            uint32_t t = w.tvHere();
+                            const DCell mc = TR.maxCell;
+                            if (mc.v == mc.s) { t &= ~(uint32_t)T_D; t |= T_MV; }
+                            else if (mc.h == mc.s) { t &= ~(uint32_t)T_D; t |= T_MH; }
+                            tvOverride = (int)t;
                         }
-                        if (cntPos < out.cap) out.buf[cntPos] = nTraces;
-                        if (out.overflow && status == JOB_OK) status = JOB_OUT_OVERFLOW;
-                        sOutLen = out.len;
+                        w.generic(G.affine, true, true, tvOverride);
+                        if (w.bad) status = JOB_REF_UB;
+                        out.patch(hdr, w.nSegs);
+                        nTraces = 1;
+                    } else {
+                        const int nCand = TR.nCand;
+                        for (int k = 0; k < nCand && status == JOB_OK; ++k)
+                            chainTracebackOne(G, out, sWin, G.cand[k], nPlanted, nTraces, status);
                     }
-                    sStatus = status;
+                    out.patch(cntPos, nTraces);
+                    if (out.overflow && status == JOB_OK) status = JOB_OUT_OVERFLOW;
                 }
+                __syncwarp();
+                if (tid == 0) { sNPlanted = nPlanted; sOutLen = out.len; sScore = maxScore; sStatus = status; }
             }
             __syncthreads();
             long long c5 = clock64();

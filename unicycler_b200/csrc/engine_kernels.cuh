@@ -137,7 +137,29 @@ __device__ __forceinline__ uint32_t cellUpdate(int& s, int& h, int& v, int sl, i
     // Branch-free formulation.  The only loop-carried chain inside a lane is su -> e -> v -> s (3 ops);
     // everything else depends on the previous column only.
     uint32_t tv;
-    if (AFF) {
+    if (AFF && !BANDED) {
+        // Fast path.  Loop-carried chain per cell: su -> VIADDMNMX -> VIMNMX3 -> s (2 ops).
+        const int a = hl + ge, b = sl + go;
+        const int hh = max(a, b);
+        const int c = vu + ge, e = su + go;
+        const int vv = __viaddmax_s32(su, go, c);
+        const int d = sd + sub;
+        const int ss = __vimax3_s32(vv, hh, d);
+        uint32_t tvH, tvV, tvM;
+        if (CT) {
+            tvH = ((a >= b) ? (uint32_t)T_H : 0u) | ((a <= b) ? (uint32_t)T_HO : 0u);
+            tvV = ((c >= e) ? (uint32_t)T_V : 0u) | ((c <= e) ? (uint32_t)T_VO : 0u);
+            tvM = ((vv >= hh) ? (uint32_t)T_MV : 0u) | ((vv <= hh) ? (uint32_t)T_MH : 0u);
+            // m = max(vv,hh):  m <= d  <=>  d == s ;  m >= d  <=>  vv == s || hh == s
+            tv = tvH | tvV | ((d == ss) ? (uint32_t)T_D : 0u) | ((vv == ss || hh == ss) ? tvM : 0u);
+        } else {
+            tvH = (a < b) ? (uint32_t)T_HO : (uint32_t)T_H;
+            tvV = (c < e) ? (uint32_t)T_VO : (uint32_t)T_V;
+            tvM = (vv < hh) ? (uint32_t)T_MH : (uint32_t)T_MV;
+            tv = tvH | tvV | ((d == ss) ? (uint32_t)T_D : tvM);
+        }
+        s = ss; h = hh; v = vv;
+    } else if (AFF) {
         const int a = hl + ge, b = sl + go;
         const int c = vu + ge, e = su + go;
         const int d = sd + sub;
@@ -209,22 +231,35 @@ __device__ __forceinline__ void upBoundary(const GridCtx& G, int s, int j, int& 
     }
 }
 
+// Loop-invariant scalars of one strip chunk, kept in registers (GridCtx lives in shared memory).
+struct StepConsts {
+    int match, mismatch, go, ge, nV, nH, lo, up;
+    uint8_t* tbase;   // trace base of this strip
+    int2* bndOut;     // boundary row written by lane 31 (nullptr: no strip below)
+};
+
 template <bool AFF, bool CT, bool BANDED, bool CAP>
-__device__ __forceinline__ void stripSteps(const GridCtx& G, int s, int c, int lane, int jlo, int jhi, int i0,
-                                           int (&Sl)[R], int (&Hl)[R], const uint32_t (&vcw)[R / 4], int& prevUpS, int& pubS,
-                                           int& pubV, int& curHc, int bS, int bV, int hcN, bool writeBnd) {
-    const int match = G.match, mismatch = G.mismatch, go = G.go, ge = G.ge;
-    const int nV = G.g.nV, nH = G.g.nH, lo = G.g.lo, up = G.g.up;
-    uint8_t* tbase = G.trace + (size_t)G.stripBase[s];
+__device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K, int c, int lane, int jlo, int jhi,
+                                           int i0, int (&Sl)[R], int (&Hl)[R], const uint32_t (&vcw)[R / 4],
+                                           int& prevUpS, int& pubS, int& pubV, int& curHc, int bS, int bV, int hcN) {
+    const int match = K.match, mismatch = K.mismatch, go = K.go, ge = K.ge;
+    const int lo = K.lo, up = K.up;
+    // capture parameters (slow variant only)
+    int capEdges = 0, hNext = 0, boxRow0 = 0, boxH = 0;
+    DCell *box = nullptr, *lastRow = nullptr, *lastCol = nullptr;
+    if (CAP) {
+        capEdges = G.capEdges; hNext = G.hNext; boxRow0 = G.boxRow0; boxH = G.boxH;
+        box = G.box; lastRow = G.lastRow; lastCol = G.lastCol;
+    }
 #pragma unroll 1
     for (int kk = 0; kk < 32; ++kk) {
         const int k = 32 * c + kk;
         int inS = __shfl_up_sync(FULLMASK, pubS, 1);
         int inV = __shfl_up_sync(FULLMASK, pubV, 1);
         int inHc = __shfl_up_sync(FULLMASK, curHc, 1);
-        int l0S = __shfl_sync(FULLMASK, bS, kk);
-        int l0V = __shfl_sync(FULLMASK, bV, kk);
-        int l0Hc = __shfl_sync(FULLMASK, hcN, kk);
+        const int l0S = __shfl_sync(FULLMASK, bS, kk);
+        const int l0V = __shfl_sync(FULLMASK, bV, kk);
+        const int l0Hc = __shfl_sync(FULLMASK, hcN, kk);
         if (lane == 0) { inS = l0S; inV = l0V; inHc = l0Hc; }
         curHc = inHc;
         const int j = jlo + k - lane;
@@ -234,39 +269,56 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, int s, int c, int l
             uint32_t tw[R / 4];
 #pragma unroll
             for (int w4 = 0; w4 < R / 4; ++w4) tw[w4] = 0u;
-            // per-byte equality of this lane's 16 vertical codes with the column's horizontal code
+            // per-byte equality of this lane's vertical codes with the column's horizontal code
             const uint32_t hc4 = (uint32_t)curHc * 0x01010101u;
             uint32_t eq[R / 4];
 #pragma unroll
             for (int w4 = 0; w4 < R / 4; ++w4) eq[w4] = __vcmpeq4(vcw[w4], hc4);
+            int vArr[CAP ? R : 1];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int i = i0 + r;
                 int mode = 0;
                 if (BANDED) {
-                    int d = j - i;
+                    const int d = j - (i0 + r);
                     mode = (d < lo || d > up) ? 3 : (d == up ? 1 : (d == lo ? 2 : 0));
                 }
-                int sub = (eq[r >> 2] & (1u << (8 * (r & 3)))) ? match : mismatch;
+                const int sub = (eq[r >> 2] & (1u << (8 * (r & 3)))) ? match : mismatch;
                 int ns, nh, nv;
-                uint32_t tv = cellUpdate<AFF, CT, BANDED>(ns, nh, nv, Sl[r], Hl[r], Su, Vu, Sd, sub, go, ge, mode);
+                const uint32_t tv = cellUpdate<AFF, CT, BANDED>(ns, nh, nv, Sl[r], Hl[r], Su, Vu, Sd, sub, go, ge, mode);
                 Sd = Sl[r];
                 Sl[r] = ns; Hl[r] = nh; Su = ns; Vu = nv;
+                if (CAP) vArr[r] = nv;
                 tw[r >> 2] |= tv << (8 * (r & 3));
-                if (CAP) {
-                    if (G.capEdges) {
-                        if (i == nV) G.lastRow[j] = DCell{ns, nh, nv};
-                        if (j == nH && i <= nV) G.lastCol[i] = DCell{ns, nh, nv};
-                    } else if (j >= G.hNext && i >= G.boxRow0 && i <= nV && mode != 3) {
-                        G.box[(size_t)(j - G.hNext) * G.boxH + (i - G.boxRow0)] = DCell{ns, nh, nv};
-                    }
-                }
             }
             prevUpS = inS;
             pubS = Su; pubV = Vu;
             static_assert(R == 8, "trace store assumes 8 rows per lane");
-            *reinterpret_cast<uint2*>(tbase + ((size_t)k * 32 + lane) * R) = make_uint2(tw[0], tw[1]);
-            if (writeBnd && lane == 31) __stcg(&G.bnd[(size_t)(s & 1) * G.bndStride + j], make_int2(Su, Vu));
+            *reinterpret_cast<uint2*>(K.tbase + ((size_t)k * 32 + lane) * R) = make_uint2(tw[0], tw[1]);
+            if (K.bndOut != nullptr && lane == 31) __stcg(&K.bndOut[j], make_int2(Su, Vu));
+            if (CAP) {
+                if (capEdges) {
+                    const int rl = K.nV - i0;
+                    if (rl >= 0 && rl < R) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            if (r == rl) lastRow[j] = DCell{Sl[r], Hl[r], vArr[r]};
+                    }
+                    if (j == K.nH) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            if (i0 + r <= K.nV) lastCol[i0 + r] = DCell{Sl[r], Hl[r], vArr[r]};
+                    }
+                } else if (j >= hNext) {
+                    DCell* col = box + (size_t)(j - hNext) * boxH - boxRow0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = i0 + r;
+                        bool inb = true;
+                        if (BANDED) { const int d = j - i; inb = (d >= lo && d <= up); }
+                        if (i >= boxRow0 && i <= K.nV && inb) col[i] = DCell{Sl[r], Hl[r], vArr[r]};
+                    }
+                }
+            }
         }
     }
 }
@@ -313,17 +365,21 @@ __device__ __noinline__ void fillGrid(const GridCtx& G) {
                     int jj = jlo + 32 * c + lane;
                     int bS = NEG_INF, bV = NEG_INF, hcN = 0;
                     if (jj <= jhi) { hcN = G.seqH[jj - 1]; upBoundary<BANDED>(G, s, jj, bS, bV); }
-                    bool writeBnd = (s + 1 < G.NS);
+                    StepConsts K;
+                    K.match = G.match; K.mismatch = G.mismatch; K.go = G.go; K.ge = G.ge;
+                    K.nV = g.nV; K.nH = g.nH; K.lo = g.lo; K.up = g.up;
+                    K.tbase = G.trace + (size_t)G.stripBase[s];
+                    K.bndOut = (s + 1 < G.NS) ? (G.bnd + (size_t)(s & 1) * G.bndStride) : nullptr;
                     bool cap;
                     int jmaxChunk = jlo + 32 * c + 31;  // largest column any lane touches in this chunk
                     if (G.capEdges) cap = ((s + 1) * SH >= g.nV) || (jmaxChunk >= g.nH);
                     else cap = (jmaxChunk >= G.hNext) && ((s + 1) * SH >= G.boxRow0);
                     if (cap)
-                        stripSteps<AFF, CT, BANDED, true>(G, s, c, lane, jlo, jhi, i0, Sl, Hl, vcw, prevUpS, pubS, pubV,
-                                                          curHc, bS, bV, hcN, writeBnd);
+                        stripSteps<AFF, CT, BANDED, true>(G, K, c, lane, jlo, jhi, i0, Sl, Hl, vcw, prevUpS, pubS, pubV,
+                                                          curHc, bS, bV, hcN);
                     else
-                        stripSteps<AFF, CT, BANDED, false>(G, s, c, lane, jlo, jhi, i0, Sl, Hl, vcw, prevUpS, pubS, pubV,
-                                                           curHc, bS, bV, hcN, writeBnd);
+                        stripSteps<AFF, CT, BANDED, false>(G, K, c, lane, jlo, jhi, i0, Sl, Hl, vcw, prevUpS, pubS, pubV,
+                                                           curHc, bS, bV, hcN);
                 }
             }
         }
@@ -333,8 +389,13 @@ __device__ __noinline__ void fillGrid(const GridCtx& G) {
 
 // ---------------------------------------------------------------------------------------
 // traceback (seqan/align/dp_traceback_impl.h, seeds/banded_chain_alignment_traceback.h)
-// in SeqAn storage coordinates (col, cv); lane 0 of warp 0 only.
+// in SeqAn storage coordinates (col, cv).  Executed by ALL lanes of warp 0 with identical
+// (warp-uniform) control flow: the walk itself is serial, but the trace bytes come from a
+// 64x64 window staged in shared memory that the 32 lanes load cooperatively (one window
+// serves >= 64 steps), and only lane 0 writes results.
 // ---------------------------------------------------------------------------------------
+constexpr int WIN = 64;
+
 struct Coord {
     int currCol, currRow, endCol, endRow, bp1, bp2;
     bool inBandFlag;
@@ -350,27 +411,70 @@ struct OutStream {
     int cap, len;
     bool overflow;
     int h0, v0;
+    int lane;
     __device__ __forceinline__ void put(int x) {
-        if (len < cap) buf[len] = x;
+        if (len < cap) { if (lane == 0) buf[len] = x; }
         else overflow = true;
         ++len;
+    }
+    __device__ __forceinline__ void patch(int pos, int x) {
+        if (pos < cap && lane == 0) buf[pos] = x;
     }
 };
 
 struct TraceWalker {
     const GridCtx& G;
     OutStream& out;
+    uint8_t* win;     // shared memory, WIN*WIN bytes, win[(row - wRow0) * WIN + (col - wCol0)]
+    int wRow0, wCol0; // matrix coordinates of the window origin; wRow0 < 0: no window loaded
+    int wRowEnd, wColEnd;  // last row / column staged
     int pc, pv;       // navigator position: column, storage row
     int nSegs;        // segments emitted for the current trace
     bool emitOn;
     bool bad;         // undefined trace value (reference: endless loop / assert)
 
-    __device__ TraceWalker(const GridCtx& g, OutStream& o) : G(g), out(o), pc(0), pv(0), nSegs(0), emitOn(true), bad(false) {}
+    __device__ TraceWalker(const GridCtx& g, OutStream& o, uint8_t* w)
+        : G(g), out(o), win(w), wRow0(-1), wCol0(0), wRowEnd(-1), wColEnd(-1), pc(0), pv(0), nSegs(0), emitOn(true), bad(false) {}
 
-    __device__ __forceinline__ uint32_t tvHere() const {
-        int i = pv - storageOffset(G.g, pc);
-        if (i <= 0 || pc <= 0 || i > G.g.nV || pc > G.g.nH) return 0;
-        return G.trace[traceAddr(G, i, pc)];
+    // Stage the window whose bottom-right corner is the 8-row group of (i, j).
+    __device__ void loadWindow(int i, int j) {
+        const int lane = threadIdx.x & 31;
+        const int gBot = (i - 1) / R;                       // row group of row i (rows 8g+1 .. 8g+8)
+        const int gTop = imax(0, gBot - (WIN / R - 1));
+        wRow0 = gTop * R + 1;
+        wCol0 = imax(1, j - (WIN - 1));
+        wRowEnd = (gBot + 1) * R;
+        wColEnd = j;
+        __syncwarp();
+        const int nGroups = gBot - gTop + 1;
+        const int nCols = j - wCol0 + 1;
+        for (int idx = lane; idx < nGroups * nCols; idx += 32) {
+            const int gq = gTop + idx / nCols;
+            const int col = wCol0 + idx % nCols;
+            const int row = gq * R + 1;
+            const int s = (row - 1) / SH;
+            const int t = ((row - 1) - s * SH) / R;
+            const int jlo = stripJlo(G.g, s), jhi = stripJhi(G.g, s);
+            uint2 v = make_uint2(0u, 0u);
+            if (col >= jlo && col <= jhi && row <= G.g.nV && s < G.NS) {
+                const int k = col - jlo + t;
+                v = *reinterpret_cast<const uint2*>(G.trace + (size_t)G.stripBase[s] + ((size_t)k * 32 + t) * R);
+            }
+            uint8_t* dst = win + (size_t)(row - wRow0) * WIN + (col - wCol0);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dst[r * WIN] = (uint8_t)(v.x >> (8 * r));
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dst[(4 + r) * WIN] = (uint8_t)(v.y >> (8 * r));
+        }
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ uint32_t tvHere() {
+        const int i = pv - storageOffset(G.g, pc);
+        const int j = pc;
+        if (i <= 0 || j <= 0 || i > G.g.nV || j > G.g.nH) return 0;
+        if (wRow0 < 0 || i < wRow0 || j < wCol0 || i > wRowEnd || j > wColEnd) loadWindow(i, j);
+        return win[(size_t)(i - wRow0) * WIN + (j - wCol0)];
     }
     __device__ Coord makeCoord(int endCol, int endRow) const {  // dp_traceback_impl.h:121-141
         Coord c;
