@@ -113,6 +113,10 @@ void ub200_lastTransferBytes(int64_t* h2d, int64_t* d2h, int64_t* traceBytes, in
 /* Reference DP-cell count and sub-DP count of one banded-chain alignment; planner only. */
 int64_t ub200_chainCells(int readLen, int refLen, const int64_t* seeds, int nSeeds, int bandSize, int* nGrids);
 
+/* Planner introspection: 8 int32 per sub-DP (kind, nH, nV, banded, lo, up, h0, v0) into out (cap grids);
+ * returns the number of sub-DPs of the banded-chain alignment, -1 if the chain is unsupported. */
+int ub200_chainPlan(int readLen, int refLen, const int64_t* seeds, int nSeeds, int bandSize, int32_t* out, int cap);
+
 /* Selects the CUDA device for this process' engine (before first use).  Returns 0 on success. */
 int ub200_setDevice(int device);
 /* Integer-pipe microbenchmark (dependent-free IADD3/VIMNMX mix on all SMs): returns int32 ops/s. */

@@ -214,6 +214,48 @@ UB_HD TrackOpts chainTrackingOptions(int32_t ch, int32_t cv, int32_t tLeap, int3
     return o;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Strip / checkpoint geometry of the device engine (shared with the host memory planner).
+// ---------------------------------------------------------------------------------------
+constexpr int32_t SH = 256;              // strip height of task grids (32 lanes x 8 rows)
+constexpr int32_t CKW = 64;              // column-checkpoint spacing == recompute tile width
+constexpr int32_t SEG = 1024;            // columns per work item
+constexpr int32_t WINBYTES = 24 * 1024;  // shared-memory trace window per control warp
+
+// first / last column of strip s (rows s*SHR+1 .. (s+1)*SHR) that holds band cells
+UB_HD int32_t stripJlo(const GridGeom& g, int32_t s, int32_t SHR) { return g.banded ? imax(1, s * SHR + 1 + g.lo) : 1; }
+UB_HD int32_t stripJhi(const GridGeom& g, int32_t s, int32_t SHR) {
+    if (!g.banded) return g.nH;
+    int32_t r1 = imin(g.nV, (s + 1) * SHR);
+    return imin(g.nH, r1 + g.up);
+}
+// number of strips that hold band cells
+UB_HD int32_t stripCount(const GridGeom& g, int32_t SHR) {
+    int32_t rowsReach = g.banded ? imin(g.nV, g.nH - g.lo) : g.nV;
+    return (rowsReach + SHR - 1) / SHR;
+}
+// first checkpoint column (in units of CKW) inside strip s, and how many the strip holds
+UB_HD int32_t ckFirst(const GridGeom& g, int32_t s) { return (stripJlo(g, s, SH) + CKW - 1) / CKW; }
+UB_HD int32_t ckCount(const GridGeom& g, int32_t s) {
+    int32_t n = stripJhi(g, s, SH) / CKW - ckFirst(g, s) + 1;
+    return n > 0 ? n : 0;
+}
+
+// A grid is "local" when one warp can fill it with the full trace kept in its shared-memory window.
+struct LocalPlan {
+    int32_t local, RR, pitch, jhi;
+};
+UB_HD LocalPlan localPlan(const GridGeom& g) {
+    LocalPlan p;
+    p.RR = (g.nV <= 128) ? 4 : 8;
+    int32_t lanes = (g.nV + p.RR - 1) / p.RR;
+    p.pitch = (lanes + 1) & ~1;
+    p.jhi = stripJhi(g, 0, 32 * p.RR);
+    p.local = (g.nV <= 32 * p.RR && (int64_t)p.jhi * p.pitch * p.RR <= (int64_t)WINBYTES) ? 1 : 0;
+    return p;
+}
+
 // Reference cell count of a grid: dimH * dimV of the allocated score matrix.
 UB_HD int64_t gridCells(int32_t nH, int32_t nV, int32_t banded, int32_t lo, int32_t up) {
     GridGeom g = makeGeom(nH, nV, banded, lo, up);

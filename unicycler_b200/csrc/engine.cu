@@ -1,4 +1,4 @@
-// B200 DP engine: persistent job kernel + host launcher.  See engine.hpp / engine_kernels.cuh.
+// B200 DP engine: persistent agent kernel + host launcher.  See engine.hpp / engine_kernels.cuh.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -19,74 +19,95 @@ namespace ub200 {
     } while (0)
 
 // ---------------------------------------------------------------------------------------
-// device: per-grid setup, init rows, tracking, chain traceback
+// device: per-grid setup, init rows, tracking, chain traceback — all executed by ONE warp
+// (the control agent of the job); G lives in that warp's shared-memory slot.
 // ---------------------------------------------------------------------------------------
 
-__device__ __noinline__ void setupGrid(GridCtx& G, const KParams& P, const JobDev& jb, const GridDesc& gd, uint8_t* scratch) {
-    const ScratchLayout& L = P.lay;
-    G.g = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
-    G.kind = gd.kind; G.h0 = gd.h0; G.v0 = gd.v0; G.hNext = gd.hNext; G.vNext = gd.vNext;
-    G.capNextH = gd.capNextH; G.capNextV = gd.capNextV;
-    G.match = jb.match; G.mismatch = jb.mismatch; G.go = jb.gapOpen; G.ge = jb.gapExtend;
-    G.fe = jb.fe; G.complete = jb.complete; G.affine = (jb.gapOpen != jb.gapExtend) ? 1 : 0;
-    G.seqH = P.seq + jb.hOff + gd.h0;
-    G.seqV = P.seq + jb.vOff + gd.v0;
-    G.trace = scratch + L.trace;
-    G.stripBase = reinterpret_cast<long long*>(scratch + L.stripBase);
-    G.bnd = reinterpret_cast<int2*>(scratch + L.bnd);
-    G.initRow = reinterpret_cast<DCell*>(scratch + L.initRow);
-    G.initCol = reinterpret_cast<DCell*>(scratch + L.initCol);
-    G.hInitNext = reinterpret_cast<DCell*>(scratch + L.hInitNext);
-    G.vInitNext = reinterpret_cast<DCell*>(scratch + L.vInitNext);
-    G.box = reinterpret_cast<DCell*>(scratch + L.box);
-    G.lastRow = reinterpret_cast<DCell*>(scratch + L.lastRow);
-    G.lastCol = reinterpret_cast<DCell*>(scratch + L.lastCol);
-    G.cand = reinterpret_cast<int*>(scratch + L.cand);
-    G.planted = reinterpret_cast<PlantedCell*>(scratch + L.planted);
-    G.colTab = reinterpret_cast<ColInfo*>(scratch + L.colTab);
-    G.bndStride = L.bndStride;
-    G.maxCand = L.maxCand; G.maxPlanted = L.maxPlanted; G.maxColTab = L.maxColTab;
-    G.maxBox = L.maxBox; G.maxTrace = L.maxTrace;
+__device__ __noinline__ void setupGrid(GridCtx& G, const KParams& P, const JobDev& jb, const GridDesc& gd, uint8_t* arena) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        const ScratchLayout& L = P.lay;
+        G.g = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
+        G.kind = gd.kind; G.h0 = gd.h0; G.v0 = gd.v0; G.hNext = gd.hNext; G.vNext = gd.vNext;
+        G.capNextH = gd.capNextH; G.capNextV = gd.capNextV;
+        G.match = jb.match; G.mismatch = jb.mismatch; G.go = jb.gapOpen; G.ge = jb.gapExtend;
+        G.fe = jb.fe; G.complete = jb.complete; G.affine = (jb.gapOpen != jb.gapExtend) ? 1 : 0;
+        G.seqH = P.seq + jb.hOff + gd.h0;
+        G.seqV = P.seq + jb.vOff + gd.v0;
+        G.rowCk = reinterpret_cast<int2*>(arena + L.rowCk);
+        G.colCk = reinterpret_cast<int2*>(arena + L.colCk);
+        G.ckBase = reinterpret_cast<int*>(arena + L.ckBase);
+        G.rowProg = reinterpret_cast<int*>(arena + L.rowProg);
+        G.segDone = reinterpret_cast<int*>(arena + L.segDone);
+        G.initRow = reinterpret_cast<DCell*>(arena + L.initRow);
+        G.initCol = reinterpret_cast<DCell*>(arena + L.initCol);
+        G.hInitNext = reinterpret_cast<DCell*>(arena + L.hInitNext);
+        G.vInitNext = reinterpret_cast<DCell*>(arena + L.vInitNext);
+        G.box = reinterpret_cast<DCell*>(arena + L.box);
+        G.lastRow = reinterpret_cast<DCell*>(arena + L.lastRow);
+        G.lastCol = reinterpret_cast<DCell*>(arena + L.lastCol);
+        G.cand = reinterpret_cast<int*>(arena + L.cand);
+        G.planted = reinterpret_cast<PlantedCell*>(arena + L.planted);
+        G.colTab = reinterpret_cast<ColInfo*>(arena + L.colTab);
+        G.maxCand = L.maxCand; G.maxPlanted = L.maxPlanted; G.maxColTab = L.maxColTab; G.pad0 = 0;
+        G.maxBox = L.maxBox;
+        const GridGeom& g = G.g;
+        G.colZeroMax = g.banded ? imin(g.nV, -g.lo) : g.nV;
+        
+        const LocalPlan lp = localPlan(g);
+        G.local = lp.local; G.RR = lp.local ? lp.RR : 8; G.rrShift = (G.RR == 4) ? 2 : 3; G.pitch = lp.pitch; G.localJhi = lp.jhi;
+        G.NS = lp.local ? 1 : stripCount(g, SH);
+        G.nSeg = (g.nH + SEG - 1) / SEG;
+        // capture mode
+        G.capEdges = (gd.kind == GRID_GLOBAL || (gd.kind == GRID_CHAIN_FINAL && !g.banded)) ? 1 : 0;
+        if (!G.capEdges) {
+            G.boxRow0 = g.banded ? colTop(g, imin(G.hNext, g.nH)) : imin(G.vNext, g.nV);
+            G.boxH = g.nV - G.boxRow0 + 1;
+            G.boxW = imax(0, g.nH - G.hNext + 1);
+        } else {
+            G.boxRow0 = 0; G.boxH = 0; G.boxW = 0;
+        }
+    }
+    __syncwarp();
+}
+
+// Per-strip tables of a task grid (checkpoint bases, progress counters).  One warp.
+__device__ __noinline__ void setupStrips(const GridCtx& G) {
+    const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
-    G.colZeroMax = g.banded ? imin(g.nV, -g.lo) : g.nV;
-    int rowsReach = g.banded ? imin(g.nV, g.nH - g.lo) : g.nV;
-    G.NS = (rowsReach + SH - 1) / SH;
-    G.lag = g.banded ? (R + 2) : 2;
-    int nchMax = 0;
-    long long base = 0;
-    for (int s = 0; s < G.NS; ++s) {
-        G.stripBase[s] = base;
-        int nch = stripChunks(g, s);
-        nchMax = imax(nchMax, nch);
-        base += (long long)nch * 32 * 32 * R;
+    int base = 0;
+    for (int s0 = 0; s0 < G.NS; s0 += 32) {
+        const int s = s0 + lane;
+        const int cnt = (s < G.NS) ? ckCount(g, s) : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(FULLMASK, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (s < G.NS) {
+            G.ckBase[s] = base + incl - cnt;
+            const int jlo = stripJlo(g, s, SH);
+            G.rowProg[s] = jlo - 1;
+            G.segDone[s] = (jlo - 1) / SEG;
+        }
+        base += __shfl_sync(FULLMASK, incl, 31);
     }
-    G.P = imax(nchMax, NWARPS * G.lag);
-    int total = 0;
-    for (int s = 0; s < G.NS; ++s) total = imax(total, (s / NWARPS) * G.P + (s % NWARPS) * G.lag + stripChunks(g, s));
-    G.totalPhases = total;
-    // capture mode
-    G.capEdges = (gd.kind == GRID_GLOBAL || (gd.kind == GRID_CHAIN_FINAL && !g.banded)) ? 1 : 0;
-    if (!G.capEdges) {
-        G.boxRow0 = g.banded ? colTop(g, imin(G.hNext, g.nH)) : imin(G.vNext, g.nV);
-        G.boxH = g.nV - G.boxRow0 + 1;
-        G.boxW = imax(0, g.nH - G.hNext + 1);
-    } else {
-        G.boxRow0 = 0; G.boxH = 0; G.boxW = 0;
-    }
+    __syncwarp();
 }
 
 // Fill the init row / column of the grid (cells the reference takes from
 // _horizontalInitCurrentMatrix / _verticalInitCurrentMatrix, or computes with the
-// Horizontal / Vertical / Zero recursions for the default profile).  All threads.
+// Horizontal / Vertical / Zero recursions for the default profile).  One warp.
 __device__ __noinline__ void initGrid(const GridCtx& G, const GridDesc& gd, int nPlanted) {
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     const DCell def = DCell{NEG_INF, NEG_INF, NEG_INF};
     if (gd.kind == GRID_GLOBAL) {
         // seqan/align/dp_meta_info.h:96-150: first row Zero if free else Horizontal; first column likewise
         const bool freeRow = G.fe & 1, freeCol = G.fe & 2;
         const int go = G.go, ge = G.ge;
-        for (int j = tid; j <= g.nH; j += NTHREADS) {
+        for (int j = lane; j <= g.nH; j += 32) {
             DCell c;
             if (j == 0 || freeRow) c = DCell{0, NEG_INF, NEG_INF};
             else if (G.affine) {
@@ -97,7 +118,7 @@ __device__ __noinline__ void initGrid(const GridCtx& G, const GridDesc& gd, int 
             } else c = DCell{j * ge, NEG_INF, NEG_INF};
             G.initRow[j] = c;
         }
-        for (int i = tid; i <= g.nV; i += NTHREADS) {
+        for (int i = lane; i <= g.nV; i += 32) {
             DCell c;
             if (i == 0 || freeCol) c = DCell{0, NEG_INF, NEG_INF};
             else if (G.affine) {
@@ -108,36 +129,30 @@ __device__ __noinline__ void initGrid(const GridCtx& G, const GridDesc& gd, int 
             G.initCol[i] = c;
         }
     } else {
-        for (int j = tid; j <= g.nH; j += NTHREADS) G.initRow[j] = def;
-        for (int i = tid; i <= g.nV; i += NTHREADS) G.initCol[i] = def;
-        for (int k = tid; k < G.capNextH; k += NTHREADS) G.hInitNext[k] = def;
-        for (int k = tid; k < G.capNextV; k += NTHREADS) G.vInitNext[k] = def;
-        __syncthreads();
+        for (int j = lane; j <= g.nH; j += 32) G.initRow[j] = def;
+        for (int i = lane; i <= g.nV; i += 32) G.initCol[i] = def;
+        for (int k = lane; k < G.capNextH; k += 32) G.hInitNext[k] = def;
+        for (int k = lane; k < G.capNextV; k += 32) G.vInitNext[k] = def;
+        __syncwarp();
         if (gd.plantZerosH > 0 || gd.plantZerosV > 0) {
             // _initiaizeBeginningOfBandedChain with all end gaps free
             // (seeds/banded_chain_alignment_impl.h:683-729): zero cells
             const DCell z = DCell{0, NEG_INF, NEG_INF};
-            for (int j = tid; j < gd.plantZerosH && j <= g.nH; j += NTHREADS) G.initRow[j] = z;
-            for (int i = tid; i < gd.plantZerosV && i <= g.nV; i += NTHREADS) G.initCol[i] = z;
+            for (int j = lane; j < gd.plantZerosH && j <= g.nH; j += 32) G.initRow[j] = z;
+            for (int i = lane; i < gd.plantZerosV && i <= g.nV; i += 32) G.initCol[i] = z;
         } else {
             // _reinitScoutState (seeds/banded_chain_alignment_scout.h:204-219)
-            for (int k = tid; k < nPlanted; k += NTHREADS) {
+            for (int k = lane; k < nPlanted; k += 32) {
                 PlantedCell pc = G.planted[k];
                 if (pc.i1 == 0 && pc.i2 <= g.nV) G.initCol[pc.i2] = pc.c;
                 if (pc.i2 == 0 && pc.i1 <= g.nH) G.initRow[pc.i1] = pc.c;
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
 }
 
-__device__ __forceinline__ DCell cellAtBox(const GridCtx& G, int i, int j) {
-    if (j == 0) return G.initCol[i];
-    if (i == 0) return G.initRow[j];
-    return G.box[(size_t)(j - G.hNext) * G.boxH + (i - G.boxRow0)];
-}
-
-// Result of the tracking pass (shared memory)
+// Result of the tracking pass (registers of the control warp; identical in all lanes)
 struct TrackResult {
     int maxScore;
     int nCand;
@@ -145,56 +160,102 @@ struct TrackResult {
     DCell maxCell;
 };
 
-struct TrackShared {
-    int maxScore;
-    int count;
-    int ub;
-    int nCols;
-};
-
-// Tracked-cell enumeration shared by both passes of the chain tracking.  Calls f(i, j, cv, opts) for
-// every cell of the grid that _determineTrackingOptions flags (seeds/banded_chain_alignment_impl.h:282-377),
-// distributing cells over all threads of the CTA.
+// Tracked-cell enumeration shared by both passes of the chain tracking.  Calls f(valid, i, j, cv, opts)
+// in lock-step for all lanes of the warp; `valid` lanes hold a cell of the grid that
+// _determineTrackingOptions flags (seeds/banded_chain_alignment_impl.h:282-377).
 template <typename F>
 __device__ __forceinline__ void forEachFlaggedCell(const GridCtx& G, int nColTab, F f) {
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     const bool chainFinal = (G.kind == GRID_CHAIN_FINAL);
     const bool feLastRow = G.fe & 4, feLastCol = G.fe & 8;
+    TrackOpts none;
+    none.lastCol = none.lastRow = none.storeCol = none.storeRow = false;
     if (G.capEdges) {
         // unbanded final matrix, hNext = vNext = 0: last row of columns 0..nH-1, then the last column
         const int nH = g.nH, nV = g.nV;
         const int total = nH + nV + 1;
-        for (int idx = tid; idx < total; idx += NTHREADS) {
-            TrackOpts o;
-            o.storeCol = o.storeRow = false;
-            int i, j;
-            if (idx < nH) { i = nV; j = idx; o.lastRow = feLastRow; o.lastCol = false; }
-            else { i = idx - nH; j = nH; o.lastCol = (i == nV) || feLastCol; o.lastRow = (i == nV); }
-            if (o.lastRow || o.lastCol) f(i, j, i, o);
+        for (int base = 0; base < total; base += 32) {
+            const int idx = base + lane;
+            TrackOpts o = none;
+            int i = 0, j = 0;
+            if (idx < total) {
+                if (idx < nH) { i = nV; j = idx; o.lastRow = feLastRow; o.lastCol = false; }
+                else { i = idx - nH; j = nH; o.lastCol = (i == nV) || feLastCol; o.lastRow = (i == nV); }
+            }
+            f(idx < total && (o.lastRow || o.lastCol), i, j, i, o);
         }
     } else if (!g.banded) {
+        // Only the perimeter of the box [boxRow0..nV] x [hNext..nH] can be flagged: row vNext (storeRow), column
+        // hNext (storeCol), the last row (CT_LAST) and the final column (CP_FINAL).
         const int nH = g.nH, nV = g.nV;
         const int bw = G.boxW, bh = G.boxH;
-        for (int idx = tid; idx < bw * bh; idx += NTHREADS) {
-            const int j = G.hNext + idx / bh;
-            const int i = G.boxRow0 + idx % bh;
-            const int cp = (j == 0) ? CP_INITIAL : (j == nH ? CP_FINAL : CP_INNER);
-            const int ct = (i == 0) ? CT_FIRST : (i == nV ? CT_LAST : CT_INNER);
-            TrackOpts o = chainTrackingOptions(j, i, 1, cp, CL_FULL, ct, G.hNext, G.vNext, chainFinal, feLastRow, feLastCol);
-            if (o.lastRow || o.lastCol || o.storeCol || o.storeRow) f(i, j, i, o);
+        const int inner = imax(0, bh - 2);
+        const int total = (bw > 0 && bh > 0) ? 2 * bw + 2 * inner : 0;
+        for (int base = 0; base < total; base += 32) {
+            const int idx = base + lane;
+            TrackOpts o = none;
+            int i = 0, j = 0;
+            bool ok = idx < total;
+            if (ok) {
+                if (idx < bw) { i = G.boxRow0; j = G.hNext + idx; }
+                else if (idx < 2 * bw) { i = nV; j = G.hNext + idx - bw; ok = bh > 1; }
+                else if (idx < 2 * bw + inner) { i = G.boxRow0 + 1 + (idx - 2 * bw); j = G.hNext; }
+                else { i = G.boxRow0 + 1 + (idx - 2 * bw - inner); j = nH; ok = bw > 1; }
+            }
+            if (ok) {
+                const int cp = (j == 0) ? CP_INITIAL : (j == nH ? CP_FINAL : CP_INNER);
+                const int ct = (i == 0) ? CT_FIRST : (i == nV ? CT_LAST : CT_INNER);
+                o = chainTrackingOptions(j, i, 1, cp, CL_FULL, ct, G.hNext, G.vNext, chainFinal, feLastRow, feLastCol);
+            }
+            f(ok && (o.lastRow || o.lastCol || o.storeCol || o.storeRow), i, j, i, o);
         }
     } else {
+        // Banded: in a column other than hNext / the final one only two cells can be flagged: the one whose
+        // storage row hits vNext (storeRow) and the last cell (CT_LAST).  One lane per column.
+        for (int base = 0; base < nColTab; base += 32) {
+            const int ccol = base + lane;
+            const bool have = ccol < nColTab;
+            ColInfo ci;
+            ci.j = 0; ci.cp = CP_INNER; ci.cl = CL_FULL; ci.rowTop = 0; ci.nCells = 0; ci.tLeap = 0; ci.tLeapLast = 0; ci.cvFirst = 0;
+            if (have) ci = G.colTab[ccol];
+            const bool full = (ci.j == G.hNext) || (ci.cp == CP_FINAL);
+            const int cLast = ci.nCells - 1;
+            int cSR = (ci.cl == CL_BOTTOM) ? (G.vNext - ci.tLeap - ci.cvFirst) : (G.vNext - ci.cvFirst);
+            const bool srOk = have && !full && cSR >= 0 && cSR < cLast;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c = pass == 0 ? cLast : cSR;
+                const bool ok = pass == 0 ? (have && !full && cLast >= 0) : srOk;
+                TrackOpts o = none;
+                int i = 0, cv = 0;
+                if (ok) {
+                    i = ci.rowTop + c;
+                    cv = ci.cvFirst + c;
+                    const int ct = (c == 0) ? CT_FIRST : (c == ci.nCells - 1 ? CT_LAST : CT_INNER);
+                    const int leap = (ct == CT_LAST) ? ci.tLeapLast : ci.tLeap;
+                    o = chainTrackingOptions(ci.j, cv, leap, ci.cp, ci.cl, ct, G.hNext, G.vNext, chainFinal, feLastRow,
+                                             feLastCol);
+                }
+                f(ok && (o.lastRow || o.lastCol || o.storeCol || o.storeRow), i, ci.j, cv, o);
+            }
+        }
         for (int ccol = 0; ccol < nColTab; ++ccol) {
             const ColInfo ci = G.colTab[ccol];
-            for (int c = tid; c < ci.nCells; c += NTHREADS) {
-                const int i = ci.rowTop + c;
-                const int cv = ci.cvFirst + c;
-                const int ct = (c == 0) ? CT_FIRST : (c == ci.nCells - 1 ? CT_LAST : CT_INNER);
-                const int leap = (ct == CT_LAST) ? ci.tLeapLast : ci.tLeap;
-                TrackOpts o = chainTrackingOptions(ci.j, cv, leap, ci.cp, ci.cl, ct, G.hNext, G.vNext, chainFinal,
-                                                   feLastRow, feLastCol);
-                if (o.lastRow || o.lastCol || o.storeCol || o.storeRow) f(i, ci.j, cv, o);
+            if (!((ci.j == G.hNext) || (ci.cp == CP_FINAL))) continue;
+            for (int base = 0; base < ci.nCells; base += 32) {
+                const int c = base + lane;
+                TrackOpts o = none;
+                int i = 0, cv = 0;
+                if (c < ci.nCells) {
+                    i = ci.rowTop + c;
+                    cv = ci.cvFirst + c;
+                    const int ct = (c == 0) ? CT_FIRST : (c == ci.nCells - 1 ? CT_LAST : CT_INNER);
+                    const int leap = (ct == CT_LAST) ? ci.tLeapLast : ci.tLeap;
+                    o = chainTrackingOptions(ci.j, cv, leap, ci.cp, ci.cl, ct, G.hNext, G.vNext, chainFinal, feLastRow,
+                                             feLastCol);
+                }
+                f(c < ci.nCells && (o.lastRow || o.lastCol || o.storeCol || o.storeRow), i, ci.j, cv, o);
             }
         }
     }
@@ -207,15 +268,15 @@ __device__ __forceinline__ DCell trackedCell(const GridCtx& G, int i, int j) {
     return G.box[(size_t)(j - G.hNext) * G.boxH + (i - G.boxRow0)];
 }
 
-// Tracking pass for banded-chain grids (all threads): stores the next grid's init row/column, finds
+// Tracking pass for banded-chain grids (one warp): stores the next grid's init row/column, finds
 // the maximum over the tracked cells and collects every tied maximum in visiting order
 // (seeds/banded_chain_alignment_scout.h:230-270).  Visiting order == ascending host position.
-__device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res, TrackShared& TS) {
-    const int tid = threadIdx.x;
+__device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res) {
+    const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
-    if (tid == 0) {
-        TS.maxScore = INT32_MIN; TS.count = 0; TS.ub = 0; TS.nCols = 0;
-        if (!G.capEdges && g.banded) {
+    int ub = 0, nCols = 0;
+    if (!G.capEdges && g.banded) {
+        if (lane == 0) {
             // literal column walk of _computeBandedAlignment for the columns right of the next grid's origin
             BandWalker w;
             w.init(g);
@@ -227,105 +288,107 @@ __device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res, Trac
                     ++n;
                 }
             }
-            if (n > G.maxColTab) { TS.ub = 1; n = G.maxColTab; }
-            TS.nCols = n;
+            if (n > G.maxColTab) { ub = 1; n = G.maxColTab; }
+            nCols = n;
         }
+        __syncwarp();
+        nCols = __shfl_sync(FULLMASK, nCols, 0);
     }
-    __syncthreads();
-    const int nCols = TS.nCols;
     const int dimV = g.dimV;
     // pass 1: init stores + maximum
-    forEachFlaggedCell(G, nCols, [&](int i, int j, int cv, const TrackOpts& o) {
+    int best = INT32_MIN;
+    forEachFlaggedCell(G, nCols, [&](bool valid, int i, int j, int cv, const TrackOpts& o) {
+        if (!valid) return;
         const DCell c = trackedCell(G, i, j);
-        if (o.storeCol) { int k = cv - G.vNext; if (k >= 0 && k < G.capNextV) G.vInitNext[k] = c; else TS.ub = 1; }
-        if (o.storeRow) { int k = j - G.hNext; if (k >= 0 && k < G.capNextH) G.hInitNext[k] = c; else TS.ub = 1; }
-        if (o.lastCol || o.lastRow) atomicMax(&TS.maxScore, c.s);
+        if (o.storeCol) { int k = cv - G.vNext; if (k >= 0 && k < G.capNextV) G.vInitNext[k] = c; else ub = 1; }
+        if (o.storeRow) { int k = j - G.hNext; if (k >= 0 && k < G.capNextH) G.hInitNext[k] = c; else ub = 1; }
+        if (o.lastCol || o.lastRow) best = max(best, c.s);
     });
-    __syncthreads();
-    const int best = TS.maxScore;
+    best = __reduce_max_sync(FULLMASK, best);
     // pass 2: every tracked cell that reaches the maximum
-    forEachFlaggedCell(G, nCols, [&](int i, int j, int cv, const TrackOpts& o) {
-        if (!(o.lastCol || o.lastRow)) return;
-        const DCell c = trackedCell(G, i, j);
-        if (c.s == best) {
-            int k = atomicAdd(&TS.count, 1);
+    int count = 0;
+    forEachFlaggedCell(G, nCols, [&](bool valid, int i, int j, int cv, const TrackOpts& o) {
+        bool hit = false;
+        if (valid && (o.lastCol || o.lastRow)) hit = (trackedCell(G, i, j).s == best);
+        const unsigned m = __ballot_sync(FULLMASK, hit);
+        if (hit) {
+            const int k = count + __popc(m & ((1u << lane) - 1u));
             if (k < G.maxCand) G.cand[k] = j * dimV + cv;
         }
+        count += __popc(m);
     });
-    __syncthreads();
-    if (tid == 0) {
-        int n = TS.count;
-        if (n > G.maxCand) { TS.ub = 1; n = G.maxCand; }
+    __syncwarp();
+    ub = __any_sync(FULLMASK, ub != 0) ? 1 : 0;
+    int n = count;
+    if (n > G.maxCand) { ub = 1; n = G.maxCand; }
+    if (lane == 0) {
         for (int a = 1; a < n; ++a) {  // insertion sort: candidates are few
             int x = G.cand[a], b = a - 1;
             while (b >= 0 && G.cand[b] > x) { G.cand[b + 1] = G.cand[b]; --b; }
             G.cand[b + 1] = x;
         }
-        res.maxScore = (n == 0) ? NEG_INF : best;
-        res.nCand = n;
-        res.status = TS.ub ? JOB_REF_UB : JOB_OK;
     }
-    __syncthreads();
+    __syncwarp();
+    res.maxScore = (n == 0) ? NEG_INF : best;
+    res.nCand = n;
+    res.status = ub ? JOB_REF_UB : JOB_OK;
 }
 
 // Tracking for the default scout (GRID_GLOBAL): first maximum in column-major visiting order with
 // strict ">" (seqan/align/dp_scout.h:163-179) over the cells dp_meta_info.h marks tracked: the last-row
 // cells when the last row is free, then the band cells of the final column (all of them when the last
-// column is free, otherwise only the corner).  All threads.
-__device__ __noinline__ void trackGlobal(const GridCtx& G, TrackResult& res, TrackShared& TS) {
-    const int tid = threadIdx.x;
+// column is free, otherwise only the corner).  One warp.
+__device__ __noinline__ void trackGlobal(const GridCtx& G, TrackResult& res) {
+    const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     const bool feLastRow = G.fe & 4, feLastCol = G.fe & 8;
     const int nH = g.nH, nV = g.nV;
     const int top = colTop(g, nH), bot = colBottom(g, nH);
     const int nRowCells = feLastRow ? nH : 0;
     const int total = nRowCells + (bot - top + 1);
-    if (tid == 0) { TS.maxScore = INT32_MIN; TS.count = INT32_MAX; TS.ub = 0; }
-    __syncthreads();
     auto cellOf = [&](int idx, int& i, int& j, bool& tracked) {
         if (idx < nRowCells) { i = nV; j = idx; tracked = !g.banded || (j - nV >= g.lo && j - nV <= g.up); }
         else { i = top + (idx - nRowCells); j = nH; tracked = feLastCol || i == nV; }
     };
-    for (int idx = tid; idx < total; idx += NTHREADS) {
+    int best = INT32_MIN;
+    for (int idx = lane; idx < total; idx += 32) {
         int i, j; bool tr;
         cellOf(idx, i, j, tr);
-        if (tr) atomicMax(&TS.maxScore, trackedCell(G, i, j).s);
+        if (tr) best = max(best, trackedCell(G, i, j).s);
     }
-    __syncthreads();
-    const int best = TS.maxScore;
-    for (int idx = tid; idx < total; idx += NTHREADS) {
+    best = __reduce_max_sync(FULLMASK, best);
+    int first = INT32_MAX;
+    for (int idx = lane; idx < total; idx += 32) {
         int i, j; bool tr;
         cellOf(idx, i, j, tr);
-        if (tr && trackedCell(G, i, j).s == best) atomicMin(&TS.count, idx);  // first in visiting order
+        if (tr && trackedCell(G, i, j).s == best) first = min(first, idx);  // first in visiting order
     }
-    __syncthreads();
-    if (tid == 0) {
-        if (TS.count == INT32_MAX || best <= NEG_INF) {
-            // default scout starts from a default (-inf) cell with strict '>': nothing tracked above -inf
-            res.maxScore = NEG_INF; res.nCand = 0;
-        } else {
-            int i, j; bool tr;
-            cellOf(TS.count, i, j, tr);
-            res.maxScore = best;
-            res.nCand = 1;
-            res.maxCell = trackedCell(G, i, j);
-            G.cand[0] = j * g.dimV + i + storageOffset(g, j);
-        }
-        res.status = JOB_OK;
+    first = __reduce_min_sync(FULLMASK, first);
+    if (first == INT32_MAX || best <= NEG_INF) {
+        // default scout starts from a default (-inf) cell with strict '>': nothing tracked above -inf
+        res.maxScore = NEG_INF; res.nCand = 0;
+    } else {
+        int i, j; bool tr;
+        cellOf(first, i, j, tr);
+        res.maxScore = best;
+        res.nCand = 1;
+        res.maxCell = trackedCell(G, i, j);
+        if (lane == 0) G.cand[0] = j * g.dimV + i + storageOffset(g, j);
     }
-    __syncthreads();
+    res.status = JOB_OK;
+    __syncwarp();
 }
 
 // One candidate of a banded-chain grid (seeds/banded_chain_alignment_traceback.h:233-355).
-// Warp-uniform: every lane of warp 0 executes it; lane 0 writes.
-__device__ __noinline__ void chainTracebackOne(const GridCtx& G, OutStream& out, uint8_t* win, int startPos,
+// Warp-uniform: every lane of the control warp executes it; lane 0 writes.
+__device__ __noinline__ void chainTracebackOne(const GridCtx& G, TraceWalker& w, OutStream& out, int startPos,
                                                int& nPlanted, int& nTraces, int& status) {
     const int lane = threadIdx.x & 31;
-    TraceWalker w(G, out, win);
     const bool affine = G.affine;
     const bool prefer = affine && G.kind == GRID_CHAIN_FINAL;
     w.pc = startPos / G.g.dimV;
     w.pv = startPos % G.g.dimV;
+    w.emitOn = true;
     const int nH = G.g.nH, nV = G.g.nV;
     int headerPos = out.len;  // placeholder for nSegs
     out.put(0);
@@ -410,103 +473,248 @@ __device__ __noinline__ void chainTracebackOne(const GridCtx& G, OutStream& out,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// fills
+// ---------------------------------------------------------------------------------------
+template <bool AFF, bool CT, bool BANDED>
+__device__ __forceinline__ void localFillRR(const GridCtx& G, uint8_t* win) {
+    const int lanes = (G.g.nV + G.RR - 1) / G.RR;
+    const int nsteps = G.localJhi + lanes - 1;
+    if (G.RR == 4) runStrip<AFF, CT, BANDED, 4, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch);
+    else runStrip<AFF, CT, BANDED, 8, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch);
+}
 template <bool AFF, bool CT>
-__device__ __forceinline__ void fillDispatch(const GridCtx& G) {
-    if (G.g.banded) fillGrid<AFF, CT, true>(G);
-    else fillGrid<AFF, CT, false>(G);
+__device__ __forceinline__ void localFillBand(const GridCtx& G, uint8_t* win) {
+    if (G.g.banded) localFillRR<AFF, CT, true>(G, win);
+    else localFillRR<AFF, CT, false>(G, win);
+}
+// Small grid: the control warp fills it with the full trace in its shared-memory window.
+__device__ __forceinline__ void localFill(const GridCtx& G, uint8_t* win) {
+    if (G.affine) { if (G.complete) localFillBand<true, true>(G, win); else localFillBand<true, false>(G, win); }
+    else { if (G.complete) localFillBand<false, true>(G, win); else localFillBand<false, false>(G, win); }
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) dpJobKernel(KParams P) {
-    __shared__ GridCtx G;
-    __shared__ TrackResult TR;
-    __shared__ TrackShared TS;
-    __shared__ __align__(16) uint8_t sWin[WIN * WIN];
-    __shared__ int sJob, sStatus, sNPlanted, sOutLen, sScore;
-    uint8_t* scratch = P.scratch + (size_t)blockIdx.x * P.scratchStride;
-    const int tid = threadIdx.x;
-    for (;;) {
-        if (tid == 0) sJob = atomicAdd(P.queue, 1);
-        __syncthreads();
-        int q = sJob;
-        if (q >= P.nJobs) return;
-        const int jobIdx = P.order[q];
-        const JobDev jb = P.jobs[jobIdx];
-        if (tid == 0) { sStatus = JOB_OK; sNPlanted = 0; sOutLen = 0; sScore = 0; }
-        long long prof[6] = {0, 0, 0, 0, 0, 0};
-        long long tJob0 = clock64();
-        __syncthreads();
-        for (int gi = 0; gi < jb.gridCount; ++gi) {
-            const GridDesc gd = P.grids[jb.gridBegin + gi];
-            long long c0 = clock64();
-            if (tid == 0) setupGrid(G, P, jb, gd, scratch);
-            __syncthreads();
-            long long c1 = clock64();
-            initGrid(G, gd, sNPlanted);
-            long long c2 = clock64();
-            // fill
-            if (G.affine) { if (G.complete) fillDispatch<true, true>(G); else fillDispatch<true, false>(G); }
-            else { if (G.complete) fillDispatch<false, true>(G); else fillDispatch<false, false>(G); }
-            __syncthreads();
-            long long c3 = clock64();
-            // tracking: all threads
-            if (gd.kind == GRID_GLOBAL) trackGlobal(G, TR, TS);
-            else trackChain(G, TR, TS);
-            long long c4 = clock64();
-            // traceback: warp 0, warp-uniform
-            if (tid < 32) {
-                OutStream out;
-                out.buf = P.out + jb.outOff; out.cap = jb.outCap; out.len = sOutLen; out.overflow = false;
-                out.h0 = gd.h0; out.v0 = gd.v0; out.lane = tid;
-                int status = TR.status;
-                const int maxScore = TR.maxScore;
-                if (status == JOB_OK && maxScore < -1000000) status = JOB_BAD_SCORE;  // the RRW throw
-                int nPlanted = 0;  // _nextInitializationCells.clear()
-                if (status == JOB_OK) {
-                    out.put(gi);
-                    const int cntPos = out.len;
-                    out.put(0);
-                    int nTraces = 0;
-                    if (gd.kind == GRID_GLOBAL) {
-                        TraceWalker w(G, out, sWin);
-                        const int pos = G.cand[0];
-                        w.pc = pos / G.g.dimV; w.pv = pos % G.g.dimV;
-                        const int hdr = out.len; out.put(0);
-                        int tvOverride = -1;
-                        if (!G.complete && G.affine) {  // _correctTraceValue
-                            uint32_t t = w.tvHere();
-                            const DCell mc = TR.maxCell;
-                            if (mc.v == mc.s) { t &= ~(uint32_t)T_D; t |= T_MV; }
-                            else if (mc.h == mc.s) { t &= ~(uint32_t)T_D; t |= T_MH; }
-                            tvOverride = (int)t;
-                        }
-                        w.generic(G.affine, true, true, tvOverride);
-                        if (w.bad) status = JOB_REF_UB;
-                        out.patch(hdr, w.nSegs);
-                        nTraces = 1;
-                    } else {
-                        const int nCand = TR.nCand;
-                        for (int k = 0; k < nCand && status == JOB_OK; ++k)
-                            chainTracebackOne(G, out, sWin, G.cand[k], nPlanted, nTraces, status);
-                    }
-                    out.patch(cntPos, nTraces);
-                    if (out.overflow && status == JOB_OK) status = JOB_OUT_OVERFLOW;
-                }
-                __syncwarp();
-                if (tid == 0) { sNPlanted = nPlanted; sOutLen = out.len; sScore = maxScore; sStatus = status; }
+// One (strip, segment) work item of a published task: score-only fill.
+__device__ __noinline__ void runItem(const GridCtx& G, int item) {
+    const int lane = threadIdx.x & 31;
+    const GridGeom& g = G.g;
+    const int seg = item / G.NS;
+    const int s = item - seg * G.NS;
+    const int jlo = stripJlo(g, s, SH), jhi = stripJhi(g, s, SH);
+    const int cBeg = imax(seg * SEG + 1, jlo);
+    const int cEnd = imin((seg + 1) * SEG, jhi);
+    if (cBeg > cEnd) return;  // the strip holds no band cells in this segment
+    const bool fromCk = cBeg > jlo;
+    if (fromCk) {  // the previous segment of this strip must be complete (its column checkpoint is our state)
+        if (lane == 0) {
+            while (ldAcquire(&G.segDone[s]) < seg) __nanosleep(256);
+        }
+        __syncwarp();
+    }
+    const int nsteps = (cEnd - cBeg + 1) + 31;
+    if (G.affine) {
+        if (g.banded) runStrip<true, false, true, 8, false>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
+        else runStrip<true, false, false, 8, false>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
+    } else {
+        if (g.banded) runStrip<false, false, true, 8, false>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
+        else runStrip<false, false, false, 8, false>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) stRelease(&G.segDone[s], seg + 1);
+}
+
+// Claims and runs one item of the oldest open task.  Returns false when no item is available.
+// wctx: this warp's shared-memory copy of the task's GridCtx; wTask: index of the task it holds.
+__device__ __noinline__ bool tryRunOneItem(const KParams& P, GridCtx& wctx, int& wTask) {
+    const int lane = threadIdx.x & 31;
+    int h = 0, item = -1;
+    if (lane == 0) {
+        h = ldAcquire(&P.cb->ringHead);
+        for (;;) {
+            if (h >= P.maxTasks) break;
+            TaskDesc* t = &P.ring[h];
+            if (ldAcquire(&t->ready) == 0) break;  // nothing published at the head (yet)
+            const int n = t->nItems;
+            if (ldVolatile(&t->nextItem) < n) {
+                const int k = atomicAdd(&t->nextItem, 1);
+                if (k < n) { item = k; break; }
             }
-            __syncthreads();
-            long long c5 = clock64();
-            prof[0] += c1 - c0; prof[1] += c2 - c1; prof[2] += c3 - c2; prof[3] += c4 - c3; prof[4] += c5 - c4;
-            if (sStatus != JOB_OK) break;
+            atomicCAS(&P.cb->ringHead, h, h + 1);  // exhausted: advance the head
+            ++h;
         }
-        if (tid == 0) {
-            JobOut jo;
-            jo.status = sStatus; jo.score = sScore; jo.outLen = sOutLen; jo.pad = 0;
-            prof[5] = clock64() - tJob0;
-            for (int k = 0; k < 6; ++k) jo.prof[k] = prof[k];
-            P.jobOut[jobIdx] = jo;
+    }
+    item = __shfl_sync(FULLMASK, item, 0);
+    h = __shfl_sync(FULLMASK, h, 0);
+    if (item < 0) return false;
+    TaskDesc* t = &P.ring[h];
+    if (wTask != h) {
+        const int* src = reinterpret_cast<const int*>(&t->ctx);
+        int* dst = reinterpret_cast<int*>(&wctx);
+        for (int k = lane; k < (int)(sizeof(GridCtx) / sizeof(int)); k += 32) dst[k] = __ldcg(&src[k]);
+        wTask = h;
+        __syncwarp();
+    }
+    runItem(wctx, item);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&t->doneItems, 1);
+    return true;
+}
+
+// Publishes the control warp's grid as a task and helps until every item of it is done.
+__device__ __noinline__ int publishAndWait(const KParams& P, const GridCtx& G, GridCtx& wctx, int& wTask) {
+    const int lane = threadIdx.x & 31;
+    setupStrips(G);
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&P.cb->ringTail, 1);
+    t = __shfl_sync(FULLMASK, t, 0);
+    if (t >= P.maxTasks) return JOB_REF_UB;  // cannot happen: the host sizes the board to the number of big grids
+    TaskDesc* td = &P.ring[t];
+    const int* src = reinterpret_cast<const int*>(&G);
+    int* dst = reinterpret_cast<int*>(&td->ctx);
+    for (int k = lane; k < (int)(sizeof(GridCtx) / sizeof(int)); k += 32) dst[k] = src[k];
+    const int nItems = G.NS * G.nSeg;
+    if (lane == 0) { td->nItems = nItems; td->nextItem = 0; td->doneItems = 0; }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) stRelease(&td->ready, 1);
+    for (;;) {
+        int d = 0;
+        if (lane == 0) d = ldAcquire(&td->doneItems);
+        d = __shfl_sync(FULLMASK, d, 0);
+        if (d >= nItems) break;
+        if (!tryRunOneItem(P, wctx, wTask)) __nanosleep(200);
+    }
+    __syncwarp();
+    return JOB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// one job, start to end, on one control warp
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ void runJob(const KParams& P, int jobIdx, GridCtx& G, GridCtx& wctx, int& wTask, uint8_t* win,
+                                    uint8_t* arena) {
+    const int lane = threadIdx.x & 31;
+    const JobDev jb = P.jobs[jobIdx];
+    int status = JOB_OK, nPlantedPrev = 0, outLen = 0, score = 0;
+    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tJob0 = clock64();
+    for (int gi = 0; gi < jb.gridCount; ++gi) {
+        const GridDesc gd = P.grids[jb.gridBegin + gi];
+        const long long c0 = clock64();
+        setupGrid(G, P, jb, gd, arena);
+        initGrid(G, gd, nPlantedPrev);
+        const long long c1 = clock64();
+        long long c2;
+        if (G.local) {
+            localFill(G, win);
+            c2 = clock64();
+            prof[1] += c2 - c1;
+        } else {
+            const int st = publishAndWait(P, G, wctx, wTask);
+            if (st != JOB_OK) status = st;
+            c2 = clock64();
+            prof[2] += c2 - c1;
         }
-        __syncthreads();
+        TrackResult TR;
+        TR.maxCell = DCell{0, 0, 0};
+        if (gd.kind == GRID_GLOBAL) trackGlobal(G, TR);
+        else trackChain(G, TR);
+        const long long c3 = clock64();
+        // traceback: warp-uniform
+        OutStream out;
+        out.buf = P.out + jb.outOff; out.cap = jb.outCap; out.len = outLen; out.overflow = false;
+        out.h0 = gd.h0; out.v0 = gd.v0; out.lane = lane;
+        if (status == JOB_OK) status = TR.status;
+        const int maxScore = TR.maxScore;
+        if (status == JOB_OK && maxScore < -1000000) status = JOB_BAD_SCORE;  // the RRW throw
+        int nPlanted = 0;  // _nextInitializationCells.clear()
+        if (status == JOB_OK) {
+            out.put(gi);
+            const int cntPos = out.len;
+            out.put(0);
+            int nTraces = 0;
+            TraceWalker w(G, out, win);
+            if (gd.kind == GRID_GLOBAL) {
+                const int pos = G.cand[0];
+                w.pc = pos / G.g.dimV; w.pv = pos % G.g.dimV;
+                const int hdr = out.len; out.put(0);
+                int tvOverride = -1;
+                if (!G.complete && G.affine) {  // _correctTraceValue
+                    uint32_t t = w.tvHere();
+                    const DCell mc = TR.maxCell;
+                    if (mc.v == mc.s) { t &= ~(uint32_t)T_D; t |= T_MV; }
+                    else if (mc.h == mc.s) { t &= ~(uint32_t)T_D; t |= T_MH; }
+                    tvOverride = (int)t;
+                }
+                w.generic(G.affine, true, true, tvOverride);
+                if (w.bad) status = JOB_REF_UB;
+                out.patch(hdr, w.nSegs);
+                nTraces = 1;
+            } else {
+                const int nCand = TR.nCand;
+                for (int k = 0; k < nCand && status == JOB_OK; ++k)
+                    chainTracebackOne(G, w, out, G.cand[k], nPlanted, nTraces, status);
+            }
+            out.patch(cntPos, nTraces);
+            if (out.overflow && status == JOB_OK) status = JOB_OUT_OVERFLOW;
+            prof[6] += w.tilesComputed; prof[7] += w.tileCycles;
+            prof[9] += (gd.kind == GRID_GLOBAL) ? 1 : TR.nCand;
+        }
+        __syncwarp();
+        nPlantedPrev = nPlanted; outLen = out.len; score = maxScore;
+        const long long c4 = clock64();
+        prof[0] += c1 - c0; prof[3] += c3 - c2; prof[4] += c4 - c3;
+        if (G.local) { prof[8] += c4 - c3; prof[10] += 1; prof[11] += c3 - c2; }
+        if (status != JOB_OK) break;
+    }
+    if (lane == 0) {
+        JobOut jo;
+        jo.status = status; jo.score = score; jo.outLen = outLen; jo.pad = 0;
+        prof[5] = clock64() - tJob0;
+        for (int k = 0; k < 12; ++k) jo.prof[k] = prof[k];
+        P.jobOut[jobIdx] = jo;
+        __threadfence();
+        atomicAdd(&P.cb->jobsDone, 1);
+    }
+    __syncwarp();
+}
+
+constexpr int CTX_STRIDE = (int)((sizeof(GridCtx) + 15) / 16 * 16);
+constexpr int SMEM_BYTES = NCTRL * WINBYTES + (NCTRL + NWARPS) * CTX_STRIDE;
+
+__global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel(KParams P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    GridCtx* wctx = reinterpret_cast<GridCtx*>(smem + NCTRL * WINBYTES + (NCTRL + warp) * CTX_STRIDE);
+    int wTask = -1;
+    int agent = -1;
+    if (warp < NCTRL) {
+        agent = blockIdx.x * NCTRL + warp;
+        if (agent >= P.nSlots) agent = -1;
+    }
+    bool queueEmpty = (agent < 0);
+    for (;;) {
+        if (!queueEmpty) {
+            int q = 0;
+            if (lane == 0) q = atomicAdd(&P.cb->jobQueue, 1);
+            q = __shfl_sync(FULLMASK, q, 0);
+            if (q < P.nJobs) {
+                GridCtx* cctx = reinterpret_cast<GridCtx*>(smem + NCTRL * WINBYTES + warp * CTX_STRIDE);
+                runJob(P, P.order[q], *cctx, *wctx, wTask, smem + warp * WINBYTES,
+                       P.scratch + (size_t)agent * P.scratchStride);
+                continue;
+            }
+            queueEmpty = true;
+        }
+        if (tryRunOneItem(P, *wctx, wTask)) continue;
+        int done = 0;
+        if (lane == 0) done = ldAcquire(&P.cb->jobsDone);
+        done = __shfl_sync(FULLMASK, done, 0);
+        if (done >= P.nJobs) break;
+        __nanosleep(500);
     }
 }
 
@@ -516,28 +724,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpJobKernel(KParams P) {
 
 int64_t referenceCells(const GridDesc& g) { return gridCells(g.nH, g.nV, g.banded, g.lo, g.up); }
 
-static long long hostStripChunks(const GridGeom& g, int s) {
-    int jlo = g.banded ? std::max(1, s * SH + 1 + g.lo) : 1;
-    int jhi = g.banded ? std::min(g.nH, std::min(g.nV, (s + 1) * SH) + g.up) : g.nH;
-    int ncols = jhi - jlo + 1;
-    return ncols > 0 ? (ncols + 62) / 32 : 0;
-}
-
-static long long hostTraceBytes(const GridDesc& gd, int& nStrips) {
+// checkpoint bytes of a task grid (0 for local grids): row checkpoints, column checkpoints
+static void hostCheckpointBytes(const GridDesc& gd, long long& rowCk, long long& colCk, int& nStrips, bool& local) {
     GridGeom g = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
-    int rowsReach = g.banded ? std::min(g.nV, g.nH - g.lo) : g.nV;
-    nStrips = (rowsReach + SH - 1) / SH;
-    long long total = 0;
-    for (int s = 0; s < nStrips; ++s) total += hostStripChunks(g, s) * 32LL * 32 * R;
-    return total;
+    LocalPlan lp = localPlan(g);
+    local = lp.local != 0;
+    rowCk = colCk = 0;
+    nStrips = 1;
+    if (local) return;
+    nStrips = stripCount(g, SH);
+    rowCk = (long long)nStrips * (g.nH + 1) * (long long)sizeof(int2);
+    long long tiles = 0;
+    for (int s = 0; s < nStrips; ++s) tiles += ckCount(g, s);
+    colCk = tiles * SH * (long long)sizeof(int2);
 }
-
-static const int CTAS_PER_SM = 1;
 
 struct Engine::Impl {
     int device = 0;
     int numSMs = 148;
-    size_t freeMemAtStart = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6];
     std::mutex mu;
@@ -550,7 +754,7 @@ struct Engine::Impl {
     void* dJobOut = nullptr; size_t capJobOut = 0;
     void* dOrder = nullptr; size_t capOrder = 0;
     void* dScratch = nullptr; size_t capScratch = 0;
-    int* dQueue = nullptr;
+    void* dRing = nullptr; size_t capRing = 0;   // ControlBlock followed by the task board
     // pinned host staging
     void* hSeq = nullptr; size_t capHSeq = 0;
     void* hOut = nullptr; size_t capHOut = 0;
@@ -560,8 +764,7 @@ struct Engine::Impl {
     std::vector<int> order;
     std::vector<JobOut> jobOut;
     KParams kp;
-    int nCtas = 0;
-    size_t seqBytes = 0, outInts = 0;
+    size_t seqBytes = 0, outInts = 0, ringBytes = 0;
 
     void growDev(void*& p, size_t& cap, size_t need) {
         if (need <= cap) return;
@@ -576,6 +779,10 @@ struct Engine::Impl {
         size_t ncap = need + need / 4 + 256;
         CUDA_CHECK(cudaMallocHost(&p, ncap));
         cap = ncap;
+    }
+    void launchOnce() {
+        CUDA_CHECK(cudaMemsetAsync(dRing, 0, ringBytes, stream));
+        dpAgentKernel<<<numSMs, NTHREADS, SMEM_BYTES, stream>>>(kp);
     }
 };
 
@@ -594,16 +801,16 @@ Engine::Engine(int device) : impl_(new Impl) {
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     impl_->numSMs = prop.multiProcessorCount;
+    CUDA_CHECK(cudaFuncSetAttribute(dpAgentKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     CUDA_CHECK(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking));
     for (auto& ev : impl_->ev) CUDA_CHECK(cudaEventCreate(&ev));
-    CUDA_CHECK(cudaMalloc(&impl_->dQueue, sizeof(int)));
 }
 
 Engine::~Engine() {
     if (!impl_) return;
     cudaSetDevice(impl_->device);
     cudaFree(impl_->dJobs); cudaFree(impl_->dGrids); cudaFree(impl_->dSeq); cudaFree(impl_->dOut);
-    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dScratch); cudaFree(impl_->dQueue);
+    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dScratch); cudaFree(impl_->dRing);
     cudaFreeHost(impl_->hSeq); cudaFreeHost(impl_->hOut);
     for (auto& ev : impl_->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(impl_->stream);
@@ -630,8 +837,9 @@ void Engine::upload(std::vector<Job*>& jobs) {
     size_t off = 0, outOff = 0;
     ScratchLayout L;
     memset(&L, 0, sizeof(L));
-    long long maxTrace = 0, maxBox = 1;
+    long long maxRowCk = 0, maxColCk = 0, maxBox = 1, ckBytes = 0;
     int maxNH = 1, maxNV = 1, maxCapH = 1, maxCapV = 1, maxStrips = 1, maxBoxW = 1;
+    size_t nTasks = 0;
     std::vector<long long> cost(nJobs, 0);
     int64_t totalCells = 0;
     for (size_t k = 0; k < nJobs; ++k) {
@@ -652,10 +860,17 @@ void Engine::upload(std::vector<Job*>& jobs) {
         j.cells = 0;
         for (const GridDesc& gd : j.grids) {
             I.gridsAll.push_back(gd);
-            int ns = 0;
-            long long tb = hostTraceBytes(gd, ns);
-            maxTrace = std::max(maxTrace, tb);
-            maxStrips = std::max(maxStrips, ns);
+            int ns = 1;
+            long long rck = 0, cck = 0;
+            bool local = false;
+            hostCheckpointBytes(gd, rck, cck, ns, local);
+            if (!local) {
+                ++nTasks;
+                ckBytes += rck + cck;
+                maxRowCk = std::max(maxRowCk, rck);
+                maxColCk = std::max(maxColCk, cck);
+                maxStrips = std::max(maxStrips, ns);
+            }
             maxNH = std::max(maxNH, gd.nH); maxNV = std::max(maxNV, gd.nV);
             maxCapH = std::max(maxCapH, gd.capNextH); maxCapV = std::max(maxCapV, gd.capNextV);
             if (gd.kind == GRID_CHAIN_INITIAL || gd.kind == GRID_CHAIN_INNER ||
@@ -682,13 +897,14 @@ void Engine::upload(std::vector<Job*>& jobs) {
     std::stable_sort(I.order.begin(), I.order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     I.seqBytes = off;
     I.outInts = outOff;
-    // scratch layout
+    // arena layout of one control agent
     size_t o = 0;
     auto place = [&](long long& field, size_t bytes) { field = (long long)o; o += alignUp(bytes, 256); };
-    place(L.trace, (size_t)maxTrace + 256);
-    place(L.stripBase, (size_t)(maxStrips + 2) * sizeof(long long));
-    L.bndStride = maxNH + 8;
-    place(L.bnd, (size_t)2 * L.bndStride * sizeof(int2));
+    place(L.rowCk, (size_t)maxRowCk + 256);
+    place(L.colCk, (size_t)maxColCk + 256);
+    place(L.ckBase, (size_t)(maxStrips + 2) * sizeof(int));
+    place(L.rowProg, (size_t)(maxStrips + 2) * sizeof(int));
+    place(L.segDone, (size_t)(maxStrips + 2) * sizeof(int));
     place(L.initRow, (size_t)(maxNH + 2) * sizeof(DCell));
     place(L.initCol, (size_t)(maxNV + 2) * sizeof(DCell));
     place(L.hInitNext, (size_t)(maxCapH + 2) * sizeof(DCell));
@@ -704,23 +920,26 @@ void Engine::upload(std::vector<Job*>& jobs) {
     place(L.colTab, (size_t)L.maxColTab * sizeof(ColInfo));
     L.total = (long long)alignUp(o, 4096);
     L.maxBox = maxBox; L.maxCapH = maxCapH; L.maxCapV = maxCapV; L.maxNH = maxNH; L.maxNV = maxNV;
-    L.maxTrace = maxTrace; L.maxStrips = maxStrips;
-    // number of resident CTAs: 2 per SM, bounded by jobs and by memory
+    L.maxRowCk = maxRowCk; L.maxColCk = maxColCk; L.maxStrips = maxStrips;
+    // number of control agents with an arena: bounded by jobs and by memory
     size_t freeB = 0, totalB = 0;
     CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
-    size_t fixed = nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + I.seqBytes + I.outInts * 4 + (64u << 20);
+    I.ringBytes = alignUp(sizeof(ControlBlock), 256) + (nTasks + 1) * sizeof(TaskDesc);
+    size_t fixed = nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + I.seqBytes + I.outInts * 4 +
+                   I.ringBytes + (64u << 20);
     size_t budget = (freeB + I.capScratch > fixed) ? (size_t)((freeB + I.capScratch - fixed) * 0.9) : 0;
     long long byMem = (long long)(budget / (size_t)L.total);
-    int nCtas = (int)std::min<long long>(std::min<long long>((long long)nJobs, (long long)CTAS_PER_SM * I.numSMs), std::max<long long>(byMem, 0));
-    if (nCtas < 1) throw std::runtime_error("unicycler_b200: not enough device memory for one DP scratch arena");
-    I.nCtas = nCtas;
+    int nSlots = (int)std::min<long long>(std::min<long long>((long long)nJobs, (long long)NCTRL * I.numSMs),
+                                          std::max<long long>(byMem, 0));
+    if (nSlots < 1) throw std::runtime_error("unicycler_b200: not enough device memory for one DP scratch arena");
     I.growDev(I.dJobs, I.capJobs, nJobs * sizeof(JobDev));
     I.growDev(I.dGrids, I.capGrids, I.gridsAll.size() * sizeof(GridDesc) + 16);
     I.growDev(I.dSeq, I.capSeq, I.seqBytes + 64);
     I.growDev(I.dOut, I.capOut, I.outInts * sizeof(int) + 64);
     I.growDev(I.dJobOut, I.capJobOut, nJobs * sizeof(JobOut));
     I.growDev(I.dOrder, I.capOrder, nJobs * sizeof(int));
-    I.growDev(I.dScratch, I.capScratch, (size_t)L.total * nCtas);
+    I.growDev(I.dScratch, I.capScratch, (size_t)L.total * nSlots);
+    I.growDev(I.dRing, I.capRing, I.ringBytes);
     I.growHost(I.hOut, I.capHOut, I.outInts * sizeof(int) + 64);
     CUDA_CHECK(cudaEventRecord(I.ev[0], I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dSeq, I.hSeq, I.seqBytes, cudaMemcpyHostToDevice, I.stream));
@@ -731,23 +950,24 @@ void Engine::upload(std::vector<Job*>& jobs) {
     KParams& kp = I.kp;
     kp.jobs = (const JobDev*)I.dJobs; kp.grids = (const GridDesc*)I.dGrids; kp.seq = (const uint8_t*)I.dSeq;
     kp.out = (int*)I.dOut; kp.jobOut = (JobOut*)I.dJobOut; kp.order = (const int*)I.dOrder;
-    kp.nJobs = (int)nJobs; kp.queue = I.dQueue; kp.scratch = (uint8_t*)I.dScratch; kp.scratchStride = L.total;
+    kp.nJobs = (int)nJobs; kp.nSlots = nSlots; kp.maxTasks = (int)nTasks;
+    kp.cb = (ControlBlock*)I.dRing;
+    kp.ring = (TaskDesc*)((uint8_t*)I.dRing + alignUp(sizeof(ControlBlock), 256));
+    kp.scratch = (uint8_t*)I.dScratch; kp.scratchStride = L.total;
     kp.lay = L;
     I.stats = EngineStats();
     I.stats.cells = totalCells;
     I.stats.h2dBytes = (int64_t)(I.seqBytes + nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + nJobs * sizeof(int));
-    I.stats.ctas = nCtas;
-    I.stats.traceBytes = 0;
-    for (const GridDesc& gd : I.gridsAll) { int ns = 0; I.stats.traceBytes += hostTraceBytes(gd, ns); }
+    I.stats.ctas = I.numSMs;
+    I.stats.traceBytes = ckBytes;
 }
 
 void Engine::launch() {
     Impl& I = *impl_;
     CUDA_CHECK(cudaSetDevice(I.device));
     if (I.kp.nJobs == 0) return;
-    CUDA_CHECK(cudaMemsetAsync(I.dQueue, 0, sizeof(int), I.stream));
     CUDA_CHECK(cudaEventRecord(I.ev[2], I.stream));
-    dpJobKernel<<<I.nCtas, NTHREADS, 0, I.stream>>>(I.kp);
+    I.launchOnce();
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventRecord(I.ev[3], I.stream));
     I.stats.launches += 1;
@@ -762,10 +982,7 @@ double Engine::launchTimed(int steps) {
     CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaStreamSynchronize(I.stream));
     CUDA_CHECK(cudaEventRecord(e0, I.stream));
-    for (int k = 0; k < steps; ++k) {
-        CUDA_CHECK(cudaMemsetAsync(I.dQueue, 0, sizeof(int), I.stream));
-        dpJobKernel<<<I.nCtas, NTHREADS, 0, I.stream>>>(I.kp);
-    }
+    for (int k = 0; k < steps; ++k) I.launchOnce();
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventRecord(e1, I.stream));
     CUDA_CHECK(cudaEventSynchronize(e1));
@@ -806,10 +1023,17 @@ void Engine::fetch(std::vector<Job*>& jobs) {
     if (cudaEventElapsedTime(&ms, I.ev[0], I.ev[1]) == cudaSuccess) I.stats.h2dMs = ms;
     if (cudaEventElapsedTime(&ms, I.ev[4], I.ev[5]) == cudaSuccess) I.stats.d2hMs = ms;
     if (getenv("UNICYCLER_B200_PROFILE")) {
-        long long tot[6] = {0, 0, 0, 0, 0, 0}, mx = 0;
-        for (size_t k = 0; k < nJobs; ++k) { for (int q = 0; q < 6; ++q) tot[q] += I.jobOut[k].prof[q]; mx = std::max(mx, I.jobOut[k].prof[5]); }
-        fprintf(stderr, "[ub200 profile] jobs=%zu ctas=%d cycles: setup=%lld init=%lld fill=%lld track=%lld traceback=%lld total=%lld maxjob=%lld\n",
-                nJobs, I.nCtas, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], mx);
+        long long tot[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+        size_t worst = 0;
+        for (size_t k = 0; k < nJobs; ++k) {
+            for (int q = 0; q < 12; ++q) tot[q] += I.jobOut[k].prof[q];
+            if (I.jobOut[k].prof[5] > mx) { mx = I.jobOut[k].prof[5]; worst = k; }
+        }
+        fprintf(stderr, "[ub200 profile] jobs=%zu agents=%d tasks=%d cycles: setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld total=%lld maxjob=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",
+                nJobs, I.kp.nSlots, I.kp.maxTasks, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], mx, tot[6], tot[7], tot[8], tot[9], tot[10], tot[11]);
+        const long long* wp = I.jobOut[worst].prof;
+        fprintf(stderr, "[ub200 profile] worst job %zu (%d grids): setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",
+                worst, I.jobsDev[worst].gridCount, wp[0], wp[1], wp[2], wp[3], wp[4], wp[6], wp[7], wp[8], wp[9], wp[10], wp[11]);
     }
     I.stats.d2hBytes = (int64_t)(nJobs * sizeof(JobOut));
     for (size_t k = 0; k < nJobs; ++k) I.stats.d2hBytes += 4LL * std::max(0, std::min(I.jobOut[k].outLen, I.jobsDev[k].outCap));
@@ -848,8 +1072,6 @@ void Engine::run(std::vector<Job*>& jobs) {
     upload(jobs);
     launch();
     fetch(jobs);
-    // retry jobs whose segment stream overflowed with a larger buffer
-    // (rare: many tied tracebacks); handled by the caller-visible status otherwise
 }
 
 }  // namespace ub200

@@ -1,21 +1,21 @@
 // Device side of the B200 DP engine (sm_100a).  See engine.hpp for the job model.
 //
-// Execution model
-//   * persistent CTAs (NWARPS warps) pull jobs from an atomic queue; a job's grids run
-//     back to back inside the CTA because grid k+1 is initialised from the traceback of
-//     grid k (seeds/banded_chain_alignment_traceback.h:296-330).
-//   * fill: the matrix is cut into horizontal strips of SH = 32*R rows.  Inside a strip
-//     lane t owns R consecutive rows and walks the columns one step behind lane t-1
-//     (anti-diagonal wavefront, cell hand-off with __shfl_up); strips are pipelined over
-//     the CTA's warps, `lag` 32-column chunks apart, with one __syncthreads per chunk
-//     phase; the row between two strips travels through an L2-resident buffer.
-//   * trace: one byte per cell (the reference's TraceBitMap_ value), written as one 16-byte
-//     store per lane and step into a skewed, fully coalesced layout:
-//        addr(i,j) = stripBase[s] + ((j - jlo(s) + t)*32 + t)*R + r,
-//        s=(i-1)/SH, t=((i-1)%SH)/R, r=(i-1)%R.
-//   * tracking + traceback: warp 0 finds the tied maxima over the tracked cells and walks
-//     the trace exactly like SeqAn's TracebackCoordinator_, in SeqAn's storage coordinates
-//     (dpgeom.hpp maps them to matrix coordinates).
+// Execution model (one persistent kernel, one CTA of NWARPS warps per SM, every WARP is an agent):
+//   * control agents (the first NCTRL warps of a CTA) pull jobs from an atomic queue and walk the job's
+//     grids in order, because grid k+1 is initialised from the traceback of grid k
+//     (seeds/banded_chain_alignment_traceback.h:296-330).
+//   * a SMALL grid (<= 256 rows, trace fits the agent's shared-memory window) is filled by the control
+//     warp itself with the full trace byte per cell (the reference's TraceBitMap_) kept in shared memory.
+//   * a BIG grid is published as a task on a global FIFO board.  Its matrix is cut into strips of 256
+//     rows x segments of SEG columns; every warp of the GPU claims (strip, segment) items in wavefront
+//     order and runs a SCORE-ONLY fill (no trace bits: ~10 instructions per cell).  Inside an item lane t
+//     owns 8 consecutive rows and walks the columns one step behind lane t-1 (anti-diagonal wavefront,
+//     cell hand-off with __shfl_up).  The row between two strips and, every CKW columns, the column state
+//     of a strip are written to HBM as CHECKPOINTS (0.16 B per cell instead of a 1 B/cell trace);
+//     release/acquire progress counters order producer and consumer items.
+//   * traceback of a big grid: the control warp RECOMPUTES the trace bytes of the 256 x CKW tile under
+//     the path from the checkpoints (bit-identical, integer arithmetic) into its shared-memory window and
+//     walks it exactly like SeqAn's TracebackCoordinator_, in SeqAn's storage coordinates (dpgeom.hpp).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -24,10 +24,9 @@
 
 namespace ub200 {
 
-constexpr int R = 8;
-constexpr int SH = 32 * R;
 constexpr int NWARPS = 16;
 constexpr int NTHREADS = NWARPS * 32;
+constexpr int NCTRL = 8;                 // control-capable warps per CTA
 constexpr unsigned FULLMASK = 0xffffffffu;
 
 struct DCell {
@@ -48,17 +47,63 @@ struct JobDev {
 
 struct JobOut {
     int status, score, outLen, pad;
-    long long prof[6];  // cycles: setup, init, fill, track, traceback, total (thread 0)
+    long long prof[12];  // cycles: setup+init, local fill, task wait, track, traceback, total; tiles, tile cycles,
+                         // local-grid traceback cycles, tracebacks, local grids, local-grid track cycles
 };
 
-struct ScratchLayout {  // byte offsets inside one CTA's scratch block
-    long long trace, stripBase, bnd, initRow, initCol, hInitNext, vInitNext, box, lastRow, lastCol, cand, planted,
-        colTab, total;
-    int bndStride, maxCand, maxPlanted, maxColTab;
-    long long maxBox;
+struct ScratchLayout {  // byte offsets inside one control agent's arena
+    long long rowCk, colCk, ckBase, rowProg, segDone, initRow, initCol, hInitNext, vInitNext, box, lastRow, lastCol,
+        cand, planted, colTab, total;
+    int maxCand, maxPlanted, maxColTab, maxStrips;
+    long long maxBox, maxRowCk, maxColCk;
     int maxCapH, maxCapV, maxNH, maxNV;
-    long long maxTrace;
-    int maxStrips, pad;
+};
+
+struct PlantedCell {
+    int i1, i2;
+    DCell c;
+};
+
+// Everything a grid needs.  Built by lane 0 of the control warp in shared memory; copied to the task
+// board (global memory) when the grid is published, and from there into the worker warp's shared slot.
+struct GridCtx {
+    GridGeom g;
+    int kind, h0, v0, hNext, vNext, capNextH, capNextV;
+    int match, mismatch, go, ge, fe, complete, affine;
+    const uint8_t* seqH;
+    const uint8_t* seqV;
+    // arena pointers
+    int2* rowCk;        // [NS][nH+1] (S,V) of the last row of every strip
+    int2* colCk;        // [ckBase[s] + c][SH] (S,H) of column (ckFirst(s)+c)*CKW
+    int* ckBase;        // per strip: first checkpoint tile index
+    int* rowProg;       // per strip: last boundary column written (release/acquire)
+    int* segDone;       // per strip: number of the next segment that may start
+    DCell *initRow, *initCol, *hInitNext, *vInitNext, *box, *lastRow, *lastCol;
+    int* cand;
+    PlantedCell* planted;
+    ColInfo* colTab;
+    // strips
+    int NS, nSeg, local, RR;   // local: filled by the control warp with RR rows per lane, trace in shared memory
+    int pitch, localJhi;       // local trace window: lanes per column (even), last column holding cells
+    int colZeroMax, rrShift;
+    // capture
+    int capEdges;  // 1: last row + last column; 0: box
+    int boxRow0, boxH, boxW;
+    // limits
+    int maxCand, maxPlanted, maxColTab, pad0;
+    long long maxBox;
+};
+
+struct TaskDesc {
+    GridCtx ctx;
+    int nItems;
+    int ready;       // release-published by the control warp
+    int nextItem;    // claimed by atomicAdd
+    int doneItems;   // completed items (release)
+};
+
+struct ControlBlock {  // zeroed before every launch
+    int jobQueue, jobsDone, ringHead, ringTail;
 };
 
 struct KParams {
@@ -69,62 +114,30 @@ struct KParams {
     JobOut* jobOut;
     const int* order;  // job processing order (largest first)
     int nJobs;
-    int* queue;
+    int nSlots;        // control agents with an arena
+    int maxTasks;
+    ControlBlock* cb;
+    TaskDesc* ring;
     uint8_t* scratch;
     long long scratchStride;
     ScratchLayout lay;
 };
 
-struct PlantedCell {
-    int i1, i2;
-    DCell c;
-};
-
-// Everything a grid needs, built once per grid by thread 0 (shared memory).
-struct GridCtx {
-    GridGeom g;
-    int kind, h0, v0, hNext, vNext, capNextH, capNextV;
-    int match, mismatch, go, ge, fe, complete, affine;
-    const uint8_t* seqH;
-    const uint8_t* seqV;
-    // scratch pointers
-    uint8_t* trace;
-    long long* stripBase;
-    int2* bnd;
-    DCell *initRow, *initCol, *hInitNext, *vInitNext, *box, *lastRow, *lastCol;
-    int* cand;
-    PlantedCell* planted;
-    ColInfo* colTab;
-    // strips / schedule
-    int NS, P, lag, totalPhases, bndStride;
-    int colZeroMax;
-    // capture
-    int capEdges;  // 1: last row + last column; 0: box
-    int boxRow0, boxH, boxW;
-    // limits
-    int maxCand, maxPlanted, maxColTab;
-    long long maxBox, maxTrace;
-};
-
-__device__ __forceinline__ int stripJlo(const GridGeom& g, int s) {
-    return g.banded ? imax(1, s * SH + 1 + g.lo) : 1;
+// ---------------------------------------------------------------------------------------
+// memory-order helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int ldAcquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-__device__ __forceinline__ int stripJhi(const GridGeom& g, int s) {
-    if (!g.banded) return g.nH;
-    int r1 = imin(g.nV, (s + 1) * SH);
-    return imin(g.nH, r1 + g.up);
+__device__ __forceinline__ void stRelease(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ int stripChunks(const GridGeom& g, int s) {
-    int ncols = stripJhi(g, s) - stripJlo(g, s) + 1;
-    return ncols > 0 ? (ncols + 62) / 32 : 0;
-}
-
-__device__ __forceinline__ size_t traceAddr(const GridCtx& G, int i, int j) {
-    int s = (i - 1) / SH;
-    int rem = (i - 1) - s * SH;
-    int t = rem / R, r = rem - t * R;
-    int k = j - stripJlo(G.g, s) + t;
-    return (size_t)G.stripBase[s] + ((size_t)k * 32 + t) * R + r;
+__device__ __forceinline__ int ldVolatile(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -134,8 +147,6 @@ __device__ __forceinline__ size_t traceAddr(const GridCtx& G, int i, int j) {
 template <bool AFF, bool CT, bool BANDED>
 __device__ __forceinline__ uint32_t cellUpdate(int& s, int& h, int& v, int sl, int hl, int su, int vu, int sd,
                                                int sub, int go, int ge, int mode) {
-    // Branch-free formulation.  The only loop-carried chain inside a lane is su -> e -> v -> s (3 ops);
-    // everything else depends on the previous column only.
     uint32_t tv;
     if (AFF && !BANDED) {
         // Fast path.  Loop-carried chain per cell: su -> VIADDMNMX -> VIMNMX3 -> s (2 ops).
@@ -214,108 +225,157 @@ __device__ __forceinline__ uint32_t cellUpdate(int& s, int& h, int& v, int sl, i
     return tv;
 }
 
-// S and V-matrix value of the cell just above strip s in column j (j >= 1)
-template <bool BANDED>
-__device__ __forceinline__ void upBoundary(const GridCtx& G, int s, int j, int& bS, int& bV) {
-    int rowAbove = s * SH;
+// Score-only variant of the same recurrences (identical S/H/V values, no trace bits).
+template <bool AFF, bool BANDED>
+__device__ __forceinline__ void cellScore(int& s, int& h, int& v, int sl, int hl, int su, int vu, int sd, int sub,
+                                          int go, int ge, int mode) {
+    if (AFF) {
+        int hh = __viaddmax_s32(sl, go, hl + ge);
+        int vv = __viaddmax_s32(su, go, vu + ge);
+        if (BANDED) {
+            vv = (mode == 1) ? NEG_INF : vv;
+            hh = (mode == 2) ? NEG_INF : hh;
+        }
+        s = __vimax3_s32(vv, hh, sd + sub);
+        h = hh; v = vv;
+    } else {
+        int tV = su + ge, tH = sl + ge;
+        if (BANDED) {
+            tV = (mode == 1) ? INT32_MIN : tV;
+            tH = (mode == 2) ? INT32_MIN : tH;
+        }
+        s = __vimax3_s32(sd + sub, tV, tH);
+        h = NEG_INF; v = NEG_INF;
+    }
     if (BANDED) {
-        int d = j - rowAbove;
+        const bool outside = (mode == 3);
+        s = outside ? NEG_INF : s; h = outside ? NEG_INF : h; v = outside ? NEG_INF : v;
+    }
+}
+
+// S and V-matrix value of the cell just above strip s in column j (j >= 0)
+template <bool BANDED>
+__device__ __forceinline__ void upBoundary(const GridCtx& G, int s, int SHR, int j, int& bS, int& bV) {
+    const int rowAbove = s * SHR;
+    if (BANDED) {
+        const int d = j - rowAbove;
         if (d < G.g.lo || d > G.g.up) { bS = NEG_INF; bV = NEG_INF; return; }
     }
     if (s == 0) {
-        DCell c = G.initRow[j];
+        const DCell c = G.initRow[j];
         bS = c.s; bV = c.v;
     } else {
-        int2 b = __ldcg(&G.bnd[(size_t)((s - 1) & 1) * G.bndStride + j]);
+        const int2 b = __ldcg(&G.rowCk[(size_t)(s - 1) * (size_t)(G.g.nH + 1) + j]);
         bS = b.x; bV = b.y;
     }
 }
 
-// Loop-invariant scalars of one strip chunk, kept in registers (GridCtx lives in shared memory).
-struct StepConsts {
-    int match, mismatch, go, ge, nV, nH, lo, up;
-    uint8_t* tbase;   // trace base of this strip
-    int2* bndOut;     // boundary row written by lane 31 (nullptr: no strip below)
+// Register state of one lane inside a strip.
+template <int RR>
+struct StripState {
+    int Sl[RR], Hl[RR];
+    uint32_t vm[(RR + 3) / 4];  // one-hot base masks of the lane's rows, one byte per row
+    int prevUpS, pubS, pubV, curHc;
 };
 
-template <bool AFF, bool CT, bool BANDED, bool CAP>
-__device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K, int c, int lane, int jlo, int jhi,
-                                           int i0, int (&Sl)[R], int (&Hl)[R], const uint32_t (&vcw)[R / 4],
-                                           int& prevUpS, int& pubS, int& pubV, int& curHc, int bS, int bV, int hcN) {
+struct StepConsts {
+    int match, mismatch, go, ge, nV, nH, lo, up;
+};
+
+// 32 wavefront steps (one chunk) of a strip.  TRACE: trace bytes to the shared-memory window;
+// otherwise (score-only) boundary row + column checkpoints to HBM.  CAP: slow variant that also captures
+// the cells the scouts may need (last row/column for final/global matrices, the corner box otherwise).
+template <bool AFF, bool CT, bool BANDED, int RR, bool TRACE, bool CAP>
+__device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K, StripState<RR>& st, int c, int lane,
+                                           int cBeg, int cEnd, int i0, int bS, int bV, int hcN, int nsteps,
+                                           uint8_t* win, int winPitch, int2* rowOut, int2* ckOut) {
     const int match = K.match, mismatch = K.mismatch, go = K.go, ge = K.ge;
     const int lo = K.lo, up = K.up;
-    // capture parameters (slow variant only)
     int capEdges = 0, hNext = 0, boxRow0 = 0, boxH = 0;
     DCell *box = nullptr, *lastRow = nullptr, *lastCol = nullptr;
     if (CAP) {
         capEdges = G.capEdges; hNext = G.hNext; boxRow0 = G.boxRow0; boxH = G.boxH;
         box = G.box; lastRow = G.lastRow; lastCol = G.lastCol;
     }
+    const int kEnd = imin(32, nsteps - 32 * c);
 #pragma unroll 1
-    for (int kk = 0; kk < 32; ++kk) {
+    for (int kk = 0; kk < kEnd; ++kk) {
         const int k = 32 * c + kk;
-        int inS = __shfl_up_sync(FULLMASK, pubS, 1);
-        int inV = __shfl_up_sync(FULLMASK, pubV, 1);
-        int inHc = __shfl_up_sync(FULLMASK, curHc, 1);
+        int inS = __shfl_up_sync(FULLMASK, st.pubS, 1);
+        int inV = __shfl_up_sync(FULLMASK, st.pubV, 1);
+        int inHc = __shfl_up_sync(FULLMASK, st.curHc, 1);
         const int l0S = __shfl_sync(FULLMASK, bS, kk);
         const int l0V = __shfl_sync(FULLMASK, bV, kk);
         const int l0Hc = __shfl_sync(FULLMASK, hcN, kk);
         if (lane == 0) { inS = l0S; inV = l0V; inHc = l0Hc; }
-        curHc = inHc;
-        const int j = jlo + k - lane;
-        const bool act = (k >= lane) && (j <= jhi);
+        st.curHc = inHc;
+        const int j = cBeg + k - lane;
+        const bool act = (k >= lane) && (j <= cEnd) && (i0 <= K.nV);  // lanes below the matrix stay idle
         if (act) {
-            int Sd = prevUpS, Su = inS, Vu = inV;
-            uint32_t tw[R / 4];
+            int Sd = st.prevUpS, Su = inS, Vu = inV;
+            uint32_t tw[(RR + 3) / 4];
 #pragma unroll
-            for (int w4 = 0; w4 < R / 4; ++w4) tw[w4] = 0u;
-            // per-byte equality of this lane's vertical codes with the column's horizontal code
-            const uint32_t hc4 = (uint32_t)curHc * 0x01010101u;
-            uint32_t eq[R / 4];
+            for (int w4 = 0; w4 < (RR + 3) / 4; ++w4) tw[w4] = 0u;
+            const uint32_t hcRep = (1u << st.curHc) * 0x01010101u;
+            uint32_t eq[(RR + 3) / 4];
 #pragma unroll
-            for (int w4 = 0; w4 < R / 4; ++w4) eq[w4] = __vcmpeq4(vcw[w4], hc4);
-            int vArr[CAP ? R : 1];
+            for (int w4 = 0; w4 < (RR + 3) / 4; ++w4) eq[w4] = st.vm[w4] & hcRep;
+            int vArr[CAP ? RR : 1];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
+            for (int r = 0; r < RR; ++r) {
                 int mode = 0;
                 if (BANDED) {
                     const int d = j - (i0 + r);
                     mode = (d < lo || d > up) ? 3 : (d == up ? 1 : (d == lo ? 2 : 0));
                 }
-                const int sub = (eq[r >> 2] & (1u << (8 * (r & 3)))) ? match : mismatch;
+                const int sub = (eq[r >> 2] & (0xffu << (8 * (r & 3)))) ? match : mismatch;
                 int ns, nh, nv;
-                const uint32_t tv = cellUpdate<AFF, CT, BANDED>(ns, nh, nv, Sl[r], Hl[r], Su, Vu, Sd, sub, go, ge, mode);
-                Sd = Sl[r];
-                Sl[r] = ns; Hl[r] = nh; Su = ns; Vu = nv;
+                if (TRACE) {
+                    const uint32_t tv = cellUpdate<AFF, CT, BANDED>(ns, nh, nv, st.Sl[r], st.Hl[r], Su, Vu, Sd, sub, go, ge, mode);
+                    tw[r >> 2] |= tv << (8 * (r & 3));
+                } else {
+                    cellScore<AFF, BANDED>(ns, nh, nv, st.Sl[r], st.Hl[r], Su, Vu, Sd, sub, go, ge, mode);
+                }
+                Sd = st.Sl[r];
+                st.Sl[r] = ns; st.Hl[r] = nh; Su = ns; Vu = nv;
                 if (CAP) vArr[r] = nv;
-                tw[r >> 2] |= tv << (8 * (r & 3));
             }
-            prevUpS = inS;
-            pubS = Su; pubV = Vu;
-            static_assert(R == 8, "trace store assumes 8 rows per lane");
-            *reinterpret_cast<uint2*>(K.tbase + ((size_t)k * 32 + lane) * R) = make_uint2(tw[0], tw[1]);
-            if (K.bndOut != nullptr && lane == 31) __stcg(&K.bndOut[j], make_int2(Su, Vu));
+            st.prevUpS = inS;
+            st.pubS = Su; st.pubV = Vu;
+            if (TRACE) {
+                uint8_t* p = win + ((size_t)(j - cBeg) * winPitch + lane) * RR;
+                if (RR == 8) *reinterpret_cast<uint2*>(p) = make_uint2(tw[0], tw[(RR + 3) / 4 - 1]);
+                else *reinterpret_cast<uint32_t*>(p) = tw[0];
+            } else {
+                if (lane == 31) __stcg(&rowOut[j], make_int2(Su, Vu));
+                if ((j & (CKW - 1)) == 0) {
+                    int2* ck = ckOut + (size_t)(j / CKW) * SH + lane * RR;
+#pragma unroll
+                    for (int r = 0; r < RR; r += 2)
+                        __stcg(reinterpret_cast<int4*>(ck + r), make_int4(st.Sl[r], st.Hl[r], st.Sl[r + 1], st.Hl[r + 1]));
+                }
+            }
             if (CAP) {
                 if (capEdges) {
                     const int rl = K.nV - i0;
-                    if (rl >= 0 && rl < R) {
+                    if (rl >= 0 && rl < RR) {
 #pragma unroll
-                        for (int r = 0; r < R; ++r)
-                            if (r == rl) lastRow[j] = DCell{Sl[r], Hl[r], vArr[r]};
+                        for (int r = 0; r < RR; ++r)
+                            if (r == rl) lastRow[j] = DCell{st.Sl[r], st.Hl[r], vArr[r]};
                     }
                     if (j == K.nH) {
 #pragma unroll
-                        for (int r = 0; r < R; ++r)
-                            if (i0 + r <= K.nV) lastCol[i0 + r] = DCell{Sl[r], Hl[r], vArr[r]};
+                        for (int r = 0; r < RR; ++r)
+                            if (i0 + r <= K.nV) lastCol[i0 + r] = DCell{st.Sl[r], st.Hl[r], vArr[r]};
                     }
                 } else if (j >= hNext) {
                     DCell* col = box + (size_t)(j - hNext) * boxH - boxRow0;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
+                    for (int r = 0; r < RR; ++r) {
                         const int i = i0 + r;
                         bool inb = true;
                         if (BANDED) { const int d = j - i; inb = (d >= lo && d <= up); }
-                        if (i >= boxRow0 && i <= K.nV && inb) col[i] = DCell{Sl[r], Hl[r], vArr[r]};
+                        if (i >= boxRow0 && i <= K.nV && inb) col[i] = DCell{st.Sl[r], st.Hl[r], vArr[r]};
                     }
                 }
             }
@@ -323,79 +383,112 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K
     }
 }
 
-template <bool AFF, bool CT, bool BANDED>
-__device__ __noinline__ void fillGrid(const GridCtx& G) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int Sl[R], Hl[R];
-    uint32_t vcw[R / 4];
-    int prevUpS = NEG_INF, pubS = NEG_INF, pubV = NEG_INF, curHc = 0;
-    int jlo = 1, jhi = 0, i0 = 1, nch = 0;
+// Runs columns cBeg..cEnd of strip s (rows s*32*RR+1 ...).  fromCk: the lane state left of cBeg comes
+// from the column checkpoint at cBeg-1 (a multiple of CKW) instead of the grid's first column.
+// nsteps <= (cEnd-cBeg+1)+31 limits the wavefront (partial tile recompute).
+//   TRACE : trace bytes of the columns into `win` (column cBeg at offset 0), nothing written to HBM
+//           except the scout captures when `capture` is set.
+//   !TRACE: score-only; boundary row, column checkpoints, rowProg published per chunk; waits on the
+//           strip above through its rowProg counter.
+template <bool AFF, bool CT, bool BANDED, int RR, bool TRACE>
+__device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEnd, bool fromCk, int nsteps,
+                                      bool capture, uint8_t* win, int winPitch) {
+    constexpr int SHR = 32 * RR;
+    const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
+    StripState<RR> st;
+    const int i0 = s * SHR + lane * RR + 1;
+    const int jlo = stripJlo(g, s, SHR);
+#pragma unroll
+    for (int w4 = 0; w4 < (RR + 3) / 4; ++w4) st.vm[w4] = 0;
+    int2* ckTile = nullptr;   // checkpoint tile pointer such that tile of column j is ckTile + (j/CKW)*SH
+    if (!TRACE || fromCk) ckTile = G.colCk + ((size_t)G.ckBase[s] - (size_t)ckFirst(g, s)) * SH;
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+        const int i = i0 + r;
+        const uint32_t code = (i <= g.nV) ? (uint32_t)G.seqV[i - 1] : 255u;
+        st.vm[r >> 2] |= (code < 8u ? (1u << code) : 0u) << (8 * (r & 3));
+    }
+    if (!fromCk) {
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            const int i = i0 + r;
+            if (jlo == 1 && i <= G.colZeroMax) { const DCell ic = G.initCol[i]; st.Sl[r] = ic.s; st.Hl[r] = ic.h; }
+            else { st.Sl[r] = NEG_INF; st.Hl[r] = NEG_INF; }
+        }
+        if (jlo == 1) st.prevUpS = (i0 - 1 <= G.colZeroMax) ? G.initCol[i0 - 1].s : NEG_INF;
+        else {
+            st.prevUpS = NEG_INF;
+            if (lane == 0) {
+                if (!TRACE && s > 0) {  // the corner cell above-left of the strip comes from the strip above
+                    const int need = imin(jlo - 1, stripJhi(g, s - 1, SHR));
+                    while (ldAcquire(&G.rowProg[s - 1]) < need) __nanosleep(128);
+                }
+                int bS, bV; upBoundary<BANDED>(G, s, SHR, jlo - 1, bS, bV); st.prevUpS = bS;
+            }
+            __syncwarp();
+        }
+    } else {
+        const int2* ck = ckTile + (size_t)((cBeg - 1) / CKW) * SH;
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            const int2 v = __ldcg(&ck[lane * RR + r]);
+            st.Sl[r] = v.x; st.Hl[r] = v.y;
+        }
+        if (lane == 0) { int bS, bV; upBoundary<BANDED>(G, s, SHR, cBeg - 1, bS, bV); st.prevUpS = bS; }
+        else st.prevUpS = __ldcg(&ck[lane * RR - 1]).x;
+    }
+    st.pubS = NEG_INF; st.pubV = NEG_INF; st.curHc = 0;
+    StepConsts K;
+    K.match = G.match; K.mismatch = G.mismatch; K.go = G.go; K.ge = G.ge;
+    K.nV = g.nV; K.nH = g.nH; K.lo = g.lo; K.up = g.up;
+    int2* rowOut = TRACE ? nullptr : G.rowCk + (size_t)s * (size_t)(g.nH + 1);
+    const int nch = (nsteps + 31) / 32;
+    int upProg = 0;                // cached progress of the strip above
+    const int upJhi = (s > 0) ? stripJhi(g, s - 1, SHR) : 0;
 #pragma unroll 1
-    for (int p = 0; p < G.totalPhases; ++p) {
-        int t = p - warp * G.lag;
-        if (t >= 0) {
-            int q = t / G.P;
-            int c = t - q * G.P;
-            int s = warp + NWARPS * q;
-            if (s < G.NS) {
-                if (c == 0) {  // strip start: load this lane's rows
-                    jlo = stripJlo(g, s);
-                    jhi = stripJhi(g, s);
-                    nch = stripChunks(g, s);
-                    i0 = s * SH + lane * R + 1;
-#pragma unroll
-                    for (int w4 = 0; w4 < R / 4; ++w4) vcw[w4] = 0;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        int i = i0 + r;
-                        uint32_t code = (i <= g.nV) ? (uint32_t)G.seqV[i - 1] : 255u;
-                        vcw[r >> 2] |= code << (8 * (r & 3));
-                        if (jlo == 1 && i <= G.colZeroMax) { DCell ic = G.initCol[i]; Sl[r] = ic.s; Hl[r] = ic.h; }
-                        else { Sl[r] = NEG_INF; Hl[r] = NEG_INF; }
-                    }
-                    if (jlo == 1) prevUpS = (i0 - 1 <= G.colZeroMax) ? G.initCol[i0 - 1].s : NEG_INF;
-                    else {
-                        prevUpS = NEG_INF;
-                        if (lane == 0) { int bS, bV; upBoundary<BANDED>(G, s, jlo - 1, bS, bV); prevUpS = bS; }
-                    }
-                    pubS = NEG_INF; pubV = NEG_INF; curHc = 0;
+    for (int c = 0; c < nch; ++c) {
+        const int jj = cBeg + 32 * c + lane;
+        if (!TRACE && s > 0) {
+            // boundary columns this chunk reads: cBeg+32c .. min(cEnd, cBeg+32c+31), all <= jhi(s-1) when in band
+            const int need = imin(imin(cEnd, cBeg + 32 * c + 31), upJhi);
+            if (upProg < need) {
+                if (lane == 0) {
+                    int p = ldAcquire(&G.rowProg[s - 1]);
+                    while (p < need) { __nanosleep(128); p = ldAcquire(&G.rowProg[s - 1]); }
+                    upProg = p;
                 }
-                if (c < nch) {
-                    int jj = jlo + 32 * c + lane;
-                    int bS = NEG_INF, bV = NEG_INF, hcN = 0;
-                    if (jj <= jhi) { hcN = G.seqH[jj - 1]; upBoundary<BANDED>(G, s, jj, bS, bV); }
-                    StepConsts K;
-                    K.match = G.match; K.mismatch = G.mismatch; K.go = G.go; K.ge = G.ge;
-                    K.nV = g.nV; K.nH = g.nH; K.lo = g.lo; K.up = g.up;
-                    K.tbase = G.trace + (size_t)G.stripBase[s];
-                    K.bndOut = (s + 1 < G.NS) ? (G.bnd + (size_t)(s & 1) * G.bndStride) : nullptr;
-                    bool cap;
-                    int jmaxChunk = jlo + 32 * c + 31;  // largest column any lane touches in this chunk
-                    if (G.capEdges) cap = ((s + 1) * SH >= g.nV) || (jmaxChunk >= g.nH);
-                    else cap = (jmaxChunk >= G.hNext) && ((s + 1) * SH >= G.boxRow0);
-                    if (cap)
-                        stripSteps<AFF, CT, BANDED, true>(G, K, c, lane, jlo, jhi, i0, Sl, Hl, vcw, prevUpS, pubS, pubV,
-                                                          curHc, bS, bV, hcN);
-                    else
-                        stripSteps<AFF, CT, BANDED, false>(G, K, c, lane, jlo, jhi, i0, Sl, Hl, vcw, prevUpS, pubS, pubV,
-                                                           curHc, bS, bV, hcN);
-                }
+                upProg = __shfl_sync(FULLMASK, upProg, 0);
             }
         }
-        __syncthreads();
+        int bS = NEG_INF, bV = NEG_INF, hcN = 0;
+        if (jj <= cEnd) { hcN = G.seqH[jj - 1]; upBoundary<BANDED>(G, s, SHR, jj, bS, bV); }
+        bool cap = false;
+        if (capture) {
+            const int jmaxChunk = imin(cEnd, cBeg + 32 * c + 31);  // largest column any lane touches in this chunk
+            if (G.capEdges) cap = ((s + 1) * SHR >= g.nV) || (jmaxChunk >= g.nH);
+            else cap = (jmaxChunk >= G.hNext) && ((s + 1) * SHR >= G.boxRow0);
+        }
+        if (cap)
+            stripSteps<AFF, CT, BANDED, RR, TRACE, true>(G, K, st, c, lane, cBeg, cEnd, i0, bS, bV, hcN, nsteps, win,
+                                                         winPitch, rowOut, ckTile);
+        else
+            stripSteps<AFF, CT, BANDED, RR, TRACE, false>(G, K, st, c, lane, cBeg, cEnd, i0, bS, bV, hcN, nsteps, win,
+                                                          winPitch, rowOut, ckTile);
+        if (!TRACE) {
+            // lane 31 has finished every column <= cBeg + 32c + 31 - 31 (and cEnd after the last chunk)
+            const int done = imin(cEnd, cBeg + 32 * c + imin(31, nsteps - 1 - 32 * c) - 31);
+            if (lane == 31 && done >= cBeg) stRelease(&G.rowProg[s], done);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // traceback (seqan/align/dp_traceback_impl.h, seeds/banded_chain_alignment_traceback.h)
-// in SeqAn storage coordinates (col, cv).  Executed by ALL lanes of warp 0 with identical
-// (warp-uniform) control flow: the walk itself is serial, but the trace bytes come from a
-// 64x64 window staged in shared memory that the 32 lanes load cooperatively (one window
-// serves >= 64 steps), and only lane 0 writes results.
+// in SeqAn storage coordinates (col, cv).  Executed by ALL lanes of the control warp with identical
+// (warp-uniform) control flow; only lane 0 writes results.  Trace bytes come from the warp's
+// shared-memory window: the whole grid for local grids, the recomputed 256 x CKW tile otherwise.
 // ---------------------------------------------------------------------------------------
-constexpr int WIN = 64;
-
 struct Coord {
     int currCol, currRow, endCol, endRow, bp1, bp2;
     bool inBandFlag;
@@ -422,59 +515,69 @@ struct OutStream {
     }
 };
 
+template <bool AFF, bool CT>
+__device__ __forceinline__ void tileDispatch(const GridCtx& G, int s, int cBeg, int cEnd, bool fromCk, int nsteps,
+                                             uint8_t* win) {
+    if (G.g.banded) runStrip<AFF, CT, true, 8, true>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
+    else runStrip<AFF, CT, false, 8, true>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
+}
+
 struct TraceWalker {
     const GridCtx& G;
     OutStream& out;
-    uint8_t* win;     // shared memory, WIN*WIN bytes, win[(row - wRow0) * WIN + (col - wCol0)]
-    int wRow0, wCol0; // matrix coordinates of the window origin; wRow0 < 0: no window loaded
-    int wRowEnd, wColEnd;  // last row / column staged
+    uint8_t* win;     // shared-memory trace window of this control warp
+    // cached tile (task grids): strip, first column, valid extent
+    int tS, tC0, tMaxRow, tMaxCol;
     int pc, pv;       // navigator position: column, storage row
     int nSegs;        // segments emitted for the current trace
     bool emitOn;
     bool bad;         // undefined trace value (reference: endless loop / assert)
+    long long tilesComputed, tileCycles;
 
     __device__ TraceWalker(const GridCtx& g, OutStream& o, uint8_t* w)
-        : G(g), out(o), win(w), wRow0(-1), wCol0(0), wRowEnd(-1), wColEnd(-1), pc(0), pv(0), nSegs(0), emitOn(true), bad(false) {}
+        : G(g), out(o), win(w), tS(-1), tC0(0), tMaxRow(-1), tMaxCol(-1), pc(0), pv(0), nSegs(0), emitOn(true),
+          bad(false), tilesComputed(0), tileCycles(0) {}
 
-    // Stage the window whose bottom-right corner is the 8-row group of (i, j).
-    __device__ void loadWindow(int i, int j) {
-        const int lane = threadIdx.x & 31;
-        const int gBot = (i - 1) / R;                       // row group of row i (rows 8g+1 .. 8g+8)
-        const int gTop = imax(0, gBot - (WIN / R - 1));
-        wRow0 = gTop * R + 1;
-        wCol0 = imax(1, j - (WIN - 1));
-        wRowEnd = (gBot + 1) * R;
-        wColEnd = j;
+    // Recompute the trace bytes of the tile that holds (i, j): rows of strip s up to the lane owning row i,
+    // columns from the checkpoint left of j up to j.
+    __device__ void computeTile(int i, int j) {
+        const GridGeom& g = G.g;
+        const int s = (i - 1) / SH;
+        const int jlo = stripJlo(g, s, SH);
+        int c0 = ((j - 1) / CKW) * CKW;          // checkpoint column left of j (tile = c0+1 .. c0+CKW)
+        bool fromCk = true;
+        int cBeg = c0 + 1;
+        if (c0 < jlo) { fromCk = false; cBeg = jlo; }
+        const int laneOfI = ((i - 1) - s * SH) / 8;
+        const int nsteps = (j - cBeg + 1) + laneOfI;
+        const long long t0 = clock64();
         __syncwarp();
-        const int nGroups = gBot - gTop + 1;
-        const int nCols = j - wCol0 + 1;
-        for (int idx = lane; idx < nGroups * nCols; idx += 32) {
-            const int gq = gTop + idx / nCols;
-            const int col = wCol0 + idx % nCols;
-            const int row = gq * R + 1;
-            const int s = (row - 1) / SH;
-            const int t = ((row - 1) - s * SH) / R;
-            const int jlo = stripJlo(G.g, s), jhi = stripJhi(G.g, s);
-            uint2 v = make_uint2(0u, 0u);
-            if (col >= jlo && col <= jhi && row <= G.g.nV && s < G.NS) {
-                const int k = col - jlo + t;
-                v = *reinterpret_cast<const uint2*>(G.trace + (size_t)G.stripBase[s] + ((size_t)k * 32 + t) * R);
-            }
-            uint8_t* dst = win + (size_t)(row - wRow0) * WIN + (col - wCol0);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) dst[r * WIN] = (uint8_t)(v.x >> (8 * r));
-#pragma unroll
-            for (int r = 0; r < 4; ++r) dst[(4 + r) * WIN] = (uint8_t)(v.y >> (8 * r));
-        }
+        if (G.affine) { if (G.complete) tileDispatch<true, true>(G, s, cBeg, j, fromCk, nsteps, win); else tileDispatch<true, false>(G, s, cBeg, j, fromCk, nsteps, win); }
+        else { if (G.complete) tileDispatch<false, true>(G, s, cBeg, j, fromCk, nsteps, win); else tileDispatch<false, false>(G, s, cBeg, j, fromCk, nsteps, win); }
         __syncwarp();
+        tS = s; tC0 = cBeg; tMaxCol = j; tMaxRow = s * SH + (laneOfI + 1) * 8;
+        ++tilesComputed;
+        tileCycles += clock64() - t0;
     }
 
     __device__ __forceinline__ uint32_t tvHere() {
         const int i = pv - storageOffset(G.g, pc);
         const int j = pc;
         if (i <= 0 || j <= 0 || i > G.g.nV || j > G.g.nH) return 0;
-        if (wRow0 < 0 || i < wRow0 || j < wCol0 || i > wRowEnd || j > wColEnd) loadWindow(i, j);
-        return win[(size_t)(i - wRow0) * WIN + (j - wCol0)];
+        if (G.local) {
+            if (j > G.localJhi) return 0;
+            const int sh = G.rrShift;
+            const int q = (i - 1) >> sh;
+            return win[((((j - 1) * G.pitch + q)) << sh) + ((i - 1) & ((1 << sh) - 1))];
+        }
+        const int s = (i - 1) / SH;
+        if (s != tS || j < tC0 || j > tMaxCol || i > tMaxRow) {
+            // columns outside the strip's band range hold no computed cells
+            if (j < stripJlo(G.g, s, SH) || j > stripJhi(G.g, s, SH)) return 0;
+            computeTile(i, j);
+        }
+        const int rem = (i - 1) - s * SH;
+        return win[((size_t)(j - tC0) * 32 + (rem >> 3)) * 8 + (rem & 7)];
     }
     __device__ Coord makeCoord(int endCol, int endRow) const {  // dp_traceback_impl.h:121-141
         Coord c;
