@@ -13,6 +13,8 @@
 #include <mutex>
 #include <random>
 #include <sstream>
+#include <atomic>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -73,6 +75,26 @@ std::vector<std::string> splitString(const std::string& in, char delim) {  // sr
         result.push_back(sub);
     }
     return result;
+}
+
+// Runs f(i) for i in [0, n) on the host cores (the per-read host stages are independent;
+// the reference gets the same parallelism from Python threads, unicycler_align.py:203-225).
+template <typename F>
+void parallelFor(int n, F f) {
+    int threads = (int)std::thread::hardware_concurrency();
+    const char* e = getenv("UNICYCLER_B200_HOST_THREADS");
+    if (e) threads = atoi(e);
+    threads = std::max(1, std::min(threads, n));
+    if (threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i); });
+    for (auto& th : pool) th.join();
+}
+
+double nowSec() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 // ------------------------------------------------------------------ global / path
@@ -442,11 +464,11 @@ int ub200_chainAlignmentBatch(int n, const char* const* readSeqs, const char* co
     if (buildChainBatch(n, readSeqs, refSeqs, seeds, seedOffsets, sc, bandSize, readNames, refNames, refOffsets, cjs, jobs))
         return -1;
     engine().run(jobs);
-    for (int i = 0; i < n; ++i) {
+    parallelFor(n, [&](int i) {
         std::string out;
         if (!finishChainJob(*cjs[(size_t)i], sc, out)) out = "";
         results[i] = dupString(out);
-    }
+    });
     return 0;
 }
 
@@ -532,15 +554,32 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
                                    const char* const* hits, void* refSeqs, int m, int mm, int go, int ge,
                                    int sensitivityLevel, char** results) {
     Scoring sc{m, mm, go, ge};
+    const double t0 = nowSec();
     std::vector<std::unique_ptr<ReadWork> > works((size_t)n);
-    std::vector<Job*> jobs;
-    for (int i = 0; i < n; ++i) {
+    // host seeding + planning: one read per task, largest reads first
+    std::vector<int> order((size_t)n);
+    for (int i = 0; i < n; ++i) order[(size_t)i] = i;
+    std::vector<size_t> len((size_t)n);
+    for (int i = 0; i < n; ++i) len[(size_t)i] = strlen(readSeqs[i]);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[(size_t)a] > len[(size_t)b]; });
+    parallelFor(n, [&](int k) {
+        const int i = order[(size_t)k];
         works[(size_t)i].reset(new ReadWork());
         prepareRead(*works[(size_t)i], readNames[i], readSeqs[i], 0, hits[i], (SeqMap*)refSeqs, sc, sensitivityLevel);
+    });
+    std::vector<Job*> jobs;
+    for (int i = 0; i < n; ++i)
         for (auto& cj : works[(size_t)i]->jobs) jobs.push_back(&cj->job);
-    }
+    const double t1 = nowSec();
     engine().run(jobs);
-    for (int i = 0; i < n; ++i) results[i] = dupString(finishRead(*works[(size_t)i], sc));
+    const double t2 = nowSec();
+    parallelFor(n, [&](int k) {
+        const int i = order[(size_t)k];
+        results[i] = dupString(finishRead(*works[(size_t)i], sc));
+    });
+    if (getenv("UNICYCLER_B200_PROFILE"))
+        fprintf(stderr, "[ub200 host] reads=%d jobs=%zu prepare=%.1f ms engine=%.1f ms finish=%.1f ms\n", n, jobs.size(),
+                (t1 - t0) * 1e3, (t2 - t1) * 1e3, (nowSec() - t2) * 1e3);
     return 0;
 }
 

@@ -123,6 +123,10 @@ struct KParams {
     ScratchLayout lay;
 };
 
+// Launch parameters live in constant memory (a by-reference kernel argument would be copied to the
+// local-memory stack of every warp).
+__constant__ KParams cP;
+
 // ---------------------------------------------------------------------------------------
 // memory-order helpers
 // ---------------------------------------------------------------------------------------
@@ -133,6 +137,20 @@ __device__ __forceinline__ int ldAcquire(const int* p) {
 }
 __device__ __forceinline__ void stRelease(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Polling load: strong (L2-coherent) but WITHOUT the L1 invalidation an acquire load carries (CCTL.IVALL
+// would wipe the L1 lines of every other warp of the SM on each poll).  Consumers branch on the polled
+// value and then read the produced data with ld.cg (L2), producers publish with st.release / fence + atomic.
+__device__ __forceinline__ int ldRelaxed(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ DCell ldcgCell(const DCell* p) {
+    const int* q = reinterpret_cast<const int*>(p);
+    DCell c;
+    c.s = __ldcg(q); c.h = __ldcg(q + 1); c.v = __ldcg(q + 2);
+    return c;
 }
 __device__ __forceinline__ int ldVolatile(const int* p) {
     int v;
@@ -254,7 +272,7 @@ __device__ __forceinline__ void cellScore(int& s, int& h, int& v, int sl, int hl
 }
 
 // S and V-matrix value of the cell just above strip s in column j (j >= 0)
-template <bool BANDED>
+template <bool BANDED, bool L2ONLY>
 __device__ __forceinline__ void upBoundary(const GridCtx& G, int s, int SHR, int j, int& bS, int& bV) {
     const int rowAbove = s * SHR;
     if (BANDED) {
@@ -262,7 +280,7 @@ __device__ __forceinline__ void upBoundary(const GridCtx& G, int s, int SHR, int
         if (d < G.g.lo || d > G.g.up) { bS = NEG_INF; bV = NEG_INF; return; }
     }
     if (s == 0) {
-        const DCell c = G.initRow[j];
+        const DCell c = L2ONLY ? ldcgCell(&G.initRow[j]) : G.initRow[j];
         bS = c.s; bV = c.v;
     } else {
         const int2 b = __ldcg(&G.rowCk[(size_t)(s - 1) * (size_t)(G.g.nH + 1) + j]);
@@ -375,6 +393,8 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K
                         const int i = i0 + r;
                         bool inb = true;
                         if (BANDED) { const int d = j - i; inb = (d >= lo && d <= up); }
+                        // unbanded: only the perimeter of the box is ever read by the tracking pass
+                        else inb = (i == boxRow0) || (i == K.nV) || (j == hNext) || (j == K.nH);
                         if (i >= boxRow0 && i <= K.nV && inb) col[i] = DCell{st.Sl[r], st.Hl[r], vArr[r]};
                     }
                 }
@@ -402,7 +422,7 @@ __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEn
 #pragma unroll
     for (int w4 = 0; w4 < (RR + 3) / 4; ++w4) st.vm[w4] = 0;
     int2* ckTile = nullptr;   // checkpoint tile pointer such that tile of column j is ckTile + (j/CKW)*SH
-    if (!TRACE || fromCk) ckTile = G.colCk + ((size_t)G.ckBase[s] - (size_t)ckFirst(g, s)) * SH;
+    if (!TRACE || fromCk) ckTile = G.colCk + ((size_t)__ldcg(&G.ckBase[s]) - (size_t)ckFirst(g, s)) * SH;
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
         const int i = i0 + r;
@@ -413,18 +433,21 @@ __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEn
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
             const int i = i0 + r;
-            if (jlo == 1 && i <= G.colZeroMax) { const DCell ic = G.initCol[i]; st.Sl[r] = ic.s; st.Hl[r] = ic.h; }
+            if (jlo == 1 && i <= G.colZeroMax) {
+                const DCell ic = TRACE ? G.initCol[i] : ldcgCell(&G.initCol[i]);
+                st.Sl[r] = ic.s; st.Hl[r] = ic.h;
+            }
             else { st.Sl[r] = NEG_INF; st.Hl[r] = NEG_INF; }
         }
-        if (jlo == 1) st.prevUpS = (i0 - 1 <= G.colZeroMax) ? G.initCol[i0 - 1].s : NEG_INF;
+        if (jlo == 1) st.prevUpS = (i0 - 1 <= G.colZeroMax) ? (TRACE ? G.initCol[i0 - 1].s : __ldcg(&G.initCol[i0 - 1].s)) : NEG_INF;
         else {
             st.prevUpS = NEG_INF;
             if (lane == 0) {
                 if (!TRACE && s > 0) {  // the corner cell above-left of the strip comes from the strip above
                     const int need = imin(jlo - 1, stripJhi(g, s - 1, SHR));
-                    while (ldAcquire(&G.rowProg[s - 1]) < need) __nanosleep(128);
+                    while (ldRelaxed(&G.rowProg[s - 1]) < need) __nanosleep(128);
                 }
-                int bS, bV; upBoundary<BANDED>(G, s, SHR, jlo - 1, bS, bV); st.prevUpS = bS;
+                int bS, bV; upBoundary<BANDED, !TRACE>(G, s, SHR, jlo - 1, bS, bV); st.prevUpS = bS;
             }
             __syncwarp();
         }
@@ -435,7 +458,7 @@ __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEn
             const int2 v = __ldcg(&ck[lane * RR + r]);
             st.Sl[r] = v.x; st.Hl[r] = v.y;
         }
-        if (lane == 0) { int bS, bV; upBoundary<BANDED>(G, s, SHR, cBeg - 1, bS, bV); st.prevUpS = bS; }
+        if (lane == 0) { int bS, bV; upBoundary<BANDED, !TRACE>(G, s, SHR, cBeg - 1, bS, bV); st.prevUpS = bS; }
         else st.prevUpS = __ldcg(&ck[lane * RR - 1]).x;
     }
     st.pubS = NEG_INF; st.pubV = NEG_INF; st.curHc = 0;
@@ -454,15 +477,15 @@ __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEn
             const int need = imin(imin(cEnd, cBeg + 32 * c + 31), upJhi);
             if (upProg < need) {
                 if (lane == 0) {
-                    int p = ldAcquire(&G.rowProg[s - 1]);
-                    while (p < need) { __nanosleep(128); p = ldAcquire(&G.rowProg[s - 1]); }
+                    int p = ldRelaxed(&G.rowProg[s - 1]);
+                    while (p < need) { __nanosleep(128); p = ldRelaxed(&G.rowProg[s - 1]); }
                     upProg = p;
                 }
                 upProg = __shfl_sync(FULLMASK, upProg, 0);
             }
         }
         int bS = NEG_INF, bV = NEG_INF, hcN = 0;
-        if (jj <= cEnd) { hcN = G.seqH[jj - 1]; upBoundary<BANDED>(G, s, SHR, jj, bS, bV); }
+        if (jj <= cEnd) { hcN = G.seqH[jj - 1]; upBoundary<BANDED, !TRACE>(G, s, SHR, jj, bS, bV); }
         bool cap = false;
         if (capture) {
             const int jmaxChunk = imin(cEnd, cBeg + 32 * c + 31);  // largest column any lane touches in this chunk
@@ -525,7 +548,11 @@ __device__ __forceinline__ void tileDispatch(const GridCtx& G, int s, int cBeg, 
 struct TraceWalker {
     const GridCtx& G;
     OutStream& out;
-    uint8_t* win;     // shared-memory trace window of this control warp
+    const uint8_t* __restrict__ win;     // shared-memory trace window of this control warp
+    uint8_t* winW;
+    // register copies of the hot GridCtx fields (G lives in shared memory)
+    const GridGeom g;
+    const int local, rrShift, pitch, localJhi, affine;
     // cached tile (task grids): strip, first column, valid extent
     int tS, tC0, tMaxRow, tMaxCol;
     int pc, pv;       // navigator position: column, storage row
@@ -535,13 +562,13 @@ struct TraceWalker {
     long long tilesComputed, tileCycles;
 
     __device__ TraceWalker(const GridCtx& g, OutStream& o, uint8_t* w)
-        : G(g), out(o), win(w), tS(-1), tC0(0), tMaxRow(-1), tMaxCol(-1), pc(0), pv(0), nSegs(0), emitOn(true),
+        : G(g), out(o), win(w), winW(w), g(g.g), local(g.local), rrShift(g.rrShift), pitch(g.pitch), localJhi(g.localJhi),
+          affine(g.affine), tS(-1), tC0(0), tMaxRow(-1), tMaxCol(-1), pc(0), pv(0), nSegs(0), emitOn(true),
           bad(false), tilesComputed(0), tileCycles(0) {}
 
     // Recompute the trace bytes of the tile that holds (i, j): rows of strip s up to the lane owning row i,
     // columns from the checkpoint left of j up to j.
     __device__ void computeTile(int i, int j) {
-        const GridGeom& g = G.g;
         const int s = (i - 1) / SH;
         const int jlo = stripJlo(g, s, SH);
         int c0 = ((j - 1) / CKW) * CKW;          // checkpoint column left of j (tile = c0+1 .. c0+CKW)
@@ -552,8 +579,8 @@ struct TraceWalker {
         const int nsteps = (j - cBeg + 1) + laneOfI;
         const long long t0 = clock64();
         __syncwarp();
-        if (G.affine) { if (G.complete) tileDispatch<true, true>(G, s, cBeg, j, fromCk, nsteps, win); else tileDispatch<true, false>(G, s, cBeg, j, fromCk, nsteps, win); }
-        else { if (G.complete) tileDispatch<false, true>(G, s, cBeg, j, fromCk, nsteps, win); else tileDispatch<false, false>(G, s, cBeg, j, fromCk, nsteps, win); }
+        if (affine) { if (G.complete) tileDispatch<true, true>(G, s, cBeg, j, fromCk, nsteps, winW); else tileDispatch<true, false>(G, s, cBeg, j, fromCk, nsteps, winW); }
+        else { if (G.complete) tileDispatch<false, true>(G, s, cBeg, j, fromCk, nsteps, winW); else tileDispatch<false, false>(G, s, cBeg, j, fromCk, nsteps, winW); }
         __syncwarp();
         tS = s; tC0 = cBeg; tMaxCol = j; tMaxRow = s * SH + (laneOfI + 1) * 8;
         ++tilesComputed;
@@ -561,19 +588,19 @@ struct TraceWalker {
     }
 
     __device__ __forceinline__ uint32_t tvHere() {
-        const int i = pv - storageOffset(G.g, pc);
+        const int i = pv - storageOffset(g, pc);
         const int j = pc;
-        if (i <= 0 || j <= 0 || i > G.g.nV || j > G.g.nH) return 0;
-        if (G.local) {
-            if (j > G.localJhi) return 0;
-            const int sh = G.rrShift;
+        if (i <= 0 || j <= 0 || i > g.nV || j > g.nH) return 0;
+        if (local) {
+            if (j > localJhi) return 0;
+            const int sh = rrShift;
             const int q = (i - 1) >> sh;
-            return win[((((j - 1) * G.pitch + q)) << sh) + ((i - 1) & ((1 << sh) - 1))];
+            return win[((((j - 1) * pitch + q)) << sh) + ((i - 1) & ((1 << sh) - 1))];
         }
         const int s = (i - 1) / SH;
         if (s != tS || j < tC0 || j > tMaxCol || i > tMaxRow) {
             // columns outside the strip's band range hold no computed cells
-            if (j < stripJlo(G.g, s, SH) || j > stripJhi(G.g, s, SH)) return 0;
+            if (j < stripJlo(g, s, SH) || j > stripJhi(g, s, SH)) return 0;
             computeTile(i, j);
         }
         const int rem = (i - 1) - s * SH;
@@ -583,11 +610,11 @@ struct TraceWalker {
         Coord c;
         c.currCol = pc; c.currRow = pv; c.endCol = endCol; c.endRow = endRow; c.bp1 = 0; c.bp2 = 0;
         c.inBandFlag = false;
-        if (G.g.banded) {
-            if (c.currCol > G.g.up) c.currRow += c.currCol - G.g.up;
-            if (c.endCol > G.g.up) c.endRow += c.endCol - G.g.up;
-            c.bp1 = imin(G.g.nH, imax(0, G.g.up));
-            c.bp2 = imin(G.g.nH, imax(0, G.g.nV + G.g.lo));
+        if (g.banded) {
+            if (c.currCol > g.up) c.currRow += c.currCol - g.up;
+            if (c.endCol > g.up) c.endRow += c.endCol - g.up;
+            c.bp1 = imin(g.nH, imax(0, g.up));
+            c.bp2 = imin(g.nH, imax(0, g.nV + g.lo));
             int mb = imin(c.bp1, c.bp2);
             if (c.currCol < mb) c.currRow -= mb - c.currCol;
             c.inBandFlag = true;
@@ -610,7 +637,7 @@ struct TraceWalker {
     __device__ __forceinline__ void moveV() { --pv; }
 
     __device__ void doTraceback(uint32_t& tv, uint32_t& last, int& frag, Coord& c) {  // dp_traceback_impl.h:335-431
-        const bool aff = G.affine;
+        const bool aff = affine;
         if (tv & T_D) {
             if (!(last & T_D)) { record(c.currCol, c.currRow, frag, last); last = T_D; frag = 0; }
             moveD(c); tv = tvHere(); --c.currCol; --c.currRow; ++frag;
@@ -653,7 +680,7 @@ struct TraceWalker {
         uint32_t tv = tvOverride >= 0 ? (uint32_t)tvOverride : tvHere();
         uint32_t last = initialDirection(tv, prefer);
         Coord c = makeCoord(0, 0);
-        const int nH = G.g.nH, nV = G.g.nV;
+        const int nH = g.nH, nV = g.nV;
         if (tail) {
             if (c.currRow != nV) record(nH, c.currRow, nV - c.currRow, T_V);
             if (c.currCol != nH) record(c.currCol, c.currRow, nH - c.currCol, T_H);

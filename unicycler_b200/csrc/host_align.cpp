@@ -8,19 +8,23 @@
 
 namespace ub200 {
 
-void toDna5(const char* s, size_t n, std::vector<uint8_t>& out) {
-    static uint8_t table[256];
-    static bool init = false;
-    if (!init) {
-        for (int i = 0; i < 256; ++i) table[i] = 4;
-        table[(int)'A'] = table[(int)'a'] = 0;
-        table[(int)'C'] = table[(int)'c'] = 1;
-        table[(int)'G'] = table[(int)'g'] = 2;
-        table[(int)'T'] = table[(int)'t'] = table[(int)'U'] = table[(int)'u'] = 3;
-        init = true;
+namespace {
+struct Dna5Table {
+    uint8_t t[256];
+    Dna5Table() {
+        for (int i = 0; i < 256; ++i) t[i] = 4;
+        t[(int)'A'] = t[(int)'a'] = 0;
+        t[(int)'C'] = t[(int)'c'] = 1;
+        t[(int)'G'] = t[(int)'g'] = 2;
+        t[(int)'T'] = t[(int)'t'] = t[(int)'U'] = t[(int)'u'] = 3;
     }
+};
+const Dna5Table kDna5;
+}  // namespace
+
+void toDna5(const char* s, size_t n, std::vector<uint8_t>& out) {
     out.resize(n);
-    for (size_t i = 0; i < n; ++i) out[i] = table[(unsigned char)s[i]];
+    for (size_t i = 0; i < n; ++i) out[i] = kDna5.t[(unsigned char)s[i]];
 }
 
 // ---------------------------------------------------------------------------------------
