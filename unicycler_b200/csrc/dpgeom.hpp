@@ -244,15 +244,16 @@ UB_HD int32_t ckCount(const GridGeom& g, int32_t s) {
 
 // A grid is "local" when one warp can fill it with the full trace kept in its shared-memory window.
 struct LocalPlan {
-    int32_t local, RR, pitch, jhi;
+    int32_t local, RR, RRS, pitch, jhi;  // rows per lane, bytes per (column, lane) slot, lanes per column, last column
 };
 UB_HD LocalPlan localPlan(const GridGeom& g) {
     LocalPlan p;
-    p.RR = (g.nV <= 128) ? 4 : 8;
+    p.RR = (g.nV <= 64) ? 2 : (g.nV <= 96) ? 3 : (g.nV <= 128) ? 4 : 8;
+    p.RRS = (p.RR == 3) ? 4 : p.RR;
     int32_t lanes = (g.nV + p.RR - 1) / p.RR;
     p.pitch = (lanes + 1) & ~1;
     p.jhi = stripJhi(g, 0, 32 * p.RR);
-    p.local = (g.nV <= 32 * p.RR && (int64_t)p.jhi * p.pitch * p.RR <= (int64_t)WINBYTES) ? 1 : 0;
+    p.local = (g.nV <= 32 * p.RR && (int64_t)p.jhi * p.pitch * p.RRS <= (int64_t)WINBYTES) ? 1 : 0;
     return p;
 }
 

@@ -49,14 +49,14 @@ __device__ __noinline__ void setupGrid(GridCtx& G, const JobDev& jb, const GridD
         G.lastCol = reinterpret_cast<DCell*>(arena + L.lastCol);
         G.cand = reinterpret_cast<int*>(arena + L.cand);
         G.planted = reinterpret_cast<PlantedCell*>(arena + L.planted);
-        G.colTab = reinterpret_cast<ColInfo*>(arena + L.colTab);
-        G.maxCand = L.maxCand; G.maxPlanted = L.maxPlanted; G.maxColTab = L.maxColTab; G.pad0 = 0;
+        G.colTab = P.colTabPool + jb.colTabBase + gd.colTabOff; G.nColTab = gd.nColTab; G.pad3 = 0;
+        G.maxCand = L.maxCand; G.maxPlanted = L.maxPlanted; G.pad0 = 0; G.pad4 = 0;
         G.maxBox = L.maxBox;
         const GridGeom& g = G.g;
         G.colZeroMax = g.banded ? imin(g.nV, -g.lo) : g.nV;
         
         const LocalPlan lp = localPlan(g);
-        G.local = lp.local; G.RR = lp.local ? lp.RR : 8; G.rrShift = (G.RR == 4) ? 2 : 3; G.pitch = lp.pitch; G.localJhi = lp.jhi;
+        G.local = lp.local; G.RR = lp.local ? lp.RR : 8; G.rrMul = 65536 / G.RR + 1; G.rrs = lp.local ? lp.RRS : 8; G.pad2 = 0; G.pitch = lp.pitch; G.localJhi = lp.jhi;
         G.NS = lp.local ? 1 : stripCount(g, SH);
         G.nSeg = (g.nH + SEG - 1) / SEG;
         // capture mode
@@ -240,23 +240,30 @@ __device__ __forceinline__ void forEachFlaggedCell(const GridCtx& G, int nColTab
                 }
                 f(ok && (o.lastRow || o.lastCol || o.storeCol || o.storeRow), i, ci.j, cv, o);
             }
-        }
-        for (int ccol = 0; ccol < nColTab; ++ccol) {
-            const ColInfo ci = G.colTab[ccol];
-            if (!((ci.j == G.hNext) || (ci.cp == CP_FINAL))) continue;
-            for (int base = 0; base < ci.nCells; base += 32) {
-                const int c = base + lane;
-                TrackOpts o = none;
-                int i = 0, cv = 0;
-                if (c < ci.nCells) {
-                    i = ci.rowTop + c;
-                    cv = ci.cvFirst + c;
-                    const int ct = (c == 0) ? CT_FIRST : (c == ci.nCells - 1 ? CT_LAST : CT_INNER);
-                    const int leap = (ct == CT_LAST) ? ci.tLeapLast : ci.tLeap;
-                    o = chainTrackingOptions(ci.j, cv, leap, ci.cp, ci.cl, ct, G.hNext, G.vNext, chainFinal, feLastRow,
-                                             feLastCol);
+            // column hNext and the final column: every cell can be flagged; all lanes walk the column of lane b
+            unsigned fullMask = __ballot_sync(FULLMASK, have && full);
+            while (fullMask) {
+                const int b = __ffs(fullMask) - 1;
+                fullMask &= fullMask - 1;
+                ColInfo cf;
+                cf.j = __shfl_sync(FULLMASK, ci.j, b); cf.cp = __shfl_sync(FULLMASK, ci.cp, b);
+                cf.cl = __shfl_sync(FULLMASK, ci.cl, b); cf.rowTop = __shfl_sync(FULLMASK, ci.rowTop, b);
+                cf.nCells = __shfl_sync(FULLMASK, ci.nCells, b); cf.tLeap = __shfl_sync(FULLMASK, ci.tLeap, b);
+                cf.tLeapLast = __shfl_sync(FULLMASK, ci.tLeapLast, b); cf.cvFirst = __shfl_sync(FULLMASK, ci.cvFirst, b);
+                for (int cb = 0; cb < cf.nCells; cb += 32) {
+                    const int c = cb + lane;
+                    TrackOpts o = none;
+                    int i = 0, cv = 0;
+                    if (c < cf.nCells) {
+                        i = cf.rowTop + c;
+                        cv = cf.cvFirst + c;
+                        const int ct = (c == 0) ? CT_FIRST : (c == cf.nCells - 1 ? CT_LAST : CT_INNER);
+                        const int leap = (ct == CT_LAST) ? cf.tLeapLast : cf.tLeap;
+                        o = chainTrackingOptions(cf.j, cv, leap, cf.cp, cf.cl, ct, G.hNext, G.vNext, chainFinal, feLastRow,
+                                                 feLastCol);
+                    }
+                    f(c < cf.nCells && (o.lastRow || o.lastCol || o.storeCol || o.storeRow), i, cf.j, cv, o);
                 }
-                f(c < ci.nCells && (o.lastRow || o.lastCol || o.storeCol || o.storeRow), i, ci.j, cv, o);
             }
         }
     }
@@ -275,26 +282,8 @@ __device__ __forceinline__ DCell trackedCell(const GridCtx& G, int i, int j) {
 __device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res) {
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
-    int ub = 0, nCols = 0;
-    if (!G.capEdges && g.banded) {
-        if (lane == 0) {
-            // literal column walk of _computeBandedAlignment for the columns right of the next grid's origin
-            BandWalker w;
-            w.init(g);
-            ColInfo ci;
-            int n = 0;
-            while (w.next(ci)) {
-                if (ci.j >= G.hNext) {
-                    if (n < G.maxColTab) G.colTab[n] = ci;
-                    ++n;
-                }
-            }
-            if (n > G.maxColTab) { ub = 1; n = G.maxColTab; }
-            nCols = n;
-        }
-        __syncwarp();
-        nCols = __shfl_sync(FULLMASK, nCols, 0);
-    }
+    int ub = 0;
+    const int nCols = (!G.capEdges && g.banded) ? G.nColTab : 0;
     const int dimV = g.dimV;
     // pass 1: init stores + maximum
     int best = INT32_MIN;
@@ -527,8 +516,12 @@ template <bool AFF, bool CT, bool BANDED>
 __device__ __forceinline__ void localFillRR(const GridCtx& G, uint8_t* win) {
     const int lanes = (G.g.nV + G.RR - 1) / G.RR;
     const int nsteps = G.localJhi + lanes - 1;
-    if (G.RR == 4) runStrip<AFF, CT, BANDED, 4, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch);
-    else runStrip<AFF, CT, BANDED, 8, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch);
+    switch (G.RR) {
+    case 2: runStrip<AFF, CT, BANDED, 2, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch); break;
+    case 3: runStrip<AFF, CT, BANDED, 3, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch); break;
+    case 4: runStrip<AFF, CT, BANDED, 4, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch); break;
+    default: runStrip<AFF, CT, BANDED, 8, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch); break;
+    }
 }
 template <bool AFF, bool CT>
 __device__ __forceinline__ void localFillBand(const GridCtx& G, uint8_t* win) {
@@ -572,55 +565,66 @@ __device__ __noinline__ void runItem(const GridCtx& G, int item) {
     if (lane == 0) stRelease(&G.segDone[s], seg + 1);
 }
 
-// Claims and runs one item of the oldest open task.  Returns false when no item is available.
-// wctx: this warp's shared-memory copy of the task's GridCtx; wTask: index of the task it holds.
-__device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask) {
-    const KParams& P = cP;
+// Runs item `item` of task t on this warp (wctx: the warp's shared-memory copy of the task's GridCtx).
+__device__ __forceinline__ void runClaimedItem(TaskDesc* t, int taskId, int item, GridCtx& wctx, int& wTask) {
     const int lane = threadIdx.x & 31;
-    int h = 0, item = -1;
-    if (lane == 0) {
-        h = ldRelaxed(&P.cb->ringHead);
-        for (;;) {
-            if (h >= P.maxTasks) break;
-            TaskDesc* t = &P.ring[h];
-            if (ldRelaxed(&t->ready) == 0) break;  // nothing published at the head (yet)
-            const int n = t->nItems;
-            if (ldVolatile(&t->nextItem) < n) {
-                const int k = atomicAdd(&t->nextItem, 1);
-                if (k < n) { item = k; break; }
-            }
-            atomicCAS(&P.cb->ringHead, h, h + 1);  // exhausted: advance the head
-            ++h;
-        }
-    }
-    item = __shfl_sync(FULLMASK, item, 0);
-    h = __shfl_sync(FULLMASK, h, 0);
-    if (item < 0) return false;
-    TaskDesc* t = &P.ring[h];
-    if (wTask != h) {
+    if (wTask != taskId) {
         const int* src = reinterpret_cast<const int*>(&t->ctx);
         int* dst = reinterpret_cast<int*>(&wctx);
         for (int k = lane; k < (int)(sizeof(GridCtx) / sizeof(int)); k += 32) dst[k] = __ldcg(&src[k]);
-        wTask = h;
+        wTask = taskId;
         __syncwarp();
     }
     runItem(wctx, item);
     __threadfence();
     __syncwarp();
     if (lane == 0) atomicAdd(&t->doneItems, 1);
+}
+
+// Claims and runs one item of the oldest open task, critical-path board first.  Returns false when no
+// item is available.
+__device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask) {
+    const KParams& P = cP;
+    const int lane = threadIdx.x & 31;
+    int h = 0, item = -1, board = 0;
+    if (lane == 0) {
+        for (board = 0; board < 2 && item < 0; ++board) {
+            h = ldRelaxed(&P.cb->ringHead[board]);
+            for (;;) {
+                if (h >= P.maxTasks) break;
+                TaskDesc* t = &P.ring[board * P.maxTasks + h];
+                if (ldRelaxed(&t->ready) == 0) break;  // nothing published at the head (yet)
+                const int n = t->nItems;
+                if (ldVolatile(&t->nextItem) < n) {
+                    const int k = atomicAdd(&t->nextItem, 1);
+                    if (k < n) { item = k; break; }
+                }
+                atomicCAS(&P.cb->ringHead[board], h, h + 1);  // exhausted: advance the head
+                ++h;
+            }
+        }
+        --board;
+    }
+    item = __shfl_sync(FULLMASK, item, 0);
+    if (item < 0) return false;
+    h = __shfl_sync(FULLMASK, h, 0);
+    board = __shfl_sync(FULLMASK, board, 0);
+    const int taskId = board * P.maxTasks + h;
+    runClaimedItem(&P.ring[taskId], taskId, item, wctx, wTask);
     return true;
 }
 
 // Publishes the control warp's grid as a task and helps until every item of it is done.
-__device__ __noinline__ int publishAndWait(const GridCtx& G, GridCtx& wctx, int& wTask) {
+__device__ __noinline__ int publishAndWait(const GridCtx& G, GridCtx& wctx, int& wTask, int board) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     setupStrips(G);
     int t = 0;
-    if (lane == 0) t = atomicAdd(&P.cb->ringTail, 1);
+    if (lane == 0) t = atomicAdd(&P.cb->ringTail[board], 1);
     t = __shfl_sync(FULLMASK, t, 0);
-    if (t >= P.maxTasks) return JOB_REF_UB;  // cannot happen: the host sizes the board to the number of big grids
-    TaskDesc* td = &P.ring[t];
+    if (t >= P.maxTasks) return JOB_REF_UB;  // cannot happen: the host sizes the boards to the number of big grids
+    const int taskId = board * P.maxTasks + t;
+    TaskDesc* td = &P.ring[taskId];
     const int* src = reinterpret_cast<const int*>(&G);
     int* dst = reinterpret_cast<int*>(&td->ctx);
     for (int k = lane; k < (int)(sizeof(GridCtx) / sizeof(int)); k += 32) dst[k] = src[k];
@@ -634,7 +638,14 @@ __device__ __noinline__ int publishAndWait(const GridCtx& G, GridCtx& wctx, int&
         if (lane == 0) d = ldRelaxed(&td->doneItems);
         d = __shfl_sync(FULLMASK, d, 0);
         if (d >= nItems) break;
-        if (!tryRunOneItem(wctx, wTask)) __nanosleep(200);
+        if (board == 0) {
+            // critical-path job: work on the own grid only, so that the control warp is free the moment it completes
+            int k = -1;
+            if (lane == 0 && ldVolatile(&td->nextItem) < nItems) { k = atomicAdd(&td->nextItem, 1); if (k >= nItems) k = -1; }
+            k = __shfl_sync(FULLMASK, k, 0);
+            if (k >= 0) runClaimedItem(td, taskId, k, wctx, wTask);
+            else __nanosleep(100);
+        } else if (!tryRunOneItem(wctx, wTask)) __nanosleep(200);
     }
     // one real acquire: the captures written by the worker warps are read with ordinary (L1-cached) loads
     if (lane == 0) (void)ldAcquire(&td->doneItems);
@@ -645,7 +656,7 @@ __device__ __noinline__ int publishAndWait(const GridCtx& G, GridCtx& wctx, int&
 // ---------------------------------------------------------------------------------------
 // one job, start to end, on one control warp
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void runJob(int jobIdx, GridCtx& G, GridCtx& wctx, int& wTask, uint8_t* win, uint8_t* arena) {
+__device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& G, GridCtx& wctx, int& wTask, uint8_t* win, uint8_t* arena) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     const JobDev jb = P.jobs[jobIdx];
@@ -664,7 +675,7 @@ __device__ __noinline__ void runJob(int jobIdx, GridCtx& G, GridCtx& wctx, int& 
             c2 = clock64();
             prof[1] += c2 - c1;
         } else {
-            const int st = publishAndWait(G, wctx, wTask);
+            const int st = publishAndWait(G, wctx, wTask, board);
             if (st != JOB_OK) status = st;
             c2 = clock64();
             prof[2] += c2 - c1;
@@ -730,7 +741,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
             q = __shfl_sync(FULLMASK, q, 0);
             if (q < P.nJobs) {
                 GridCtx* cctx = reinterpret_cast<GridCtx*>(smem + NCTRL * WINBYTES + cw * CTX_STRIDE);
-                runJob(P.order[q], *cctx, *wctx, wTask, smem + cw * WINBYTES,
+                runJob(P.order[q], q < P.nHiJobs ? 0 : 1, *cctx, *wctx, wTask, smem + cw * WINBYTES,
                        P.scratch + (size_t)agent * P.scratchStride);
                 continue;
             }
@@ -781,6 +792,8 @@ struct Engine::Impl {
     void* dOut = nullptr; size_t capOut = 0;
     void* dJobOut = nullptr; size_t capJobOut = 0;
     void* dOrder = nullptr; size_t capOrder = 0;
+    void* dColTab = nullptr; size_t capColTab = 0;
+    std::vector<ColInfo> colTabAll;
     void* dScratch = nullptr; size_t capScratch = 0;
     void* dRing = nullptr; size_t capRing = 0;   // ControlBlock followed by the task board
     // pinned host staging
@@ -838,7 +851,7 @@ Engine::~Engine() {
     if (!impl_) return;
     cudaSetDevice(impl_->device);
     cudaFree(impl_->dJobs); cudaFree(impl_->dGrids); cudaFree(impl_->dSeq); cudaFree(impl_->dOut);
-    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dScratch); cudaFree(impl_->dRing);
+    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dScratch); cudaFree(impl_->dRing);
     cudaFreeHost(impl_->hSeq); cudaFreeHost(impl_->hOut);
     for (auto& ev : impl_->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(impl_->stream);
@@ -856,6 +869,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     const size_t nJobs = jobs.size();
     I.jobsDev.assign(nJobs, JobDev());
     I.gridsAll.clear();
+    I.colTabAll.clear();
     I.order.resize(nJobs);
     // sequences
     size_t seqBytes = 0;
@@ -866,7 +880,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     ScratchLayout L;
     memset(&L, 0, sizeof(L));
     long long maxRowCk = 0, maxColCk = 0, maxBox = 1, ckBytes = 0;
-    int maxNH = 1, maxNV = 1, maxCapH = 1, maxCapV = 1, maxStrips = 1, maxBoxW = 1;
+    int maxNH = 1, maxNV = 1, maxCapH = 1, maxCapV = 1, maxStrips = 1;
     size_t nTasks = 0;
     std::vector<long long> cost(nJobs, 0);
     int64_t totalCells = 0;
@@ -885,6 +899,8 @@ void Engine::upload(std::vector<Job*>& jobs) {
         d.complete = j.complete;
         d.gridBegin = (int)I.gridsAll.size();
         d.gridCount = (int)j.grids.size();
+        d.colTabBase = (long long)I.colTabAll.size();
+        I.colTabAll.insert(I.colTabAll.end(), j.colTab.begin(), j.colTab.end());
         j.cells = 0;
         for (const GridDesc& gd : j.grids) {
             I.gridsAll.push_back(gd);
@@ -907,7 +923,8 @@ void Engine::upload(std::vector<Job*>& jobs) {
                 int row0 = g.banded ? colTop(g, std::min(gd.hNext, g.nH)) : std::min(gd.vNext, g.nV);
                 long long bh = g.nV - row0 + 1, bw = std::max(0, g.nH - gd.hNext + 1);
                 maxBox = std::max(maxBox, bh * bw);
-                maxBoxW = std::max(maxBoxW, (int)bw + 2);
+                if (g.banded && gd.nColTab == 0 && bw > 0)
+                    throw std::runtime_error("unicycler_b200: banded chain grid without host-planned column table");
             }
             int64_t c = referenceCells(gd);
             j.cells += c;
@@ -945,15 +962,13 @@ void Engine::upload(std::vector<Job*>& jobs) {
     place(L.cand, (size_t)L.maxCand * sizeof(int));
     L.maxPlanted = 4096;
     place(L.planted, (size_t)L.maxPlanted * sizeof(PlantedCell));
-    L.maxColTab = maxBoxW + 8;
-    place(L.colTab, (size_t)L.maxColTab * sizeof(ColInfo));
     L.total = (long long)alignUp(o, 4096);
     L.maxBox = maxBox; L.maxCapH = maxCapH; L.maxCapV = maxCapV; L.maxNH = maxNH; L.maxNV = maxNV;
     L.maxRowCk = maxRowCk; L.maxColCk = maxColCk; L.maxStrips = maxStrips;
     // number of control agents with an arena: bounded by jobs and by memory
     size_t freeB = 0, totalB = 0;
     CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
-    I.ringBytes = alignUp(sizeof(ControlBlock), 256) + (nTasks + 1) * sizeof(TaskDesc);
+    I.ringBytes = alignUp(sizeof(ControlBlock), 256) + 2 * (nTasks + 1) * sizeof(TaskDesc);
     size_t fixed = nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + I.seqBytes + I.outInts * 4 +
                    I.ringBytes + (64u << 20);
     size_t budget = (freeB + I.capScratch > fixed) ? (size_t)((freeB + I.capScratch - fixed) * 0.9) : 0;
@@ -967,6 +982,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.growDev(I.dOut, I.capOut, I.outInts * sizeof(int) + 64);
     I.growDev(I.dJobOut, I.capJobOut, nJobs * sizeof(JobOut));
     I.growDev(I.dOrder, I.capOrder, nJobs * sizeof(int));
+    I.growDev(I.dColTab, I.capColTab, I.colTabAll.size() * sizeof(ColInfo) + 64);
     I.growDev(I.dScratch, I.capScratch, (size_t)L.total * nSlots);
     I.growDev(I.dRing, I.capRing, I.ringBytes);
     I.growHost(I.hOut, I.capHOut, I.outInts * sizeof(int) + 64);
@@ -975,11 +991,15 @@ void Engine::upload(std::vector<Job*>& jobs) {
     CUDA_CHECK(cudaMemcpyAsync(I.dJobs, I.jobsDev.data(), nJobs * sizeof(JobDev), cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dGrids, I.gridsAll.data(), I.gridsAll.size() * sizeof(GridDesc), cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dOrder, I.order.data(), nJobs * sizeof(int), cudaMemcpyHostToDevice, I.stream));
+    if (!I.colTabAll.empty())
+        CUDA_CHECK(cudaMemcpyAsync(I.dColTab, I.colTabAll.data(), I.colTabAll.size() * sizeof(ColInfo), cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaEventRecord(I.ev[1], I.stream));
     KParams& kp = I.kp;
     kp.jobs = (const JobDev*)I.dJobs; kp.grids = (const GridDesc*)I.dGrids; kp.seq = (const uint8_t*)I.dSeq;
     kp.out = (int*)I.dOut; kp.jobOut = (JobOut*)I.dJobOut; kp.order = (const int*)I.dOrder;
-    kp.nJobs = (int)nJobs; kp.nSlots = nSlots; kp.maxTasks = (int)nTasks;
+    kp.colTabPool = (const ColInfo*)I.dColTab;
+    kp.nJobs = (int)nJobs; kp.nSlots = nSlots; kp.maxTasks = (int)nTasks + 1;
+    kp.nHiJobs = std::max(4, (int)nJobs / 10);
     kp.cb = (ControlBlock*)I.dRing;
     kp.ring = (TaskDesc*)((uint8_t*)I.dRing + alignUp(sizeof(ControlBlock), 256));
     kp.scratch = (uint8_t*)I.dScratch; kp.scratchStride = L.total;
@@ -987,7 +1007,8 @@ void Engine::upload(std::vector<Job*>& jobs) {
     CUDA_CHECK(cudaMemcpyToSymbolAsync(cP, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, I.stream));
     I.stats = EngineStats();
     I.stats.cells = totalCells;
-    I.stats.h2dBytes = (int64_t)(I.seqBytes + nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + nJobs * sizeof(int));
+    I.stats.h2dBytes = (int64_t)(I.seqBytes + nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + nJobs * sizeof(int) +
+                                 I.colTabAll.size() * sizeof(ColInfo));
     I.stats.ctas = I.numSMs;
     I.stats.traceBytes = ckBytes;
 }

@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include "dpgeom.hpp"
+
 namespace ub200 {
 
 static const int NEG_INF = INT32_MIN / 2;  // seqan/align/dp_cell.h:122-124
@@ -44,6 +46,9 @@ struct GridDesc {
     int32_t plantZerosH, plantZerosV;  // >0: _initiaizeBeginningOfBandedChain(sizeH, sizeV) precedes this grid
     int32_t glue;
     int32_t checkScore;      // 1: the explicit "score < -1000000 -> throw" after this grid (always true inside too)
+    // banded chain grids: the column descriptors of _computeBandedAlignment for the columns >= hNext
+    // (host-side BandWalker), index into the job's / batch's ColInfo pool
+    int32_t colTabOff, nColTab;
 };
 
 struct Seg {                 // seqan/align/dp_trace_segment.h (TraceSegment_)
@@ -75,6 +80,7 @@ struct Job {
     int32_t freeFirstRow = 0, freeFirstCol = 0, freeLastRow = 0, freeLastCol = 0;
     int32_t complete = 0;        // CompleteTrace (chain) vs SingleTrace (global/path)
     std::vector<GridDesc> grids;
+    std::vector<ColInfo> colTab;  // pool referenced by GridDesc::colTabOff (relative to this job)
     JobResult result;
     // DP cells as the reference counts them (dimH*dimV per sub-DP)
     int64_t cells = 0;

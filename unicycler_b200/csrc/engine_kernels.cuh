@@ -40,7 +40,7 @@ struct JobDev {
     int fe;  // bit0 firstRow, bit1 firstCol, bit2 lastRow, bit3 lastCol
     int complete;
     int gridBegin, gridCount;
-    long long outOff;
+    long long outOff, colTabBase;
     int outCap;
     int pad;
 };
@@ -53,8 +53,8 @@ struct JobOut {
 
 struct ScratchLayout {  // byte offsets inside one control agent's arena
     long long rowCk, colCk, ckBase, rowProg, segDone, initRow, initCol, hInitNext, vInitNext, box, lastRow, lastCol,
-        cand, planted, colTab, total;
-    int maxCand, maxPlanted, maxColTab, maxStrips;
+        cand, planted, total;
+    int maxCand, maxPlanted, maxStrips, pad;
     long long maxBox, maxRowCk, maxColCk;
     int maxCapH, maxCapV, maxNH, maxNV;
 };
@@ -81,16 +81,18 @@ struct GridCtx {
     DCell *initRow, *initCol, *hInitNext, *vInitNext, *box, *lastRow, *lastCol;
     int* cand;
     PlantedCell* planted;
-    ColInfo* colTab;
+    const ColInfo* colTab;   // host-planned column descriptors of this grid (banded chain grids)
+    int nColTab, pad3;
     // strips
     int NS, nSeg, local, RR;   // local: filled by the control warp with RR rows per lane, trace in shared memory
     int pitch, localJhi;       // local trace window: lanes per column (even), last column holding cells
-    int colZeroMax, rrShift;
+    int colZeroMax, rrMul;     // rrMul: (x * rrMul) >> 16 == x / RR for x < 1024
+    int rrs, pad2;             // bytes per (column, lane) slot of the local trace window
     // capture
     int capEdges;  // 1: last row + last column; 0: box
     int boxRow0, boxH, boxW;
     // limits
-    int maxCand, maxPlanted, maxColTab, pad0;
+    int maxCand, maxPlanted, pad0, pad4;
     long long maxBox;
 };
 
@@ -103,7 +105,8 @@ struct TaskDesc {
 };
 
 struct ControlBlock {  // zeroed before every launch
-    int jobQueue, jobsDone, ringHead, ringTail;
+    int jobQueue, jobsDone;
+    int ringHead[2], ringTail[2];  // task boards: [0] jobs on the critical path (longest chains), [1] the rest
 };
 
 struct KParams {
@@ -113,11 +116,13 @@ struct KParams {
     int* out;
     JobOut* jobOut;
     const int* order;  // job processing order (largest first)
+    const ColInfo* colTabPool;
     int nJobs;
     int nSlots;        // control agents with an arena
-    int maxTasks;
+    int maxTasks;      // capacity of each task board
+    int nHiJobs;       // the first nHiJobs jobs of `order` publish on board 0
     ControlBlock* cb;
-    TaskDesc* ring;
+    TaskDesc* ring;    // [2][maxTasks]
     uint8_t* scratch;
     long long scratchStride;
     ScratchLayout lay;
@@ -360,9 +365,11 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K
             }
             st.prevUpS = inS;
             st.pubS = Su; st.pubV = Vu;
-            if (TRACE) {
-                uint8_t* p = win + ((size_t)(j - cBeg) * winPitch + lane) * RR;
-                if (RR == 8) *reinterpret_cast<uint2*>(p) = make_uint2(tw[0], tw[(RR + 3) / 4 - 1]);
+            if constexpr (TRACE) {
+                constexpr int RRS = (RR == 3) ? 4 : RR;
+                uint8_t* p = win + ((j - cBeg) * winPitch + lane) * RRS;
+                if constexpr (RR == 8) *reinterpret_cast<uint2*>(p) = make_uint2(tw[0], tw[(RR + 3) / 4 - 1]);
+                else if constexpr (RR == 2) *reinterpret_cast<uint16_t*>(p) = (uint16_t)tw[0];
                 else *reinterpret_cast<uint32_t*>(p) = tw[0];
             } else {
                 if (lane == 31) __stcg(&rowOut[j], make_int2(Su, Vu));
@@ -552,7 +559,7 @@ struct TraceWalker {
     uint8_t* winW;
     // register copies of the hot GridCtx fields (G lives in shared memory)
     const GridGeom g;
-    const int local, rrShift, pitch, localJhi, affine;
+    const int local, rrMul, rr, rrs, pitch, localJhi, affine;
     // cached tile (task grids): strip, first column, valid extent
     int tS, tC0, tMaxRow, tMaxCol;
     int pc, pv;       // navigator position: column, storage row
@@ -562,7 +569,7 @@ struct TraceWalker {
     long long tilesComputed, tileCycles;
 
     __device__ TraceWalker(const GridCtx& g, OutStream& o, uint8_t* w)
-        : G(g), out(o), win(w), winW(w), g(g.g), local(g.local), rrShift(g.rrShift), pitch(g.pitch), localJhi(g.localJhi),
+        : G(g), out(o), win(w), winW(w), g(g.g), local(g.local), rrMul(g.rrMul), rr(g.RR), rrs(g.rrs), pitch(g.pitch), localJhi(g.localJhi),
           affine(g.affine), tS(-1), tC0(0), tMaxRow(-1), tMaxCol(-1), pc(0), pv(0), nSegs(0), emitOn(true),
           bad(false), tilesComputed(0), tileCycles(0) {}
 
@@ -593,9 +600,8 @@ struct TraceWalker {
         if (i <= 0 || j <= 0 || i > g.nV || j > g.nH) return 0;
         if (local) {
             if (j > localJhi) return 0;
-            const int sh = rrShift;
-            const int q = (i - 1) >> sh;
-            return win[((((j - 1) * pitch + q)) << sh) + ((i - 1) & ((1 << sh) - 1))];
+            const int q = ((i - 1) * rrMul) >> 16;
+            return win[((j - 1) * pitch + q) * rrs + ((i - 1) - q * rr)];
         }
         const int s = (i - 1) / SH;
         if (s != tS || j < tC0 || j > tMaxCol || i > tMaxRow) {
@@ -640,7 +646,8 @@ struct TraceWalker {
         const bool aff = affine;
         if (tv & T_D) {
             if (!(last & T_D)) { record(c.currCol, c.currRow, frag, last); last = T_D; frag = 0; }
-            moveD(c); tv = tvHere(); --c.currCol; --c.currRow; ++frag;
+            // run of diagonal steps (identical to re-entering this branch once per step)
+            do { moveD(c); tv = tvHere(); --c.currCol; --c.currRow; ++frag; } while ((tv & T_D) && !c.reachedEnd());
         } else if ((tv & T_MV) && (tv & T_V)) {
             if (!(last & T_V)) { record(c.currCol, c.currRow, frag, last); last = T_V; frag = 0; }
             if (aff) {

@@ -39,8 +39,10 @@ struct Planner {
     long zerosH = 0, zerosV = 0;    // pending _initiaizeBeginningOfBandedChain sizes
     bool ok = true;
     std::vector<GridDesc>& out;
+    std::vector<ColInfo>* colTab;
 
-    Planner(long h, long v, long band, std::vector<GridDesc>& o) : lenH(h), lenV(v), b(band), out(o) {}
+    Planner(long h, long v, long band, std::vector<GridDesc>& o, std::vector<ColInfo>* ct)
+        : lenH(h), lenV(v), b(band), out(o), colTab(ct) {}
 
     static long hShiftBegin(const ChainSeed& s) { return s.upperDiag - (s.beginH - s.beginV); }
     static long vShiftBegin(const ChainSeed& s) { return (s.beginH - s.beginV) - s.lowerDiag; }
@@ -76,6 +78,18 @@ struct Planner {
             if (lo <= -(long)g.nV && up >= (long)g.nH) { g.banded = 0; g.lo = 0; g.up = 0; }
         }
         if (kind == GRID_CHAIN_FINAL && !g.banded && (hNext != 0 || vNext != 0)) ok = false;
+        g.colTabOff = 0; g.nColTab = 0;
+        if (colTab && ok && g.banded && kind != GRID_GLOBAL) {
+            // literal column walk of _computeBandedAlignment; the tracking pass needs the columns right of
+            // the next grid's origin (seeds/banded_chain_alignment_impl.h:282-377)
+            g.colTabOff = (int32_t)colTab->size();
+            BandWalker w;
+            w.init(makeGeom(g.nH, g.nV, g.banded, g.lo, g.up));
+            ColInfo ci;
+            while (w.next(ci))
+                if (ci.j >= g.hNext) colTab->push_back(ci);
+            g.nColTab = (int32_t)colTab->size() - g.colTabOff;
+        }
         out.push_back(g);
     }
 
@@ -234,10 +248,11 @@ struct Planner {
 }  // namespace
 
 bool planChain(const std::vector<ChainSeed>& chain, long lenH, long lenV, long bandExtension,
-               std::vector<GridDesc>& grids) {
+               std::vector<GridDesc>& grids, std::vector<ColInfo>* colTab) {
     grids.clear();
+    if (colTab) colTab->clear();
     if (chain.empty() || lenH < 1 || lenV < 1) return false;
-    Planner p(lenH, lenV, bandExtension, grids);
+    Planner p(lenH, lenV, bandExtension, grids, colTab);
     p.run(chain);
     if (!p.ok) grids.clear();
     return p.ok;
@@ -263,6 +278,7 @@ bool planGlobal(long lenH, long lenV, bool banded, long lo, long up, bool freeFi
     if (banded && lo <= -lenV && up >= lenH) { g.banded = 0; g.lo = 0; g.up = 0; }
     g.hNext = 0; g.vNext = 0; g.capNextH = 0; g.capNextV = 0; g.plantZerosH = 0; g.plantZerosV = 0;
     g.glue = GLUE_ASSIGN; g.checkScore = 1;
+    g.colTabOff = 0; g.nColTab = 0;
     grids.push_back(g);
     return true;
 }

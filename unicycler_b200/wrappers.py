@@ -67,6 +67,8 @@ def load_library():
     L.ub200_lastTransferBytes.restype = None
     L.ub200_chainCells.argtypes = [c_int, c_int, POINTER(c_int64), c_int, c_int, POINTER(c_int)]
     L.ub200_chainCells.restype = c_int64
+    L.ub200_chainPlan.argtypes = [c_int, c_int, POINTER(c_int64), c_int, c_int, POINTER(ctypes.c_int32), c_int]
+    L.ub200_chainPlan.restype = c_int
     L.ub200_setDevice.argtypes = [c_int]
     L.ub200_setDevice.restype = c_int
     L.ub200_intPeakOpsPerSec.argtypes = []
@@ -243,6 +245,16 @@ def chain_cells(read_len, ref_len, seeds, band_size):
     n = c_int()
     cells = load_library().ub200_chainCells(read_len, ref_len, _seed_array(seeds), len(seeds), band_size, ctypes.byref(n))
     return cells, n.value
+
+
+def chain_plan(read_len, ref_len, seeds, band_size, cap=8192):
+    """Sub-DP plan of one banded-chain alignment: list of (kind, nH, nV, banded, lo, up, h0, v0)."""
+    L = load_library()
+    out = (ctypes.c_int32 * (8 * cap))()
+    k = L.ub200_chainPlan(read_len, ref_len, _seed_array(seeds), len(seeds), band_size, out, cap)
+    if k < 0:
+        return None
+    return [tuple(out[8 * i:8 * i + 8]) for i in range(min(k, cap))]
 
 
 def set_device(device):
