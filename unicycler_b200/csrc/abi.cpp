@@ -26,6 +26,7 @@
 #include "seeding.hpp"
 
 using namespace ub200;
+namespace ub200 { extern std::atomic<long long> g_seedProf[6]; }
 
 typedef std::unordered_map<std::string, std::string> SeqMap;  // include/ref_seqs.h:18
 
@@ -85,11 +86,20 @@ void parallelFor(int n, F f) {
     const char* e = getenv("UNICYCLER_B200_HOST_THREADS");
     if (e) threads = atoi(e);
     threads = std::max(1, std::min(threads, n));
-    if (threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
+    if (threads == 1) {
+        g_hostBusy.fetch_add(1);
+        for (int i = 0; i < n; ++i) f(i);
+        g_hostBusy.fetch_sub(1);
+        return;
+    }
     std::atomic<int> next(0);
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; ++t)
-        pool.emplace_back([&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i); });
+        pool.emplace_back([&]() {
+            g_hostBusy.fetch_add(1);  // a busy core: inner stages may only borrow the idle ones
+            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i);
+            g_hostBusy.fetch_sub(1);
+        });
     for (auto& th : pool) th.join();
 }
 
@@ -562,15 +572,31 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     std::vector<size_t> len((size_t)n);
     for (int i = 0; i < n; ++i) len[(size_t)i] = strlen(readSeqs[i]);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[(size_t)a] > len[(size_t)b]; });
+    std::vector<double> readMs((size_t)n, 0.0);
     parallelFor(n, [&](int k) {
         const int i = order[(size_t)k];
+        const double ta = nowSec();
         works[(size_t)i].reset(new ReadWork());
         prepareRead(*works[(size_t)i], readNames[i], readSeqs[i], 0, hits[i], (SeqMap*)refSeqs, sc, sensitivityLevel);
+        readMs[(size_t)i] = (nowSec() - ta) * 1e3;
     });
+    if (getenv("UNICYCLER_B200_HOST_ONLY")) {
+        std::vector<double> v = readMs;
+        std::sort(v.begin(), v.end());
+        double sum = 0; for (double x : v) sum += x;
+        fprintf(stderr, "[ub200 host] per-read prepare ms: max %.1f, 2nd %.1f, median %.1f, sum %.1f\n", v.back(), v.size() > 1 ? v[v.size() - 2] : 0.0, v[v.size() / 2], sum);
+    }
     std::vector<Job*> jobs;
     for (int i = 0; i < n; ++i)
         for (auto& cj : works[(size_t)i]->jobs) jobs.push_back(&cj->job);
     const double t1 = nowSec();
+    if (getenv("UNICYCLER_B200_HOST_ONLY")) {  // developer aid: time the host stage without a GPU
+        fprintf(stderr, "[ub200 host] reads=%d jobs=%zu prepare=%.1f ms (kmers %.1f, linetrace %.1f [fillCloud %.1f, densest point %.1f], seeds+chain %.1f thread-ms)\n", n,
+                jobs.size(), (t1 - t0) * 1e3, g_seedProf[0] / 1e6, g_seedProf[1] / 1e6, g_seedProf[3] / 1e6, g_seedProf[4] / 1e6, g_seedProf[2] / 1e6);
+        for (int q = 0; q < 6; ++q) g_seedProf[q] = 0;
+        for (int i = 0; i < n; ++i) results[i] = dupString("");
+        return 0;
+    }
     engine().run(jobs);
     const double t2 = nowSec();
     parallelFor(n, [&](int k) {

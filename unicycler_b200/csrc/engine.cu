@@ -1082,6 +1082,10 @@ void Engine::fetch(std::vector<Job*>& jobs) {
         }
         fprintf(stderr, "[ub200 profile] jobs=%zu agents=%d tasks=%d cycles: setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld total=%lld maxjob=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",
                 nJobs, I.kp.nSlots, I.kp.maxTasks, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], mx, tot[6], tot[7], tot[8], tot[9], tot[10], tot[11]);
+        unsigned long long dbg[8];
+        if (cudaMemcpyFromSymbol(dbg, gDbg, sizeof(dbg)) == cudaSuccess) {
+            fprintf(stderr, "[ub200 dbg] unbanded trace strips=%llu total=%llu steps-cycles=%llu nsteps=%llu | banded strips=%llu total=%llu steps-cycles=%llu nsteps=%llu (cumulative)\n", dbg[3], dbg[0], dbg[1], dbg[2], dbg[7], dbg[4], dbg[5], dbg[6]);
+        }
         const long long* wp = I.jobOut[worst].prof;
         fprintf(stderr, "[ub200 profile] worst job %zu (%d grids): setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",
                 worst, I.jobsDev[worst].gridCount, wp[0], wp[1], wp[2], wp[3], wp[4], wp[6], wp[7], wp[8], wp[9], wp[10], wp[11]);

@@ -131,6 +131,7 @@ struct KParams {
 // Launch parameters live in constant memory (a by-reference kernel argument would be copied to the
 // local-memory stack of every warp).
 __constant__ KParams cP;
+__device__ unsigned long long gDbg[8];   // developer counters (cycles), lane 0 of control warps
 
 // ---------------------------------------------------------------------------------------
 // memory-order helpers
@@ -423,6 +424,8 @@ __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEn
     constexpr int SHR = 32 * RR;
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
+    const long long dbg0 = clock64();
+    long long dbgSteps = 0;
     StripState<RR> st;
     const int i0 = s * SHR + lane * RR + 1;
     const int jlo = stripJlo(g, s, SHR);
@@ -499,17 +502,26 @@ __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEn
             if (G.capEdges) cap = ((s + 1) * SHR >= g.nV) || (jmaxChunk >= g.nH);
             else cap = (jmaxChunk >= G.hNext) && ((s + 1) * SHR >= G.boxRow0);
         }
+        const long long dbg1 = clock64();
         if (cap)
             stripSteps<AFF, CT, BANDED, RR, TRACE, true>(G, K, st, c, lane, cBeg, cEnd, i0, bS, bV, hcN, nsteps, win,
                                                          winPitch, rowOut, ckTile);
         else
             stripSteps<AFF, CT, BANDED, RR, TRACE, false>(G, K, st, c, lane, cBeg, cEnd, i0, bS, bV, hcN, nsteps, win,
                                                           winPitch, rowOut, ckTile);
+        dbgSteps += clock64() - dbg1;
         if (!TRACE) {
             // lane 31 has finished every column <= cBeg + 32c + 31 - 31 (and cEnd after the last chunk)
             const int done = imin(cEnd, cBeg + 32 * c + imin(31, nsteps - 1 - 32 * c) - 31);
             if (lane == 31 && done >= cBeg) stRelease(&G.rowProg[s], done);
         }
+    }
+    if (TRACE && lane == 0) {
+        const int o = BANDED ? 4 : 0;
+        atomicAdd(&gDbg[o + 0], (unsigned long long)(clock64() - dbg0));
+        atomicAdd(&gDbg[o + 1], (unsigned long long)dbgSteps);
+        atomicAdd(&gDbg[o + 2], (unsigned long long)nsteps);
+        atomicAdd(&gDbg[o + 3], 1ull);
     }
 }
 

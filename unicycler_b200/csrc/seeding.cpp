@@ -5,6 +5,11 @@
 // on purpose: several decisions sum doubles in container order.
 #include "seeding.hpp"
 
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <thread>
+
 #include <algorithm>
 #include <cmath>
 #include <limits>
@@ -14,6 +19,35 @@
 #include <unordered_set>
 
 namespace ub200 {
+
+// Host-core accounting shared with the per-read thread pool (abi.cpp): a stage may borrow cores that no
+// read-level task is using.
+std::atomic<int> g_hostBusy(0);
+static int hostCores() {
+    static const int n = [] {
+        const char* e = getenv("UNICYCLER_B200_HOST_THREADS");
+        int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+        return v < 1 ? 1 : v;
+    }();
+    return n;
+}
+int acquireSpareHostThreads(int want) {
+    for (;;) {
+        int busy = g_hostBusy.load();
+        int spare = hostCores() - busy;
+        int take = spare < want ? spare : want;
+        if (take <= 0) return 0;
+        if (g_hostBusy.compare_exchange_weak(busy, busy + take)) return take;
+    }
+}
+void releaseSpareHostThreads(int n) { g_hostBusy.fetch_sub(n); }
+
+// developer timers of the host seeding stages (seconds, summed over threads)
+std::atomic<long long> g_seedProf[6];
+static inline long long nowNs() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 
 // include/settings.h
 static const int LINE_TRACING_START_POINT_SEARCH_RADIUS = 100;
@@ -34,10 +68,60 @@ SensitivityParams sensitivityParams(int level) {
     return p;
 }
 
+namespace {
+inline int baseCode(char c) {  // upper-case ACGT -> 0..3, anything else -> -1
+    switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return -1; }
+}
+inline uint32_t kmerHash(uint32_t code) { return (code * 2654435761u) >> 7; }
+
+// Calls f(i, clean, code) for every k-mer start i of seq: clean k-mers carry their 2-bit code.
+template <typename F>
+inline void forEachKmer(const std::string& seq, int k, F f) {
+    const int n = (int)seq.size() - k + 1;
+    if (n <= 0) return;
+    const uint32_t codeMask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+    uint32_t code = 0;
+    int run = 0;  // number of consecutive clean characters ending at the current one
+    for (int p = 0; p < (int)seq.size(); ++p) {
+        const int b = baseCode(seq[(size_t)p]);
+        if (b < 0) { run = 0; code = 0; }
+        else { ++run; code = ((code << 2) | (uint32_t)b) & codeMask; }
+        const int i = p - k + 1;
+        if (i >= 0) f(i, run >= k, code);
+    }
+}
+}  // namespace
+
 void buildKmerPositions(const std::string& sequence, int kSize, KmerPosMap& out) {
-    out.clear();
-    int kCount = (int)sequence.size() - kSize + 1;
-    for (int i = 0; i < kCount; ++i) out[sequence.substr((size_t)i, (size_t)kSize)].push_back(i);
+    out = KmerPosMap();
+    out.k = kSize;
+    const int kCount = (int)sequence.size() - kSize + 1;
+    if (kCount <= 0) return;
+    if (kSize > 16) {  // codes would not fit 32 bits: literal keys only (never the case for sensitivity 0..3)
+        for (int i = 0; i < kCount; ++i) out.other[sequence.substr((size_t)i, (size_t)kSize)].push_back(i);
+        return;
+    }
+    uint32_t slots = 16;
+    while (slots < (uint32_t)kCount * 2u) slots <<= 1;
+    out.mask = slots - 1;
+    out.head.assign(slots, -1);
+    out.key.assign(slots, 0);
+    out.next.assign((size_t)kCount, -1);
+    // lists are built back to front so that they read in ascending position order
+    std::vector<uint32_t> codes((size_t)kCount);
+    std::vector<uint8_t> clean((size_t)kCount);
+    forEachKmer(sequence, kSize, [&](int i, bool ok, uint32_t code) { codes[(size_t)i] = code; clean[(size_t)i] = ok; });
+    for (int i = kCount - 1; i >= 0; --i) {
+        if (!clean[(size_t)i]) continue;
+        const uint32_t code = codes[(size_t)i];
+        uint32_t sl = kmerHash(code) & out.mask;
+        while (out.head[sl] != -1 && out.key[sl] != code) sl = (sl + 1) & out.mask;
+        out.key[sl] = code;
+        out.next[(size_t)i] = out.head[sl];
+        out.head[sl] = i;
+    }
+    for (int i = 0; i < kCount; ++i)
+        if (!clean[(size_t)i]) out.other[sequence.substr((size_t)i, (size_t)kSize)].push_back(i);
 }
 
 std::string reverseComplement(const std::string& s) {
@@ -370,12 +454,34 @@ double getPointDensityScore(int radius, Point p, const Cloud& cloud) {
 }
 
 Point getHighestDensityPoint(int radius, const Cloud& cloud) {
+    // Every point's score is independent; the winner is the first strictly greater score in cloud order
+    // (semi_global_align.cpp:577-589), so the scores can be computed on spare host cores and scanned in order.
+    const size_t n = cloud.pts.size();
+    std::vector<double> score(n);
+    int helpers = 0;
+    if (n >= 2048) helpers = acquireSpareHostThreads(7);
+    if (helpers == 0) {
+        for (size_t i = 0; i < n; ++i) score[i] = getPointDensityScore(radius, cloud.pts[i], cloud);
+    } else {
+        std::atomic<size_t> next(0);
+        auto work = [&]() {
+            for (;;) {
+                const size_t b = next.fetch_add(256);
+                if (b >= n) break;
+                const size_t e = std::min(n, b + 256);
+                for (size_t i = b; i < e; ++i) score[i] = getPointDensityScore(radius, cloud.pts[i], cloud);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < helpers; ++t) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+        releaseSpareHostThreads(helpers);
+    }
     Point best = cloud.pts[0];
     double bestScore = 0.0;
-    for (const Point& p : cloud.pts) {
-        double s = getPointDensityScore(radius, p, cloud);
-        if (s > bestScore) { bestScore = s; best = p; }
-    }
+    for (size_t i = 0; i < n; ++i)
+        if (score[i] > bestScore) { bestScore = score[i]; best = cloud.pts[i]; }
     return best;
 }
 
@@ -422,8 +528,12 @@ double scorePointSet(const PointSet& pointSet, const PointVector& traceDots, boo
 PointSet lineTracing(const PointVector& common, PointSet& usedPoints, const Cloud& cloud, int readLen, int refLen,
                      int lineNum, int verbosity, std::string& console, bool& failedLine, double& pointSetScore) {
     Cloud startCloud;
+    const long long tA = nowNs();
     fillCloud(startCloud, common, usedPoints);
+    const long long tB = nowNs();
     Point startPoint = getHighestDensityPoint(LINE_TRACING_START_POINT_SEARCH_RADIUS, startCloud);
+    g_seedProf[3] += tB - tA;
+    g_seedProf[4] += nowNs() - tB;
     Point p = startPoint;
     PointVector traceDots;
     traceDots.push_back(p);
@@ -599,18 +709,39 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
     if (verbosity > 2)
         out.console += "Range: " + refName + ": " + std::to_string(refStart) + " - " + std::to_string(refEnd) + "\n";
     // common k-mers :197-207
+    const long long t0 = nowNs();
     PointVector common;
-    const int maxI = refLen - kSize + 1;
-    std::string kmer;
-    for (int i = 0; i < maxI; ++i) {
-        kmer.assign(trimmedRefSeq, (size_t)i, (size_t)kSize);
-        KmerPosMap::const_iterator it = readKmers.find(kmer);
-        if (it != readKmers.end())
-            for (int pos : it->second) common.push_back(Point(pos, i));
+    if (readKmers.k != kSize) return;
+    if (kSize > 16) {
+        const int maxI = refLen - kSize + 1;
+        std::string kmer;
+        for (int i = 0; i < maxI; ++i) {
+            kmer.assign(trimmedRefSeq, (size_t)i, (size_t)kSize);
+            auto it = readKmers.other.find(kmer);
+            if (it != readKmers.other.end())
+                for (int pos : it->second) common.push_back(Point(pos, i));
+        }
+    } else {
+        std::string kmer;
+        forEachKmer(trimmedRefSeq, kSize, [&](int i, bool ok, uint32_t code) {
+            if (ok) {
+                if (readKmers.head.empty()) return;
+                uint32_t sl = kmerHash(code) & readKmers.mask;
+                while (readKmers.head[sl] != -1 && readKmers.key[sl] != code) sl = (sl + 1) & readKmers.mask;
+                for (int pos = readKmers.head[sl]; pos != -1; pos = readKmers.next[(size_t)pos]) common.push_back(Point(pos, i));
+            } else if (!readKmers.other.empty()) {
+                kmer.assign(trimmedRefSeq, (size_t)i, (size_t)kSize);
+                auto it = readKmers.other.find(kmer);
+                if (it != readKmers.other.end())
+                    for (int pos : it->second) common.push_back(Point(pos, i));
+            }
+        });
     }
     if (verbosity > 2)
         out.console += "    common " + std::to_string(kSize) + "-mers: " + std::to_string(common.size()) + "\n";
     if (common.empty()) return;  // the reference dereferences an empty vector here (undefined); no alignment
+    const long long t1 = nowNs();
+    g_seedProf[0] += t1 - t0;
     PointSet usedPoints;
     Cloud cloud;
     fillCloud(cloud, common, usedPoints);
@@ -627,6 +758,9 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
         if (!failedLine && lineNum >= sp.minLineTraceCount - 1) break;
         if (usedPoints.size() >= common.size()) break;
     }
+    const long long t2 = nowNs();
+    g_seedProf[1] += t2 - t1;
+    struct Fin { long long t; ~Fin() { g_seedProf[2] += nowNs() - t; } } fin{t2};
     for (const PointSet& good : goodPointSets) {
         PointVector pts;
         pts.reserve(good.size());

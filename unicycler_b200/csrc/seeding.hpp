@@ -3,6 +3,8 @@
 // reference's runtime and floating-point / container-order sensitive, so it stays on the host and keeps
 // the reference's container types and iteration orders (SURVEY.md §7 hard part 4).
 #pragma once
+#include <atomic>
+#include <cstdint>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -11,7 +13,18 @@
 
 namespace ub200 {
 
-typedef std::unordered_map<std::string, std::vector<int> > KmerPosMap;  // include/kmers.h:26
+// All k-mer start positions of a read (KmerPositions, include/kmers.h:26 / src/kmers.cpp:51-65).  The
+// reference keys an unordered_map by the k-mer STRING; only the per-k-mer position lists (ascending) are ever
+// observed, so k-mers made of upper-case ACGT only are keyed by their 2-bit code in an open-addressing table
+// and every other k-mer (N, lower case, ...) keeps the literal string key.
+struct KmerPosMap {
+    int k = 0;
+    uint32_t mask = 0;
+    std::vector<int32_t> head;   // slot -> first position, -1 = empty
+    std::vector<uint32_t> key;   // slot -> 2-bit code
+    std::vector<int32_t> next;   // position -> next position with the same k-mer
+    std::unordered_map<std::string, std::vector<int> > other;
+};
 
 struct SensitivityParams {  // include/settings.h:17-42
     int kSize, bandSize, minLineTraceCount, maxLineTraceCount;
@@ -33,6 +46,12 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
                const SensitivityParams& sp, int verbosity, const std::string& refName, int refStart, int refEnd,
                RangeSeeds& out);
 
-std::string reverseComplement(const std::string& s);  // src/string_functions.cpp:52-79
+std::string reverseComplement(const std::string& s);
+
+// Host-core accounting: read-level tasks register themselves as busy; inner loops may borrow idle cores.
+extern std::atomic<int> g_hostBusy;
+int acquireSpareHostThreads(int want);
+void releaseSpareHostThreads(int n);
+  // src/string_functions.cpp:52-79
 
 }  // namespace ub200
