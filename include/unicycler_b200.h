@@ -113,7 +113,7 @@ void ub200_lastTransferBytes(int64_t* h2d, int64_t* d2h, int64_t* traceBytes, in
 /* Reference DP-cell count and sub-DP count of one banded-chain alignment; planner only. */
 int64_t ub200_chainCells(int readLen, int refLen, const int64_t* seeds, int nSeeds, int bandSize, int* nGrids);
 
-/* Planner introspection: 8 int32 per sub-DP (kind, nH, nV, banded, lo, up, h0, v0) into out (cap grids);
+/* Planner introspection: 10 int32 per sub-DP (kind, nH, nV, banded, lo, up, h0, v0, hNext, vNext) into out (cap grids);
  * returns the number of sub-DPs of the banded-chain alignment, -1 if the chain is unsupported. */
 int ub200_chainPlan(int readLen, int refLen, const int64_t* seeds, int nSeeds, int bandSize, int32_t* out, int cap);
 

@@ -524,7 +524,7 @@ int64_t ub200_chainCells(int readLen, int refLen, const int64_t* seeds, int nSee
     return cells;
 }
 
-// Planner introspection: writes 8 int32 per sub-DP (kind, nH, nV, banded, lo, up, h0, v0); returns the grid count.
+// Planner introspection: writes 10 int32 per sub-DP (kind, nH, nV, banded, lo, up, h0, v0, hNext, vNext); returns the grid count.
 int ub200_chainPlan(int readLen, int refLen, const int64_t* seeds, int nSeeds, int bandSize, int32_t* out, int cap) {
     std::vector<ChainSeed> chain;
     seedsFromArray(seeds, nSeeds, chain);
@@ -532,8 +532,9 @@ int ub200_chainPlan(int readLen, int refLen, const int64_t* seeds, int nSeeds, i
     if (!planChain(chain, readLen, refLen, bandSize, grids)) return -1;
     for (size_t k = 0; k < grids.size() && (int)k < cap; ++k) {
         const GridDesc& g = grids[k];
-        int32_t* o = out + 8 * k;
+        int32_t* o = out + 10 * k;
         o[0] = g.kind; o[1] = g.nH; o[2] = g.nV; o[3] = g.banded; o[4] = g.lo; o[5] = g.up; o[6] = g.h0; o[7] = g.v0;
+        o[8] = g.hNext; o[9] = g.vNext;
     }
     return (int)grids.size();
 }

@@ -221,7 +221,7 @@ UB_HD TrackOpts chainTrackingOptions(int32_t ch, int32_t cv, int32_t tLeap, int3
 constexpr int32_t SH = 256;              // strip height of task grids (32 lanes x 8 rows)
 constexpr int32_t CKW = 64;              // column-checkpoint spacing == recompute tile width
 constexpr int32_t SEG = 1024;            // columns per work item
-constexpr int32_t WINBYTES = 24 * 1024;  // shared-memory trace window per control warp
+constexpr int32_t WINBYTES = 46 * 1024;  // shared-memory window per control warp (trace bytes, or the pass-1 box)
 
 // first / last column of strip s (rows s*SHR+1 .. (s+1)*SHR) that holds band cells
 UB_HD int32_t stripJlo(const GridGeom& g, int32_t s, int32_t SHR) { return g.banded ? imax(1, s * SHR + 1 + g.lo) : 1; }

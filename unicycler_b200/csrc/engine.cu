@@ -23,7 +23,7 @@ namespace ub200 {
 // (the control agent of the job); G lives in that warp's shared-memory slot.
 // ---------------------------------------------------------------------------------------
 
-__device__ __noinline__ void setupGrid(GridCtx& G, const JobDev& jb, const GridDesc& gd, uint8_t* arena) {
+__device__ __noinline__ void setupGrid(GridCtx& G, const JobDev& jb, const GridDesc& gd, uint8_t* arena, uint8_t* fastSeq = nullptr) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     if (lane == 0) {
@@ -67,6 +67,19 @@ __device__ __noinline__ void setupGrid(GridCtx& G, const JobDev& jb, const GridD
             G.boxW = imax(0, g.nH - G.hNext + 1);
         } else {
             G.boxRow0 = 0; G.boxH = 0; G.boxW = 0;
+        }
+        // pass-1 fast mode: chain grids with a successor whose box (one extra row / column for the neighbours
+        // of its first cells) fits the shared-memory window as (S,H,V) triples
+        G.fastOk = 0; G.fastR0 = 1; G.fastC0 = 1; G.fastPitch = 1;
+        G.fastSeqH = fastSeq; G.fastSeqV = fastSeq ? fastSeq + FASTSEQ_H : nullptr;
+        if (P.fastEnabled && fastSeq && lp.local && !G.capEdges && (gd.kind == GRID_CHAIN_INITIAL || gd.kind == GRID_CHAIN_INNER) &&
+            G.boxW > 0) {
+            G.fastR0 = imax(1, G.boxRow0 - 1);
+            G.fastC0 = imax(1, G.hNext - 1);
+            G.fastPitch = g.nV - G.fastR0 + 1;
+            const long long cells = (long long)G.fastPitch * (g.nH - G.fastC0 + 1);
+            G.fastOk = (G.fastPitch > 0 && cells > 0 && cells * (long long)sizeof(DCell) <= (long long)WINBYTES &&
+                        g.nH - G.fastC0 + 1 <= FASTSEQ_H && G.fastPitch <= FASTSEQ_V) ? 1 : 0;
         }
     }
     __syncwarp();
@@ -275,11 +288,18 @@ __device__ __forceinline__ DCell trackedCell(const GridCtx& G, int i, int j) {
     if (G.capEdges) return (i == G.g.nV) ? G.lastRow[j] : G.lastCol[i];
     return G.box[(size_t)(j - G.hNext) * G.boxH + (i - G.boxRow0)];
 }
+// pass-1 fast mode: the box lives in the shared-memory window
+__device__ __forceinline__ DCell trackedCellFast(const GridCtx& G, const DCell* boxS, int i, int j) {
+    if (j == 0) return G.initCol[i];
+    if (i == 0) return G.initRow[j];
+    return boxS[(j - G.fastC0) * G.fastPitch + (i - G.fastR0)];
+}
 
 // Tracking pass for banded-chain grids (one warp): stores the next grid's init row/column, finds
 // the maximum over the tracked cells and collects every tied maximum in visiting order
 // (seeds/banded_chain_alignment_scout.h:230-270).  Visiting order == ascending host position.
-__device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res) {
+template <bool FAST>
+__device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res, const DCell* boxS) {
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     int ub = 0;
@@ -289,7 +309,7 @@ __device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res) {
     int best = INT32_MIN;
     forEachFlaggedCell(G, nCols, [&](bool valid, int i, int j, int cv, const TrackOpts& o) {
         if (!valid) return;
-        const DCell c = trackedCell(G, i, j);
+        const DCell c = FAST ? trackedCellFast(G, boxS, i, j) : trackedCell(G, i, j);
         if (o.storeCol) { int k = cv - G.vNext; if (k >= 0 && k < G.capNextV) G.vInitNext[k] = c; else ub = 1; }
         if (o.storeRow) { int k = j - G.hNext; if (k >= 0 && k < G.capNextH) G.hInitNext[k] = c; else ub = 1; }
         if (o.lastCol || o.lastRow) best = max(best, c.s);
@@ -299,7 +319,7 @@ __device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res) {
     int count = 0;
     forEachFlaggedCell(G, nCols, [&](bool valid, int i, int j, int cv, const TrackOpts& o) {
         bool hit = false;
-        if (valid && (o.lastCol || o.lastRow)) hit = (trackedCell(G, i, j).s == best);
+        if (valid && (o.lastCol || o.lastRow)) hit = ((FAST ? trackedCellFast(G, boxS, i, j) : trackedCell(G, i, j)).s == best);
         const unsigned m = __ballot_sync(FULLMASK, hit);
         if (hit) {
             const int k = count + __popc(m & ((1u << lane) - 1u));
@@ -369,11 +389,66 @@ __device__ __noinline__ void trackGlobal(const GridCtx& G, TrackResult& res) {
     __syncwarp();
 }
 
+// Crossing cell of a chain traceback -> next grid's initialisation cell
+// (seeds/banded_chain_alignment_traceback.h:296-322).  Returns true when the cell was inserted into
+// _nextInitializationCells (the std::set of the reference).  Warp-uniform; lane 0 writes.
+__device__ __forceinline__ bool plantCrossing(const GridCtx& G, int hInit, int vInit, uint32_t last, int& nPlanted,
+                                              int& status) {
+    const int lane = threadIdx.x & 31;
+    const bool affine = G.affine;
+    bool inserted = false;
+    DCell* cellPtr = nullptr;
+    int i1, i2;
+    if (vInit <= 0) {
+        if (hInit < 0 || hInit >= G.capNextH) status = JOB_REF_UB;
+        else cellPtr = &G.hInitNext[hInit];
+        i1 = hInit; i2 = 0;
+    } else {
+        if (vInit >= G.capNextV) status = JOB_REF_UB;
+        else cellPtr = &G.vInitNext[vInit];
+        i1 = 0; i2 = vInit;
+    }
+    if (cellPtr) {
+        DCell cell = *cellPtr;
+        if (affine) {  // _correctDPCellForAffineGaps, traceback.h:211-231
+            if (last & T_D) { cell.v = NEG_INF; cell.h = NEG_INF; }
+            else if (last & T_V) cell.h = NEG_INF;
+            else cell.v = NEG_INF;
+        }
+        __syncwarp();
+        if (lane == 0) *cellPtr = cell;
+        // std::set<Triple<unsigned, unsigned, DPCell>>::insert: same position => equivalent
+        // unless one cell is component-wise smaller (dp_cell_affine.h:113-118)
+        bool dup = false;
+        for (int k = 0; k < nPlanted; ++k) {
+            PlantedCell pcell = G.planted[k];
+            if (pcell.i1 == i1 && pcell.i2 == i2) {
+                bool lt, gt;
+                if (affine) {
+                    lt = cell.s < pcell.c.s && cell.h < pcell.c.h && cell.v < pcell.c.v;
+                    gt = pcell.c.s < cell.s && pcell.c.h < cell.h && pcell.c.v < cell.v;
+                } else { lt = cell.s < pcell.c.s; gt = pcell.c.s < cell.s; }
+                if (!lt && !gt) { dup = true; break; }
+            }
+        }
+        if (!dup) {
+            if (nPlanted < G.maxPlanted) {
+                if (lane == 0) G.planted[nPlanted] = PlantedCell{i1, i2, cell};
+                ++nPlanted;
+                inserted = true;
+            } else status = JOB_REF_UB;
+        }
+        __syncwarp();
+    }
+    return inserted;
+}
+
 // One candidate of a banded-chain grid (seeds/banded_chain_alignment_traceback.h:233-355).
 // Warp-uniform: every lane of the control warp executes it; lane 0 writes.
+// REPLAY (pass 2): the crossing cell was planted by pass 1; `insertedIn` is its verdict.
+template <bool REPLAY>
 __device__ __forceinline__ void chainTracebackOne(const GridCtx& G, TraceWalker& w, OutStream& out, int startPos,
-                                               int& nPlanted, int& nTraces, int& status) {
-    const int lane = threadIdx.x & 31;
+                                                  bool insertedIn, int& nPlanted, int& nTraces, int& status) {
     const bool affine = G.affine;
     const bool prefer = affine && G.kind == GRID_CHAIN_FINAL;
     w.pc = startPos / G.g.dimV;
@@ -397,50 +472,7 @@ __device__ __forceinline__ void chainTracebackOne(const GridCtx& G, TraceWalker&
         w.emitOn = true;
         const int hInit = c.currCol - c.endCol;
         const int vInit = c.currRow - c.endRow;
-        bool inserted = false;
-        DCell* cellPtr = nullptr;
-        int i1, i2;
-        if (vInit <= 0) {
-            if (hInit < 0 || hInit >= G.capNextH) status = JOB_REF_UB;
-            else cellPtr = &G.hInitNext[hInit];
-            i1 = hInit; i2 = 0;
-        } else {
-            if (vInit >= G.capNextV) status = JOB_REF_UB;
-            else cellPtr = &G.vInitNext[vInit];
-            i1 = 0; i2 = vInit;
-        }
-        if (cellPtr) {
-            DCell cell = *cellPtr;
-            if (affine) {  // _correctDPCellForAffineGaps, traceback.h:211-231
-                if (last & T_D) { cell.v = NEG_INF; cell.h = NEG_INF; }
-                else if (last & T_V) cell.h = NEG_INF;
-                else cell.v = NEG_INF;
-            }
-            __syncwarp();
-            if (lane == 0) *cellPtr = cell;
-            // std::set<Triple<unsigned, unsigned, DPCell>>::insert: same position => equivalent
-            // unless one cell is component-wise smaller (dp_cell_affine.h:113-118)
-            bool dup = false;
-            for (int k = 0; k < nPlanted; ++k) {
-                PlantedCell pcell = G.planted[k];
-                if (pcell.i1 == i1 && pcell.i2 == i2) {
-                    bool lt, gt;
-                    if (affine) {
-                        lt = cell.s < pcell.c.s && cell.h < pcell.c.h && cell.v < pcell.c.v;
-                        gt = pcell.c.s < cell.s && pcell.c.h < cell.h && pcell.c.v < cell.v;
-                    } else { lt = cell.s < pcell.c.s; gt = pcell.c.s < cell.s; }
-                    if (!lt && !gt) { dup = true; break; }
-                }
-            }
-            if (!dup) {
-                if (nPlanted < G.maxPlanted) {
-                    if (lane == 0) G.planted[nPlanted] = PlantedCell{i1, i2, cell};
-                    ++nPlanted;
-                    inserted = true;
-                } else status = JOB_REF_UB;
-            }
-            __syncwarp();
-        }
+        const bool inserted = REPLAY ? insertedIn : plantCrossing(G, hInit, vInit, last, nPlanted, status);
         if (inserted) {
             if (vInit < 0) w.record(c.currCol, c.currRow, -vInit, last);
             else if (hInit < 0) w.record(c.currCol, c.currRow, -hInit, last);
@@ -464,26 +496,51 @@ __device__ __forceinline__ void chainTracebackOne(const GridCtx& G, TraceWalker&
 }
 
 struct TbResult {
-    int status, outLen, nPlanted, pad;
+    int status, nPlanted, pad0, pad1;
     long long tiles, tileCycles;
 };
 
-// All tracebacks of one grid (walker and output cursor live in registers of this function).
-__device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, int* outBuf, int outCap, int outLen, int gi,
-                                               int h0, int v0, int nCand, DCell maxCell) {
+// Reserves `n` ints of the job's segment stream; returns the start or -1 on overflow.
+__device__ __forceinline__ int reserveOut(int jobIdx, int outCap, int n) {
     const int lane = threadIdx.x & 31;
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(&cP.jobState[jobIdx].outCursor, n);
+    pos = __shfl_sync(FULLMASK, pos, 0);
+    if (pos < 0 || pos + n > outCap) return -1;
+    return pos;
+}
+// worst-case size of one grid's record: header + per trace (count + segments; a trace has at most
+// nH + nV + 4 segments of 4 ints)
+__device__ __forceinline__ int recordBound(const GridCtx& G, int nTraces) {
+    long long n = 3 + (long long)nTraces * (1 + 4LL * ((long long)G.g.nH + G.g.nV + 6));
+    return n > 0x3fffffff ? 0x3fffffff : (int)n;
+}
+
+// All tracebacks of one grid into a reserved record [gi, nTraces, reserved, traces...] (walker and output
+// cursor live in registers of this function).  rec == nullptr: pass-1 in-line grid (plants the next grid's
+// cells); otherwise the pass-2 replay of a recorded grid.
+__device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, int jobIdx, int* outBuf, int outCap, int gi,
+                                               int h0, int v0, int nCand, DCell maxCell, const GridRec* rec) {
+    const int lane = threadIdx.x & 31;
+    TbResult r;
+    r.status = JOB_OK; r.nPlanted = 0; r.pad0 = r.pad1 = 0; r.tiles = 0; r.tileCycles = 0;
+    const int nTr = (G.kind == GRID_GLOBAL) ? 1 : nCand;
+    const int reserved = recordBound(G, nTr);
+    const int pos = reserveOut(jobIdx, outCap, reserved);
+    if (pos < 0) { r.status = JOB_OUT_OVERFLOW; return r; }
     OutStream out;
-    out.buf = outBuf; out.cap = outCap; out.len = outLen; out.overflow = false;
+    out.buf = outBuf; out.cap = pos + reserved; out.len = pos; out.overflow = false;
     out.h0 = h0; out.v0 = v0; out.lane = lane;
     int status = JOB_OK, nPlanted = 0;
     out.put(gi);
     const int cntPos = out.len;
     out.put(0);
+    out.put(reserved);
     int nTraces = 0;
     TraceWalker w(G, out, win);
     if (G.kind == GRID_GLOBAL) {
-        const int pos = G.cand[0];
-        w.pc = pos / G.g.dimV; w.pv = pos % G.g.dimV;
+        const int pos0 = G.cand[0];
+        w.pc = pos0 / G.g.dimV; w.pv = pos0 % G.g.dimV;
         const int hdr = out.len; out.put(0);
         int tvOverride = -1;
         if (!G.complete && G.affine) {  // _correctTraceValue
@@ -496,42 +553,103 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, i
         if (w.bad) status = JOB_REF_UB;
         out.patch(hdr, w.nSegs);
         nTraces = 1;
+    } else if (rec == nullptr) {
+        for (int k = 0; k < nCand && status == JOB_OK; ++k)
+            chainTracebackOne<false>(G, w, out, G.cand[k], false, nPlanted, nTraces, status);
     } else {
         for (int k = 0; k < nCand && status == JOB_OK; ++k)
-            chainTracebackOne(G, w, out, G.cand[k], nPlanted, nTraces, status);
+            chainTracebackOne<true>(G, w, out, rec->cand[k], (rec->inserted >> k) & 1, nPlanted, nTraces, status);
     }
     out.patch(cntPos, nTraces);
     if (out.overflow && status == JOB_OK) status = JOB_OUT_OVERFLOW;
     __syncwarp();
-    TbResult r;
-    r.status = status; r.outLen = out.len; r.nPlanted = nPlanted; r.pad = 0;
+    r.status = status; r.nPlanted = nPlanted;
     r.tiles = w.tilesComputed; r.tileCycles = w.tileCycles;
     return r;
+}
+
+// Pass 1 of a fast grid: for every tied maximum walk (trace values derived on demand from the box) to the
+// crossing with the next grid's origin and plant the crossing cell.  Returns false when the walk left the
+// box (a gap run crossing the origin line): the caller falls back to the in-line path.
+__device__ __noinline__ bool fastShortWalks(const GridCtx& G, uint8_t* win, int nCand, int& nPlanted, int& insertedMask,
+                                            int& status) {
+    OutStream out;
+    out.buf = nullptr; out.cap = 0; out.len = 0; out.overflow = false; out.h0 = 0; out.v0 = 0; out.lane = 1;  // never writes
+    TraceWalker w(G, out, win);
+    w.lazy = true;
+    w.emitOn = false;
+    insertedMask = 0;
+    nPlanted = 0;
+    const long long dbgT0 = clock64();
+    long long dbgPlant = 0;
+    for (int k = 0; k < nCand && status == JOB_OK; ++k) {
+        const int startPos = G.cand[k];
+        w.pc = startPos / G.g.dimV;
+        w.pv = startPos % G.g.dimV;
+        uint32_t tv = w.tvHere();
+        uint32_t last = TraceWalker::initialDirection(tv, false);
+        Coord c = w.makeCoord(G.hNext, G.vNext);
+        int frag = 0;
+        while (!c.reachedEnd() && tv != T_NONE) w.doTraceback(tv, last, frag, c);
+        if (w.outOfBox) return false;
+        if (w.bad) { status = JOB_REF_UB; break; }
+        const int hInit = c.currCol - c.endCol;
+        const int vInit = c.currRow - c.endRow;
+        const long long dbgP0 = clock64();
+        if (plantCrossing(G, hInit, vInit, last, nPlanted, status)) insertedMask |= 1 << k;
+        dbgPlant += clock64() - dbgP0;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&gDbg[8], (unsigned long long)(clock64() - dbgT0));
+        atomicAdd(&gDbg[9], (unsigned long long)dbgPlant);
+        atomicAdd(&gDbg[10], (unsigned long long)w.tilesComputed);
+        atomicAdd(&gDbg[11], (unsigned long long)nCand);
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------
 // fills
 // ---------------------------------------------------------------------------------------
-template <bool AFF, bool CT, bool BANDED>
-__device__ __forceinline__ void localFillRR(const GridCtx& G, uint8_t* win) {
+template <bool AFF, bool CT, bool BANDED, int MODE>
+__device__ __forceinline__ void localFillRR(const GridCtx& G, uint8_t* win, bool capture) {
     const int lanes = (G.g.nV + G.RR - 1) / G.RR;
     const int nsteps = G.localJhi + lanes - 1;
     switch (G.RR) {
-    case 2: runStrip<AFF, CT, BANDED, 2, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch); break;
-    case 3: runStrip<AFF, CT, BANDED, 3, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch); break;
-    case 4: runStrip<AFF, CT, BANDED, 4, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch); break;
-    default: runStrip<AFF, CT, BANDED, 8, true>(G, 0, 1, G.localJhi, false, nsteps, true, win, G.pitch); break;
+    case 2: runStrip<AFF, CT, BANDED, 2, MODE>(G, 0, 1, G.localJhi, false, nsteps, capture, win, G.pitch); break;
+    case 3: runStrip<AFF, CT, BANDED, 3, MODE>(G, 0, 1, G.localJhi, false, nsteps, capture, win, G.pitch); break;
+    case 4: runStrip<AFF, CT, BANDED, 4, MODE>(G, 0, 1, G.localJhi, false, nsteps, capture, win, G.pitch); break;
+    default: runStrip<AFF, CT, BANDED, 8, MODE>(G, 0, 1, G.localJhi, false, nsteps, capture, win, G.pitch); break;
     }
 }
 template <bool AFF, bool CT>
-__device__ __forceinline__ void localFillBand(const GridCtx& G, uint8_t* win) {
-    if (G.g.banded) localFillRR<AFF, CT, true>(G, win);
-    else localFillRR<AFF, CT, false>(G, win);
+__device__ __forceinline__ void localFillBand(const GridCtx& G, uint8_t* win, bool capture) {
+    if (G.g.banded) localFillRR<AFF, CT, true, MODE_TRACE>(G, win, capture);
+    else localFillRR<AFF, CT, false, MODE_TRACE>(G, win, capture);
 }
 // Small grid: the control warp fills it with the full trace in its shared-memory window.
-__device__ __forceinline__ void localFill(const GridCtx& G, uint8_t* win) {
-    if (G.affine) { if (G.complete) localFillBand<true, true>(G, win); else localFillBand<true, false>(G, win); }
-    else { if (G.complete) localFillBand<false, true>(G, win); else localFillBand<false, false>(G, win); }
+__device__ __forceinline__ void localFill(const GridCtx& G, uint8_t* win, bool capture) {
+    if (G.affine) { if (G.complete) localFillBand<true, true>(G, win, capture); else localFillBand<true, false>(G, win, capture); }
+    else { if (G.complete) localFillBand<false, true>(G, win, capture); else localFillBand<false, false>(G, win, capture); }
+    __syncwarp();
+}
+// Pass-1 fast mode: score-only fill, the box cells (S,H,V) go to the shared-memory window.
+__device__ __forceinline__ void localFillFast(const GridCtx& G, uint8_t* win) {
+    {   // stage the base codes of the box rows / columns for the lazy trace derivation
+        const int lane = threadIdx.x & 31;
+        uint8_t* sh = const_cast<uint8_t*>(G.fastSeqH);
+        uint8_t* sv = const_cast<uint8_t*>(G.fastSeqV);
+        const int nc = G.g.nH - G.fastC0 + 1, nr = G.fastPitch;
+        for (int c = lane; c < nc; c += 32) sh[c] = G.seqH[G.fastC0 + c - 1];
+        for (int r = lane; r < nr; r += 32) sv[r] = G.seqV[G.fastR0 + r - 1];
+    }
+    if (G.affine) {
+        if (G.g.banded) localFillRR<true, false, true, MODE_FAST>(G, win, true);
+        else localFillRR<true, false, false, MODE_FAST>(G, win, true);
+    } else {
+        if (G.g.banded) localFillRR<false, false, true, MODE_FAST>(G, win, true);
+        else localFillRR<false, false, false, MODE_FAST>(G, win, true);
+    }
     __syncwarp();
 }
 
@@ -554,11 +672,11 @@ __device__ __noinline__ void runItem(const GridCtx& G, int item) {
     }
     const int nsteps = (cEnd - cBeg + 1) + 31;
     if (G.affine) {
-        if (g.banded) runStrip<true, false, true, 8, false>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
-        else runStrip<true, false, false, 8, false>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
+        if (g.banded) runStrip<true, false, true, 8, MODE_TASK>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
+        else runStrip<true, false, false, 8, MODE_TASK>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
     } else {
-        if (g.banded) runStrip<false, false, true, 8, false>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
-        else runStrip<false, false, false, 8, false>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
+        if (g.banded) runStrip<false, false, true, 8, MODE_TASK>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
+        else runStrip<false, false, false, 8, MODE_TASK>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
     }
     __threadfence();
     __syncwarp();
@@ -654,69 +772,209 @@ __device__ __noinline__ int publishAndWait(const GridCtx& G, GridCtx& wctx, int&
 }
 
 // ---------------------------------------------------------------------------------------
-// one job, start to end, on one control warp
+// pass 2: one recorded grid, start to end, on any control-capable warp
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& G, GridCtx& wctx, int& wTask, uint8_t* win, uint8_t* arena) {
+__device__ __noinline__ void runPass2Grid(int jobIdx, int gi, GridCtx& G, uint8_t* win, uint8_t* mini) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     const JobDev jb = P.jobs[jobIdx];
-    int status = JOB_OK, nPlantedPrev = 0, outLen = 0, score = 0;
-    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const long long tJob0 = clock64();
-    for (int gi = 0; gi < jb.gridCount; ++gi) {
-        const GridDesc gd = P.grids[jb.gridBegin + gi];
-        const long long c0 = clock64();
-        setupGrid(G, jb, gd, arena);
-        initGrid(G, gd, nPlantedPrev);
-        const long long c1 = clock64();
-        long long c2;
-        if (G.local) {
-            localFill(G, win);
-            c2 = clock64();
-            prof[1] += c2 - c1;
-        } else {
-            const int st = publishAndWait(G, wctx, wTask, board);
-            if (st != JOB_OK) status = st;
-            c2 = clock64();
-            prof[2] += c2 - c1;
-        }
-        TrackResult TR;
-        TR.maxCell = DCell{0, 0, 0};
-        if (gd.kind == GRID_GLOBAL) trackGlobal(G, TR);
-        else trackChain(G, TR);
-        const long long c3 = clock64();
-        // traceback: warp-uniform
-        if (status == JOB_OK) status = TR.status;
-        const int maxScore = TR.maxScore;
-        if (status == JOB_OK && maxScore < -1000000) status = JOB_BAD_SCORE;  // the RRW throw
-        int nPlanted = 0;  // _nextInitializationCells.clear()
-        if (status == JOB_OK) {
-            const TbResult tb = tracebackGrid(G, win, P.out + jb.outOff, jb.outCap, outLen, gi, gd.h0, gd.v0, TR.nCand, TR.maxCell);
-            status = tb.status; nPlanted = tb.nPlanted; outLen = tb.outLen;
-            prof[6] += tb.tiles; prof[7] += tb.tileCycles;
-            prof[9] += (gd.kind == GRID_GLOBAL) ? 1 : TR.nCand;
-        }
-        __syncwarp();
-        nPlantedPrev = nPlanted; score = maxScore;
-        const long long c4 = clock64();
-        prof[0] += c1 - c0; prof[3] += c3 - c2; prof[4] += c4 - c3;
-        if (G.local) { prof[8] += c4 - c3; prof[10] += 1; prof[11] += c3 - c2; }
-        if (status != JOB_OK) break;
+    const GridRec* rec = &P.gridRecs[jb.gridBegin + gi];
+    if (rec->state != 1) return;  // done in line by pass 1
+    const GridDesc gd = P.grids[jb.gridBegin + gi];
+    setupGrid(G, jb, gd, nullptr);
+    if (lane == 0) {  // only the init row / column are needed (this warp's mini arena)
+        G.initRow = reinterpret_cast<DCell*>(mini);
+        G.initCol = reinterpret_cast<DCell*>(mini + P.miniInitCol);
     }
-    if (lane == 0) {
-        JobOut jo;
-        jo.status = status; jo.score = score; jo.outLen = outLen; jo.pad = 0;
-        prof[5] = clock64() - tJob0;
-        for (int k = 0; k < 12; ++k) jo.prof[k] = prof[k];
-        P.jobOut[jobIdx] = jo;
+    __syncwarp();
+    const GridGeom& g = G.g;
+    const DCell def = DCell{NEG_INF, NEG_INF, NEG_INF};
+    for (int j = lane; j <= g.nH; j += 32) G.initRow[j] = def;
+    for (int i = lane; i <= g.nV; i += 32) G.initCol[i] = def;
+    __syncwarp();
+    if (gd.plantZerosH > 0 || gd.plantZerosV > 0) {
+        const DCell z = DCell{0, NEG_INF, NEG_INF};
+        for (int j = lane; j < gd.plantZerosH && j <= g.nH; j += 32) G.initRow[j] = z;
+        for (int i = lane; i < gd.plantZerosV && i <= g.nV; i += 32) G.initCol[i] = z;
+    } else {
+        for (int k = lane; k < rec->nPlantedIn; k += 32) {
+            const PlantedCell pc = rec->plantedIn[k];
+            if (pc.i1 == 0 && pc.i2 <= g.nV) G.initCol[pc.i2] = pc.c;
+            if (pc.i2 == 0 && pc.i1 <= g.nH) G.initRow[pc.i1] = pc.c;
+        }
+    }
+    __syncwarp();
+    localFill(G, win, false);
+    const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, rec->nCand,
+                                      DCell{0, 0, 0}, rec);
+    if (tb.status != JOB_OK && lane == 0) atomicMax(&P.jobState[jobIdx].status, tb.status);
+    __syncwarp();
+}
+
+// Marks the job complete (all passes done): final status and stream length.
+__device__ __forceinline__ void finalizeJob(int jobIdx) {
+    const KParams& P = cP;
+    if ((threadIdx.x & 31) == 0) {
+        const int st2 = ldRelaxed(&P.jobState[jobIdx].status);
+        JobOut* jo = &P.jobOut[jobIdx];
+        if (jo->status == JOB_OK && st2 != JOB_OK) jo->status = st2;
+        jo->outLen = ldRelaxed(&P.jobState[jobIdx].outCursor);
         __threadfence();
         atomicAdd(&P.cb->jobsDone, 1);
     }
     __syncwarp();
 }
 
+// Claims and runs one pass-2 grid.  Returns false when none is available.
+__device__ __noinline__ bool tryRunPass2(GridCtx& G, uint8_t* win, uint8_t* mini) {
+    const KParams& P = cP;
+    const int lane = threadIdx.x & 31;
+    int h = 0, item = -1;
+    if (lane == 0) {
+        h = ldRelaxed(&P.cb->p2Head);
+        for (;;) {
+            if (h >= P.nJobs) break;
+            P2Entry* e = &P.p2ring[h];
+            if (ldRelaxed(&e->ready) == 0) break;
+            const int n = e->nItems;
+            if (ldVolatile(&e->nextItem) < n) {
+                const int k = atomicAdd(&e->nextItem, 1);
+                if (k < n) { item = k; break; }
+            }
+            atomicCAS(&P.cb->p2Head, h, h + 1);
+            ++h;
+        }
+        if (item >= 0) __threadfence();  // acquire: the records were written before `ready`
+    }
+    item = __shfl_sync(FULLMASK, item, 0);
+    if (item < 0) return false;
+    h = __shfl_sync(FULLMASK, h, 0);
+    P2Entry* e = &P.p2ring[h];
+    const int jobIdx = e->jobIdx;
+    runPass2Grid(jobIdx, item, G, win, mini);
+    __threadfence();
+    __syncwarp();
+    int d = 0;
+    if (lane == 0) d = atomicAdd(&e->doneItems, 1) + 1;
+    d = __shfl_sync(FULLMASK, d, 0);
+    if (d == e->nItems) finalizeJob(jobIdx);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// one job on its control warp: pass 1 over all grids (everything that decides the NEXT grid's
+// initialisation), in-line tracebacks for the grids that cannot take the fast path
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& G, GridCtx& wctx, int& wTask, uint8_t* win, uint8_t* arena,
+                                    uint8_t* fastSeq) {
+    const KParams& P = cP;
+    const int lane = threadIdx.x & 31;
+    const JobDev jb = P.jobs[jobIdx];
+    int status = JOB_OK, nPlantedPrev = 0, score = 0, nFast = 0;
+    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tJob0 = clock64();
+    for (int gi = 0; gi < jb.gridCount; ++gi) {
+        const GridDesc gd = P.grids[jb.gridBegin + gi];
+        GridRec* rec = &P.gridRecs[jb.gridBegin + gi];
+        const long long c0 = clock64();
+        setupGrid(G, jb, gd, arena, fastSeq);
+        initGrid(G, gd, nPlantedPrev);
+        const long long c1 = clock64();
+        long long c2 = c1, c3 = c1;
+        TrackResult TR;
+        TR.maxCell = DCell{0, 0, 0};
+        int nPlanted = 0;  // _nextInitializationCells.clear()
+        bool done = false;
+        // ---- fast path: score-only fill, tracking and crossing walks; trace fill + tracebacks go to pass 2
+        if (G.fastOk && nPlantedPrev <= MAXREC) {
+            localFillFast(G, win);
+            c2 = clock64();
+            trackChain<true>(G, TR, reinterpret_cast<const DCell*>(win));
+            c3 = clock64();
+            int st = (TR.status != JOB_OK) ? TR.status : ((TR.maxScore < -1000000) ? JOB_BAD_SCORE : JOB_OK);
+            if (st == JOB_OK && TR.nCand <= MAXREC) {
+                int insertedMask = 0;
+                if (fastShortWalks(G, win, TR.nCand, nPlanted, insertedMask, st) && st == JOB_OK) {
+                    if (lane == 0) {
+                        rec->state = 1; rec->nCand = TR.nCand; rec->inserted = insertedMask; rec->nPlantedIn = nPlantedPrev;
+                        for (int k = 0; k < TR.nCand; ++k) rec->cand[k] = G.cand[k];
+                    }
+                    ++nFast;
+                    done = true;
+                }
+            }
+            if (!done && st != JOB_OK && st != JOB_REF_UB) { status = st; done = true; }  // bad score: same verdict in line
+            prof[1] += c2 - c1; prof[11] += c3 - c2; prof[8] += clock64() - c3; prof[10] += 1;
+        }
+        // ---- in-line path (big grids, final grids, anything the fast path declined)
+        if (!done) {
+            if (lane == 0) rec->state = 0;
+            const long long d1 = clock64();
+            if (G.local) {
+                localFill(G, win, true);
+                c2 = clock64();
+                prof[1] += c2 - d1;
+            } else {
+                const int st = publishAndWait(G, wctx, wTask, board);
+                if (st != JOB_OK) status = st;
+                c2 = clock64();
+                prof[2] += c2 - d1;
+            }
+            if (gd.kind == GRID_GLOBAL) trackGlobal(G, TR);
+            else trackChain<false>(G, TR, nullptr);
+            c3 = clock64();
+            if (status == JOB_OK) status = TR.status;
+            if (status == JOB_OK && TR.maxScore < -1000000) status = JOB_BAD_SCORE;  // the RRW throw
+            nPlanted = 0;
+            if (status == JOB_OK) {
+                const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, TR.nCand,
+                                                  TR.maxCell, nullptr);
+                status = tb.status; nPlanted = tb.nPlanted;
+                prof[6] += tb.tiles; prof[7] += tb.tileCycles;
+                prof[9] += (gd.kind == GRID_GLOBAL) ? 1 : TR.nCand;
+            }
+            prof[3] += c3 - c2; prof[4] += clock64() - c3;
+        }
+        __syncwarp();
+        // the next grid's record carries the cells that initialise it (pass 2 redoes grids independently)
+        if (gi + 1 < jb.gridCount && nPlanted <= MAXREC) {
+            GridRec* nx = rec + 1;
+            for (int k = lane; k < nPlanted; k += 32) nx->plantedIn[k] = G.planted[k];
+        }
+        nPlantedPrev = nPlanted; score = TR.maxScore;
+        prof[0] += c1 - c0;
+        if (status != JOB_OK) break;
+    }
+    if (lane == 0) {
+        JobOut jo;
+        jo.status = status; jo.score = score; jo.outLen = 0; jo.pad = 0;
+        prof[5] = clock64() - tJob0;
+        for (int k = 0; k < 12; ++k) jo.prof[k] = prof[k];
+        P.jobOut[jobIdx] = jo;
+    }
+    __syncwarp();
+    if (status == JOB_OK && nFast > 0) {
+        // hand the recorded grids to pass 2
+        int t = 0;
+        __threadfence();
+        if (lane == 0) {
+            t = atomicAdd(&P.cb->p2Tail, 1);
+            P2Entry* e = &P.p2ring[t];
+            e->jobIdx = jobIdx; e->nItems = jb.gridCount; e->nextItem = 0; e->doneItems = 0;
+            __threadfence();
+            stRelease(&e->ready, 1);
+        }
+        __syncwarp();
+    } else {
+        __threadfence();
+        finalizeJob(jobIdx);
+    }
+}
+
 constexpr int CTX_STRIDE = (int)((sizeof(GridCtx) + 15) / 16 * 16);
-constexpr int SMEM_BYTES = NCTRL * WINBYTES + (NCTRL + NWARPS) * CTX_STRIDE;
+constexpr int SMEM_CTX = NCTRL * WINBYTES;
+constexpr int SMEM_FASTSEQ = SMEM_CTX + (NCTRL + NWARPS) * CTX_STRIDE;
+constexpr int SMEM_BYTES = SMEM_FASTSEQ + NCTRL * (FASTSEQ_H + FASTSEQ_V);
 
 __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
     const KParams& P = cP;
@@ -734,20 +992,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
     }
     bool queueEmpty = (agent < 0);
     int idle = 0;
+    GridCtx* cctx = (cw >= 0) ? reinterpret_cast<GridCtx*>(smem + NCTRL * WINBYTES + cw * CTX_STRIDE) : nullptr;
+    uint8_t* win = (cw >= 0) ? smem + cw * WINBYTES : nullptr;
+    uint8_t* mini = (cw >= 0) ? P.mini + (size_t)(cw * gridDim.x + blockIdx.x) * P.miniStride : nullptr;
     for (;;) {
         if (!queueEmpty) {
             int q = 0;
             if (lane == 0) q = atomicAdd(&P.cb->jobQueue, 1);
             q = __shfl_sync(FULLMASK, q, 0);
             if (q < P.nJobs) {
-                GridCtx* cctx = reinterpret_cast<GridCtx*>(smem + NCTRL * WINBYTES + cw * CTX_STRIDE);
-                runJob(P.order[q], q < P.nHiJobs ? 0 : 1, *cctx, *wctx, wTask, smem + cw * WINBYTES,
-                       P.scratch + (size_t)agent * P.scratchStride);
+                runJob(P.order[q], q < P.nHiJobs ? 0 : 1, *cctx, *wctx, wTask, win, P.scratch + (size_t)agent * P.scratchStride,
+                       smem + SMEM_FASTSEQ + cw * (FASTSEQ_H + FASTSEQ_V));
                 continue;
             }
             queueEmpty = true;
         }
         if (tryRunOneItem(*wctx, wTask)) { idle = 0; continue; }
+        if (cw >= 0 && tryRunPass2(*cctx, win, mini)) { idle = 0; continue; }
         int done = 0;
         if (lane == 0) done = ldRelaxed(&P.cb->jobsDone);
         done = __shfl_sync(FULLMASK, done, 0);
@@ -795,7 +1056,9 @@ struct Engine::Impl {
     void* dColTab = nullptr; size_t capColTab = 0;
     std::vector<ColInfo> colTabAll;
     void* dScratch = nullptr; size_t capScratch = 0;
-    void* dRing = nullptr; size_t capRing = 0;   // ControlBlock followed by the task board
+    void* dRing = nullptr; size_t capRing = 0;   // ControlBlock, task boards, pass-2 board, job states (zeroed per launch)
+    void* dRecs = nullptr; size_t capRecs = 0;   // pass-1 grid records
+    void* dMini = nullptr; size_t capMini = 0;   // init row / column of pass-2 grids, one per control warp
     // pinned host staging
     void* hSeq = nullptr; size_t capHSeq = 0;
     void* hOut = nullptr; size_t capHOut = 0;
@@ -851,7 +1114,7 @@ Engine::~Engine() {
     if (!impl_) return;
     cudaSetDevice(impl_->device);
     cudaFree(impl_->dJobs); cudaFree(impl_->dGrids); cudaFree(impl_->dSeq); cudaFree(impl_->dOut);
-    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dScratch); cudaFree(impl_->dRing);
+    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dScratch); cudaFree(impl_->dRing); cudaFree(impl_->dRecs); cudaFree(impl_->dMini);
     cudaFreeHost(impl_->hSeq); cudaFreeHost(impl_->hOut);
     for (auto& ev : impl_->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(impl_->stream);
@@ -932,8 +1195,10 @@ void Engine::upload(std::vector<Job*>& jobs) {
             cost[k] += 100000 + c / 16;
         }
         totalCells += j.cells;
-        // segment stream capacity: records + segments
-        long long cap = 4LL * ((long long)j.lenH + j.lenV) * 2 + 64LL * (long long)j.grids.size() + 1024;
+        // segment stream capacity: every grid reserves its worst case (3 + traces * (1 + 4 * (nH + nV + 6)) ints)
+        long long cap = 0;
+        for (const GridDesc& gd : j.grids) cap += 3 + 2LL * (1 + 4LL * ((long long)gd.nH + gd.nV + 6));
+        cap += 4LL * ((long long)j.lenH + j.lenV) + 1024;
         if (cap > (1LL << 30)) cap = 1LL << 30;
         d.outOff = (long long)outOff;
         d.outCap = (int)cap;
@@ -968,7 +1233,18 @@ void Engine::upload(std::vector<Job*>& jobs) {
     // number of control agents with an arena: bounded by jobs and by memory
     size_t freeB = 0, totalB = 0;
     CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
-    I.ringBytes = alignUp(sizeof(ControlBlock), 256) + 2 * (nTasks + 1) * sizeof(TaskDesc);
+    const size_t offRing = alignUp(sizeof(ControlBlock), 256);
+    const size_t offP2 = offRing + alignUp(2 * (nTasks + 1) * sizeof(TaskDesc), 256);
+    const size_t offState = offP2 + alignUp((nJobs + 1) * sizeof(P2Entry), 256);
+    I.ringBytes = offState + (nJobs + 1) * sizeof(JobState);
+    // mini arenas: init row / column of the largest LOCAL grid, for every control-capable warp
+    int maxLocalNH = 1, maxLocalNV = 1;
+    for (const GridDesc& gd : I.gridsAll) {
+        GridGeom g = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
+        if (localPlan(g).local) { maxLocalNH = std::max(maxLocalNH, gd.nH); maxLocalNV = std::max(maxLocalNV, gd.nV); }
+    }
+    const size_t miniInitCol = alignUp((size_t)(maxLocalNH + 2) * sizeof(DCell), 256);
+    const size_t miniStride = miniInitCol + alignUp((size_t)(maxLocalNV + 2) * sizeof(DCell), 256);
     size_t fixed = nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + I.seqBytes + I.outInts * 4 +
                    I.ringBytes + (64u << 20);
     size_t budget = (freeB + I.capScratch > fixed) ? (size_t)((freeB + I.capScratch - fixed) * 0.9) : 0;
@@ -985,6 +1261,8 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.growDev(I.dColTab, I.capColTab, I.colTabAll.size() * sizeof(ColInfo) + 64);
     I.growDev(I.dScratch, I.capScratch, (size_t)L.total * nSlots);
     I.growDev(I.dRing, I.capRing, I.ringBytes);
+    I.growDev(I.dRecs, I.capRecs, (I.gridsAll.size() + 1) * sizeof(GridRec));
+    I.growDev(I.dMini, I.capMini, miniStride * (size_t)NCTRL * I.numSMs);
     I.growHost(I.hOut, I.capHOut, I.outInts * sizeof(int) + 64);
     CUDA_CHECK(cudaEventRecord(I.ev[0], I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dSeq, I.hSeq, I.seqBytes, cudaMemcpyHostToDevice, I.stream));
@@ -1001,7 +1279,12 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.nJobs = (int)nJobs; kp.nSlots = nSlots; kp.maxTasks = (int)nTasks + 1;
     kp.nHiJobs = std::max(4, (int)nJobs / 10);
     kp.cb = (ControlBlock*)I.dRing;
-    kp.ring = (TaskDesc*)((uint8_t*)I.dRing + alignUp(sizeof(ControlBlock), 256));
+    kp.ring = (TaskDesc*)((uint8_t*)I.dRing + offRing);
+    kp.p2ring = (P2Entry*)((uint8_t*)I.dRing + offP2);
+    kp.jobState = (JobState*)((uint8_t*)I.dRing + offState);
+    kp.gridRecs = (GridRec*)I.dRecs;
+    kp.mini = (uint8_t*)I.dMini; kp.miniStride = (long long)miniStride; kp.miniInitCol = (long long)miniInitCol;
+    kp.fastEnabled = getenv("UNICYCLER_B200_NO_FAST") ? 0 : 1; kp.pad5 = 0;
     kp.scratch = (uint8_t*)I.dScratch; kp.scratchStride = L.total;
     kp.lay = L;
     CUDA_CHECK(cudaMemcpyToSymbolAsync(cP, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, I.stream));
@@ -1082,9 +1365,10 @@ void Engine::fetch(std::vector<Job*>& jobs) {
         }
         fprintf(stderr, "[ub200 profile] jobs=%zu agents=%d tasks=%d cycles: setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld total=%lld maxjob=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",
                 nJobs, I.kp.nSlots, I.kp.maxTasks, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], mx, tot[6], tot[7], tot[8], tot[9], tot[10], tot[11]);
-        unsigned long long dbg[8];
+        unsigned long long dbg[16];
         if (cudaMemcpyFromSymbol(dbg, gDbg, sizeof(dbg)) == cudaSuccess) {
             fprintf(stderr, "[ub200 dbg] unbanded trace strips=%llu total=%llu steps-cycles=%llu nsteps=%llu | banded strips=%llu total=%llu steps-cycles=%llu nsteps=%llu (cumulative)\n", dbg[3], dbg[0], dbg[1], dbg[2], dbg[7], dbg[4], dbg[5], dbg[6]);
+            fprintf(stderr, "[ub200 dbg] short walks: cycles=%llu plant-cycles=%llu lazyTv=%llu candidates=%llu (cumulative)\n", dbg[8], dbg[9], dbg[10], dbg[11]);
         }
         const long long* wp = I.jobOut[worst].prof;
         fprintf(stderr, "[ub200 profile] worst job %zu (%d grids): setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",
@@ -1104,8 +1388,11 @@ void Engine::fetch(std::vector<Job*>& jobs) {
         const int* p = hOut + d.outOff;
         int pos = 0;
         while (pos < jo.outLen) {
+            // record: [grid index, traces, reserved ints, traces...]; records are written by many warps, in any order
+            const int recBegin = pos;
             int gi = p[pos++];
             int nTr = p[pos++];
+            const int reserved = p[pos++];
             auto& traces = r.gridTraces.at((size_t)gi);
             traces.resize((size_t)nTr);
             for (int t = 0; t < nTr; ++t) {
@@ -1117,6 +1404,7 @@ void Engine::fetch(std::vector<Job*>& jobs) {
                     traces[(size_t)t][(size_t)s] = sg;
                 }
             }
+            pos = recBegin + reserved;
         }
     }
 }

@@ -26,7 +26,11 @@ namespace ub200 {
 
 constexpr int NWARPS = 16;
 constexpr int NTHREADS = NWARPS * 32;
-constexpr int NCTRL = 8;                 // control-capable warps per CTA
+constexpr int NCTRL = 4;                 // control-capable warps per CTA
+constexpr int MODE_TASK = 0;             // score-only strip item of a published grid (checkpoints to HBM)
+constexpr int MODE_TRACE = 1;            // full trace bytes into the shared-memory window
+constexpr int MODE_FAST = 2;             // score-only local fill, box cells (S,H,V) into the shared-memory window
+constexpr int MAXREC = 4;                // candidates / planted cells a pass-1 grid record can hold
 constexpr unsigned FULLMASK = 0xffffffffu;
 
 struct DCell {
@@ -94,6 +98,29 @@ struct GridCtx {
     // limits
     int maxCand, maxPlanted, pad0, pad4;
     long long maxBox;
+    // pass-1 fast mode: the box cells (S,H,V) of rows >= fastR0, columns >= fastC0 live in the shared-memory window
+    int fastOk, fastR0, fastC0, fastPitch;
+    const uint8_t* fastSeqH;   // shared memory: base codes of columns fastC0.. (index j - fastC0)
+    const uint8_t* fastSeqV;   // shared memory: base codes of rows fastR0..    (index i - fastR0)
+};
+constexpr int FASTSEQ_H = 768, FASTSEQ_V = 256;   // capacity of the staged code windows
+
+// Pass-1 record of a chain grid: everything pass 2 needs to redo the grid on its own.
+struct GridRec {
+    int state;        // 0: not fast (done in line by pass 1), 1: fast (pass 2 fills the trace and walks)
+    int nCand, inserted, nPlantedIn;
+    int cand[MAXREC];
+    PlantedCell plantedIn[MAXREC];
+};
+
+struct JobState {     // zeroed before every launch
+    int outCursor;    // ints reserved in the job's segment stream
+    int status;       // max over the statuses of pass-2 grids
+    int pad0, pad1;
+};
+
+struct P2Entry {      // pass-2 board entry: one job whose pass 1 is complete
+    int jobIdx, nItems, ready, nextItem, doneItems, pad0, pad1, pad2;
 };
 
 struct TaskDesc {
@@ -107,6 +134,7 @@ struct TaskDesc {
 struct ControlBlock {  // zeroed before every launch
     int jobQueue, jobsDone;
     int ringHead[2], ringTail[2];  // task boards: [0] jobs on the critical path (longest chains), [1] the rest
+    int p2Head, p2Tail;            // pass-2 board
 };
 
 struct KParams {
@@ -123,6 +151,12 @@ struct KParams {
     int nHiJobs;       // the first nHiJobs jobs of `order` publish on board 0
     ControlBlock* cb;
     TaskDesc* ring;    // [2][maxTasks]
+    P2Entry* p2ring;   // [nJobs]
+    JobState* jobState;
+    GridRec* gridRecs; // [total grids]
+    uint8_t* mini;     // per control warp: initRow/initCol for pass-2 grids
+    long long miniStride, miniInitCol;
+    int fastEnabled, pad5;
     uint8_t* scratch;
     long long scratchStride;
     ScratchLayout lay;
@@ -131,7 +165,7 @@ struct KParams {
 // Launch parameters live in constant memory (a by-reference kernel argument would be copied to the
 // local-memory stack of every warp).
 __constant__ KParams cP;
-__device__ unsigned long long gDbg[8];   // developer counters (cycles), lane 0 of control warps
+__device__ unsigned long long gDbg[16];   // developer counters (cycles), lane 0 of control warps
 
 // ---------------------------------------------------------------------------------------
 // memory-order helpers
@@ -309,10 +343,11 @@ struct StepConsts {
 // 32 wavefront steps (one chunk) of a strip.  TRACE: trace bytes to the shared-memory window;
 // otherwise (score-only) boundary row + column checkpoints to HBM.  CAP: slow variant that also captures
 // the cells the scouts may need (last row/column for final/global matrices, the corner box otherwise).
-template <bool AFF, bool CT, bool BANDED, int RR, bool TRACE, bool CAP>
+template <bool AFF, bool CT, bool BANDED, int RR, int MODE, bool CAP>
 __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K, StripState<RR>& st, int c, int lane,
                                            int cBeg, int cEnd, int i0, int bS, int bV, int hcN, int nsteps,
                                            uint8_t* win, int winPitch, int2* rowOut, int2* ckOut) {
+    constexpr bool TRACE = (MODE == MODE_TRACE);
     const int match = K.match, mismatch = K.mismatch, go = K.go, ge = K.ge;
     const int lo = K.lo, up = K.up;
     int capEdges = 0, hNext = 0, boxRow0 = 0, boxH = 0;
@@ -372,7 +407,7 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K
                 if constexpr (RR == 8) *reinterpret_cast<uint2*>(p) = make_uint2(tw[0], tw[(RR + 3) / 4 - 1]);
                 else if constexpr (RR == 2) *reinterpret_cast<uint16_t*>(p) = (uint16_t)tw[0];
                 else *reinterpret_cast<uint32_t*>(p) = tw[0];
-            } else {
+            } else if constexpr (MODE == MODE_TASK) {
                 if (lane == 31) __stcg(&rowOut[j], make_int2(Su, Vu));
                 if ((j & (CKW - 1)) == 0) {
                     int2* ck = ckOut + (size_t)(j / CKW) * SH + lane * RR;
@@ -381,7 +416,18 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K
                         __stcg(reinterpret_cast<int4*>(ck + r), make_int4(st.Sl[r], st.Hl[r], st.Sl[r + 1], st.Hl[r + 1]));
                 }
             }
-            if (CAP) {
+            if constexpr (CAP && MODE == MODE_FAST) {
+                // pass-1 fast mode: (S,H,V) of the box cells into the shared-memory window
+                const int fc0 = G.fastC0, fr0 = G.fastR0, fp = G.fastPitch;
+                if (j >= fc0) {
+                    DCell* col = reinterpret_cast<DCell*>(win) + (j - fc0) * fp - fr0;
+#pragma unroll
+                    for (int r = 0; r < RR; ++r) {
+                        const int i = i0 + r;
+                        if (i >= fr0 && i <= K.nV) col[i] = DCell{st.Sl[r], st.Hl[r], vArr[r]};
+                    }
+                }
+            } else if (CAP) {
                 if (capEdges) {
                     const int rl = K.nV - i0;
                     if (rl >= 0 && rl < RR) {
@@ -418,10 +464,12 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K
 //           except the scout captures when `capture` is set.
 //   !TRACE: score-only; boundary row, column checkpoints, rowProg published per chunk; waits on the
 //           strip above through its rowProg counter.
-template <bool AFF, bool CT, bool BANDED, int RR, bool TRACE>
+template <bool AFF, bool CT, bool BANDED, int RR, int MODE>
 __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEnd, bool fromCk, int nsteps,
                                       bool capture, uint8_t* win, int winPitch) {
     constexpr int SHR = 32 * RR;
+    constexpr bool TRACE = (MODE == MODE_TRACE);
+    constexpr bool L2ONLY = (MODE == MODE_TASK);   // worker warps read the arena through L2 only
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     const long long dbg0 = clock64();
@@ -432,7 +480,7 @@ __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEn
 #pragma unroll
     for (int w4 = 0; w4 < (RR + 3) / 4; ++w4) st.vm[w4] = 0;
     int2* ckTile = nullptr;   // checkpoint tile pointer such that tile of column j is ckTile + (j/CKW)*SH
-    if (!TRACE || fromCk) ckTile = G.colCk + ((size_t)__ldcg(&G.ckBase[s]) - (size_t)ckFirst(g, s)) * SH;
+    if (MODE == MODE_TASK || fromCk) ckTile = G.colCk + ((size_t)__ldcg(&G.ckBase[s]) - (size_t)ckFirst(g, s)) * SH;
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
         const int i = i0 + r;
@@ -444,20 +492,20 @@ __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEn
         for (int r = 0; r < RR; ++r) {
             const int i = i0 + r;
             if (jlo == 1 && i <= G.colZeroMax) {
-                const DCell ic = TRACE ? G.initCol[i] : ldcgCell(&G.initCol[i]);
+                const DCell ic = L2ONLY ? ldcgCell(&G.initCol[i]) : G.initCol[i];
                 st.Sl[r] = ic.s; st.Hl[r] = ic.h;
             }
             else { st.Sl[r] = NEG_INF; st.Hl[r] = NEG_INF; }
         }
-        if (jlo == 1) st.prevUpS = (i0 - 1 <= G.colZeroMax) ? (TRACE ? G.initCol[i0 - 1].s : __ldcg(&G.initCol[i0 - 1].s)) : NEG_INF;
+        if (jlo == 1) st.prevUpS = (i0 - 1 <= G.colZeroMax) ? (L2ONLY ? __ldcg(&G.initCol[i0 - 1].s) : G.initCol[i0 - 1].s) : NEG_INF;
         else {
             st.prevUpS = NEG_INF;
             if (lane == 0) {
-                if (!TRACE && s > 0) {  // the corner cell above-left of the strip comes from the strip above
+                if (MODE == MODE_TASK && s > 0) {  // the corner cell above-left of the strip comes from the strip above
                     const int need = imin(jlo - 1, stripJhi(g, s - 1, SHR));
                     while (ldRelaxed(&G.rowProg[s - 1]) < need) __nanosleep(128);
                 }
-                int bS, bV; upBoundary<BANDED, !TRACE>(G, s, SHR, jlo - 1, bS, bV); st.prevUpS = bS;
+                int bS, bV; upBoundary<BANDED, L2ONLY>(G, s, SHR, jlo - 1, bS, bV); st.prevUpS = bS;
             }
             __syncwarp();
         }
@@ -468,21 +516,21 @@ __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEn
             const int2 v = __ldcg(&ck[lane * RR + r]);
             st.Sl[r] = v.x; st.Hl[r] = v.y;
         }
-        if (lane == 0) { int bS, bV; upBoundary<BANDED, !TRACE>(G, s, SHR, cBeg - 1, bS, bV); st.prevUpS = bS; }
+        if (lane == 0) { int bS, bV; upBoundary<BANDED, L2ONLY>(G, s, SHR, cBeg - 1, bS, bV); st.prevUpS = bS; }
         else st.prevUpS = __ldcg(&ck[lane * RR - 1]).x;
     }
     st.pubS = NEG_INF; st.pubV = NEG_INF; st.curHc = 0;
     StepConsts K;
     K.match = G.match; K.mismatch = G.mismatch; K.go = G.go; K.ge = G.ge;
     K.nV = g.nV; K.nH = g.nH; K.lo = g.lo; K.up = g.up;
-    int2* rowOut = TRACE ? nullptr : G.rowCk + (size_t)s * (size_t)(g.nH + 1);
+    int2* rowOut = (MODE == MODE_TASK) ? G.rowCk + (size_t)s * (size_t)(g.nH + 1) : nullptr;
     const int nch = (nsteps + 31) / 32;
     int upProg = 0;                // cached progress of the strip above
     const int upJhi = (s > 0) ? stripJhi(g, s - 1, SHR) : 0;
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
         const int jj = cBeg + 32 * c + lane;
-        if (!TRACE && s > 0) {
+        if (MODE == MODE_TASK && s > 0) {
             // boundary columns this chunk reads: cBeg+32c .. min(cEnd, cBeg+32c+31), all <= jhi(s-1) when in band
             const int need = imin(imin(cEnd, cBeg + 32 * c + 31), upJhi);
             if (upProg < need) {
@@ -495,29 +543,30 @@ __device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEn
             }
         }
         int bS = NEG_INF, bV = NEG_INF, hcN = 0;
-        if (jj <= cEnd) { hcN = G.seqH[jj - 1]; upBoundary<BANDED, !TRACE>(G, s, SHR, jj, bS, bV); }
+        if (jj <= cEnd) { hcN = G.seqH[jj - 1]; upBoundary<BANDED, L2ONLY>(G, s, SHR, jj, bS, bV); }
         bool cap = false;
         if (capture) {
             const int jmaxChunk = imin(cEnd, cBeg + 32 * c + 31);  // largest column any lane touches in this chunk
-            if (G.capEdges) cap = ((s + 1) * SHR >= g.nV) || (jmaxChunk >= g.nH);
+            if (MODE == MODE_FAST) cap = jmaxChunk >= G.fastC0;
+            else if (G.capEdges) cap = ((s + 1) * SHR >= g.nV) || (jmaxChunk >= g.nH);
             else cap = (jmaxChunk >= G.hNext) && ((s + 1) * SHR >= G.boxRow0);
         }
         const long long dbg1 = clock64();
         if (cap)
-            stripSteps<AFF, CT, BANDED, RR, TRACE, true>(G, K, st, c, lane, cBeg, cEnd, i0, bS, bV, hcN, nsteps, win,
+            stripSteps<AFF, CT, BANDED, RR, MODE, true>(G, K, st, c, lane, cBeg, cEnd, i0, bS, bV, hcN, nsteps, win,
                                                          winPitch, rowOut, ckTile);
         else
-            stripSteps<AFF, CT, BANDED, RR, TRACE, false>(G, K, st, c, lane, cBeg, cEnd, i0, bS, bV, hcN, nsteps, win,
+            stripSteps<AFF, CT, BANDED, RR, MODE, false>(G, K, st, c, lane, cBeg, cEnd, i0, bS, bV, hcN, nsteps, win,
                                                           winPitch, rowOut, ckTile);
         dbgSteps += clock64() - dbg1;
-        if (!TRACE) {
+        if (MODE == MODE_TASK) {
             // lane 31 has finished every column <= cBeg + 32c + 31 - 31 (and cEnd after the last chunk)
             const int done = imin(cEnd, cBeg + 32 * c + imin(31, nsteps - 1 - 32 * c) - 31);
             if (lane == 31 && done >= cBeg) stRelease(&G.rowProg[s], done);
         }
     }
-    if (TRACE && lane == 0) {
-        const int o = BANDED ? 4 : 0;
+    if (MODE != MODE_TASK && lane == 0) {
+        const int o = (MODE == MODE_FAST) ? 4 : 0;
         atomicAdd(&gDbg[o + 0], (unsigned long long)(clock64() - dbg0));
         atomicAdd(&gDbg[o + 1], (unsigned long long)dbgSteps);
         atomicAdd(&gDbg[o + 2], (unsigned long long)nsteps);
@@ -560,8 +609,62 @@ struct OutStream {
 template <bool AFF, bool CT>
 __device__ __forceinline__ void tileDispatch(const GridCtx& G, int s, int cBeg, int cEnd, bool fromCk, int nsteps,
                                              uint8_t* win) {
-    if (G.g.banded) runStrip<AFF, CT, true, 8, true>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
-    else runStrip<AFF, CT, false, 8, true>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
+    if (G.g.banded) runStrip<AFF, CT, true, 8, MODE_TRACE>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
+    else runStrip<AFF, CT, false, 8, MODE_TRACE>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
+}
+
+// Recomputes the trace bytes of the tile that holds (i, j): rows of strip s up to the lane owning row i,
+// columns from the checkpoint left of j up to j.  Returns (strip, first column, last column, last row).
+__device__ __noinline__ int4 computeTileFn(const GridCtx& G, uint8_t* win, int i, int j) {
+    const GridGeom& g = G.g;
+    const int s = (i - 1) / SH;
+    const int jlo = stripJlo(g, s, SH);
+    const int c0 = ((j - 1) / CKW) * CKW;          // checkpoint column left of j (tile = c0+1 .. c0+CKW)
+    bool fromCk = true;
+    int cBeg = c0 + 1;
+    if (c0 < jlo) { fromCk = false; cBeg = jlo; }
+    const int laneOfI = ((i - 1) - s * SH) / 8;
+    const int nsteps = (j - cBeg + 1) + laneOfI;
+    __syncwarp();
+    if (G.affine) { if (G.complete) tileDispatch<true, true>(G, s, cBeg, j, fromCk, nsteps, win); else tileDispatch<true, false>(G, s, cBeg, j, fromCk, nsteps, win); }
+    else { if (G.complete) tileDispatch<false, true>(G, s, cBeg, j, fromCk, nsteps, win); else tileDispatch<false, false>(G, s, cBeg, j, fromCk, nsteps, win); }
+    __syncwarp();
+    return make_int4(s, cBeg, j, s * SH + (laneOfI + 1) * 8);
+}
+
+// Pass-1 lazy trace value of cell (i, j): derived from the (S,H,V) of its three neighbours exactly like the
+// trace fill would (same cellUpdate).  One out-of-line copy (the walker calls it from many places).
+// Bit 31 of the result: a neighbour lies outside the captured box.
+__device__ __forceinline__ DCell fastCellAt(const GridCtx& G, const uint8_t* win, int i, int j, bool& outOfBox) {
+    const GridGeom& g = G.g;
+    if (g.banded) { const int d = j - i; if (d < g.lo || d > g.up) return DCell{NEG_INF, NEG_INF, NEG_INF}; }
+    if (i == 0) return G.initRow[j];
+    if (j == 0) return G.initCol[i];
+    if (i < G.fastR0 || j < G.fastC0) { outOfBox = true; return DCell{NEG_INF, NEG_INF, NEG_INF}; }
+    return reinterpret_cast<const DCell*>(win)[(j - G.fastC0) * G.fastPitch + (i - G.fastR0)];
+}
+__device__ __noinline__ uint32_t lazyTvFn(const GridCtx& G, const uint8_t* win, int i, int j) {
+    const GridGeom& g = G.g;
+    if (g.banded) { const int d = j - i; if (d < g.lo || d > g.up) return 0; }
+    bool oob = false;
+    const DCell L = fastCellAt(G, win, i, j - 1, oob), U = fastCellAt(G, win, i - 1, j, oob), D = fastCellAt(G, win, i - 1, j - 1, oob);
+    // (i, j) inside the box: the staged base codes cover it
+    const int sub = (i >= G.fastR0 && j >= G.fastC0)
+                        ? ((G.fastSeqH[j - G.fastC0] == G.fastSeqV[i - G.fastR0]) ? G.match : G.mismatch)
+                        : ((G.seqH[j - 1] == G.seqV[i - 1]) ? G.match : G.mismatch);
+    int mode = 0;
+    if (g.banded) { const int d = j - i; mode = (d == g.up) ? 1 : (d == g.lo ? 2 : 0); }
+    int ns, nh, nv;
+    const int go = G.go, ge = G.ge;
+    uint32_t tv;
+    if (G.affine) {
+        if (g.banded) tv = cellUpdate<true, true, true>(ns, nh, nv, L.s, L.h, U.s, U.v, D.s, sub, go, ge, mode);
+        else tv = cellUpdate<true, true, false>(ns, nh, nv, L.s, L.h, U.s, U.v, D.s, sub, go, ge, mode);
+    } else {
+        if (g.banded) tv = cellUpdate<false, true, true>(ns, nh, nv, L.s, L.h, U.s, U.v, D.s, sub, go, ge, mode);
+        else tv = cellUpdate<false, true, false>(ns, nh, nv, L.s, L.h, U.s, U.v, D.s, sub, go, ge, mode);
+    }
+    return tv | (oob ? 0x80000000u : 0u);
 }
 
 struct TraceWalker {
@@ -572,6 +675,9 @@ struct TraceWalker {
     // register copies of the hot GridCtx fields (G lives in shared memory)
     const GridGeom g;
     const int local, rrMul, rr, rrs, pitch, localJhi, affine;
+    // pass-1 lazy mode: no trace bytes exist; the trace value of a cell is derived on demand from the
+    // (S,H,V) of its three neighbours held in the shared-memory box (same cellUpdate as the trace fill)
+    bool lazy, outOfBox;
     // cached tile (task grids): strip, first column, valid extent
     int tS, tC0, tMaxRow, tMaxCol;
     int pc, pv;       // navigator position: column, storage row
@@ -580,28 +686,16 @@ struct TraceWalker {
     bool bad;         // undefined trace value (reference: endless loop / assert)
     long long tilesComputed, tileCycles;
 
-    __device__ TraceWalker(const GridCtx& g, OutStream& o, uint8_t* w)
+    __device__ __forceinline__ TraceWalker(const GridCtx& g, OutStream& o, uint8_t* w)
         : G(g), out(o), win(w), winW(w), g(g.g), local(g.local), rrMul(g.rrMul), rr(g.RR), rrs(g.rrs), pitch(g.pitch), localJhi(g.localJhi),
-          affine(g.affine), tS(-1), tC0(0), tMaxRow(-1), tMaxCol(-1), pc(0), pv(0), nSegs(0), emitOn(true),
+          affine(g.affine), lazy(false), outOfBox(false), tS(-1), tC0(0), tMaxRow(-1), tMaxCol(-1), pc(0), pv(0), nSegs(0), emitOn(true),
           bad(false), tilesComputed(0), tileCycles(0) {}
 
-    // Recompute the trace bytes of the tile that holds (i, j): rows of strip s up to the lane owning row i,
-    // columns from the checkpoint left of j up to j.
-    __device__ void computeTile(int i, int j) {
-        const int s = (i - 1) / SH;
-        const int jlo = stripJlo(g, s, SH);
-        int c0 = ((j - 1) / CKW) * CKW;          // checkpoint column left of j (tile = c0+1 .. c0+CKW)
-        bool fromCk = true;
-        int cBeg = c0 + 1;
-        if (c0 < jlo) { fromCk = false; cBeg = jlo; }
-        const int laneOfI = ((i - 1) - s * SH) / 8;
-        const int nsteps = (j - cBeg + 1) + laneOfI;
+    // Recompute the trace bytes of the tile that holds (i, j) (free function: the walker must stay in registers)
+    __device__ __forceinline__ void computeTile(int i, int j) {
         const long long t0 = clock64();
-        __syncwarp();
-        if (affine) { if (G.complete) tileDispatch<true, true>(G, s, cBeg, j, fromCk, nsteps, winW); else tileDispatch<true, false>(G, s, cBeg, j, fromCk, nsteps, winW); }
-        else { if (G.complete) tileDispatch<false, true>(G, s, cBeg, j, fromCk, nsteps, winW); else tileDispatch<false, false>(G, s, cBeg, j, fromCk, nsteps, winW); }
-        __syncwarp();
-        tS = s; tC0 = cBeg; tMaxCol = j; tMaxRow = s * SH + (laneOfI + 1) * 8;
+        const int4 t = computeTileFn(G, winW, i, j);
+        tS = t.x; tC0 = t.y; tMaxCol = t.z; tMaxRow = t.w;
         ++tilesComputed;
         tileCycles += clock64() - t0;
     }
@@ -610,6 +704,11 @@ struct TraceWalker {
         const int i = pv - storageOffset(g, pc);
         const int j = pc;
         if (i <= 0 || j <= 0 || i > g.nV || j > g.nH) return 0;
+        if (lazy) {
+            const uint32_t r = lazyTvFn(G, win, i, j);
+            if (r >> 31) outOfBox = true;
+            return r & 0xffu;
+        }
         if (local) {
             if (j > localJhi) return 0;
             const int q = ((i - 1) * rrMul) >> 16;
@@ -624,7 +723,7 @@ struct TraceWalker {
         const int rem = (i - 1) - s * SH;
         return win[((size_t)(j - tC0) * 32 + (rem >> 3)) * 8 + (rem & 7)];
     }
-    __device__ Coord makeCoord(int endCol, int endRow) const {  // dp_traceback_impl.h:121-141
+    __device__ __forceinline__ Coord makeCoord(int endCol, int endRow) const {  // dp_traceback_impl.h:121-141
         Coord c;
         c.currCol = pc; c.currRow = pv; c.endCol = endCol; c.endRow = endRow; c.bp1 = 0; c.bp2 = 0;
         c.inBandFlag = false;
@@ -654,7 +753,7 @@ struct TraceWalker {
     __device__ __forceinline__ void moveD(const Coord& c) { if (c.isInBand()) { --pc; } else { --pc; --pv; } }
     __device__ __forceinline__ void moveV() { --pv; }
 
-    __device__ void doTraceback(uint32_t& tv, uint32_t& last, int& frag, Coord& c) {  // dp_traceback_impl.h:335-431
+    __device__ __forceinline__ void doTraceback(uint32_t& tv, uint32_t& last, int& frag, Coord& c) {  // dp_traceback_impl.h:335-431
         const bool aff = affine;
         if (tv & T_D) {
             if (!(last & T_D)) { record(c.currCol, c.currRow, frag, last); last = T_D; frag = 0; }
@@ -695,7 +794,7 @@ struct TraceWalker {
     }
     // generic _computeTraceback (dp_traceback_impl.h:463-526); tvOverride >= 0 replaces the
     // start cell's trace value (the SingleTrace _correctTraceValue patch, dp_algorithm_impl.h:1354-1370)
-    __device__ void generic(bool prefer, bool head, bool tail, int tvOverride) {
+    __device__ __forceinline__ void generic(bool prefer, bool head, bool tail, int tvOverride) {
         uint32_t tv = tvOverride >= 0 ? (uint32_t)tvOverride : tvHere();
         uint32_t last = initialDirection(tv, prefer);
         Coord c = makeCoord(0, 0);

@@ -248,13 +248,13 @@ def chain_cells(read_len, ref_len, seeds, band_size):
 
 
 def chain_plan(read_len, ref_len, seeds, band_size, cap=8192):
-    """Sub-DP plan of one banded-chain alignment: list of (kind, nH, nV, banded, lo, up, h0, v0)."""
+    """Sub-DP plan of one banded-chain alignment: list of (kind, nH, nV, banded, lo, up, h0, v0, hNext, vNext)."""
     L = load_library()
-    out = (ctypes.c_int32 * (8 * cap))()
+    out = (ctypes.c_int32 * (10 * cap))()
     k = L.ub200_chainPlan(read_len, ref_len, _seed_array(seeds), len(seeds), band_size, out, cap)
     if k < 0:
         return None
-    return [tuple(out[8 * i:8 * i + 8]) for i in range(min(k, cap))]
+    return [tuple(out[10 * i:10 * i + 10]) for i in range(min(k, cap))]
 
 
 def set_device(device):
