@@ -1,5 +1,6 @@
 // B200 DP engine: persistent agent kernel + host launcher.  See engine.hpp / engine_kernels.cuh.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -1409,12 +1410,22 @@ void Engine::fetch(std::vector<Job*>& jobs) {
     }
 }
 
+static double wallMs() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 void Engine::run(std::vector<Job*>& jobs) {
     std::lock_guard<std::mutex> lock(impl_->mu);
     if (jobs.empty()) return;
+    const double t0 = wallMs();
     upload(jobs);
+    const double t1 = wallMs();
     launch();
+    CUDA_CHECK(cudaStreamSynchronize(impl_->stream));
+    const double t2 = wallMs();
     fetch(jobs);
+    if (getenv("UNICYCLER_B200_PROFILE"))
+        fprintf(stderr, "[ub200 engine] upload=%.1f ms kernel(sync)=%.1f ms fetch=%.1f ms\n", t1 - t0, t2 - t1, wallMs() - t2);
 }
 
 }  // namespace ub200
