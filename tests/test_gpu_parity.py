@@ -168,3 +168,44 @@ def test_against_reference_library_directly(ub):
         for a, b, gg, pp in zip(s1s, s2s, g, p):
             assert mask_ms(gg) == mask_ms(ref.fully_global(a, b, SCHEME, banded, band))
             assert mask_ms(pp) == mask_ms(ref.path(a, b, SCHEME, banded, band))
+
+
+def test_in_line_path_matches_two_pass_path(ub, monkeypatch):
+    """The engine has two routes for a small chain grid: the two-pass route (score-only pass 1 + recorded pass 2)
+    and the in-line route (full trace fill + traceback on the control warp, also the fallback).  Both must give the
+    reference's strings."""
+    d = load_golden('semiglobal_contained.json.gz')
+    jobs = golden_chain_jobs(d)
+    monkeypatch.setenv('UNICYCLER_B200_NO_FAST', '1')
+    got = ub.chain_alignment_batch(jobs, tuple(d['scheme']), jobs[0]['band'])
+    monkeypatch.delenv('UNICYCLER_B200_NO_FAST')
+    bad = [(j['readName'], j['refName']) for j, g in zip(jobs, got) if mask_ms(g) != j['result']]
+    assert not bad, bad[:5]
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_LIB), reason='oracle/_ref not built')
+def test_semi_global_with_ambiguous_and_lower_case_bases(ub):
+    """k-mers that are not pure upper-case ACGT take the literal-string route of the k-mer index
+    (src/kmers.cpp:51-65 keys by string); N matches N in the DP (Dna5).  Compared with the reference library."""
+    from refdriver import AbiLib
+    ref = AbiLib(REF_LIB)
+    rng = random.Random(77)
+    contig = ''.join(rng.choice('ACGT') for _ in range(6000))
+    contig = contig[:1500] + 'NNNNNNNNNNNN' + contig[1512:3000] + contig[3000:3100].lower() + contig[3100:]
+    reads = []
+    for k in range(4):
+        start = rng.randint(200, 2500)
+        seq = _mutate(contig[start:start + 2500].upper(), 0.1, rng)
+        if k % 2:
+            seq = seq[:700] + 'NNN' + seq[703:]
+        reads.append(('r%d' % k, seq, '0,%d,+,ctg,%d,%d' % (len(seq), start, start + 2500)))
+    refs = [('ctg', contig)]
+    h = ub.new_ref_seqs()
+    ub.add_ref_seq(h, 'ctg', contig)
+    out = ub.semi_global_alignment_batch([r[0] for r in reads], [r[1] for r in reads], [r[2] for r in reads], h, SCHEME, 0)
+    hr = ref.new_refs(refs)
+    for r, o in zip(reads, out):
+        want = ref.semi_global(r[0], r[1], r[2], hr, SCHEME)
+        assert mask_semi_global(o) == mask_semi_global(want), r[0]
+    ref.delete_refs(hr)
+    ub.delete_ref_seqs(h)

@@ -75,3 +75,21 @@ def test_chain_planner_matches_oracle_grid_sequence(setname):
         lines += [' '.join(str(x) for x in s) for s in j['seeds']]
     out = subprocess.run([exe], input='\n'.join(lines).encode(), stdout=subprocess.PIPE, check=True).stdout.decode()
     assert ' bad 0' in out and 'jobs %d ' % len(jobs) in out, out
+
+
+def test_chain_plan_is_consistent_with_cell_count(ub):
+    """ub200_chainPlan (planner introspection) lists the same sub-DPs whose reference cell counts ub200_chainCells sums."""
+    d = load_golden('semiglobal_small.json.gz')
+    for j in golden_chain_jobs(d)[:5]:
+        plan = ub.chain_plan(len(j['readSeq']), len(j['refSeq']), j['seeds'], j['band'])
+        cells, n = ub.chain_cells(len(j['readSeq']), len(j['refSeq']), j['seeds'], j['band'])
+        assert len(plan) == n
+        total = 0
+        for kind, nH, nV, banded, lo, up, h0, v0, hNext, vNext in plan:
+            assert 0 <= h0 and h0 + nH <= len(j['readSeq']) and 0 <= v0 and v0 + nV <= len(j['refSeq'])
+            if banded:
+                dimv = min(nV + 1, min(nH, up) - max(lo, -nV) + 1)
+                total += (nH + 1 - max(0, lo)) * dimv
+            else:
+                total += (nH + 1) * (nV + 1)
+        assert total == cells

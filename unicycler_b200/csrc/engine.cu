@@ -513,7 +513,7 @@ __device__ __forceinline__ int reserveOut(int jobIdx, int outCap, int n) {
 // worst-case size of one grid's record: header + per trace (count + segments; a trace has at most
 // nH + nV + 4 segments of 4 ints)
 __device__ __forceinline__ int recordBound(const GridCtx& G, int nTraces) {
-    long long n = 3 + (long long)nTraces * (1 + 4LL * ((long long)G.g.nH + G.g.nV + 6));
+    long long n = 4 + (long long)nTraces * (1 + 4LL * ((long long)G.g.nH + G.g.nV + 6));
     return n > 0x3fffffff ? 0x3fffffff : (int)n;
 }
 
@@ -537,6 +537,7 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, i
     const int cntPos = out.len;
     out.put(0);
     out.put(reserved);
+    out.put(0);   // ints actually used (patched below); finalizeJob compacts the stream with it
     int nTraces = 0;
     TraceWalker w(G, out, win);
     if (G.kind == GRID_GLOBAL) {
@@ -562,6 +563,7 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, i
             chainTracebackOne<true>(G, w, out, rec->cand[k], (rec->inserted >> k) & 1, nPlanted, nTraces, status);
     }
     out.patch(cntPos, nTraces);
+    out.patch(cntPos + 2, out.len - pos);
     if (out.overflow && status == JOB_OK) status = JOB_OUT_OVERFLOW;
     __syncwarp();
     r.status = status; r.nPlanted = nPlanted;
@@ -812,14 +814,45 @@ __device__ __noinline__ void runPass2Grid(int jobIdx, int gi, GridCtx& G, uint8_
     __syncwarp();
 }
 
-// Marks the job complete (all passes done): final status and stream length.
-__device__ __forceinline__ void finalizeJob(int jobIdx) {
+// Marks the job complete (all passes done): final status; the records of the segment stream (reserved at their
+// worst-case size by many warps) are compacted in place so that the host copies only what was written.
+__device__ __noinline__ void finalizeJob(int jobIdx) {
     const KParams& P = cP;
-    if ((threadIdx.x & 31) == 0) {
-        const int st2 = ldRelaxed(&P.jobState[jobIdx].status);
+    const int lane = threadIdx.x & 31;
+    __threadfence();
+    const int end = ldRelaxed(&P.jobState[jobIdx].outCursor);
+    int* buf = P.out + P.jobs[jobIdx].outOff;
+    const int cap = P.jobs[jobIdx].outCap;
+    const int st2 = ldRelaxed(&P.jobState[jobIdx].status);
+    int st = __ldcg(&P.jobOut[jobIdx].status);
+    if (st == JOB_OK && st2 != JOB_OK) st = st2;
+    int dst = 0;
+    if (st == JOB_OK && end <= cap) {
+        int src = 0;
+        while (src < end) {
+            const int reserved = __ldcg(&buf[src + 2]);
+            const int used = __ldcg(&buf[src + 3]);
+            if (reserved < 4 || used < 4 || used > reserved) { st = JOB_REF_UB; break; }  // a record was never completed
+            if (dst != src) {
+                for (int k = 0; k < used; k += 32) {
+                    int v = 0;
+                    if (k + lane < used) v = __ldcg(&buf[src + k + lane]);
+                    __syncwarp();
+                    if (k + lane < used) buf[dst + k + lane] = v;
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            if (lane == 0) buf[dst + 2] = used;
+            dst += used;
+            src += reserved;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
         JobOut* jo = &P.jobOut[jobIdx];
-        if (jo->status == JOB_OK && st2 != JOB_OK) jo->status = st2;
-        jo->outLen = ldRelaxed(&P.jobState[jobIdx].outCursor);
+        jo->status = st;
+        jo->outLen = dst;
         __threadfence();
         atomicAdd(&P.cb->jobsDone, 1);
     }
@@ -1394,6 +1427,7 @@ void Engine::fetch(std::vector<Job*>& jobs) {
             int gi = p[pos++];
             int nTr = p[pos++];
             const int reserved = p[pos++];
+            ++pos;  // ints used (== reserved after the device-side compaction)
             auto& traces = r.gridTraces.at((size_t)gi);
             traces.resize((size_t)nTr);
             for (int t = 0; t < nTr; ++t) {
