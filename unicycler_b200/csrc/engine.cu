@@ -19,6 +19,25 @@ namespace ub200 {
                                      __FILE__ + ":" + std::to_string(__LINE__));                             \
     } while (0)
 
+// Layout of a big grid's persistent block (shared by host sizing and device setup).
+struct PersistLayout {
+    long long rowCk, colCk, ckBase, rowProg, segDone, initRow, initCol, total;
+};
+__host__ __device__ inline PersistLayout persistLayout(int nH, int nV, int NS, int ckTiles) {
+    PersistLayout p;
+    long long o = 0;
+    auto place = [&](long long& f, long long bytes) { f = o; o += (bytes + 255) / 256 * 256; };
+    place(p.rowCk, (long long)NS * (nH + 1) * (long long)sizeof(int2));
+    place(p.colCk, (long long)ckTiles * SH * (long long)sizeof(int2));
+    place(p.ckBase, (long long)(NS + 2) * 4);
+    place(p.rowProg, (long long)(NS + 2) * 4);
+    place(p.segDone, (long long)(NS + 2) * 4);
+    place(p.initRow, (long long)(nH + 2) * (long long)sizeof(DCell));
+    place(p.initCol, (long long)(nV + 2) * (long long)sizeof(DCell));
+    p.total = o;
+    return p;
+}
+
 // ---------------------------------------------------------------------------------------
 // device: per-grid setup, init rows, tracking, chain traceback — all executed by ONE warp
 // (the control agent of the job); G lives in that warp's shared-memory slot.
@@ -60,6 +79,18 @@ __device__ __noinline__ void setupGrid(GridCtx& G, const JobDev& jb, const GridD
         G.local = lp.local; G.RR = lp.local ? lp.RR : 8; G.rrMul = 65536 / G.RR + 1; G.rrs = lp.local ? lp.RRS : 8; G.pad2 = 0; G.pitch = lp.pitch; G.localJhi = lp.jhi;
         G.NS = lp.local ? 1 : stripCount(g, SH);
         G.nSeg = (g.nH + SEG - 1) / SEG;
+        if (!lp.local && P.persist != nullptr && gd.persistOff >= 0) {
+            // big grid with its own persistent block: [rowCk | colCk | ckBase | rowProg | segDone | initRow | initCol]
+            uint8_t* pb = P.persist + gd.persistOff;
+            PersistLayout pl = persistLayout(g.nH, g.nV, G.NS, gd.ckTiles);
+            G.rowCk = reinterpret_cast<int2*>(pb + pl.rowCk);
+            G.colCk = reinterpret_cast<int2*>(pb + pl.colCk);
+            G.ckBase = reinterpret_cast<int*>(pb + pl.ckBase);
+            G.rowProg = reinterpret_cast<int*>(pb + pl.rowProg);
+            G.segDone = reinterpret_cast<int*>(pb + pl.segDone);
+            G.initRow = reinterpret_cast<DCell*>(pb + pl.initRow);
+            G.initCol = reinterpret_cast<DCell*>(pb + pl.initCol);
+        }
         // capture mode
         G.capEdges = (gd.kind == GRID_GLOBAL || (gd.kind == GRID_CHAIN_FINAL && !g.banded)) ? 1 : 0;
         if (!G.capEdges) {
@@ -513,19 +544,20 @@ __device__ __forceinline__ int reserveOut(int jobIdx, int outCap, int n) {
 // worst-case size of one grid's record: header + per trace (count + segments; a trace has at most
 // nH + nV + 4 segments of 4 ints)
 __device__ __forceinline__ int recordBound(const GridCtx& G, int nTraces) {
-    long long n = 4 + (long long)nTraces * (1 + 4LL * ((long long)G.g.nH + G.g.nV + 6));
+    long long n = 5 + (long long)nTraces * (1 + 4LL * ((long long)G.g.nH + G.g.nV + 6));
     return n > 0x3fffffff ? 0x3fffffff : (int)n;
 }
 
 // All tracebacks of one grid into a reserved record [gi, nTraces, reserved, traces...] (walker and output
 // cursor live in registers of this function).  rec == nullptr: pass-1 in-line grid (plants the next grid's
 // cells); otherwise the pass-2 replay of a recorded grid.
+// candSel >= 0 (pass 2 of a big grid): only that candidate, as a record of its own.
 __device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, int jobIdx, int* outBuf, int outCap, int gi,
-                                               int h0, int v0, int nCand, DCell maxCell, const GridRec* rec) {
+                                               int h0, int v0, int nCand, DCell maxCell, const GridRec* rec, int candSel) {
     const int lane = threadIdx.x & 31;
     TbResult r;
     r.status = JOB_OK; r.nPlanted = 0; r.pad0 = r.pad1 = 0; r.tiles = 0; r.tileCycles = 0;
-    const int nTr = (G.kind == GRID_GLOBAL) ? 1 : nCand;
+    const int nTr = (G.kind == GRID_GLOBAL || candSel >= 0) ? 1 : nCand;
     const int reserved = recordBound(G, nTr);
     const int pos = reserveOut(jobIdx, outCap, reserved);
     if (pos < 0) { r.status = JOB_OUT_OVERFLOW; return r; }
@@ -538,6 +570,7 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, i
     out.put(0);
     out.put(reserved);
     out.put(0);   // ints actually used (patched below); finalizeJob compacts the stream with it
+    out.put(candSel >= 0 ? candSel : 0);   // index of the record's first candidate (the host orders a grid's records by it)
     int nTraces = 0;
     TraceWalker w(G, out, win);
     if (G.kind == GRID_GLOBAL) {
@@ -558,6 +591,8 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, i
     } else if (rec == nullptr) {
         for (int k = 0; k < nCand && status == JOB_OK; ++k)
             chainTracebackOne<false>(G, w, out, G.cand[k], false, nPlanted, nTraces, status);
+    } else if (candSel >= 0) {
+        chainTracebackOne<true>(G, w, out, rec->cand[candSel], (rec->inserted >> candSel) & 1, nPlanted, nTraces, status);
     } else {
         for (int k = 0; k < nCand && status == JOB_OK; ++k)
             chainTracebackOne<true>(G, w, out, rec->cand[k], (rec->inserted >> k) & 1, nPlanted, nTraces, status);
@@ -571,20 +606,16 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, i
     return r;
 }
 
-// Pass 1 of a fast grid: for every tied maximum walk (trace values derived on demand from the box) to the
-// crossing with the next grid's origin and plant the crossing cell.  Returns false when the walk left the
-// box (a gap run crossing the origin line): the caller falls back to the in-line path.
-__device__ __noinline__ bool fastShortWalks(const GridCtx& G, uint8_t* win, int nCand, int& nPlanted, int& insertedMask,
-                                            int& status) {
+// Pass 1 of a big chain grid with a persistent block: the crossing walks with the generic walker (trace tiles
+// recomputed from the checkpoints), nothing emitted; the full tracebacks are pass-2 items.
+__device__ __noinline__ void bigShortWalks(const GridCtx& G, uint8_t* win, int nCand, int& nPlanted, int& insertedMask,
+                                           int& status, long long& tiles, long long& tileCycles) {
     OutStream out;
     out.buf = nullptr; out.cap = 0; out.len = 0; out.overflow = false; out.h0 = 0; out.v0 = 0; out.lane = 1;  // never writes
     TraceWalker w(G, out, win);
-    w.lazy = true;
     w.emitOn = false;
     insertedMask = 0;
     nPlanted = 0;
-    const long long dbgT0 = clock64();
-    long long dbgPlant = 0;
     for (int k = 0; k < nCand && status == JOB_OK; ++k) {
         const int startPos = G.cand[k];
         w.pc = startPos / G.g.dimV;
@@ -594,19 +625,126 @@ __device__ __noinline__ bool fastShortWalks(const GridCtx& G, uint8_t* win, int 
         Coord c = w.makeCoord(G.hNext, G.vNext);
         int frag = 0;
         while (!c.reachedEnd() && tv != T_NONE) w.doTraceback(tv, last, frag, c);
-        if (w.outOfBox) return false;
         if (w.bad) { status = JOB_REF_UB; break; }
-        const int hInit = c.currCol - c.endCol;
-        const int vInit = c.currRow - c.endRow;
-        const long long dbgP0 = clock64();
-        if (plantCrossing(G, hInit, vInit, last, nPlanted, status)) insertedMask |= 1 << k;
-        dbgPlant += clock64() - dbgP0;
+        if (plantCrossing(G, c.currCol - c.endCol, c.currRow - c.endRow, last, nPlanted, status)) insertedMask |= 1 << k;
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&gDbg[8], (unsigned long long)(clock64() - dbgT0));
-        atomicAdd(&gDbg[9], (unsigned long long)dbgPlant);
-        atomicAdd(&gDbg[10], (unsigned long long)w.tilesComputed);
-        atomicAdd(&gDbg[11], (unsigned long long)nCand);
+    tiles += w.tilesComputed; tileCycles += w.tileCycles;
+}
+
+// ---- lean crossing walk of pass 1 (matrix coordinates, trace values derived on demand from the box) ----
+struct LeanCtx {
+    const DCell* box;
+    const DCell *initRow, *initCol;
+    const uint8_t *sH, *sV;
+    int r0, c0, pitch, nV, nH, lo, up, match, mismatch, go, ge;
+    bool oob;
+};
+template <bool BANDED>
+__device__ __forceinline__ DCell leanCell(LeanCtx& L, int i, int j) {
+    if (BANDED) { const int d = j - i; if (d < L.lo || d > L.up) return DCell{NEG_INF, NEG_INF, NEG_INF}; }
+    if (i == 0) return L.initRow[j];
+    if (j == 0) return L.initCol[i];
+    if (i < L.r0 || j < L.c0) { L.oob = true; return DCell{NEG_INF, NEG_INF, NEG_INF}; }
+    return L.box[(j - L.c0) * L.pitch + (i - L.r0)];
+}
+// same value as TraceWalker::tvHere() in lazy mode (lazyTvFn)
+template <bool AFF, bool BANDED>
+__device__ __forceinline__ uint32_t leanTv(LeanCtx& L, int i, int j) {
+    if (i <= 0 || j <= 0 || i > L.nV || j > L.nH) return 0;
+    int mode = 0;
+    if (BANDED) {
+        const int d = j - i;
+        if (d < L.lo || d > L.up) return 0;
+        mode = (d == L.up) ? 1 : (d == L.lo ? 2 : 0);
+    }
+    const DCell l = leanCell<BANDED>(L, i, j - 1), u = leanCell<BANDED>(L, i - 1, j), d = leanCell<BANDED>(L, i - 1, j - 1);
+    if (i < L.r0 || j < L.c0) { L.oob = true; return 0; }
+    const int sub = (L.sH[j - L.c0] == L.sV[i - L.r0]) ? L.match : L.mismatch;
+    int ns, nh, nv;
+    return cellUpdate<AFF, true, BANDED>(ns, nh, nv, l.s, l.h, u.s, u.v, d.s, sub, L.go, L.ge, mode);
+}
+struct Crossing { int hInit, vInit; uint32_t last; int bad; };
+// The first part of chainTracebackOne for a non-final chain grid (seeds/banded_chain_alignment_traceback.h:296-307):
+// from the tracked maximum to the crossing with the next grid's origin.  Same decisions as
+// TraceWalker::doTraceback, without the storage-coordinate and segment bookkeeping.
+template <bool AFF, bool BANDED>
+__device__ __noinline__ Crossing leanCrossing(LeanCtx L, int i, int j, Coord c) {
+    Crossing r;
+    r.bad = 0;
+    uint32_t tv = leanTv<AFF, BANDED>(L, i, j);
+    uint32_t last = TraceWalker::initialDirection(tv, false);
+    int cc = c.currCol, cr = c.currRow;
+    const int ec = c.endCol, er = c.endRow;
+    while (!(cc <= ec || cr <= er) && tv != T_NONE) {
+        if (tv & T_D) {
+            last = T_D;
+            do { --i; --j; tv = leanTv<AFF, BANDED>(L, i, j); --cc; --cr; } while ((tv & T_D) && !(cc <= ec || cr <= er));
+        } else if ((tv & T_MV) && (tv & T_V)) {
+            last = T_V;
+            if (AFF) {
+                while ((!(tv & T_VO) || (tv & T_V)) && cr != 1) { --i; tv = leanTv<AFF, BANDED>(L, i, j); --cr; }
+                --i; tv = leanTv<AFF, BANDED>(L, i, j); --cr;
+            } else { --i; tv = leanTv<AFF, BANDED>(L, i, j); --cr; }
+        } else if ((tv & T_MV) && (tv & T_VO)) {
+            last = T_V;
+            --i; tv = leanTv<AFF, BANDED>(L, i, j); --cr;
+        } else if ((tv & T_MH) && (tv & T_H)) {
+            last = T_H;
+            if (AFF) {
+                while ((!(tv & T_HO) || (tv & T_H)) && cc != 1) { --j; tv = leanTv<AFF, BANDED>(L, i, j); --cc; }
+                --j; tv = leanTv<AFF, BANDED>(L, i, j); --cc;
+            } else { --j; tv = leanTv<AFF, BANDED>(L, i, j); --cc; }
+        } else if ((tv & T_MH) && (tv & T_HO)) {
+            last = T_H;
+            --j; tv = leanTv<AFF, BANDED>(L, i, j); --cc;
+        } else {
+            r.bad = 1; tv = T_NONE;
+        }
+    }
+    r.hInit = cc - ec; r.vInit = cr - er; r.last = last;
+    if (L.oob) r.bad |= 2;
+    return r;
+}
+
+// Pass 1 of a fast grid: for every tied maximum walk (trace values derived on demand from the box) to the
+// crossing with the next grid's origin and plant the crossing cell.  Returns false when the walk left the
+// box (a gap run crossing the origin line): the caller falls back to the in-line path.
+__device__ __noinline__ bool fastShortWalks(const GridCtx& G, uint8_t* win, int nCand, int& nPlanted, int& insertedMask,
+                                            int& status) {
+    OutStream out;
+    out.buf = nullptr; out.cap = 0; out.len = 0; out.overflow = false; out.h0 = 0; out.v0 = 0; out.lane = 1;  // never writes
+    TraceWalker w(G, out, win);   // only for makeCoord / storage geometry
+    LeanCtx L;
+    L.box = reinterpret_cast<const DCell*>(win);
+    L.initRow = G.initRow; L.initCol = G.initCol; L.sH = G.fastSeqH; L.sV = G.fastSeqV;
+    L.r0 = G.fastR0; L.c0 = G.fastC0; L.pitch = G.fastPitch; L.nV = G.g.nV; L.nH = G.g.nH; L.lo = G.g.lo; L.up = G.g.up;
+    L.match = G.match; L.mismatch = G.mismatch; L.go = G.go; L.ge = G.ge; L.oob = false;
+    insertedMask = 0;
+    nPlanted = 0;
+    const bool debugBoth = cP.fastEnabled == 2;
+    for (int k = 0; k < nCand && status == JOB_OK; ++k) {
+        const int startPos = G.cand[k];
+        w.pc = startPos / G.g.dimV;
+        w.pv = startPos % G.g.dimV;
+        const Coord c = w.makeCoord(G.hNext, G.vNext);
+        const int j = w.pc, i = w.pv - storageOffset(G.g, w.pc);
+        Crossing x;
+        if (G.affine) x = G.g.banded ? leanCrossing<true, true>(L, i, j, c) : leanCrossing<true, false>(L, i, j, c);
+        else x = G.g.banded ? leanCrossing<false, true>(L, i, j, c) : leanCrossing<false, false>(L, i, j, c);
+        if (x.bad & 2) return false;            // left the box (a gap run crossing the origin line)
+        if (x.bad) { status = JOB_REF_UB; break; }
+        if (debugBoth) {  // developer check: the generic walker in lazy mode must find the same crossing
+            w.lazy = true; w.emitOn = false; w.outOfBox = false;
+            uint32_t tv = w.tvHere();
+            uint32_t last = TraceWalker::initialDirection(tv, false);
+            Coord c2 = w.makeCoord(G.hNext, G.vNext);
+            int frag = 0;
+            while (!c2.reachedEnd() && tv != T_NONE) w.doTraceback(tv, last, frag, c2);
+            if (w.outOfBox || c2.currCol - c2.endCol != x.hInit || c2.currRow - c2.endRow != x.vInit || last != x.last) {
+                status = JOB_REF_UB; break;
+            }
+        }
+        if (plantCrossing(G, x.hInit, x.vInit, x.last, nPlanted, status)) insertedMask |= 1 << k;
     }
     return true;
 }
@@ -777,13 +915,26 @@ __device__ __noinline__ int publishAndWait(const GridCtx& G, GridCtx& wctx, int&
 // ---------------------------------------------------------------------------------------
 // pass 2: one recorded grid, start to end, on any control-capable warp
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void runPass2Grid(int jobIdx, int gi, GridCtx& G, uint8_t* win, uint8_t* mini) {
+__device__ __noinline__ void runPass2Grid(int jobIdx, int item, GridCtx& G, uint8_t* win, uint8_t* mini) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
+    const int gi = item / MAXREC, ksel = item - gi * MAXREC;
     const JobDev jb = P.jobs[jobIdx];
     const GridRec* rec = &P.gridRecs[jb.gridBegin + gi];
-    if (rec->state != 1) return;  // done in line by pass 1
+    const int state = rec->state;
+    if (state == 0) return;                                   // done in line by pass 1
+    if (state == 1 && ksel != 0) return;                       // small grid: item 0 walks every candidate
+    if (state == 2 && ksel >= rec->nCand) return;              // big grid: one candidate per item
     const GridDesc gd = P.grids[jb.gridBegin + gi];
+    if (state == 2) {
+        // checkpoints, init row and column live in the grid's persistent block
+        setupGrid(G, jb, gd, nullptr);
+        const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, rec->nCand,
+                                          DCell{0, 0, 0}, rec, ksel);
+        if (tb.status != JOB_OK && lane == 0) atomicMax(&P.jobState[jobIdx].status, tb.status);
+        __syncwarp();
+        return;
+    }
     setupGrid(G, jb, gd, nullptr);
     if (lane == 0) {  // only the init row / column are needed (this warp's mini arena)
         G.initRow = reinterpret_cast<DCell*>(mini);
@@ -809,7 +960,7 @@ __device__ __noinline__ void runPass2Grid(int jobIdx, int gi, GridCtx& G, uint8_
     __syncwarp();
     localFill(G, win, false);
     const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, rec->nCand,
-                                      DCell{0, 0, 0}, rec);
+                                      DCell{0, 0, 0}, rec, -1);
     if (tb.status != JOB_OK && lane == 0) atomicMax(&P.jobState[jobIdx].status, tb.status);
     __syncwarp();
 }
@@ -832,7 +983,7 @@ __device__ __noinline__ void finalizeJob(int jobIdx) {
         while (src < end) {
             const int reserved = __ldcg(&buf[src + 2]);
             const int used = __ldcg(&buf[src + 3]);
-            if (reserved < 4 || used < 4 || used > reserved) { st = JOB_REF_UB; break; }  // a record was never completed
+            if (reserved < 5 || used < 5 || used > reserved) { st = JOB_REF_UB; break; }  // a record was never completed
             if (dst != src) {
                 for (int k = 0; k < used; k += 32) {
                     int v = 0;
@@ -960,9 +1111,21 @@ __device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& G, GridCtx& 
             if (status == JOB_OK) status = TR.status;
             if (status == JOB_OK && TR.maxScore < -1000000) status = JOB_BAD_SCORE;  // the RRW throw
             nPlanted = 0;
-            if (status == JOB_OK) {
+            const bool deferBig = status == JOB_OK && !G.local && P.persist != nullptr && gd.persistOff >= 0 &&
+                                  gd.kind != GRID_GLOBAL && TR.nCand <= MAXREC && nPlantedPrev <= MAXREC && P.fastEnabled;
+            if (deferBig) {
+                // big chain grid: only the crossing walks here, one pass-2 item per tied maximum
+                int insertedMask = 0;
+                if (gd.kind != GRID_CHAIN_FINAL)
+                    bigShortWalks(G, win, TR.nCand, nPlanted, insertedMask, status, prof[6], prof[7]);
+                if (lane == 0) {
+                    rec->state = 2; rec->nCand = TR.nCand; rec->inserted = insertedMask; rec->nPlantedIn = nPlantedPrev;
+                    for (int k = 0; k < TR.nCand; ++k) rec->cand[k] = G.cand[k];
+                }
+                ++nFast;
+            } else if (status == JOB_OK) {
                 const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, TR.nCand,
-                                                  TR.maxCell, nullptr);
+                                                  TR.maxCell, nullptr, -1);
                 status = tb.status; nPlanted = tb.nPlanted;
                 prof[6] += tb.tiles; prof[7] += tb.tileCycles;
                 prof[9] += (gd.kind == GRID_GLOBAL) ? 1 : TR.nCand;
@@ -994,7 +1157,7 @@ __device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& G, GridCtx& 
         if (lane == 0) {
             t = atomicAdd(&P.cb->p2Tail, 1);
             P2Entry* e = &P.p2ring[t];
-            e->jobIdx = jobIdx; e->nItems = jb.gridCount; e->nextItem = 0; e->doneItems = 0;
+            e->jobIdx = jobIdx; e->nItems = jb.gridCount * MAXREC; e->nextItem = 0; e->doneItems = 0;
             __threadfence();
             stRelease(&e->ready, 1);
         }
@@ -1093,6 +1256,7 @@ struct Engine::Impl {
     void* dRing = nullptr; size_t capRing = 0;   // ControlBlock, task boards, pass-2 board, job states (zeroed per launch)
     void* dRecs = nullptr; size_t capRecs = 0;   // pass-1 grid records
     void* dMini = nullptr; size_t capMini = 0;   // init row / column of pass-2 grids, one per control warp
+    void* dPersist = nullptr; size_t capPersist = 0;  // persistent blocks of the big chain grids
     // pinned host staging
     void* hSeq = nullptr; size_t capHSeq = 0;
     void* hOut = nullptr; size_t capHOut = 0;
@@ -1148,7 +1312,7 @@ Engine::~Engine() {
     if (!impl_) return;
     cudaSetDevice(impl_->device);
     cudaFree(impl_->dJobs); cudaFree(impl_->dGrids); cudaFree(impl_->dSeq); cudaFree(impl_->dOut);
-    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dScratch); cudaFree(impl_->dRing); cudaFree(impl_->dRecs); cudaFree(impl_->dMini);
+    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dScratch); cudaFree(impl_->dRing); cudaFree(impl_->dRecs); cudaFree(impl_->dMini); cudaFree(impl_->dPersist);
     cudaFreeHost(impl_->hSeq); cudaFreeHost(impl_->hOut);
     for (auto& ev : impl_->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(impl_->stream);
@@ -1177,6 +1341,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     ScratchLayout L;
     memset(&L, 0, sizeof(L));
     long long maxRowCk = 0, maxColCk = 0, maxBox = 1, ckBytes = 0;
+    long long maxRowCkNP = 0, maxColCkNP = 0, persistTotal = 0;   // NP: grids without a persistent block
     int maxNH = 1, maxNV = 1, maxCapH = 1, maxCapV = 1, maxStrips = 1;
     size_t nTasks = 0;
     std::vector<long long> cost(nJobs, 0);
@@ -1211,6 +1376,15 @@ void Engine::upload(std::vector<Job*>& jobs) {
                 maxRowCk = std::max(maxRowCk, rck);
                 maxColCk = std::max(maxColCk, cck);
                 maxStrips = std::max(maxStrips, ns);
+                GridDesc& gg = I.gridsAll.back();
+                gg.ckTiles = (int32_t)(cck / (SH * (long long)sizeof(int2)));
+                if (gd.kind != GRID_GLOBAL) {   // chain grids: checkpoints must outlive the leader's next grid (pass 2)
+                    gg.persistOff = persistTotal;
+                    persistTotal += persistLayout(gd.nH, gd.nV, ns, gg.ckTiles).total;
+                } else {
+                    maxRowCkNP = std::max(maxRowCkNP, rck);
+                    maxColCkNP = std::max(maxColCkNP, cck);
+                }
             }
             maxNH = std::max(maxNH, gd.nH); maxNV = std::max(maxNV, gd.nV);
             maxCapH = std::max(maxCapH, gd.capNextH); maxCapV = std::max(maxCapV, gd.capNextV);
@@ -1231,8 +1405,9 @@ void Engine::upload(std::vector<Job*>& jobs) {
         totalCells += j.cells;
         // segment stream capacity: every grid reserves its worst case (3 + traces * (1 + 4 * (nH + nV + 6)) ints)
         long long cap = 0;
-        for (const GridDesc& gd : j.grids) cap += 3 + 2LL * (1 + 4LL * ((long long)gd.nH + gd.nV + 6));
+        for (const GridDesc& gd : j.grids) cap += 5 + 2LL * (1 + 4LL * ((long long)gd.nH + gd.nV + 6));
         cap += 4LL * ((long long)j.lenH + j.lenV) + 1024;
+        cap *= std::max(1, j.outScale);
         if (cap > (1LL << 30)) cap = 1LL << 30;
         d.outOff = (long long)outOff;
         d.outCap = (int)cap;
@@ -1242,6 +1417,12 @@ void Engine::upload(std::vector<Job*>& jobs) {
     std::stable_sort(I.order.begin(), I.order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     I.seqBytes = off;
     I.outInts = outOff;
+    // persistent blocks only if they fit comfortably (otherwise big grids are traced back in line from the arena)
+    size_t freeB0 = 0, totalB0 = 0;
+    CUDA_CHECK(cudaMemGetInfo(&freeB0, &totalB0));
+    const bool usePersist = persistTotal > 0 && (size_t)persistTotal <= (freeB0 + I.capPersist) / 3 && !getenv("UNICYCLER_B200_NO_PERSIST");
+    if (usePersist) { maxRowCk = maxRowCkNP; maxColCk = maxColCkNP; }
+    else for (GridDesc& gg : I.gridsAll) gg.persistOff = -1;
     // arena layout of one control agent
     size_t o = 0;
     auto place = [&](long long& field, size_t bytes) { field = (long long)o; o += alignUp(bytes, 256); };
@@ -1280,7 +1461,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     const size_t miniInitCol = alignUp((size_t)(maxLocalNH + 2) * sizeof(DCell), 256);
     const size_t miniStride = miniInitCol + alignUp((size_t)(maxLocalNV + 2) * sizeof(DCell), 256);
     size_t fixed = nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + I.seqBytes + I.outInts * 4 +
-                   I.ringBytes + (64u << 20);
+                   I.ringBytes + (usePersist ? (size_t)persistTotal : 0) + (64u << 20);
     size_t budget = (freeB + I.capScratch > fixed) ? (size_t)((freeB + I.capScratch - fixed) * 0.9) : 0;
     long long byMem = (long long)(budget / (size_t)L.total);
     int nSlots = (int)std::min<long long>(std::min<long long>((long long)nJobs, (long long)NCTRL * I.numSMs),
@@ -1297,6 +1478,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.growDev(I.dRing, I.capRing, I.ringBytes);
     I.growDev(I.dRecs, I.capRecs, (I.gridsAll.size() + 1) * sizeof(GridRec));
     I.growDev(I.dMini, I.capMini, miniStride * (size_t)NCTRL * I.numSMs);
+    if (usePersist) I.growDev(I.dPersist, I.capPersist, (size_t)persistTotal + 256);
     I.growHost(I.hOut, I.capHOut, I.outInts * sizeof(int) + 64);
     CUDA_CHECK(cudaEventRecord(I.ev[0], I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dSeq, I.hSeq, I.seqBytes, cudaMemcpyHostToDevice, I.stream));
@@ -1317,8 +1499,9 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.p2ring = (P2Entry*)((uint8_t*)I.dRing + offP2);
     kp.jobState = (JobState*)((uint8_t*)I.dRing + offState);
     kp.gridRecs = (GridRec*)I.dRecs;
+    kp.persist = usePersist ? (uint8_t*)I.dPersist : nullptr;
     kp.mini = (uint8_t*)I.dMini; kp.miniStride = (long long)miniStride; kp.miniInitCol = (long long)miniInitCol;
-    kp.fastEnabled = getenv("UNICYCLER_B200_NO_FAST") ? 0 : 1; kp.pad5 = 0;
+    kp.fastEnabled = getenv("UNICYCLER_B200_NO_FAST") ? 0 : (getenv("UNICYCLER_B200_CHECK_FAST") ? 2 : 1); kp.pad5 = 0;
     kp.scratch = (uint8_t*)I.dScratch; kp.scratchStride = L.total;
     kp.lay = L;
     CUDA_CHECK(cudaMemcpyToSymbolAsync(cP, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, I.stream));
@@ -1402,7 +1585,6 @@ void Engine::fetch(std::vector<Job*>& jobs) {
         unsigned long long dbg[16];
         if (cudaMemcpyFromSymbol(dbg, gDbg, sizeof(dbg)) == cudaSuccess) {
             fprintf(stderr, "[ub200 dbg] unbanded trace strips=%llu total=%llu steps-cycles=%llu nsteps=%llu | banded strips=%llu total=%llu steps-cycles=%llu nsteps=%llu (cumulative)\n", dbg[3], dbg[0], dbg[1], dbg[2], dbg[7], dbg[4], dbg[5], dbg[6]);
-            fprintf(stderr, "[ub200 dbg] short walks: cycles=%llu plant-cycles=%llu lazyTv=%llu candidates=%llu (cumulative)\n", dbg[8], dbg[9], dbg[10], dbg[11]);
         }
         const long long* wp = I.jobOut[worst].prof;
         fprintf(stderr, "[ub200 profile] worst job %zu (%d grids): setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",
@@ -1421,6 +1603,8 @@ void Engine::fetch(std::vector<Job*>& jobs) {
         if (jo.status != JOB_OK) continue;
         const int* p = hOut + d.outOff;
         int pos = 0;
+        // a big grid's candidates arrive as separate records: (grid, first candidate) -> order of arrival
+        std::vector<std::pair<std::pair<int, int>, std::vector<std::vector<Seg> > > > parts;
         while (pos < jo.outLen) {
             // record: [grid index, traces, reserved ints, traces...]; records are written by many warps, in any order
             const int recBegin = pos;
@@ -1428,7 +1612,9 @@ void Engine::fetch(std::vector<Job*>& jobs) {
             int nTr = p[pos++];
             const int reserved = p[pos++];
             ++pos;  // ints used (== reserved after the device-side compaction)
-            auto& traces = r.gridTraces.at((size_t)gi);
+            const int firstCand = p[pos++];
+            parts.emplace_back(std::make_pair(gi, firstCand), std::vector<std::vector<Seg> >());
+            auto& traces = parts.back().second;
             traces.resize((size_t)nTr);
             for (int t = 0; t < nTr; ++t) {
                 int nSeg = p[pos++];
@@ -1440,6 +1626,11 @@ void Engine::fetch(std::vector<Job*>& jobs) {
                 }
             }
             pos = recBegin + reserved;
+        }
+        std::stable_sort(parts.begin(), parts.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        for (auto& part : parts) {
+            auto& dst = r.gridTraces.at((size_t)part.first.first);
+            for (auto& t : part.second) dst.push_back(std::move(t));
         }
     }
 }
@@ -1460,6 +1651,16 @@ void Engine::run(std::vector<Job*>& jobs) {
     fetch(jobs);
     if (getenv("UNICYCLER_B200_PROFILE"))
         fprintf(stderr, "[ub200 engine] upload=%.1f ms kernel(sync)=%.1f ms fetch=%.1f ms\n", t1 - t0, t2 - t1, wallMs() - t2);
+    // jobs whose segment stream overflowed (many tied tracebacks) are rerun with a larger stream
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        std::vector<Job*> again;
+        for (Job* j : jobs)
+            if (j->result.status == JOB_OUT_OVERFLOW) { j->outScale *= 8; again.push_back(j); }
+        if (again.empty()) break;
+        upload(again);
+        launch();
+        fetch(again);
+    }
 }
 
 }  // namespace ub200

@@ -49,6 +49,10 @@ struct GridDesc {
     // banded chain grids: the column descriptors of _computeBandedAlignment for the columns >= hNext
     // (host-side BandWalker), index into the job's / batch's ColInfo pool
     int32_t colTabOff, nColTab;
+    // big grids (filled by worker items): the grid's persistent block (checkpoints, progress counters, init
+    // row/column) inside the batch's persistent buffer, set by Engine::upload; -1: none (per-agent arena)
+    int64_t persistOff;
+    int32_t ckTiles, pad;    // number of 256-row column-checkpoint tiles of the grid
 };
 
 struct Seg {                 // seqan/align/dp_trace_segment.h (TraceSegment_)
@@ -81,6 +85,7 @@ struct Job {
     int32_t complete = 0;        // CompleteTrace (chain) vs SingleTrace (global/path)
     std::vector<GridDesc> grids;
     std::vector<ColInfo> colTab;  // pool referenced by GridDesc::colTabOff (relative to this job)
+    int32_t outScale = 1;         // multiplier of the segment-stream capacity (raised when a run overflowed)
     JobResult result;
     // DP cells as the reference counts them (dimH*dimV per sub-DP)
     int64_t cells = 0;

@@ -30,7 +30,7 @@ constexpr int NCTRL = 4;                 // control-capable warps per CTA
 constexpr int MODE_TASK = 0;             // score-only strip item of a published grid (checkpoints to HBM)
 constexpr int MODE_TRACE = 1;            // full trace bytes into the shared-memory window
 constexpr int MODE_FAST = 2;             // score-only local fill, box cells (S,H,V) into the shared-memory window
-constexpr int MAXREC = 4;                // candidates / planted cells a pass-1 grid record can hold
+constexpr int MAXREC = 8;                // candidates / planted cells a pass-1 grid record can hold
 constexpr unsigned FULLMASK = 0xffffffffu;
 
 struct DCell {
@@ -107,7 +107,8 @@ constexpr int FASTSEQ_H = 768, FASTSEQ_V = 256;   // capacity of the staged code
 
 // Pass-1 record of a chain grid: everything pass 2 needs to redo the grid on its own.
 struct GridRec {
-    int state;        // 0: not fast (done in line by pass 1), 1: fast (pass 2 fills the trace and walks)
+    int state;        // 0: done in line by pass 1; 1: small grid (pass 2 fills the trace and walks all candidates);
+                      // 2: big grid with a persistent block (pass 2 walks one candidate per item)
     int nCand, inserted, nPlantedIn;
     int cand[MAXREC];
     PlantedCell plantedIn[MAXREC];
@@ -154,6 +155,7 @@ struct KParams {
     P2Entry* p2ring;   // [nJobs]
     JobState* jobState;
     GridRec* gridRecs; // [total grids]
+    uint8_t* persist;  // persistent blocks of the big grids (GridDesc::persistOff), nullptr: disabled
     uint8_t* mini;     // per control warp: initRow/initCol for pass-2 grids
     long long miniStride, miniInitCol;
     int fastEnabled, pad5;

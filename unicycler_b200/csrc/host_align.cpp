@@ -78,7 +78,7 @@ struct Planner {
             if (lo <= -(long)g.nV && up >= (long)g.nH) { g.banded = 0; g.lo = 0; g.up = 0; }
         }
         if (kind == GRID_CHAIN_FINAL && !g.banded && (hNext != 0 || vNext != 0)) ok = false;
-        g.colTabOff = 0; g.nColTab = 0;
+        g.colTabOff = 0; g.nColTab = 0; g.persistOff = -1; g.ckTiles = 0; g.pad = 0;
         if (colTab && ok && g.banded && kind != GRID_GLOBAL) {
             // literal column walk of _computeBandedAlignment; the tracking pass needs the columns right of
             // the next grid's origin (seeds/banded_chain_alignment_impl.h:282-377)
@@ -278,7 +278,7 @@ bool planGlobal(long lenH, long lenV, bool banded, long lo, long up, bool freeFi
     if (banded && lo <= -lenV && up >= lenH) { g.banded = 0; g.lo = 0; g.up = 0; }
     g.hNext = 0; g.vNext = 0; g.capNextH = 0; g.capNextV = 0; g.plantZerosH = 0; g.plantZerosV = 0;
     g.glue = GLUE_ASSIGN; g.checkScore = 1;
-    g.colTabOff = 0; g.nColTab = 0;
+    g.colTabOff = 0; g.nColTab = 0; g.persistOff = -1; g.ckTiles = 0; g.pad = 0;
     grids.push_back(g);
     return true;
 }
