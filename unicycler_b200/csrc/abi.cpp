@@ -363,13 +363,14 @@ int ub200_globalAlignmentBatch(int n, const char* const* s1, const char* const* 
     const bool path = mode == 1;
     std::vector<std::unique_ptr<PairJob> > pjs((size_t)n);
     std::vector<Job*> jobs;
-    for (int i = 0; i < n; ++i) {
+    parallelFor(n, [&](int i) {
         pjs[(size_t)i].reset(new PairJob());
         buildPairJob(*pjs[(size_t)i], s1[i], s2[i], sc, useBanding, bandSize, path);
+    });
+    for (int i = 0; i < n; ++i)
         if (pjs[(size_t)i]->planned) jobs.push_back(&pjs[(size_t)i]->job);
-    }
     engine().run(jobs);
-    for (int i = 0; i < n; ++i) results[i] = dupString(finishPairJob(*pjs[(size_t)i], sc, path));
+    parallelFor(n, [&](int i) { results[i] = dupString(finishPairJob(*pjs[(size_t)i], sc, path)); });
     return 0;
 }
 
@@ -387,27 +388,37 @@ char* getRandomSequenceAlignmentScores(int seqLength, int n, int m, int mm, int 
     const long long cellsPerPair = (long long)(seqLength + 1) * (seqLength + 1);
     long long perBatch = std::max(1LL, std::min<long long>(n, (1LL << 32) / std::max(1LL, cellsPerPair)));
     perBatch = std::min(perBatch, 65536LL);
-    std::string a((size_t)seqLength, 'A'), b((size_t)seqLength, 'A');
     for (long long done = 0; done < n; done += perBatch) {
-        long long cnt = std::min<long long>(perBatch, n - done);
-        std::vector<std::unique_ptr<PairJob> > pjs((size_t)cnt);
-        std::vector<Job*> jobs;
+        const long long cnt = std::min<long long>(perBatch, n - done);
+        // the random stream is drawn in the reference's order (s1 then s2 of each pair); everything else is
+        // independent per pair and runs on the host cores
+        std::vector<std::string> as((size_t)cnt, std::string((size_t)seqLength, 'A')), bs((size_t)cnt, std::string((size_t)seqLength, 'A'));
         for (long long i = 0; i < cnt; ++i) {
-            for (int k = 0; k < seqLength; ++k) a[(size_t)k] = bases[dist(gen)];
-            for (int k = 0; k < seqLength; ++k) b[(size_t)k] = bases[dist(gen)];
-            pjs[(size_t)i].reset(new PairJob());
-            buildPairJob(*pjs[(size_t)i], a.c_str(), b.c_str(), sc, false, 0, false);
-            if (pjs[(size_t)i]->planned) jobs.push_back(&pjs[(size_t)i]->job);
+            for (int k = 0; k < seqLength; ++k) as[(size_t)i][(size_t)k] = bases[dist(gen)];
+            for (int k = 0; k < seqLength; ++k) bs[(size_t)i][(size_t)k] = bases[dist(gen)];
         }
+        std::vector<std::unique_ptr<PairJob> > pjs((size_t)cnt);
+        parallelFor((int)cnt, [&](int i) {
+            pjs[(size_t)i].reset(new PairJob());
+            buildPairJob(*pjs[(size_t)i], as[(size_t)i].c_str(), bs[(size_t)i].c_str(), sc, false, 0, false);
+        });
+        std::vector<Job*> jobs;
+        for (long long i = 0; i < cnt; ++i)
+            if (pjs[(size_t)i]->planned) jobs.push_back(&pjs[(size_t)i]->job);
         engine().run(jobs);
-        for (long long i = 0; i < cnt; ++i) {
+        std::vector<double> batchScores((size_t)cnt, 0.0);
+        std::vector<char> have((size_t)cnt, 0);
+        parallelFor((int)cnt, [&](int i) {
             PairJob& pj = *pjs[(size_t)i];
-            if (!pj.planned || pj.job.result.status != JOB_OK) continue;  // "if (alignment != 0)"
+            if (!pj.planned || pj.job.result.status != JOB_OK) return;  // "if (alignment != 0)"
             AlignmentRecord rec;
             scoreAlignment(pj.job.result.gridTraces[0][0], false, pj.H.data(), (long)pj.H.size(), pj.V.data(),
                            (long)pj.V.size(), 0, true, true, true, sc, rec);
-            scores.push_back(rec.scaledScore);
-        }
+            batchScores[(size_t)i] = rec.scaledScore;
+            have[(size_t)i] = 1;
+        });
+        for (long long i = 0; i < cnt; ++i)
+            if (have[(size_t)i]) scores.push_back(batchScores[(size_t)i]);
     }
     double mean = 0.0, sd = 0.0;  // getMeanAndStDev :187-202 (population sd)
     if (!scores.empty()) {

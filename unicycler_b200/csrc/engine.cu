@@ -43,7 +43,8 @@ __host__ __device__ inline PersistLayout persistLayout(int nH, int nV, int NS, i
 // (the control agent of the job); G lives in that warp's shared-memory slot.
 // ---------------------------------------------------------------------------------------
 
-__device__ __noinline__ void setupGrid(GridCtx& G, const JobDev& jb, const GridDesc& gd, uint8_t* arena, uint8_t* fastSeq = nullptr) {
+__device__ __noinline__ void setupGrid(GridCtx& Gin, const JobDev& jb, const GridDesc& gd, uint8_t* arena, uint8_t* fastSeq = nullptr) {
+    GridCtx& G = *toShared(&Gin);
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     if (lane == 0) {
@@ -78,7 +79,8 @@ __device__ __noinline__ void setupGrid(GridCtx& G, const JobDev& jb, const GridD
         const LocalPlan lp = localPlan(g);
         G.local = lp.local; G.RR = lp.local ? lp.RR : 8; G.rrMul = 65536 / G.RR + 1; G.rrs = lp.local ? lp.RRS : 8; G.pad2 = 0; G.pitch = lp.pitch; G.localJhi = lp.jhi;
         G.NS = lp.local ? 1 : stripCount(g, SH);
-        G.nSeg = (g.nH + SEG - 1) / SEG;
+        // banded strips are short (band width + 256 columns): one item per strip; unbanded rows are cut into segments
+        G.nSeg = g.banded ? 1 : (g.nH + SEG - 1) / SEG;
         if (!lp.local && P.persist != nullptr && gd.persistOff >= 0) {
             // big grid with its own persistent block: [rowCk | colCk | ckBase | rowProg | segDone | initRow | initCol]
             uint8_t* pb = P.persist + gd.persistOff;
@@ -118,7 +120,8 @@ __device__ __noinline__ void setupGrid(GridCtx& G, const JobDev& jb, const GridD
 }
 
 // Per-strip tables of a task grid (checkpoint bases, progress counters).  One warp.
-__device__ __noinline__ void setupStrips(const GridCtx& G) {
+__device__ __noinline__ void setupStrips(const GridCtx& Gin) {
+    const GridCtx& G = *toShared(&Gin);
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     int base = 0;
@@ -135,7 +138,7 @@ __device__ __noinline__ void setupStrips(const GridCtx& G) {
             G.ckBase[s] = base + incl - cnt;
             const int jlo = stripJlo(g, s, SH);
             G.rowProg[s] = jlo - 1;
-            G.segDone[s] = (jlo - 1) / SEG;
+            G.segDone[s] = g.banded ? 0 : (jlo - 1) / SEG;
         }
         base += __shfl_sync(FULLMASK, incl, 31);
     }
@@ -145,7 +148,8 @@ __device__ __noinline__ void setupStrips(const GridCtx& G) {
 // Fill the init row / column of the grid (cells the reference takes from
 // _horizontalInitCurrentMatrix / _verticalInitCurrentMatrix, or computes with the
 // Horizontal / Vertical / Zero recursions for the default profile).  One warp.
-__device__ __noinline__ void initGrid(const GridCtx& G, const GridDesc& gd, int nPlanted) {
+__device__ __noinline__ void initGrid(const GridCtx& Gin, const GridDesc& gd, int nPlanted) {
+    const GridCtx& G = *toShared(&Gin);
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     const DCell def = DCell{NEG_INF, NEG_INF, NEG_INF};
@@ -331,7 +335,9 @@ __device__ __forceinline__ DCell trackedCellFast(const GridCtx& G, const DCell* 
 // the maximum over the tracked cells and collects every tied maximum in visiting order
 // (seeds/banded_chain_alignment_scout.h:230-270).  Visiting order == ascending host position.
 template <bool FAST>
-__device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res, const DCell* boxS) {
+__device__ __noinline__ void trackChain(const GridCtx& Gin, TrackResult& res, const DCell* boxIn) {
+    const GridCtx& G = *toShared(&Gin);
+    const DCell* boxS = FAST ? toShared(boxIn) : nullptr;
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     int ub = 0;
@@ -380,7 +386,8 @@ __device__ __noinline__ void trackChain(const GridCtx& G, TrackResult& res, cons
 // strict ">" (seqan/align/dp_scout.h:163-179) over the cells dp_meta_info.h marks tracked: the last-row
 // cells when the last row is free, then the band cells of the final column (all of them when the last
 // column is free, otherwise only the corner).  One warp.
-__device__ __noinline__ void trackGlobal(const GridCtx& G, TrackResult& res) {
+__device__ __noinline__ void trackGlobal(const GridCtx& Gin, TrackResult& res) {
+    const GridCtx& G = *toShared(&Gin);
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     const bool feLastRow = G.fe & 4, feLastCol = G.fe & 8;
@@ -552,8 +559,9 @@ __device__ __forceinline__ int recordBound(const GridCtx& G, int nTraces) {
 // cursor live in registers of this function).  rec == nullptr: pass-1 in-line grid (plants the next grid's
 // cells); otherwise the pass-2 replay of a recorded grid.
 // candSel >= 0 (pass 2 of a big grid): only that candidate, as a record of its own.
-__device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, int jobIdx, int* outBuf, int outCap, int gi,
+__device__ __noinline__ TbResult tracebackGrid(const GridCtx& Gin, uint8_t* win, int jobIdx, int* outBuf, int outCap, int gi,
                                                int h0, int v0, int nCand, DCell maxCell, const GridRec* rec, int candSel) {
+    const GridCtx& G = *toShared(&Gin);
     const int lane = threadIdx.x & 31;
     TbResult r;
     r.status = JOB_OK; r.nPlanted = 0; r.pad0 = r.pad1 = 0; r.tiles = 0; r.tileCycles = 0;
@@ -608,8 +616,9 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& G, uint8_t* win, i
 
 // Pass 1 of a big chain grid with a persistent block: the crossing walks with the generic walker (trace tiles
 // recomputed from the checkpoints), nothing emitted; the full tracebacks are pass-2 items.
-__device__ __noinline__ void bigShortWalks(const GridCtx& G, uint8_t* win, int nCand, int& nPlanted, int& insertedMask,
+__device__ __noinline__ void bigShortWalks(const GridCtx& Gin, uint8_t* win, int nCand, int& nPlanted, int& insertedMask,
                                            int& status, long long& tiles, long long& tileCycles) {
+    const GridCtx& G = *toShared(&Gin);
     OutStream out;
     out.buf = nullptr; out.cap = 0; out.len = 0; out.overflow = false; out.h0 = 0; out.v0 = 0; out.lane = 1;  // never writes
     TraceWalker w(G, out, win);
@@ -669,6 +678,7 @@ struct Crossing { int hInit, vInit; uint32_t last; int bad; };
 // TraceWalker::doTraceback, without the storage-coordinate and segment bookkeeping.
 template <bool AFF, bool BANDED>
 __device__ __noinline__ Crossing leanCrossing(LeanCtx L, int i, int j, Coord c) {
+    L.box = toShared(L.box); L.sH = toShared(L.sH); L.sV = toShared(L.sV);
     Crossing r;
     r.bad = 0;
     uint32_t tv = leanTv<AFF, BANDED>(L, i, j);
@@ -709,8 +719,9 @@ __device__ __noinline__ Crossing leanCrossing(LeanCtx L, int i, int j, Coord c) 
 // Pass 1 of a fast grid: for every tied maximum walk (trace values derived on demand from the box) to the
 // crossing with the next grid's origin and plant the crossing cell.  Returns false when the walk left the
 // box (a gap run crossing the origin line): the caller falls back to the in-line path.
-__device__ __noinline__ bool fastShortWalks(const GridCtx& G, uint8_t* win, int nCand, int& nPlanted, int& insertedMask,
+__device__ __noinline__ bool fastShortWalks(const GridCtx& Gin, uint8_t* win, int nCand, int& nPlanted, int& insertedMask,
                                             int& status) {
+    const GridCtx& G = *toShared(&Gin);
     OutStream out;
     out.buf = nullptr; out.cap = 0; out.len = 0; out.overflow = false; out.h0 = 0; out.v0 = 0; out.lane = 1;  // never writes
     TraceWalker w(G, out, win);   // only for makeCoord / storage geometry
@@ -778,8 +789,8 @@ __device__ __forceinline__ void localFill(const GridCtx& G, uint8_t* win, bool c
 __device__ __forceinline__ void localFillFast(const GridCtx& G, uint8_t* win) {
     {   // stage the base codes of the box rows / columns for the lazy trace derivation
         const int lane = threadIdx.x & 31;
-        uint8_t* sh = const_cast<uint8_t*>(G.fastSeqH);
-        uint8_t* sv = const_cast<uint8_t*>(G.fastSeqV);
+        uint8_t* sh = toShared(const_cast<uint8_t*>(G.fastSeqH));
+        uint8_t* sv = toShared(const_cast<uint8_t*>(G.fastSeqV));
         const int nc = G.g.nH - G.fastC0 + 1, nr = G.fastPitch;
         for (int c = lane; c < nc; c += 32) sh[c] = G.seqH[G.fastC0 + c - 1];
         for (int r = lane; r < nr; r += 32) sv[r] = G.seqV[G.fastR0 + r - 1];
@@ -795,14 +806,15 @@ __device__ __forceinline__ void localFillFast(const GridCtx& G, uint8_t* win) {
 }
 
 // One (strip, segment) work item of a published task: score-only fill.
-__device__ __noinline__ void runItem(const GridCtx& G, int item) {
+__device__ __noinline__ void runItem(const GridCtx& Gin, int item) {
+    const GridCtx& G = *toShared(&Gin);
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     const int seg = item / G.NS;
     const int s = item - seg * G.NS;
     const int jlo = stripJlo(g, s, SH), jhi = stripJhi(g, s, SH);
-    const int cBeg = imax(seg * SEG + 1, jlo);
-    const int cEnd = imin((seg + 1) * SEG, jhi);
+    const int cBeg = g.banded ? jlo : imax(seg * SEG + 1, jlo);
+    const int cEnd = g.banded ? jhi : imin((seg + 1) * SEG, jhi);
     if (cBeg > cEnd) return;  // the strip holds no band cells in this segment
     const bool fromCk = cBeg > jlo;
     if (fromCk) {  // the previous segment of this strip must be complete (its column checkpoint is our state)
@@ -874,7 +886,8 @@ __device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask) {
 }
 
 // Publishes the control warp's grid as a task and helps until every item of it is done.
-__device__ __noinline__ int publishAndWait(const GridCtx& G, GridCtx& wctx, int& wTask, int board) {
+__device__ __noinline__ int publishAndWait(const GridCtx& Gin, GridCtx& wctx, int& wTask, int board) {
+    const GridCtx& G = *toShared(&Gin);
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     setupStrips(G);
@@ -915,7 +928,8 @@ __device__ __noinline__ int publishAndWait(const GridCtx& G, GridCtx& wctx, int&
 // ---------------------------------------------------------------------------------------
 // pass 2: one recorded grid, start to end, on any control-capable warp
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void runPass2Grid(int jobIdx, int item, GridCtx& G, uint8_t* win, uint8_t* mini) {
+__device__ __noinline__ void runPass2Grid(int jobIdx, int item, GridCtx& Gin, uint8_t* win, uint8_t* mini) {
+    GridCtx& G = *toShared(&Gin);
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     const int gi = item / MAXREC, ksel = item - gi * MAXREC;
@@ -1050,8 +1064,9 @@ __device__ __noinline__ bool tryRunPass2(GridCtx& G, uint8_t* win, uint8_t* mini
 // one job on its control warp: pass 1 over all grids (everything that decides the NEXT grid's
 // initialisation), in-line tracebacks for the grids that cannot take the fast path
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& G, GridCtx& wctx, int& wTask, uint8_t* win, uint8_t* arena,
+__device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& Gin, GridCtx& wctx, int& wTask, uint8_t* win, uint8_t* arena,
                                     uint8_t* fastSeq) {
+    GridCtx& G = *toShared(&Gin);
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     const JobDev jb = P.jobs[jobIdx];
@@ -1175,7 +1190,7 @@ constexpr int SMEM_BYTES = SMEM_FASTSEQ + NCTRL * (FASTSEQ_H + FASTSEQ_V);
 
 __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
     const KParams& P = cP;
-    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* const smem = gSmem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     GridCtx* wctx = reinterpret_cast<GridCtx*>(smem + NCTRL * WINBYTES + (NCTRL + warp) * CTX_STRIDE);
     int wTask = -1;
@@ -1405,8 +1420,12 @@ void Engine::upload(std::vector<Job*>& jobs) {
         totalCells += j.cells;
         // segment stream capacity: every grid reserves its worst case (3 + traces * (1 + 4 * (nH + nV + 6)) ints)
         long long cap = 0;
-        for (const GridDesc& gd : j.grids) cap += 5 + 2LL * (1 + 4LL * ((long long)gd.nH + gd.nV + 6));
-        cap += 4LL * ((long long)j.lenH + j.lenV) + 1024;
+        if (j.grids.size() == 1 && j.grids[0].kind == GRID_GLOBAL) {
+            cap = 5 + (1 + 4LL * ((long long)j.grids[0].nH + j.grids[0].nV + 6)) + 8;   // exactly one trace
+        } else {
+            for (const GridDesc& gd : j.grids) cap += 5 + 2LL * (1 + 4LL * ((long long)gd.nH + gd.nV + 6));
+            cap += 4LL * ((long long)j.lenH + j.lenV) + 1024;
+        }
         cap *= std::max(1, j.outScale);
         if (cap > (1LL << 30)) cap = 1LL << 30;
         d.outOff = (long long)outOff;
@@ -1560,12 +1579,23 @@ void Engine::fetch(std::vector<Job*>& jobs) {
     CUDA_CHECK(cudaStreamSynchronize(I.stream));
     // copy back only the used part of every job's segment stream
     int* hOut = (int*)I.hOut;
+    size_t end = 0, used = 0;
     for (size_t k = 0; k < nJobs; ++k) {
         const JobDev& d = I.jobsDev[k];
         int len = std::min(I.jobOut[k].outLen, d.outCap);
-        if (len > 0)
-            CUDA_CHECK(cudaMemcpyAsync(hOut + d.outOff, (int*)I.dOut + d.outOff, (size_t)len * sizeof(int),
-                                       cudaMemcpyDeviceToHost, I.stream));
+        if (len > 0) { end = std::max(end, (size_t)d.outOff + (size_t)len); used += (size_t)len; }
+    }
+    if (nJobs > 64 && (end <= 4 * used || nJobs > 4096)) {
+        // many small jobs: one copy of everything up to the last used int beats one copy per job
+        if (end > 0) CUDA_CHECK(cudaMemcpyAsync(hOut, I.dOut, end * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+    } else {
+        for (size_t k = 0; k < nJobs; ++k) {
+            const JobDev& d = I.jobsDev[k];
+            int len = std::min(I.jobOut[k].outLen, d.outCap);
+            if (len > 0)
+                CUDA_CHECK(cudaMemcpyAsync(hOut + d.outOff, (int*)I.dOut + d.outOff, (size_t)len * sizeof(int),
+                                           cudaMemcpyDeviceToHost, I.stream));
+        }
     }
     CUDA_CHECK(cudaEventRecord(I.ev[5], I.stream));
     CUDA_CHECK(cudaStreamSynchronize(I.stream));

@@ -169,6 +169,19 @@ struct KParams {
 __constant__ KParams cP;
 __device__ unsigned long long gDbg[16];   // developer counters (cycles), lane 0 of control warps
 
+// All per-warp working state (GridCtx slots, windows, staged codes) lives in the kernel's dynamic shared
+// memory.  Out-of-line functions receive generic pointers to it; toShared() rebases such a pointer on the
+// shared array so that the compiler emits LDS/STS instead of generic loads through the L1TEX path.
+extern __shared__ __align__(16) uint8_t gSmem[];
+template <typename T>
+__device__ __forceinline__ T* toShared(T* p) {
+    return reinterpret_cast<T*>(gSmem + ((uint32_t)__cvta_generic_to_shared(p) - (uint32_t)__cvta_generic_to_shared(gSmem)));
+}
+template <typename T>
+__device__ __forceinline__ const T* toShared(const T* p) {
+    return reinterpret_cast<const T*>(gSmem + ((uint32_t)__cvta_generic_to_shared(p) - (uint32_t)__cvta_generic_to_shared(gSmem)));
+}
+
 // ---------------------------------------------------------------------------------------
 // memory-order helpers
 // ---------------------------------------------------------------------------------------
@@ -467,8 +480,10 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K
 //   !TRACE: score-only; boundary row, column checkpoints, rowProg published per chunk; waits on the
 //           strip above through its rowProg counter.
 template <bool AFF, bool CT, bool BANDED, int RR, int MODE>
-__device__ __noinline__ void runStrip(const GridCtx& G, int s, int cBeg, int cEnd, bool fromCk, int nsteps,
-                                      bool capture, uint8_t* win, int winPitch) {
+__device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int cEnd, bool fromCk, int nsteps,
+                                      bool capture, uint8_t* winIn, int winPitch) {
+    const GridCtx& G = *toShared(&Gin);
+    uint8_t* win = (MODE == MODE_TASK) ? nullptr : toShared(winIn);
     constexpr int SHR = 32 * RR;
     constexpr bool TRACE = (MODE == MODE_TRACE);
     constexpr bool L2ONLY = (MODE == MODE_TASK);   // worker warps read the arena through L2 only
@@ -617,7 +632,8 @@ __device__ __forceinline__ void tileDispatch(const GridCtx& G, int s, int cBeg, 
 
 // Recomputes the trace bytes of the tile that holds (i, j): rows of strip s up to the lane owning row i,
 // columns from the checkpoint left of j up to j.  Returns (strip, first column, last column, last row).
-__device__ __noinline__ int4 computeTileFn(const GridCtx& G, uint8_t* win, int i, int j) {
+__device__ __noinline__ int4 computeTileFn(const GridCtx& Gin, uint8_t* win, int i, int j) {
+    const GridCtx& G = *toShared(&Gin);
     const GridGeom& g = G.g;
     const int s = (i - 1) / SH;
     const int jlo = stripJlo(g, s, SH);
@@ -645,14 +661,16 @@ __device__ __forceinline__ DCell fastCellAt(const GridCtx& G, const uint8_t* win
     if (i < G.fastR0 || j < G.fastC0) { outOfBox = true; return DCell{NEG_INF, NEG_INF, NEG_INF}; }
     return reinterpret_cast<const DCell*>(win)[(j - G.fastC0) * G.fastPitch + (i - G.fastR0)];
 }
-__device__ __noinline__ uint32_t lazyTvFn(const GridCtx& G, const uint8_t* win, int i, int j) {
+__device__ __noinline__ uint32_t lazyTvFn(const GridCtx& Gin, const uint8_t* winIn, int i, int j) {
+    const GridCtx& G = *toShared(&Gin);
+    const uint8_t* win = toShared(winIn);
     const GridGeom& g = G.g;
     if (g.banded) { const int d = j - i; if (d < g.lo || d > g.up) return 0; }
     bool oob = false;
     const DCell L = fastCellAt(G, win, i, j - 1, oob), U = fastCellAt(G, win, i - 1, j, oob), D = fastCellAt(G, win, i - 1, j - 1, oob);
     // (i, j) inside the box: the staged base codes cover it
     const int sub = (i >= G.fastR0 && j >= G.fastC0)
-                        ? ((G.fastSeqH[j - G.fastC0] == G.fastSeqV[i - G.fastR0]) ? G.match : G.mismatch)
+                        ? ((toShared(G.fastSeqH)[j - G.fastC0] == toShared(G.fastSeqV)[i - G.fastR0]) ? G.match : G.mismatch)
                         : ((G.seqH[j - 1] == G.seqV[i - 1]) ? G.match : G.mismatch);
     int mode = 0;
     if (g.banded) { const int d = j - i; mode = (d == g.up) ? 1 : (d == g.lo ? 2 : 0); }
@@ -689,7 +707,7 @@ struct TraceWalker {
     long long tilesComputed, tileCycles;
 
     __device__ __forceinline__ TraceWalker(const GridCtx& g, OutStream& o, uint8_t* w)
-        : G(g), out(o), win(w), winW(w), g(g.g), local(g.local), rrMul(g.rrMul), rr(g.RR), rrs(g.rrs), pitch(g.pitch), localJhi(g.localJhi),
+        : G(g), out(o), win(toShared(w)), winW(w), g(g.g), local(g.local), rrMul(g.rrMul), rr(g.RR), rrs(g.rrs), pitch(g.pitch), localJhi(g.localJhi),
           affine(g.affine), lazy(false), outOfBox(false), tS(-1), tC0(0), tMaxRow(-1), tMaxCol(-1), pc(0), pv(0), nSegs(0), emitOn(true),
           bad(false), tilesComputed(0), tileCycles(0) {}
 
