@@ -688,7 +688,25 @@ __device__ __noinline__ Crossing leanCrossing(LeanCtx L, int i, int j, Coord c) 
     while (!(cc <= ec || cr <= er) && tv != T_NONE) {
         if (tv & T_D) {
             last = T_D;
-            do { --i; --j; tv = leanTv<AFF, BANDED>(L, i, j); --cc; --cr; } while ((tv & T_D) && !(cc <= ec || cr <= er));
+            // Diagonal run.  Only the DIAGONAL bit of the next cell decides whether the run goes on, and it is set
+            // exactly when S(i,j) == S(i-1,j-1) + sub(i,j) (dp_formula_affine.h:124-139, dp_formula_linear.h:150-185):
+            // two box cells instead of a full cell update.  The full trace value is derived where the run stops.
+            for (;;) {
+                --i; --j; --cc; --cr;
+                const bool atEnd = (cc <= ec || cr <= er);
+                bool inside = i > 0 && j > 0 && i <= L.nV && j <= L.nH;
+                if (BANDED && inside) { const int dd = j - i; inside = (dd >= L.lo && dd <= L.up); }
+                bool isD = false;
+                if (inside && !atEnd && i > L.r0 && j > L.c0) {
+                    const int sHere = L.box[(j - L.c0) * L.pitch + (i - L.r0)].s;
+                    const int sDiag = L.box[(j - 1 - L.c0) * L.pitch + (i - 1 - L.r0)].s;
+                    const int sub = (L.sH[j - L.c0] == L.sV[i - L.r0]) ? L.match : L.mismatch;
+                    isD = (sHere == sDiag + sub);
+                    if (isD) continue;
+                }
+                tv = leanTv<AFF, BANDED>(L, i, j);
+                if (!((tv & T_D) && !atEnd)) break;
+            }
         } else if ((tv & T_MV) && (tv & T_V)) {
             last = T_V;
             if (AFF) {
