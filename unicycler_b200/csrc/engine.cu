@@ -551,7 +551,7 @@ __device__ __forceinline__ int reserveOut(int jobIdx, int outCap, int n) {
 // worst-case size of one grid's record: header + per trace (count + segments; a trace has at most
 // nH + nV + 4 segments of 4 ints)
 __device__ __forceinline__ int recordBound(const GridCtx& G, int nTraces) {
-    long long n = 5 + (long long)nTraces * (1 + 4LL * ((long long)G.g.nH + G.g.nV + 6));
+    long long n = 6 + (long long)nTraces * (1 + 4LL * ((long long)G.g.nH + G.g.nV + 6));
     return n > 0x3fffffff ? 0x3fffffff : (int)n;
 }
 
@@ -560,7 +560,8 @@ __device__ __forceinline__ int recordBound(const GridCtx& G, int nTraces) {
 // cells); otherwise the pass-2 replay of a recorded grid.
 // candSel >= 0 (pass 2 of a big grid): only that candidate, as a record of its own.
 __device__ __noinline__ TbResult tracebackGrid(const GridCtx& Gin, uint8_t* win, int jobIdx, int* outBuf, int outCap, int gi,
-                                               int h0, int v0, int nCand, DCell maxCell, const GridRec* rec, int candSel) {
+                                               int h0, int v0, int nCand, DCell maxCell, const GridRec* rec, int candSel,
+                                               int segTag) {
     const GridCtx& G = *toShared(&Gin);
     const int lane = threadIdx.x & 31;
     TbResult r;
@@ -579,6 +580,7 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& Gin, uint8_t* win,
     out.put(reserved);
     out.put(0);   // ints actually used (patched below); finalizeJob compacts the stream with it
     out.put(candSel >= 0 ? candSel : 0);   // index of the record's first candidate (the host orders a grid's records by it)
+    out.put(segTag);                       // chain segment that wrote the record (finalizeJob drops discarded segments)
     int nTraces = 0;
     TraceWalker w(G, out, win);
     if (G.kind == GRID_GLOBAL) {
@@ -943,6 +945,14 @@ __device__ __noinline__ int publishAndWait(const GridCtx& Gin, GridCtx& wctx, in
     return JOB_OK;
 }
 
+// Segment that owns grid gi after the chain has been resolved (finalizeSpine).
+__device__ __forceinline__ int ownerOf(const JobState& js, int gi) {
+    int seg = js.ownerSeg[0];
+    for (int t = 1; t < js.nOwner; ++t)
+        if (gi >= js.ownerFrom[t]) seg = js.ownerSeg[t];
+    return seg;
+}
+
 // ---------------------------------------------------------------------------------------
 // pass 2: one recorded grid, start to end, on any control-capable warp
 // ---------------------------------------------------------------------------------------
@@ -952,7 +962,8 @@ __device__ __noinline__ void runPass2Grid(int jobIdx, int item, GridCtx& Gin, ui
     const int lane = threadIdx.x & 31;
     const int gi = item / MAXREC, ksel = item - gi * MAXREC;
     const JobDev jb = P.jobs[jobIdx];
-    const GridRec* rec = &P.gridRecs[jb.gridBegin + gi];
+    const int owner = ownerOf(P.jobState[jobIdx], gi);
+    const GridRec* rec = &P.gridRecs[jb.recBase + (long long)owner * jb.gridCount + gi];
     const int state = rec->state;
     if (state == 0) return;                                   // done in line by pass 1
     if (state == 1 && ksel != 0) return;                       // small grid: item 0 walks every candidate
@@ -962,7 +973,7 @@ __device__ __noinline__ void runPass2Grid(int jobIdx, int item, GridCtx& Gin, ui
         // checkpoints, init row and column live in the grid's persistent block
         setupGrid(G, jb, gd, nullptr);
         const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, rec->nCand,
-                                          DCell{0, 0, 0}, rec, ksel);
+                                          DCell{0, 0, 0}, rec, ksel, owner);
         if (tb.status != JOB_OK && lane == 0) atomicMax(&P.jobState[jobIdx].status, tb.status);
         __syncwarp();
         return;
@@ -992,7 +1003,7 @@ __device__ __noinline__ void runPass2Grid(int jobIdx, int item, GridCtx& Gin, ui
     __syncwarp();
     localFill(G, win, false);
     const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, rec->nCand,
-                                      DCell{0, 0, 0}, rec, -1);
+                                      DCell{0, 0, 0}, rec, -1, owner);
     if (tb.status != JOB_OK && lane == 0) atomicMax(&P.jobState[jobIdx].status, tb.status);
     __syncwarp();
 }
@@ -1015,7 +1026,9 @@ __device__ __noinline__ void finalizeJob(int jobIdx) {
         while (src < end) {
             const int reserved = __ldcg(&buf[src + 2]);
             const int used = __ldcg(&buf[src + 3]);
-            if (reserved < 5 || used < 5 || used > reserved) { st = JOB_REF_UB; break; }  // a record was never completed
+            if (reserved < 6 || used < 6 || used > reserved) { st = JOB_REF_UB; break; }  // a record was never completed
+            // records written by a speculative segment outside the range it finally owns are dropped
+            if (ownerOf(P.jobState[jobIdx], __ldcg(&buf[src])) != __ldcg(&buf[src + 5])) { src += reserved; continue; }
             if (dst != src) {
                 for (int k = 0; k < used; k += 32) {
                     int v = 0;
@@ -1079,21 +1092,152 @@ __device__ __noinline__ bool tryRunPass2(GridCtx& G, uint8_t* win, uint8_t* mini
 }
 
 // ---------------------------------------------------------------------------------------
-// one job on its control warp: pass 1 over all grids (everything that decides the NEXT grid's
-// initialisation), in-line tracebacks for the grids that cannot take the fast path
+// Pass 1.  A seed chain is a serial spine (grid k+1 starts from the cells grid k's traceback crosses), so a long
+// chain is walked by several control warps at once: segment p > 0 starts at its first grid from a GUESSED
+// initialisation cell (the corner of the grid, reached diagonally — where an exact seed leaves the previous
+// anchor) in its own score frame (scores relative to the guess: every decision of the DP is invariant under a
+// constant shift of the finite scores).  When the warp of segment p runs past its range it keeps walking until
+// the cell(s) it would plant equal the ones segment q recorded for the same grid; from there on q's records are
+// the true ones (same cells => same continuation) and p stops.  finalizeSpine() follows the merges from segment 0
+// and thereby decides which segment owns which grids; everything else is discarded.  No guess is trusted
+// without this check, so the result is exactly the serial one.
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& Gin, GridCtx& wctx, int& wTask, uint8_t* win, uint8_t* arena,
-                                    uint8_t* fastSeq) {
+__device__ __forceinline__ bool sameShape(int a, int b) { return (a == NEG_INF) == (b == NEG_INF); }
+
+// my planted cells (frame A) vs the cells recorded as initialisation of the same grid in frame B:
+// equal up to one constant shift of the finite components?  delta = A - B.
+__device__ __forceinline__ bool plantedMatch(const PlantedCell* mine, int nMine, const PlantedCell* theirs, int nTheirs,
+                                             int& delta) {
+    if (nMine != nTheirs || nMine < 1 || nMine > MAXREC) return false;
+    const PlantedCell a0 = mine[0];
+    const PlantedCell b0 = theirs[0];
+    delta = a0.c.s - b0.c.s;
+    for (int k = 0; k < nMine; ++k) {
+        const PlantedCell a = mine[k];
+        const PlantedCell b = theirs[k];
+        if (a.i1 != b.i1 || a.i2 != b.i2) return false;
+        if (a.c.s == NEG_INF || b.c.s == NEG_INF) return false;
+        if (a.c.s - b.c.s != delta) return false;
+        if (!sameShape(a.c.h, b.c.h) || !sameShape(a.c.v, b.c.v)) return false;
+        if (a.c.h != NEG_INF && a.c.h - b.c.h != delta) return false;
+        if (a.c.v != NEG_INF && a.c.v - b.c.v != delta) return false;
+    }
+    return true;
+}
+
+// Resolves the chain of merges (run by the last segment warp of the job to stop) and hands the job on.
+__device__ __noinline__ void finalizeSpine(int jobIdx) {
+    const KParams& P = cP;
+    const int lane = threadIdx.x & 31;
+    const JobDev jb = P.jobs[jobIdx];
+    JobState* js = &P.jobState[jobIdx];
+    __threadfence();
+    int status = JOB_OK, nOwner = 0, cur = 0, from = 0, offset = 0, score = 0;
+    for (int guard = 0; guard <= MAXSEG; ++guard) {
+        if (lane == 0) { js->ownerSeg[nOwner] = cur; js->ownerFrom[nOwner] = from; }
+        ++nOwner;
+        const int syncSeg = ldRelaxed(&js->segSyncSeg[cur]);
+        const int to = ldRelaxed(&js->segSyncGrid[cur]);
+        if (syncSeg == -2) { status = ldRelaxed(&js->segFailStatus[cur]); break; }
+        // the -1 000 000 abort of the reference (dp_algorithm_impl.h:1591-1593) in absolute scores: segment 0 checks
+        // it while walking, the relative frames are checked here
+        const GridRec* recs = &P.gridRecs[jb.recBase + (long long)cur * jb.gridCount];
+        int worst = INT32_MAX;
+        for (int k = from + lane; k < to; k += 32) worst = min(worst, __ldcg(&recs[k].relMax));
+        worst = __reduce_min_sync(FULLMASK, worst);
+        if (to > from && cur != 0 && (long long)worst + offset < -1000000) { status = JOB_BAD_SCORE; break; }
+        if (to > from) score = __ldcg(&recs[to - 1].relMax) + offset;
+        if (syncSeg < 0) break;   // reached the end of the chain
+        offset += ldRelaxed(&js->segDelta[cur]);
+        from = to;
+        cur = syncSeg;
+    }
+    if (lane == 0) {
+        js->ownerSeg[nOwner] = -1; js->ownerFrom[nOwner] = jb.gridCount;
+        js->nOwner = nOwner;
+        JobOut* jo = &P.jobOut[jobIdx];
+        jo->status = status; jo->score = score; jo->outLen = 0; jo->pad = 0;
+    }
+    __threadfence();
+    __syncwarp();
+    if (status == JOB_OK && jb.gridCount > 1) {
+        // hand the recorded grids to pass 2 (grids done in line are skipped there)
+        if (lane == 0) {
+            const int t = atomicAdd(&P.cb->p2Tail, 1);
+            P2Entry* e = &P.p2ring[t];
+            e->jobIdx = jobIdx; e->nItems = jb.gridCount * MAXREC; e->nextItem = 0; e->doneItems = 0;
+            __threadfence();
+            stRelease(&e->ready, 1);
+        }
+        __syncwarp();
+    } else {
+        finalizeJob(jobIdx);
+    }
+}
+
+__device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx& Gin, GridCtx& wctx, int& wTask, uint8_t* win,
+                                        uint8_t* arena, uint8_t* fastSeq) {
     GridCtx& G = *toShared(&Gin);
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     const JobDev jb = P.jobs[jobIdx];
-    int status = JOB_OK, nPlantedPrev = 0, score = 0, nFast = 0;
-    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    JobState* js = &P.jobState[jobIdx];
+    GridRec* recs = &P.gridRecs[jb.recBase + (long long)seg * jb.gridCount];
+    PlantedCell* planted = reinterpret_cast<PlantedCell*>(arena + P.lay.planted);
+    int status = JOB_OK, nPlantedPrev = 0;
+    int syncSeg = -1, syncGrid = jb.gridCount, syncDelta = 0;
+    unsigned long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long tJob0 = clock64();
-    for (int gi = 0; gi < jb.gridCount; ++gi) {
+    int gi = jb.segStart[seg];
+    const PlantedCell guess = PlantedCell{0, 0, DCell{0, NEG_INF, NEG_INF}};
+    bool cancelled = false;
+    if (seg > 0) {
+        // an earlier segment that already ran past this one's first grid has cancelled it
+        int c = 0;
+        if (lane == 0) c = atomicCAS(&js->segClaim[seg], 0, 1);
+        c = __shfl_sync(FULLMASK, c, 0);
+        cancelled = (c != 0);
+        // guessed initialisation: the corner cell, reached diagonally, score 0 (this segment's frame)
+        if (lane == 0 && !cancelled) { planted[0] = guess; recs[gi].plantedIn[0] = guess; recs[gi].nPlantedIn = 1; }
+        nPlantedPrev = 1;
+        __syncwarp();
+    }
+    if (cancelled) gi = jb.gridCount;   // nothing to do: falls through to the stop protocol as a failed segment
+    for (; gi < jb.gridCount; ++gi) {
+        // ---- merge check: beyond the own range, do the cells I am about to plant equal what a later segment started from?
+        bool merged = false;
+        for (int q = seg + 1; q < jb.nSeg && !merged; ++q) {
+            if (jb.segStart[q] > gi) break;
+            int prog = 0, gone = 0;
+            if (lane == 0) {
+                // a live segment is never overtaken (both would work on the same grid): wait for it; a segment
+                // that has not been started yet is cancelled instead (its warp may be queued behind this one)
+                for (;;) {
+                    prog = ldRelaxed(&js->segProgress[q]);
+                    const int claim = ldRelaxed(&js->segClaim[q]);
+                    if (claim == 2) { gone = 1; break; }
+                    if (gi == jb.segStart[q]) break;           // its first grid starts from the (known) guess
+                    if (claim == 0) { if (atomicCAS(&js->segClaim[q], 0, 2) == 0) { gone = 1; break; } continue; }
+                    if (prog >= gi || ldRelaxed(&js->segStop[q])) break;
+                    __nanosleep(500);
+                }
+                __threadfence();
+            }
+            prog = __shfl_sync(FULLMASK, prog, 0);
+            gone = __shfl_sync(FULLMASK, gone, 0);
+            if (gone) continue;
+            int delta = 0;
+            bool match;
+            if (gi == jb.segStart[q]) match = plantedMatch(planted, nPlantedPrev, &guess, 1, delta);
+            else if (prog >= gi) {
+                const GridRec* theirs = &P.gridRecs[jb.recBase + (long long)q * jb.gridCount + gi];
+                match = plantedMatch(planted, nPlantedPrev, theirs->plantedIn, __ldcg(&theirs->nPlantedIn), delta);
+            } else continue;   // q stopped before reaching this grid
+            if (match) { merged = true; syncSeg = q; syncGrid = gi; syncDelta = delta; }
+        }
+        if (merged) break;
         const GridDesc gd = P.grids[jb.gridBegin + gi];
-        GridRec* rec = &P.gridRecs[jb.gridBegin + gi];
+        GridRec* rec = &recs[gi];
         const long long c0 = clock64();
         setupGrid(G, jb, gd, arena, fastSeq);
         initGrid(G, gd, nPlantedPrev);
@@ -1103,21 +1247,22 @@ __device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& Gin, GridCtx
         TR.maxCell = DCell{0, 0, 0};
         int nPlanted = 0;  // _nextInitializationCells.clear()
         bool done = false;
+        const bool absoluteFrame = (seg == 0);
         // ---- fast path: score-only fill, tracking and crossing walks; trace fill + tracebacks go to pass 2
         if (G.fastOk && nPlantedPrev <= MAXREC) {
             localFillFast(G, win);
             c2 = clock64();
             trackChain<true>(G, TR, reinterpret_cast<const DCell*>(win));
             c3 = clock64();
-            int st = (TR.status != JOB_OK) ? TR.status : ((TR.maxScore < -1000000) ? JOB_BAD_SCORE : JOB_OK);
+            int st = (TR.status != JOB_OK) ? TR.status : ((absoluteFrame && TR.maxScore < -1000000) ? JOB_BAD_SCORE : JOB_OK);
             if (st == JOB_OK && TR.nCand <= MAXREC) {
                 int insertedMask = 0;
                 if (fastShortWalks(G, win, TR.nCand, nPlanted, insertedMask, st) && st == JOB_OK) {
                     if (lane == 0) {
                         rec->state = 1; rec->nCand = TR.nCand; rec->inserted = insertedMask; rec->nPlantedIn = nPlantedPrev;
+                        rec->relMax = TR.maxScore;
                         for (int k = 0; k < TR.nCand; ++k) rec->cand[k] = G.cand[k];
                     }
-                    ++nFast;
                     done = true;
                 }
             }
@@ -1126,7 +1271,7 @@ __device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& Gin, GridCtx
         }
         // ---- in-line path (big grids, final grids, anything the fast path declined)
         if (!done) {
-            if (lane == 0) rec->state = 0;
+            if (lane == 0) { rec->state = 0; rec->nPlantedIn = nPlantedPrev; }
             const long long d1 = clock64();
             if (G.local) {
                 localFill(G, win, true);
@@ -1142,23 +1287,25 @@ __device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& Gin, GridCtx
             else trackChain<false>(G, TR, nullptr);
             c3 = clock64();
             if (status == JOB_OK) status = TR.status;
-            if (status == JOB_OK && TR.maxScore < -1000000) status = JOB_BAD_SCORE;  // the RRW throw
+            if (status == JOB_OK && absoluteFrame && TR.maxScore < -1000000) status = JOB_BAD_SCORE;  // the RRW throw
+            if (lane == 0) rec->relMax = TR.maxScore;
             nPlanted = 0;
             const bool deferBig = status == JOB_OK && !G.local && P.persist != nullptr && gd.persistOff >= 0 &&
                                   gd.kind != GRID_GLOBAL && TR.nCand <= MAXREC && nPlantedPrev <= MAXREC && P.fastEnabled;
             if (deferBig) {
                 // big chain grid: only the crossing walks here, one pass-2 item per tied maximum
                 int insertedMask = 0;
+                long long tiles = 0, tileCycles = 0;
                 if (gd.kind != GRID_CHAIN_FINAL)
-                    bigShortWalks(G, win, TR.nCand, nPlanted, insertedMask, status, prof[6], prof[7]);
+                    bigShortWalks(G, win, TR.nCand, nPlanted, insertedMask, status, tiles, tileCycles);
+                prof[6] += tiles; prof[7] += tileCycles;
                 if (lane == 0) {
-                    rec->state = 2; rec->nCand = TR.nCand; rec->inserted = insertedMask; rec->nPlantedIn = nPlantedPrev;
+                    rec->state = 2; rec->nCand = TR.nCand; rec->inserted = insertedMask;
                     for (int k = 0; k < TR.nCand; ++k) rec->cand[k] = G.cand[k];
                 }
-                ++nFast;
             } else if (status == JOB_OK) {
                 const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, TR.nCand,
-                                                  TR.maxCell, nullptr, -1);
+                                                  TR.maxCell, nullptr, -1, seg);
                 status = tb.status; nPlanted = tb.nPlanted;
                 prof[6] += tb.tiles; prof[7] += tb.tileCycles;
                 prof[9] += (gd.kind == GRID_GLOBAL) ? 1 : TR.nCand;
@@ -1166,39 +1313,38 @@ __device__ __noinline__ void runJob(int jobIdx, int board, GridCtx& Gin, GridCtx
             prof[3] += c3 - c2; prof[4] += clock64() - c3;
         }
         __syncwarp();
-        // the next grid's record carries the cells that initialise it (pass 2 redoes grids independently)
-        if (gi + 1 < jb.gridCount && nPlanted <= MAXREC) {
+        // the next grid's record carries the cells that initialise it (pass 2 and merge checks read them)
+        if (gi + 1 < jb.gridCount) {
             GridRec* nx = rec + 1;
-            for (int k = lane; k < nPlanted; k += 32) nx->plantedIn[k] = G.planted[k];
+            if (nPlanted <= MAXREC)
+                for (int k = lane; k < nPlanted; k += 32) nx->plantedIn[k] = G.planted[k];
+            if (lane == 0) nx->nPlantedIn = nPlanted;
         }
-        nPlantedPrev = nPlanted; score = TR.maxScore;
+        nPlantedPrev = nPlanted;
         prof[0] += c1 - c0;
         if (status != JOB_OK) break;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) stRelease(&js->segProgress[seg], gi + 1);
     }
+    // ---- this segment's warp stops
     if (lane == 0) {
-        JobOut jo;
-        jo.status = status; jo.score = score; jo.outLen = 0; jo.pad = 0;
-        prof[5] = clock64() - tJob0;
-        for (int k = 0; k < 12; ++k) jo.prof[k] = prof[k];
-        P.jobOut[jobIdx] = jo;
+        if (cancelled) status = JOB_INVALID;   // never on the resolved chain: the cancelling segment ran past it
+        if (status != JOB_OK) { js->segSyncSeg[seg] = -2; js->segSyncGrid[seg] = gi; js->segFailStatus[seg] = status; }
+        else { js->segSyncSeg[seg] = syncSeg; js->segSyncGrid[seg] = syncGrid; js->segDelta[seg] = syncDelta; }
+        prof[5] = (unsigned long long)(clock64() - tJob0);
+        JobOut* jo = &P.jobOut[jobIdx];
+        for (int k = 0; k < 12; ++k)
+            if (k == 5) atomicMax(reinterpret_cast<unsigned long long*>(&jo->prof[k]), prof[k]);
+            else atomicAdd(reinterpret_cast<unsigned long long*>(&jo->prof[k]), prof[k]);
+        __threadfence();
+        stRelease(&js->segStop[seg], 1);
     }
     __syncwarp();
-    if (status == JOB_OK && nFast > 0) {
-        // hand the recorded grids to pass 2
-        int t = 0;
-        __threadfence();
-        if (lane == 0) {
-            t = atomicAdd(&P.cb->p2Tail, 1);
-            P2Entry* e = &P.p2ring[t];
-            e->jobIdx = jobIdx; e->nItems = jb.gridCount * MAXREC; e->nextItem = 0; e->doneItems = 0;
-            __threadfence();
-            stRelease(&e->ready, 1);
-        }
-        __syncwarp();
-    } else {
-        __threadfence();
-        finalizeJob(jobIdx);
-    }
+    int stoppedCount = 0;
+    if (lane == 0) stoppedCount = atomicAdd(&js->segStopped, 1) + 1;
+    stoppedCount = __shfl_sync(FULLMASK, stoppedCount, 0);
+    if (stoppedCount == jb.nSeg) finalizeSpine(jobIdx);
 }
 
 constexpr int CTX_STRIDE = (int)((sizeof(GridCtx) + 15) / 16 * 16);
@@ -1230,9 +1376,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
             int q = 0;
             if (lane == 0) q = atomicAdd(&P.cb->jobQueue, 1);
             q = __shfl_sync(FULLMASK, q, 0);
-            if (q < P.nJobs) {
-                runJob(P.order[q], q < P.nHiJobs ? 0 : 1, *cctx, *wctx, wTask, win, P.scratch + (size_t)agent * P.scratchStride,
-                       smem + SMEM_FASTSEQ + cw * (FASTSEQ_H + FASTSEQ_V));
+            if (q < P.nEntries) {
+                const int entry = P.order[q];
+                runSegment(entry / MAXSEG, entry % MAXSEG, q < P.nHiJobs ? 0 : 1, *cctx, *wctx, wTask, win,
+                           P.scratch + (size_t)agent * P.scratchStride, smem + SMEM_FASTSEQ + cw * (FASTSEQ_H + FASTSEQ_V));
                 continue;
             }
             queueEmpty = true;
@@ -1317,6 +1464,7 @@ struct Engine::Impl {
     }
     void launchOnce() {
         CUDA_CHECK(cudaMemsetAsync(dRing, 0, ringBytes, stream));
+        CUDA_CHECK(cudaMemsetAsync(dJobOut, 0, (size_t)kp.nJobs * sizeof(JobOut), stream));
         dpAgentKernel<<<numSMs, NTHREADS, SMEM_BYTES, stream>>>();
     }
 };
@@ -1364,8 +1512,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.jobsDev.assign(nJobs, JobDev());
     I.gridsAll.clear();
     I.colTabAll.clear();
-    I.order.resize(nJobs);
-    // sequences
+        // sequences
     size_t seqBytes = 0;
     for (Job* j : jobs) seqBytes += alignUp((size_t)j->lenH + 16, 16) + alignUp((size_t)j->lenV + 16, 16);
     I.growHost(I.hSeq, I.capHSeq, seqBytes + 64);
@@ -1450,8 +1597,6 @@ void Engine::upload(std::vector<Job*>& jobs) {
         d.outCap = (int)cap;
         outOff += (size_t)cap;
     }
-    for (size_t k = 0; k < nJobs; ++k) I.order[k] = (int)k;
-    std::stable_sort(I.order.begin(), I.order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     I.seqBytes = off;
     I.outInts = outOff;
     // persistent blocks only if they fit comfortably (otherwise big grids are traced back in line from the arena)
@@ -1501,7 +1646,47 @@ void Engine::upload(std::vector<Job*>& jobs) {
                    I.ringBytes + (usePersist ? (size_t)persistTotal : 0) + (64u << 20);
     size_t budget = (freeB + I.capScratch > fixed) ? (size_t)((freeB + I.capScratch - fixed) * 0.9) : 0;
     long long byMem = (long long)(budget / (size_t)L.total);
-    int nSlots = (int)std::min<long long>(std::min<long long>((long long)nJobs, (long long)NCTRL * I.numSMs),
+    // pass-1 work list: long chains are cut into speculative segments (runSegment); a segment starts at a gap
+    // rectangle that follows an anchor, where an exact seed makes the guessed initialisation cell likely
+    std::vector<int> jobOrder(nJobs);
+    for (size_t k = 0; k < nJobs; ++k) jobOrder[k] = (int)k;
+    std::stable_sort(jobOrder.begin(), jobOrder.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    const bool noSplit = getenv("UNICYCLER_B200_NO_SPLIT") != nullptr;
+    size_t nRecs = 0;
+    // every work-list entry must get a control warp at kernel start (a segment waits for the ones after it), so
+    // extra segments are only handed out while warps with an arena remain; longest chains first
+    long long extraBudget = std::min<long long>((long long)NCTRL * I.numSMs, std::max<long long>(byMem, 0)) - (long long)nJobs;
+    for (int jk : jobOrder) {
+        const size_t k = (size_t)jk;
+        Job& j = *jobs[k];
+        JobDev& d = I.jobsDev[k];
+        const int n = (int)j.grids.size();
+        int nSeg = 1;
+        d.segStart[0] = 0;
+        if (!noSplit && j.complete && n >= 128 && extraBudget > 0) {
+            const int want = (int)std::min<long long>(std::min(MAXSEG, n / 64), extraBudget + 1);
+            for (int p = 1; p < want; ++p) {
+                int g = (int)((long long)p * n / want);
+                // snap forward to an unbanded inner grid that follows a banded one
+                while (g < n - 1 && !(j.grids[(size_t)g].kind == GRID_CHAIN_INNER && !j.grids[(size_t)g].banded &&
+                                      j.grids[(size_t)g - 1].banded && j.grids[(size_t)g - 1].kind == GRID_CHAIN_INNER))
+                    ++g;
+                if (g >= n - 1 || g <= d.segStart[nSeg - 1] + 8) continue;
+                d.segStart[nSeg++] = g;
+            }
+        }
+        for (int p = nSeg; p <= MAXSEG; ++p) d.segStart[p] = n;
+        extraBudget -= nSeg - 1;
+        d.nSeg = nSeg;
+        d.pad2 = 0;
+        d.recBase = (long long)nRecs;
+        nRecs += (size_t)nSeg * (size_t)n;
+    }
+    I.order.clear();
+    for (int jk : jobOrder)
+        for (int p = 0; p < I.jobsDev[(size_t)jk].nSeg; ++p) I.order.push_back(jk * MAXSEG + p);
+    const size_t nEntries = I.order.size();
+    int nSlots = (int)std::min<long long>(std::min<long long>((long long)nEntries, (long long)NCTRL * I.numSMs),
                                           std::max<long long>(byMem, 0));
     if (nSlots < 1) throw std::runtime_error("unicycler_b200: not enough device memory for one DP scratch arena");
     I.growDev(I.dJobs, I.capJobs, nJobs * sizeof(JobDev));
@@ -1509,11 +1694,11 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.growDev(I.dSeq, I.capSeq, I.seqBytes + 64);
     I.growDev(I.dOut, I.capOut, I.outInts * sizeof(int) + 64);
     I.growDev(I.dJobOut, I.capJobOut, nJobs * sizeof(JobOut));
-    I.growDev(I.dOrder, I.capOrder, nJobs * sizeof(int));
+    I.growDev(I.dOrder, I.capOrder, nEntries * sizeof(int));
     I.growDev(I.dColTab, I.capColTab, I.colTabAll.size() * sizeof(ColInfo) + 64);
     I.growDev(I.dScratch, I.capScratch, (size_t)L.total * nSlots);
     I.growDev(I.dRing, I.capRing, I.ringBytes);
-    I.growDev(I.dRecs, I.capRecs, (I.gridsAll.size() + 1) * sizeof(GridRec));
+    I.growDev(I.dRecs, I.capRecs, (nRecs + 1) * sizeof(GridRec));
     I.growDev(I.dMini, I.capMini, miniStride * (size_t)NCTRL * I.numSMs);
     if (usePersist) I.growDev(I.dPersist, I.capPersist, (size_t)persistTotal + 256);
     I.growHost(I.hOut, I.capHOut, I.outInts * sizeof(int) + 64);
@@ -1521,7 +1706,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     CUDA_CHECK(cudaMemcpyAsync(I.dSeq, I.hSeq, I.seqBytes, cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dJobs, I.jobsDev.data(), nJobs * sizeof(JobDev), cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dGrids, I.gridsAll.data(), I.gridsAll.size() * sizeof(GridDesc), cudaMemcpyHostToDevice, I.stream));
-    CUDA_CHECK(cudaMemcpyAsync(I.dOrder, I.order.data(), nJobs * sizeof(int), cudaMemcpyHostToDevice, I.stream));
+    CUDA_CHECK(cudaMemcpyAsync(I.dOrder, I.order.data(), nEntries * sizeof(int), cudaMemcpyHostToDevice, I.stream));
     if (!I.colTabAll.empty())
         CUDA_CHECK(cudaMemcpyAsync(I.dColTab, I.colTabAll.data(), I.colTabAll.size() * sizeof(ColInfo), cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaEventRecord(I.ev[1], I.stream));
@@ -1530,7 +1715,8 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.out = (int*)I.dOut; kp.jobOut = (JobOut*)I.dJobOut; kp.order = (const int*)I.dOrder;
     kp.colTabPool = (const ColInfo*)I.dColTab;
     kp.nJobs = (int)nJobs; kp.nSlots = nSlots; kp.maxTasks = (int)nTasks + 1;
-    kp.nHiJobs = std::max(4, (int)nJobs / 10);
+    kp.nEntries = (int)nEntries; kp.pad6 = 0;
+    kp.nHiJobs = std::max(8, (int)nEntries / 8);
     kp.cb = (ControlBlock*)I.dRing;
     kp.ring = (TaskDesc*)((uint8_t*)I.dRing + offRing);
     kp.p2ring = (P2Entry*)((uint8_t*)I.dRing + offP2);
@@ -1661,6 +1847,7 @@ void Engine::fetch(std::vector<Job*>& jobs) {
             const int reserved = p[pos++];
             ++pos;  // ints used (== reserved after the device-side compaction)
             const int firstCand = p[pos++];
+            ++pos;  // chain segment tag (already filtered on the device)
             parts.emplace_back(std::make_pair(gi, firstCand), std::vector<std::vector<Seg> >());
             auto& traces = parts.back().second;
             traces.resize((size_t)nTr);

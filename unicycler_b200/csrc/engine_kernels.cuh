@@ -30,6 +30,7 @@ constexpr int NCTRL = 4;                 // control-capable warps per CTA
 constexpr int MODE_TASK = 0;             // score-only strip item of a published grid (checkpoints to HBM)
 constexpr int MODE_TRACE = 1;            // full trace bytes into the shared-memory window
 constexpr int MODE_FAST = 2;             // score-only local fill, box cells (S,H,V) into the shared-memory window
+constexpr int MAXSEG = 8;                // speculative segments of one seed chain
 constexpr int MAXREC = 8;                // candidates / planted cells a pass-1 grid record can hold
 constexpr unsigned FULLMASK = 0xffffffffu;
 
@@ -46,7 +47,10 @@ struct JobDev {
     int gridBegin, gridCount;
     long long outOff, colTabBase;
     int outCap;
-    int pad;
+    int nSeg;                  // the chain is walked by nSeg control warps at once (speculative segments)
+    int segStart[MAXSEG + 1];  // first grid of every segment; segStart[nSeg] = gridCount
+    int pad2;
+    long long recBase;         // GridRec index of (segment 0, grid 0); record of (p, k) = recBase + p * gridCount + k
 };
 
 struct JobOut {
@@ -110,6 +114,7 @@ struct GridRec {
     int state;        // 0: done in line by pass 1; 1: small grid (pass 2 fills the trace and walks all candidates);
                       // 2: big grid with a persistent block (pass 2 walks one candidate per item)
     int nCand, inserted, nPlantedIn;
+    int relMax, pad;  // grid maximum in the writing segment's score frame
     int cand[MAXREC];
     PlantedCell plantedIn[MAXREC];
 };
@@ -117,7 +122,16 @@ struct GridRec {
 struct JobState {     // zeroed before every launch
     int outCursor;    // ints reserved in the job's segment stream
     int status;       // max over the statuses of pass-2 grids
-    int pad0, pad1;
+    int segStopped;   // number of segments whose control warp has stopped
+    int nOwner;       // resolved chain: grids [ownerFrom[t], ownerFrom[t+1]) belong to segment ownerSeg[t]
+    int segProgress[MAXSEG];   // grids finished by the segment (next grid to process), release-published
+    int segStop[MAXSEG];       // 1: the segment's warp has stopped
+    int segClaim[MAXSEG];      // 0: not started, 1: started by its warp, 2: cancelled by an earlier segment that ran past it
+    int segSyncSeg[MAXSEG];    // segment it merged into (-1: reached the end of the chain, -2: failed)
+    int segSyncGrid[MAXSEG];   // grid at which it merged / failed
+    int segDelta[MAXSEG];      // score of its frame minus score of the frame it merged into, at the merge cell
+    int segFailStatus[MAXSEG];
+    int ownerSeg[MAXSEG + 1], ownerFrom[MAXSEG + 1];
 };
 
 struct P2Entry {      // pass-2 board entry: one job whose pass 1 is complete
@@ -144,7 +158,8 @@ struct KParams {
     const uint8_t* seq;
     int* out;
     JobOut* jobOut;
-    const int* order;  // job processing order (largest first)
+    const int* order;  // pass-1 work list: jobIdx * MAXSEG + segment, longest chains first
+    int nEntries, pad6;
     const ColInfo* colTabPool;
     int nJobs;
     int nSlots;        // control agents with an arena
