@@ -80,7 +80,7 @@ __device__ __noinline__ void setupGrid(GridCtx& Gin, const JobDev& jb, const Gri
         G.local = lp.local; G.RR = lp.local ? lp.RR : 8; G.rrMul = 65536 / G.RR + 1; G.rrs = lp.local ? lp.RRS : 8; G.pad2 = 0; G.pitch = lp.pitch; G.localJhi = lp.jhi;
         G.NS = lp.local ? 1 : stripCount(g, SH);
         // banded strips are short (band width + 256 columns): one item per strip; unbanded rows are cut into segments
-        G.nSeg = g.banded ? 1 : (g.nH + SEG - 1) / SEG;
+        G.nSeg = 1;   // one item per strip: a strip is a serial walk over its columns; strips pipeline with a two-chunk lag
         if (!lp.local && P.persist != nullptr && gd.persistOff >= 0) {
             // big grid with its own persistent block: [rowCk | colCk | ckBase | rowProg | segDone | initRow | initCol]
             uint8_t* pb = P.persist + gd.persistOff;
@@ -138,7 +138,7 @@ __device__ __noinline__ void setupStrips(const GridCtx& Gin) {
             G.ckBase[s] = base + incl - cnt;
             const int jlo = stripJlo(g, s, SH);
             G.rowProg[s] = jlo - 1;
-            G.segDone[s] = g.banded ? 0 : (jlo - 1) / SEG;
+            G.segDone[s] = 0;
         }
         base += __shfl_sync(FULLMASK, incl, 31);
     }
@@ -833,13 +833,18 @@ __device__ __noinline__ void runItem(const GridCtx& Gin, int item) {
     const int seg = item / G.NS;
     const int s = item - seg * G.NS;
     const int jlo = stripJlo(g, s, SH), jhi = stripJhi(g, s, SH);
-    const int cBeg = g.banded ? jlo : imax(seg * SEG + 1, jlo);
-    const int cEnd = g.banded ? jhi : imin((seg + 1) * SEG, jhi);
-    if (cBeg > cEnd) return;  // the strip holds no band cells in this segment
+    const int cBeg = jlo;
+    const int cEnd = jhi;
+    if (cBeg > cEnd) {  // the strip holds no band cells (cannot happen for s < NS; keep the chain of claims alive)
+        if (lane == 0) atomicMax(G.readyUpTo, s + 1);
+        return;
+    }
     const bool fromCk = cBeg > jlo;
     if (fromCk) {  // the previous segment of this strip must be complete (its column checkpoint is our state)
         if (lane == 0) {
+            const long long w0 = clock64();
             while (ldRelaxed(&G.segDone[s]) < seg) __nanosleep(256);
+            atomicAdd(&gDbg[11], (unsigned long long)(clock64() - w0));
         }
         __syncwarp();
     }
@@ -874,29 +879,35 @@ __device__ __forceinline__ void runClaimedItem(TaskDesc* t, int taskId, int item
 
 // Claims and runs one item of the oldest open task, critical-path board first.  Returns false when no
 // item is available.
-__device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask) {
+__device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask, bool* sawOpen = nullptr) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
-    int h = 0, item = -1, board = 0;
+    int h = 0, item = -1, board = 0, open = 0;
     if (lane == 0) {
         for (board = 0; board < 2 && item < 0; ++board) {
             h = ldRelaxed(&P.cb->ringHead[board]);
-            for (;;) {
-                if (h >= P.maxTasks) break;
+            // Strips are claimed in order, and only once the strip above is two chunks in (readyUpTo): a warp
+            // never parks on a strip whose turn is far away, it looks at the next tasks instead.
+            for (int scanned = 0; scanned < 48 && h < P.maxTasks; ++scanned, ++h) {
                 TaskDesc* t = &P.ring[board * P.maxTasks + h];
-                if (ldRelaxed(&t->ready) == 0) break;  // nothing published at the head (yet)
+                if (ldRelaxed(&t->ready) == 0) break;  // nothing published here (yet)
                 const int n = t->nItems;
-                if (ldVolatile(&t->nextItem) < n) {
-                    const int k = atomicAdd(&t->nextItem, 1);
-                    if (k < n) { item = k; break; }
+                for (;;) {
+                    const int k = ldVolatile(&t->nextItem);
+                    if (k >= n) {
+                        if (scanned == 0) atomicCAS(&P.cb->ringHead[board], h, h + 1);  // exhausted head: advance
+                        break;
+                    }
+                    if (k > ldRelaxed(&t->readyUpTo)) { open = 1; break; }   // upstream strip not far enough yet
+                    if (atomicCAS(&t->nextItem, k, k + 1) == k) { item = k; break; }
                 }
-                atomicCAS(&P.cb->ringHead[board], h, h + 1);  // exhausted: advance the head
-                ++h;
+                if (item >= 0) break;
             }
         }
         --board;
     }
     item = __shfl_sync(FULLMASK, item, 0);
+    if (sawOpen) *sawOpen = __shfl_sync(FULLMASK, open, 0) != 0;
     if (item < 0) return false;
     h = __shfl_sync(FULLMASK, h, 0);
     board = __shfl_sync(FULLMASK, board, 0);
@@ -920,24 +931,30 @@ __device__ __noinline__ int publishAndWait(const GridCtx& Gin, GridCtx& wctx, in
     const int* src = reinterpret_cast<const int*>(&G);
     int* dst = reinterpret_cast<int*>(&td->ctx);
     for (int k = lane; k < (int)(sizeof(GridCtx) / sizeof(int)); k += 32) dst[k] = src[k];
+    __syncwarp();
     const int nItems = G.NS * G.nSeg;
-    if (lane == 0) { td->nItems = nItems; td->nextItem = 0; td->doneItems = 0; }
+    if (lane == 0) {
+        td->nItems = nItems; td->nextItem = 0; td->doneItems = 0; td->readyUpTo = 0;
+        td->ctx.readyUpTo = &td->readyUpTo;
+    }
     __threadfence();
     __syncwarp();
     if (lane == 0) stRelease(&td->ready, 1);
+    (void)board;
     for (;;) {
         int d = 0;
         if (lane == 0) d = ldRelaxed(&td->doneItems);
         d = __shfl_sync(FULLMASK, d, 0);
         if (d >= nItems) break;
-        if (board == 0) {
-            // critical-path job: work on the own grid only, so that the control warp is free the moment it completes
-            int k = -1;
-            if (lane == 0 && ldVolatile(&td->nextItem) < nItems) { k = atomicAdd(&td->nextItem, 1); if (k >= nItems) k = -1; }
-            k = __shfl_sync(FULLMASK, k, 0);
-            if (k >= 0) runClaimedItem(td, taskId, k, wctx, wTask);
-            else __nanosleep(100);
-        } else if (!tryRunOneItem(wctx, wTask)) __nanosleep(200);
+        // the control warp works on its own grid only, so that it is free the moment the grid completes
+        int k = -1;
+        if (lane == 0) {
+            const int nx = ldVolatile(&td->nextItem);
+            if (nx < nItems && nx <= ldRelaxed(&td->readyUpTo) && atomicCAS(&td->nextItem, nx, nx + 1) == nx) k = nx;
+        }
+        k = __shfl_sync(FULLMASK, k, 0);
+        if (k >= 0) runClaimedItem(td, taskId, k, wctx, wTask);
+        else __nanosleep(200);
     }
     // one real acquire: the captures written by the worker warps are read with ordinary (L1-cached) loads
     if (lane == 0) (void)ldAcquire(&td->doneItems);
@@ -1384,7 +1401,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
             }
             queueEmpty = true;
         }
-        if (tryRunOneItem(*wctx, wTask)) { idle = 0; continue; }
+        bool sawOpen = false;
+        if (tryRunOneItem(*wctx, wTask, &sawOpen)) { idle = 0; continue; }
+        if (sawOpen) idle = 0;   // strips are about to become claimable: poll again soon
         if (cw >= 0 && tryRunPass2(*cctx, win, mini)) { idle = 0; continue; }
         int done = 0;
         if (lane == 0) done = ldRelaxed(&P.cb->jobsDone);
@@ -1818,6 +1837,7 @@ void Engine::fetch(std::vector<Job*>& jobs) {
                 nJobs, I.kp.nSlots, I.kp.maxTasks, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], mx, tot[6], tot[7], tot[8], tot[9], tot[10], tot[11]);
         unsigned long long dbg[16];
         if (cudaMemcpyFromSymbol(dbg, gDbg, sizeof(dbg)) == cudaSuccess) {
+            fprintf(stderr, "[ub200 dbg] worker items=%llu strip-cycles=%llu (rowProg wait %llu) segDone-wait=%llu cells=%llu (cumulative)\n", dbg[14], dbg[12], dbg[13], dbg[11], dbg[15]);
             fprintf(stderr, "[ub200 dbg] unbanded trace strips=%llu total=%llu steps-cycles=%llu nsteps=%llu | banded strips=%llu total=%llu steps-cycles=%llu nsteps=%llu (cumulative)\n", dbg[3], dbg[0], dbg[1], dbg[2], dbg[7], dbg[4], dbg[5], dbg[6]);
         }
         const long long* wp = I.jobOut[worst].prof;

@@ -86,6 +86,7 @@ struct GridCtx {
     int* ckBase;        // per strip: first checkpoint tile index
     int* rowProg;       // per strip: last boundary column written (release/acquire)
     int* segDone;       // per strip: number of the next segment that may start
+    int* readyUpTo;     // task board entry: highest strip index that may be claimed (its upstream strip is far enough)
     DCell *initRow, *initCol, *hInitNext, *vInitNext, *box, *lastRow, *lastCol;
     int* cand;
     PlantedCell* planted;
@@ -142,8 +143,10 @@ struct TaskDesc {
     GridCtx ctx;
     int nItems;
     int ready;       // release-published by the control warp
-    int nextItem;    // claimed by atomicAdd
+    int nextItem;    // claimed by compare-and-swap, in order
     int doneItems;   // completed items (release)
+    int readyUpTo;   // items <= readyUpTo may be claimed: strip s+1 becomes claimable once strip s is two chunks in
+    int pad0, pad1, pad2;
 };
 
 struct ControlBlock {  // zeroed before every launch
@@ -505,7 +508,7 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
     const long long dbg0 = clock64();
-    long long dbgSteps = 0;
+    long long dbgSteps = 0, dbgWait = 0;
     StripState<RR> st;
     const int i0 = s * SHR + lane * RR + 1;
     const int jlo = stripJlo(g, s, SHR);
@@ -558,6 +561,9 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
     int2* rowOut = (MODE == MODE_TASK) ? G.rowCk + (size_t)s * (size_t)(g.nH + 1) : nullptr;
     const int nch = (nsteps + 31) / 32;
     int upProg = 0;                // cached progress of the strip above
+    // the strip below becomes claimable once this one is two chunks past that strip's first column
+    bool signalled = false;
+    const int signalAt = imin(cEnd, stripJlo(g, s + 1, SHR) + 63);
     const int upJhi = (s > 0) ? stripJhi(g, s - 1, SHR) : 0;
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
@@ -567,9 +573,11 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
             const int need = imin(imin(cEnd, cBeg + 32 * c + 31), upJhi);
             if (upProg < need) {
                 if (lane == 0) {
+                    const long long w0 = clock64();
                     int p = ldRelaxed(&G.rowProg[s - 1]);
                     while (p < need) { __nanosleep(128); p = ldRelaxed(&G.rowProg[s - 1]); }
                     upProg = p;
+                    dbgWait += clock64() - w0;
                 }
                 upProg = __shfl_sync(FULLMASK, upProg, 0);
             }
@@ -594,8 +602,17 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
         if (MODE == MODE_TASK) {
             // lane 31 has finished every column <= cBeg + 32c + 31 - 31 (and cEnd after the last chunk)
             const int done = imin(cEnd, cBeg + 32 * c + imin(31, nsteps - 1 - 32 * c) - 31);
-            if (lane == 31 && done >= cBeg) stRelease(&G.rowProg[s], done);
+            if (lane == 31 && done >= cBeg) {
+                stRelease(&G.rowProg[s], done);
+                if (!signalled && done >= signalAt) { atomicMax(G.readyUpTo, s + 1); signalled = true; }
+            }
         }
+    }
+    if (MODE == MODE_TASK && lane == 0) {
+        atomicAdd(&gDbg[12], (unsigned long long)(clock64() - dbg0));
+        atomicAdd(&gDbg[13], (unsigned long long)dbgWait);
+        atomicAdd(&gDbg[14], 1ull);
+        atomicAdd(&gDbg[15], (unsigned long long)(cEnd - cBeg + 1) * 256ull);
     }
     if (MODE != MODE_TASK && lane == 0) {
         const int o = (MODE == MODE_FAST) ? 4 : 0;
