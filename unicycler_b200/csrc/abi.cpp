@@ -193,8 +193,18 @@ bool finishChainJob(ChainJob& cj, const Scoring& sc, std::string& out) {
 }
 
 // ------------------------------------------------------------------ semi-global (one read)
+struct RangeUnit {  // one (reference, strand, range) of a read: alignReadToReferenceRange, semi_global_align.cpp:135
+    std::string refName;
+    char strand = '+';
+    int refStart = 0, refEnd = 0;
+    std::string console;
+    std::vector<std::unique_ptr<ChainJob> > jobs;
+};
 struct ReadWork {
     std::string readName, posSeq, negSeq, console;
+    KmerPosMap posKmers, negKmers;
+    SensitivityParams sp;
+    std::vector<RangeUnit> units;                  // in the reference's iteration order
     std::vector<std::unique_ptr<ChainJob> > jobs;  // in the reference's output order
 };
 
@@ -252,37 +262,54 @@ void prepareRead(ReadWork& w, const char* readNameC, const char* readSeqC, int v
             for (const auto& rr : r.second)
                 w.console += "    " + r.first + ": " + std::to_string(rr.first) + " - " + std::to_string(rr.second) + "\n";
     }
-    KmerPosMap posKmers, negKmers;
+    // k-mer indexes of the strands that are needed, and the list of range units in the reference's iteration order
+    w.sp = sp;
     bool havePos = false, haveNeg = false;
     for (const auto& r : simplified) {
         std::string refName = r.first;
-        char strand = refName.back();
+        const char strand = refName.back();
         refName.pop_back();
-        const std::string& refSeq = refSeqs->at(refName);
-        const std::string* readSeq;
-        const KmerPosMap* kmers;
         if (strand == '+') {
-            if (!havePos) { buildKmerPositions(w.posSeq, sp.kSize, posKmers); havePos = true; }
-            readSeq = &w.posSeq; kmers = &posKmers;
-        } else {
-            if (!haveNeg) { w.negSeq = reverseComplement(w.posSeq); buildKmerPositions(w.negSeq, sp.kSize, negKmers); haveNeg = true; }
-            readSeq = &w.negSeq; kmers = &negKmers;
+            if (!havePos) { buildKmerPositions(w.posSeq, sp.kSize, w.posKmers); havePos = true; }
+        } else if (!haveNeg) {
+            w.negSeq = reverseComplement(w.posSeq);
+            buildKmerPositions(w.negSeq, sp.kSize, w.negKmers);
+            haveNeg = true;
         }
         for (const auto& range : r.second) {
-            const int refStart = range.first, refEnd = range.second;
-            std::string trimmed = refSeq.substr((size_t)refStart, (size_t)(refEnd - refStart));
-            RangeSeeds rs;
-            seedRange(*readSeq, *kmers, trimmed, sp, verbosity, refName, refStart, refEnd, rs);
-            w.console += rs.console;
-            for (const auto& chain : rs.chains) {
-                std::unique_ptr<ChainJob> cj(new ChainJob());
-                cj->readName = w.readName + strand;
-                cj->refName = refName;
-                cj->refOffset = refStart;
-                buildChainJob(*cj, readSeq->data(), readSeq->size(), trimmed.data(), trimmed.size(), chain, sc, sp.bandSize);
-                w.jobs.push_back(std::move(cj));
-            }
+            w.units.emplace_back();
+            RangeUnit& u = w.units.back();
+            u.refName = refName; u.strand = strand; u.refStart = range.first; u.refEnd = range.second;
         }
+    }
+    (void)sc;
+}
+
+// One range unit of a read: seeding + planning of its chain jobs (independent of every other unit).
+void seedUnit(ReadWork& w, RangeUnit& u, int verbosity, SeqMap* refSeqs, const Scoring& sc) {
+    const std::string& refSeq = refSeqs->at(u.refName);
+    const std::string& readSeq = (u.strand == '+') ? w.posSeq : w.negSeq;
+    const KmerPosMap& kmers = (u.strand == '+') ? w.posKmers : w.negKmers;
+    std::string trimmed = refSeq.substr((size_t)u.refStart, (size_t)(u.refEnd - u.refStart));
+    RangeSeeds rs;
+    seedRange(readSeq, kmers, trimmed, w.sp, verbosity, u.refName, u.refStart, u.refEnd, rs);
+    u.console = rs.console;
+    for (const auto& chain : rs.chains) {
+        std::unique_ptr<ChainJob> cj(new ChainJob());
+        cj->readName = w.readName + u.strand;
+        cj->refName = u.refName;
+        cj->refOffset = u.refStart;
+        buildChainJob(*cj, readSeq.data(), readSeq.size(), trimmed.data(), trimmed.size(), chain, sc, w.sp.bandSize);
+        u.jobs.push_back(std::move(cj));
+    }
+}
+
+// Collects the units' results in the reference's order.
+void collectUnits(ReadWork& w) {
+    for (RangeUnit& u : w.units) {
+        w.console += u.console;
+        for (auto& cj : u.jobs) w.jobs.push_back(std::move(cj));
+        u.jobs.clear();
     }
 }
 
@@ -566,6 +593,8 @@ char* semiGlobalAlignment(char* readName, char* readSeq, int verbosity, char* hi
     Scoring sc{m, mm, go, ge};
     ReadWork w;
     prepareRead(w, readName, readSeq, verbosity, hits, (SeqMap*)refSeqs, sc, sensitivityLevel);
+    parallelFor((int)w.units.size(), [&](int k) { seedUnit(w, w.units[(size_t)k], verbosity, (SeqMap*)refSeqs, sc); });
+    collectUnits(w);
     std::vector<Job*> jobs;
     for (auto& cj : w.jobs) jobs.push_back(&cj->job);
     engine().run(jobs);
@@ -584,20 +613,28 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     std::vector<size_t> len((size_t)n);
     for (int i = 0; i < n; ++i) len[(size_t)i] = strlen(readSeqs[i]);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[(size_t)a] > len[(size_t)b]; });
-    std::vector<double> readMs((size_t)n, 0.0);
+    // stage A: per read — ranges and k-mer indexes
     parallelFor(n, [&](int k) {
         const int i = order[(size_t)k];
-        const double ta = nowSec();
         works[(size_t)i].reset(new ReadWork());
         prepareRead(*works[(size_t)i], readNames[i], readSeqs[i], 0, hits[i], (SeqMap*)refSeqs, sc, sensitivityLevel);
-        readMs[(size_t)i] = (nowSec() - ta) * 1e3;
     });
-    if (getenv("UNICYCLER_B200_HOST_ONLY")) {
-        std::vector<double> v = readMs;
-        std::sort(v.begin(), v.end());
-        double sum = 0; for (double x : v) sum += x;
-        fprintf(stderr, "[ub200 host] per-read prepare ms: max %.1f, 2nd %.1f, median %.1f, sum %.1f\n", v.back(), v.size() > 1 ? v[v.size() - 2] : 0.0, v[v.size() / 2], sum);
-    }
+    // stage B: per (read, reference range) — seeding and planning, most expensive units first
+    std::vector<std::pair<int, int> > unitList;
+    for (int i = 0; i < n; ++i)
+        for (size_t u = 0; u < works[(size_t)i]->units.size(); ++u) unitList.emplace_back(i, (int)u);
+    std::stable_sort(unitList.begin(), unitList.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+        const RangeUnit& ua = works[(size_t)a.first]->units[(size_t)a.second];
+        const RangeUnit& ub = works[(size_t)b.first]->units[(size_t)b.second];
+        const double ca = (double)len[(size_t)a.first] * (ua.refEnd - ua.refStart);
+        const double cb = (double)len[(size_t)b.first] * (ub.refEnd - ub.refStart);
+        return ca > cb;
+    });
+    parallelFor((int)unitList.size(), [&](int k) {
+        ReadWork& w = *works[(size_t)unitList[(size_t)k].first];
+        seedUnit(w, w.units[(size_t)unitList[(size_t)k].second], 0, (SeqMap*)refSeqs, sc);
+    });
+    for (int i = 0; i < n; ++i) collectUnits(*works[(size_t)i]);
     std::vector<Job*> jobs;
     for (int i = 0; i < n; ++i)
         for (auto& cj : works[(size_t)i]->jobs) jobs.push_back(&cj->job);
