@@ -882,36 +882,33 @@ __device__ __forceinline__ void runClaimedItem(TaskDesc* t, int taskId, int item
 __device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask, bool* sawOpen = nullptr) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
-    int h = 0, item = -1, board = 0, open = 0;
+    int item = -1, taskId = -1, open = 0;
     if (lane == 0) {
-        for (board = 0; board < 2 && item < 0; ++board) {
-            h = ldRelaxed(&P.cb->ringHead[board]);
-            // Strips are claimed in order, and only once the strip above is two chunks in (readyUpTo): a warp
-            // never parks on a strip whose turn is far away, it looks at the next tasks instead.
-            for (int scanned = 0; scanned < 48 && h < P.maxTasks; ++scanned, ++h) {
-                TaskDesc* t = &P.ring[board * P.maxTasks + h];
-                if (ldRelaxed(&t->ready) == 0) break;  // nothing published here (yet)
+        // Pop a token (critical-path ring first): it names a task that had a claimable strip.  Strips are claimed
+        // in order and only once the strip above is two chunks in (readyUpTo), so no warp parks on a far-away strip.
+        for (int board = 0; board < 2 && item < 0; ++board) {
+            for (int tries = 0; tries < 8 && item < 0; ++tries) {
+                const int h = ldRelaxed(&P.cb->tokHead[board]);
+                const int tl = ldRelaxed(&P.cb->tokTail[board]);
+                if (h >= tl || h >= P.maxTokens) break;
+                if (atomicCAS(&P.cb->tokHead[board], h, h + 1) != h) continue;
+                int tok = 0;
+                while ((tok = ldRelaxed(&P.tokRing[(size_t)board * P.maxTokens + h])) == 0) __nanosleep(32);
+                TaskDesc* t = &P.ring[tok - 1];
                 const int n = t->nItems;
                 for (;;) {
                     const int k = ldVolatile(&t->nextItem);
-                    if (k >= n) {
-                        if (scanned == 0) atomicCAS(&P.cb->ringHead[board], h, h + 1);  // exhausted head: advance
-                        break;
-                    }
-                    if (k > ldRelaxed(&t->readyUpTo)) { open = 1; break; }   // upstream strip not far enough yet
-                    if (atomicCAS(&t->nextItem, k, k + 1) == k) { item = k; break; }
+                    if (k >= n) break;
+                    if (k > ldRelaxed(&t->readyUpTo)) { open = 1; break; }   // taken meanwhile by the task's own warp
+                    if (atomicCAS(&t->nextItem, k, k + 1) == k) { item = k; taskId = tok - 1; break; }
                 }
-                if (item >= 0) break;
             }
         }
-        --board;
     }
     item = __shfl_sync(FULLMASK, item, 0);
     if (sawOpen) *sawOpen = __shfl_sync(FULLMASK, open, 0) != 0;
     if (item < 0) return false;
-    h = __shfl_sync(FULLMASK, h, 0);
-    board = __shfl_sync(FULLMASK, board, 0);
-    const int taskId = board * P.maxTasks + h;
+    taskId = __shfl_sync(FULLMASK, taskId, 0);
     runClaimedItem(&P.ring[taskId], taskId, item, wctx, wTask);
     return true;
 }
@@ -936,10 +933,11 @@ __device__ __noinline__ int publishAndWait(const GridCtx& Gin, GridCtx& wctx, in
     if (lane == 0) {
         td->nItems = nItems; td->nextItem = 0; td->doneItems = 0; td->readyUpTo = 0;
         td->ctx.readyUpTo = &td->readyUpTo;
+        td->ctx.taskId = taskId;
     }
     __threadfence();
     __syncwarp();
-    if (lane == 0) stRelease(&td->ready, 1);
+    if (lane == 0) { stRelease(&td->ready, 1); pushToken(taskId); }
     (void)board;
     for (;;) {
         int d = 0;
@@ -1251,6 +1249,15 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
                 match = plantedMatch(planted, nPlantedPrev, theirs->plantedIn, __ldcg(&theirs->nPlantedIn), delta);
             } else continue;   // q stopped before reaching this grid
             if (match) { merged = true; syncSeg = q; syncGrid = gi; syncDelta = delta; }
+            else {
+                // no merge here: this warp redoes grid gi itself.  Segment q may still be working on the very same
+                // grid (same persistent block, same task counters): let it finish that grid first.
+                if (lane == 0) {
+                    while (ldRelaxed(&js->segProgress[q]) <= gi && !ldRelaxed(&js->segStop[q])) __nanosleep(500);
+                    __threadfence();
+                }
+                __syncwarp();
+            }
         }
         if (merged) break;
         const GridDesc gd = P.grids[jb.gridBegin + gi];
@@ -1541,6 +1548,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     memset(&L, 0, sizeof(L));
     long long maxRowCk = 0, maxColCk = 0, maxBox = 1, ckBytes = 0;
     long long maxRowCkNP = 0, maxColCkNP = 0, persistTotal = 0;   // NP: grids without a persistent block
+    size_t totalStrips = 0;
     int maxNH = 1, maxNV = 1, maxCapH = 1, maxCapV = 1, maxStrips = 1;
     size_t nTasks = 0;
     std::vector<long long> cost(nJobs, 0);
@@ -1571,6 +1579,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
             hostCheckpointBytes(gd, rck, cck, ns, local);
             if (!local) {
                 ++nTasks;
+                totalStrips += (size_t)ns;
                 ckBytes += rck + cck;
                 maxRowCk = std::max(maxRowCk, rck);
                 maxColCk = std::max(maxColCk, cck);
@@ -1652,7 +1661,9 @@ void Engine::upload(std::vector<Job*>& jobs) {
     const size_t offRing = alignUp(sizeof(ControlBlock), 256);
     const size_t offP2 = offRing + alignUp(2 * (nTasks + 1) * sizeof(TaskDesc), 256);
     const size_t offState = offP2 + alignUp((nJobs + 1) * sizeof(P2Entry), 256);
-    I.ringBytes = offState + (nJobs + 1) * sizeof(JobState);
+    const size_t offTok = offState + alignUp((nJobs + 1) * sizeof(JobState), 256);
+    const size_t maxTokens = totalStrips + nTasks + 64;
+    I.ringBytes = offTok + 2 * maxTokens * sizeof(int);
     // mini arenas: init row / column of the largest LOCAL grid, for every control-capable warp
     int maxLocalNH = 1, maxLocalNV = 1;
     for (const GridDesc& gd : I.gridsAll) {
@@ -1682,16 +1693,31 @@ void Engine::upload(std::vector<Job*>& jobs) {
         const int n = (int)j.grids.size();
         int nSeg = 1;
         d.segStart[0] = 0;
-        if (!noSplit && j.complete && n >= 128 && extraBudget > 0) {
-            const int want = (int)std::min<long long>(std::min(MAXSEG, n / 64), extraBudget + 1);
-            for (int p = 1; p < want; ++p) {
-                int g = (int)((long long)p * n / want);
-                // snap forward to an unbanded inner grid that follows a banded one
-                while (g < n - 1 && !(j.grids[(size_t)g].kind == GRID_CHAIN_INNER && !j.grids[(size_t)g].banded &&
-                                      j.grids[(size_t)g - 1].banded && j.grids[(size_t)g - 1].kind == GRID_CHAIN_INNER))
-                    ++g;
-                if (g >= n - 1 || g <= d.segStart[nSeg - 1] + 8) continue;
+        if (!noSplit && j.complete && n >= 16 && extraBudget > 0) {
+            // latency model of the serial spine (cycles): ~100 k per small grid; a big rectangle is filled as a
+            // pipeline of strips, (columns/32 + 2 x strips) chunks of ~16 k cycles
+            std::vector<double> gc((size_t)n);
+            double total = 0;
+            for (int g = 0; g < n; ++g) {
+                const GridDesc& gd = j.grids[(size_t)g];
+                GridGeom gg = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
+                double c = 100e3;
+                if (!localPlan(gg).local) c = ((double)gd.nH / 32.0 + 2.0 * stripCount(gg, SH)) * 16e3 + 200e3;
+                gc[(size_t)g] = c;
+                total += c;
+            }
+            const int want = (int)std::min<long long>(std::min<long long>(MAXSEG, (long long)(total / 4e6 + 0.5)), extraBudget + 1);
+            double acc = 0;
+            int nextP = 1;
+            for (int g = 1; g < n - 1 && nextP < want; ++g) {
+                acc += gc[(size_t)g - 1];
+                if (acc < total * nextP / want) continue;
+                // a segment starts at an unbanded inner grid that follows an anchor strip
+                const bool ok = j.grids[(size_t)g].kind == GRID_CHAIN_INNER && !j.grids[(size_t)g].banded &&
+                                j.grids[(size_t)g - 1].banded && j.grids[(size_t)g - 1].kind == GRID_CHAIN_INNER;
+                if (!ok || g <= d.segStart[nSeg - 1] + 4) continue;
                 d.segStart[nSeg++] = g;
+                ++nextP;
             }
         }
         for (int p = nSeg; p <= MAXSEG; ++p) d.segStart[p] = n;
@@ -1740,6 +1766,8 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.ring = (TaskDesc*)((uint8_t*)I.dRing + offRing);
     kp.p2ring = (P2Entry*)((uint8_t*)I.dRing + offP2);
     kp.jobState = (JobState*)((uint8_t*)I.dRing + offState);
+    kp.tokRing = (int*)((uint8_t*)I.dRing + offTok);
+    kp.maxTokens = (int)maxTokens; kp.pad7 = 0;
     kp.gridRecs = (GridRec*)I.dRecs;
     kp.persist = usePersist ? (uint8_t*)I.dPersist : nullptr;
     kp.mini = (uint8_t*)I.dMini; kp.miniStride = (long long)miniStride; kp.miniInitCol = (long long)miniInitCol;

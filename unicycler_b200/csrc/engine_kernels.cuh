@@ -87,6 +87,7 @@ struct GridCtx {
     int* rowProg;       // per strip: last boundary column written (release/acquire)
     int* segDone;       // per strip: number of the next segment that may start
     int* readyUpTo;     // task board entry: highest strip index that may be claimed (its upstream strip is far enough)
+    long long taskId;   // index of the task board entry (board * maxTasks + slot)
     DCell *initRow, *initCol, *hInitNext, *vInitNext, *box, *lastRow, *lastCol;
     int* cand;
     PlantedCell* planted;
@@ -153,6 +154,7 @@ struct ControlBlock {  // zeroed before every launch
     int jobQueue, jobsDone;
     int ringHead[2], ringTail[2];  // task boards: [0] jobs on the critical path (longest chains), [1] the rest
     int p2Head, p2Tail;            // pass-2 board
+    int tokHead[2], tokTail[2];    // token rings: one token per strip that became claimable
 };
 
 struct KParams {
@@ -170,6 +172,8 @@ struct KParams {
     int nHiJobs;       // the first nHiJobs jobs of `order` publish on board 0
     ControlBlock* cb;
     TaskDesc* ring;    // [2][maxTasks]
+    int* tokRing;      // [2][maxTokens] task id + 1 of a task with a claimable strip
+    int maxTokens, pad7;
     P2Entry* p2ring;   // [nJobs]
     JobState* jobState;
     GridRec* gridRecs; // [total grids]
@@ -229,6 +233,13 @@ __device__ __forceinline__ int ldVolatile(const int* p) {
     int v;
     asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+// A strip of task `taskId` became claimable: hand a token to the idle warps.
+__device__ __forceinline__ void pushToken(long long taskId) {
+    const int board = (int)(taskId / cP.maxTasks);
+    const int pos = atomicAdd(&cP.cb->tokTail[board], 1);
+    if (pos < cP.maxTokens) stRelease(&cP.tokRing[(size_t)board * cP.maxTokens + pos], (int)taskId + 1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -604,7 +615,12 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
             const int done = imin(cEnd, cBeg + 32 * c + imin(31, nsteps - 1 - 32 * c) - 31);
             if (lane == 31 && done >= cBeg) {
                 stRelease(&G.rowProg[s], done);
-                if (!signalled && done >= signalAt) { atomicMax(G.readyUpTo, s + 1); signalled = true; }
+                if (!signalled && done >= signalAt) {
+                    atomicMax(G.readyUpTo, s + 1);
+                    __threadfence();
+                    if (s + 1 < G.NS) pushToken(G.taskId);
+                    signalled = true;
+                }
             }
         }
     }
