@@ -55,6 +55,7 @@ struct JobDev {
 
 struct JobOut {
     int status, score, outLen, pad;
+    long long tSpine, tFinal;   // ns after kernel start: pass 1 resolved / job complete
     long long prof[12];  // cycles: setup+init, local fill, task wait, track, traceback, total; tiles, tile cycles,
                          // local-grid traceback cycles, tracebacks, local grids, local-grid track cycles
 };
@@ -155,6 +156,7 @@ struct ControlBlock {  // zeroed before every launch
     int ringHead[2], ringTail[2];  // task boards: [0] jobs on the critical path (longest chains), [1] the rest
     int p2Head, p2Tail;            // pass-2 board
     int tokHead[2], tokTail[2];    // token rings: one token per strip that became claimable
+    unsigned long long t0;         // %globaltimer at kernel start (developer timeline)
 };
 
 struct KParams {
@@ -228,6 +230,11 @@ __device__ __forceinline__ DCell ldcgCell(const DCell* p) {
     DCell c;
     c.s = __ldcg(q); c.h = __ldcg(q + 1); c.v = __ldcg(q + 2);
     return c;
+}
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ int ldVolatile(const int* p) {
     int v;
