@@ -220,6 +220,7 @@ UB_HD TrackOpts chainTrackingOptions(int32_t ch, int32_t cv, int32_t tLeap, int3
 // ---------------------------------------------------------------------------------------
 constexpr int32_t SH = 256;              // strip height of task grids (32 lanes x 8 rows)
 constexpr int32_t CKW = 64;              // column-checkpoint spacing == recompute tile width
+constexpr int32_t CKR = 64;              // row-checkpoint spacing == recompute tile height (32 lanes x 2 rows)
 constexpr int32_t SEG = 1024;            // columns per work item
 constexpr int32_t WINBYTES = 46 * 1024;  // shared-memory window per control warp (trace bytes, or the pass-1 box)
 

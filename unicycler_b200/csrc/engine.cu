@@ -27,7 +27,7 @@ __host__ __device__ inline PersistLayout persistLayout(int nH, int nV, int NS, i
     PersistLayout p;
     long long o = 0;
     auto place = [&](long long& f, long long bytes) { f = o; o += (bytes + 255) / 256 * 256; };
-    place(p.rowCk, (long long)NS * (nH + 1) * (long long)sizeof(int2));
+    place(p.rowCk, (long long)NS * (SH / CKR) * (nH + 1) * (long long)sizeof(int2));
     place(p.colCk, (long long)ckTiles * SH * (long long)sizeof(int2));
     place(p.ckBase, (long long)(NS + 2) * 4);
     place(p.rowProg, (long long)(NS + 2) * 4);
@@ -1439,7 +1439,7 @@ static void hostCheckpointBytes(const GridDesc& gd, long long& rowCk, long long&
     nStrips = 1;
     if (local) return;
     nStrips = stripCount(g, SH);
-    rowCk = (long long)nStrips * (g.nH + 1) * (long long)sizeof(int2);
+    rowCk = (long long)nStrips * (SH / CKR) * (g.nH + 1) * (long long)sizeof(int2);
     long long tiles = 0;
     for (int s = 0; s < nStrips; ++s) tiles += ckCount(g, s);
     colCk = tiles * SH * (long long)sizeof(int2);

@@ -82,7 +82,8 @@ struct GridCtx {
     const uint8_t* seqH;
     const uint8_t* seqV;
     // arena pointers
-    int2* rowCk;        // [NS][nH+1] (S,V) of the last row of every strip
+    int2* rowCk;        // [NS * SH / CKR][nH+1] (S,V) of every CKR-th row (row checkpoints; the last one of a strip is
+                        // also the boundary the strip below starts from)
     int2* colCk;        // [ckBase[s] + c][SH] (S,H) of column (ckFirst(s)+c)*CKW
     int* ckBase;        // per strip: first checkpoint tile index
     int* rowProg;       // per strip: last boundary column written (release/acquire)
@@ -374,7 +375,7 @@ __device__ __forceinline__ void upBoundary(const GridCtx& G, int s, int SHR, int
         const DCell c = L2ONLY ? ldcgCell(&G.initRow[j]) : G.initRow[j];
         bS = c.s; bV = c.v;
     } else {
-        const int2 b = __ldcg(&G.rowCk[(size_t)(s - 1) * (size_t)(G.g.nH + 1) + j]);
+        const int2 b = __ldcg(&G.rowCk[(size_t)(s * (SHR / CKR) - 1) * (size_t)(G.g.nH + 1) + j]);
         bS = b.x; bV = b.y;
     }
 }
@@ -459,7 +460,7 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K
                 else if constexpr (RR == 2) *reinterpret_cast<uint16_t*>(p) = (uint16_t)tw[0];
                 else *reinterpret_cast<uint32_t*>(p) = tw[0];
             } else if constexpr (MODE == MODE_TASK) {
-                if (lane == 31) __stcg(&rowOut[j], make_int2(Su, Vu));
+                if ((lane & 7) == 7) __stcg(&rowOut[(size_t)(lane >> 3) * (size_t)(K.nH + 1) + j], make_int2(Su, Vu));
                 if ((j & (CKW - 1)) == 0) {
                     int2* ck = ckOut + (size_t)(j / CKW) * SH + lane * RR;
 #pragma unroll
@@ -533,7 +534,10 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
 #pragma unroll
     for (int w4 = 0; w4 < (RR + 3) / 4; ++w4) st.vm[w4] = 0;
     int2* ckTile = nullptr;   // checkpoint tile pointer such that tile of column j is ckTile + (j/CKW)*SH
-    if (MODE == MODE_TASK || fromCk) ckTile = G.colCk + ((size_t)__ldcg(&G.ckBase[s]) - (size_t)ckFirst(g, s)) * SH;
+    // column checkpoints are kept per 256-row strip; a 64-row tile (SHR == CKR) reads its quarter of them
+    const int s256 = (s * SHR) / SH;
+    const int ckRowOff = (s * SHR) % SH;
+    if (MODE == MODE_TASK || fromCk) ckTile = G.colCk + ((size_t)__ldcg(&G.ckBase[s256]) - (size_t)ckFirst(g, s256)) * SH;
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
         const int i = i0 + r;
@@ -563,7 +567,7 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
             __syncwarp();
         }
     } else {
-        const int2* ck = ckTile + (size_t)((cBeg - 1) / CKW) * SH;
+        const int2* ck = ckTile + (size_t)((cBeg - 1) / CKW) * SH + ckRowOff;
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
             const int2 v = __ldcg(&ck[lane * RR + r]);
@@ -576,7 +580,7 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
     StepConsts K;
     K.match = G.match; K.mismatch = G.mismatch; K.go = G.go; K.ge = G.ge;
     K.nV = g.nV; K.nH = g.nH; K.lo = g.lo; K.up = g.up;
-    int2* rowOut = (MODE == MODE_TASK) ? G.rowCk + (size_t)s * (size_t)(g.nH + 1) : nullptr;
+    int2* rowOut = (MODE == MODE_TASK) ? G.rowCk + (size_t)s * (SH / CKR) * (size_t)(g.nH + 1) : nullptr;
     const int nch = (nsteps + 31) / 32;
     int upProg = 0;                // cached progress of the strip above
     // the strip below becomes claimable once this one is two chunks past that strip's first column
@@ -681,8 +685,8 @@ struct OutStream {
 template <bool AFF, bool CT>
 __device__ __forceinline__ void tileDispatch(const GridCtx& G, int s, int cBeg, int cEnd, bool fromCk, int nsteps,
                                              uint8_t* win) {
-    if (G.g.banded) runStrip<AFF, CT, true, 8, MODE_TRACE>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
-    else runStrip<AFF, CT, false, 8, MODE_TRACE>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
+    if (G.g.banded) runStrip<AFF, CT, true, 2, MODE_TRACE>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
+    else runStrip<AFF, CT, false, 2, MODE_TRACE>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
 }
 
 // Recomputes the trace bytes of the tile that holds (i, j): rows of strip s up to the lane owning row i,
@@ -690,19 +694,19 @@ __device__ __forceinline__ void tileDispatch(const GridCtx& G, int s, int cBeg, 
 __device__ __noinline__ int4 computeTileFn(const GridCtx& Gin, uint8_t* win, int i, int j) {
     const GridCtx& G = *toShared(&Gin);
     const GridGeom& g = G.g;
-    const int s = (i - 1) / SH;
-    const int jlo = stripJlo(g, s, SH);
+    const int b = (i - 1) / CKR;                    // 64-row block (32 lanes x 2 rows)
+    const int jlo = stripJlo(g, b, CKR);
     const int c0 = ((j - 1) / CKW) * CKW;          // checkpoint column left of j (tile = c0+1 .. c0+CKW)
     bool fromCk = true;
     int cBeg = c0 + 1;
     if (c0 < jlo) { fromCk = false; cBeg = jlo; }
-    const int laneOfI = ((i - 1) - s * SH) / 8;
+    const int laneOfI = ((i - 1) - b * CKR) / 2;
     const int nsteps = (j - cBeg + 1) + laneOfI;
     __syncwarp();
-    if (G.affine) { if (G.complete) tileDispatch<true, true>(G, s, cBeg, j, fromCk, nsteps, win); else tileDispatch<true, false>(G, s, cBeg, j, fromCk, nsteps, win); }
-    else { if (G.complete) tileDispatch<false, true>(G, s, cBeg, j, fromCk, nsteps, win); else tileDispatch<false, false>(G, s, cBeg, j, fromCk, nsteps, win); }
+    if (G.affine) { if (G.complete) tileDispatch<true, true>(G, b, cBeg, j, fromCk, nsteps, win); else tileDispatch<true, false>(G, b, cBeg, j, fromCk, nsteps, win); }
+    else { if (G.complete) tileDispatch<false, true>(G, b, cBeg, j, fromCk, nsteps, win); else tileDispatch<false, false>(G, b, cBeg, j, fromCk, nsteps, win); }
     __syncwarp();
-    return make_int4(s, cBeg, j, s * SH + (laneOfI + 1) * 8);
+    return make_int4(b, cBeg, j, b * CKR + (laneOfI + 1) * 2);
 }
 
 // Pass-1 lazy trace value of cell (i, j): derived from the (S,H,V) of its three neighbours exactly like the
@@ -789,14 +793,14 @@ struct TraceWalker {
             const int q = ((i - 1) * rrMul) >> 16;
             return win[((j - 1) * pitch + q) * rrs + ((i - 1) - q * rr)];
         }
-        const int s = (i - 1) / SH;
-        if (s != tS || j < tC0 || j > tMaxCol || i > tMaxRow) {
-            // columns outside the strip's band range hold no computed cells
-            if (j < stripJlo(g, s, SH) || j > stripJhi(g, s, SH)) return 0;
+        const int b = (i - 1) / CKR;
+        if (b != tS || j < tC0 || j > tMaxCol || i > tMaxRow) {
+            // columns outside the block's band range hold no computed cells
+            if (j < stripJlo(g, b, CKR) || j > stripJhi(g, b, CKR)) return 0;
             computeTile(i, j);
         }
-        const int rem = (i - 1) - s * SH;
-        return win[((size_t)(j - tC0) * 32 + (rem >> 3)) * 8 + (rem & 7)];
+        const int rem = (i - 1) - b * CKR;
+        return win[((j - tC0) * 32 + (rem >> 1)) * 2 + (rem & 1)];
     }
     __device__ __forceinline__ Coord makeCoord(int endCol, int endRow) const {  // dp_traceback_impl.h:121-141
         Coord c;
