@@ -8,6 +8,13 @@ import textwrap
 from oracle_lib import ROOT
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sock:
+        sock.bind(('127.0.0.1', 0))
+        return sock.getsockname()[1]
+
+
 def test_partition_by_cost_balances_and_covers():
     sys.path.insert(0, ROOT)
     from unicycler_b200.sharding import partition_by_cost
@@ -53,7 +60,7 @@ def test_broadcast_and_all_gather_world2(tmp_path):
     ''' % ROOT))
     env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29541')
     out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-                          '--master-addr', '127.0.0.1', '--master-port', '29541', str(script)],
+                          '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), str(script)],
                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=240)
     text = out.stdout.decode()
     assert out.returncode == 0, text

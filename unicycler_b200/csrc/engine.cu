@@ -1,11 +1,14 @@
 // B200 DP engine: persistent agent kernel + host launcher.  See engine.hpp / engine_kernels.cuh.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "engine_kernels.cuh"
 
@@ -1460,7 +1463,6 @@ struct Engine::Impl {
     void* dJobOut = nullptr; size_t capJobOut = 0;
     void* dOrder = nullptr; size_t capOrder = 0;
     void* dColTab = nullptr; size_t capColTab = 0;
-    std::vector<ColInfo> colTabAll;
     void* dScratch = nullptr; size_t capScratch = 0;
     void* dRing = nullptr; size_t capRing = 0;   // ControlBlock, task boards, pass-2 board, job states (zeroed per launch)
     void* dRecs = nullptr; size_t capRecs = 0;   // pass-1 grid records
@@ -1469,9 +1471,10 @@ struct Engine::Impl {
     // pinned host staging
     void* hSeq = nullptr; size_t capHSeq = 0;
     void* hOut = nullptr; size_t capHOut = 0;
+    void* hGrids = nullptr; size_t capHGrids = 0; size_t nGrids = 0;      // GridDesc of every job, back to back
+    void* hColTab = nullptr; size_t capHColTab = 0; size_t nColTab = 0;   // host-planned column tables
     // last plan
     std::vector<JobDev> jobsDev;
-    std::vector<GridDesc> gridsAll;
     std::vector<int> order;
     std::vector<JobOut> jobOut;
     KParams kp;
@@ -1523,7 +1526,7 @@ Engine::~Engine() {
     cudaSetDevice(impl_->device);
     cudaFree(impl_->dJobs); cudaFree(impl_->dGrids); cudaFree(impl_->dSeq); cudaFree(impl_->dOut);
     cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dScratch); cudaFree(impl_->dRing); cudaFree(impl_->dRecs); cudaFree(impl_->dMini); cudaFree(impl_->dPersist);
-    cudaFreeHost(impl_->hSeq); cudaFreeHost(impl_->hOut);
+    cudaFreeHost(impl_->hSeq); cudaFreeHost(impl_->hOut); cudaFreeHost(impl_->hGrids); cudaFreeHost(impl_->hColTab);
     for (auto& ev : impl_->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(impl_->stream);
     delete impl_;
@@ -1534,86 +1537,128 @@ EngineStats Engine::lastStats() const { return impl_->stats; }
 
 static size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// f(i) for i in [0, n) on a few host threads (staging and parsing are independent per job)
+template <typename F>
+static void engineParallelFor(int n, F f) {
+    int threads = std::min<int>(8, (int)std::thread::hardware_concurrency());
+    if (const char* e = getenv("UNICYCLER_B200_HOST_THREADS")) threads = atoi(e);
+    threads = std::max(1, std::min(threads, n / 4));
+    if (threads <= 1) { for (int i = 0; i < n; ++i) f(i); return; }
+    std::atomic<int> next(0);
+    std::exception_ptr err;
+    std::mutex errMu;
+    auto body = [&]() {
+        try { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i); }
+        catch (...) { std::lock_guard<std::mutex> lk(errMu); if (!err) err = std::current_exception(); }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(body);
+    body();
+    for (auto& th : pool) th.join();
+    if (err) std::rethrow_exception(err);
+}
+
+static double wallMs() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 void Engine::upload(std::vector<Job*>& jobs) {
     Impl& I = *impl_;
     CUDA_CHECK(cudaSetDevice(I.device));
+    double tU[6] = {wallMs(), 0, 0, 0, 0, 0};
     const size_t nJobs = jobs.size();
     I.jobsDev.assign(nJobs, JobDev());
-    I.gridsAll.clear();
-    I.colTabAll.clear();
-        // sequences
-    size_t seqBytes = 0;
-    for (Job* j : jobs) seqBytes += alignUp((size_t)j->lenH + 16, 16) + alignUp((size_t)j->lenV + 16, 16);
-    I.growHost(I.hSeq, I.capHSeq, seqBytes + 64);
-    uint8_t* hs = (uint8_t*)I.hSeq;
-    size_t off = 0, outOff = 0;
-    ScratchLayout L;
-    memset(&L, 0, sizeof(L));
-    long long maxRowCk = 0, maxColCk = 0, maxBox = 1, ckBytes = 0;
-    long long maxRowCkNP = 0, maxColCkNP = 0, persistTotal = 0;   // NP: grids without a persistent block
-    size_t totalStrips = 0;
-    int maxNH = 1, maxNV = 1, maxCapH = 1, maxCapV = 1, maxStrips = 1;
-    size_t nTasks = 0;
-    std::vector<long long> cost(nJobs, 0);
-    int64_t totalCells = 0;
+    // offsets of every job in the staging buffers (sequences, grid descriptors, column tables)
+    size_t off = 0, outOff = 0, nGridsAll = 0, nColTabAll = 0;
     for (size_t k = 0; k < nJobs; ++k) {
-        Job& j = *jobs[k];
+        const Job& j = *jobs[k];
         JobDev& d = I.jobsDev[k];
         d.hOff = (long long)off;
-        memcpy(hs + off, j.H, (size_t)j.lenH);
         off += alignUp((size_t)j.lenH + 16, 16);
         d.vOff = (long long)off;
-        memcpy(hs + off, j.V, (size_t)j.lenV);
         off += alignUp((size_t)j.lenV + 16, 16);
+        d.gridBegin = (int)nGridsAll;
+        d.gridCount = (int)j.grids.size();
+        nGridsAll += j.grids.size();
+        d.colTabBase = (long long)nColTabAll;
+        nColTabAll += j.colTab.size();
+    }
+    I.growHost(I.hSeq, I.capHSeq, off + 64);
+    I.growHost(I.hGrids, I.capHGrids, (nGridsAll + 1) * sizeof(GridDesc));
+    I.growHost(I.hColTab, I.capHColTab, (nColTabAll + 1) * sizeof(ColInfo));
+    I.nGrids = nGridsAll;
+    I.nColTab = nColTabAll;
+    uint8_t* hs = (uint8_t*)I.hSeq;
+    GridDesc* hGrids = (GridDesc*)I.hGrids;
+    ColInfo* hColTab = (ColInfo*)I.hColTab;
+    ScratchLayout L;
+    memset(&L, 0, sizeof(L));
+    // per-job aggregates, filled by the host cores in parallel and reduced below
+    struct JobAgg {
+        long long maxRowCkNP = 0, maxColCkNP = 0, maxRowCk = 0, maxColCk = 0, maxBox = 1, ckBytes = 0, persist = 0, cost = 0, cap = 0;
+        size_t strips = 0, tasks = 0;
+        int maxNH = 1, maxNV = 1, maxCapH = 1, maxCapV = 1, maxStrips = 1, maxLocalNH = 1, maxLocalNV = 1;
+        bool missingColTab = false;
+    };
+    std::vector<JobAgg> agg(nJobs);
+    engineParallelFor((int)nJobs, [&](int kk) {
+        const size_t k = (size_t)kk;
+        Job& j = *jobs[k];
+        JobDev& d = I.jobsDev[k];
+        JobAgg& a = agg[k];
+        memcpy(hs + d.hOff, j.H, (size_t)j.lenH);
+        memcpy(hs + d.vOff, j.V, (size_t)j.lenV);
         d.lenH = j.lenH; d.lenV = j.lenV;
         d.match = j.match; d.mismatch = j.mismatch; d.gapOpen = j.gapOpen; d.gapExtend = j.gapExtend;
         d.fe = (j.freeFirstRow ? 1 : 0) | (j.freeFirstCol ? 2 : 0) | (j.freeLastRow ? 4 : 0) | (j.freeLastCol ? 8 : 0);
         d.complete = j.complete;
-        d.gridBegin = (int)I.gridsAll.size();
-        d.gridCount = (int)j.grids.size();
-        d.colTabBase = (long long)I.colTabAll.size();
-        I.colTabAll.insert(I.colTabAll.end(), j.colTab.begin(), j.colTab.end());
+        if (!j.colTab.empty()) memcpy(hColTab + d.colTabBase, j.colTab.data(), j.colTab.size() * sizeof(ColInfo));
         j.cells = 0;
-        for (const GridDesc& gd : j.grids) {
-            I.gridsAll.push_back(gd);
-            int ns = 1;
-            long long rck = 0, cck = 0;
-            bool local = false;
-            hostCheckpointBytes(gd, rck, cck, ns, local);
+        GridDesc* out = hGrids + d.gridBegin;
+        for (size_t q = 0; q < j.grids.size(); ++q) {
+            const GridDesc& gd = j.grids[q];
+            GridDesc& gg = out[q];
+            gg = gd;
+            const GridGeom g = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
+            const bool local = localPlan(g).local != 0;
             if (!local) {
-                ++nTasks;
-                totalStrips += (size_t)ns;
-                ckBytes += rck + cck;
-                maxRowCk = std::max(maxRowCk, rck);
-                maxColCk = std::max(maxColCk, cck);
-                maxStrips = std::max(maxStrips, ns);
-                GridDesc& gg = I.gridsAll.back();
-                gg.ckTiles = (int32_t)(cck / (SH * (long long)sizeof(int2)));
+                const int ns = stripCount(g, SH);
+                const long long rck = (long long)ns * (SH / CKR) * (g.nH + 1) * (long long)sizeof(int2);
+                long long tiles = 0;
+                for (int s = 0; s < ns; ++s) tiles += ckCount(g, s);
+                const long long cck = tiles * SH * (long long)sizeof(int2);
+                ++a.tasks;
+                a.strips += (size_t)ns;
+                a.ckBytes += rck + cck;
+                a.maxRowCk = std::max(a.maxRowCk, rck);
+                a.maxColCk = std::max(a.maxColCk, cck);
+                a.maxStrips = std::max(a.maxStrips, ns);
+                gg.ckTiles = (int32_t)tiles;
                 if (gd.kind != GRID_GLOBAL) {   // chain grids: checkpoints must outlive the leader's next grid (pass 2)
-                    gg.persistOff = persistTotal;
-                    persistTotal += persistLayout(gd.nH, gd.nV, ns, gg.ckTiles).total;
+                    gg.persistOff = a.persist;  // relative to the job's first block; rebased below
+                    a.persist += persistLayout(gd.nH, gd.nV, ns, gg.ckTiles).total;
                 } else {
-                    maxRowCkNP = std::max(maxRowCkNP, rck);
-                    maxColCkNP = std::max(maxColCkNP, cck);
+                    a.maxRowCkNP = std::max(a.maxRowCkNP, rck);
+                    a.maxColCkNP = std::max(a.maxColCkNP, cck);
                 }
+            } else {
+                a.maxLocalNH = std::max(a.maxLocalNH, gd.nH);
+                a.maxLocalNV = std::max(a.maxLocalNV, gd.nV);
             }
-            maxNH = std::max(maxNH, gd.nH); maxNV = std::max(maxNV, gd.nV);
-            maxCapH = std::max(maxCapH, gd.capNextH); maxCapV = std::max(maxCapV, gd.capNextV);
+            a.maxNH = std::max(a.maxNH, gd.nH); a.maxNV = std::max(a.maxNV, gd.nV);
+            a.maxCapH = std::max(a.maxCapH, gd.capNextH); a.maxCapV = std::max(a.maxCapV, gd.capNextV);
             if (gd.kind == GRID_CHAIN_INITIAL || gd.kind == GRID_CHAIN_INNER ||
                 (gd.kind == GRID_CHAIN_FINAL && gd.banded)) {
-                GridGeom g = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
                 int row0 = g.banded ? colTop(g, std::min(gd.hNext, g.nH)) : std::min(gd.vNext, g.nV);
                 long long bh = g.nV - row0 + 1, bw = std::max(0, g.nH - gd.hNext + 1);
-                maxBox = std::max(maxBox, bh * bw);
-                if (g.banded && gd.nColTab == 0 && bw > 0)
-                    throw std::runtime_error("unicycler_b200: banded chain grid without host-planned column table");
+                a.maxBox = std::max(a.maxBox, bh * bw);
+                if (g.banded && gd.nColTab == 0 && bw > 0) a.missingColTab = true;
             }
-            int64_t c = referenceCells(gd);
+            const int64_t c = referenceCells(gd);
             j.cells += c;
             // latency estimate in cycles: every grid costs a serial control round trip, big grids are spread over the GPU
-            cost[k] += 100000 + c / 16;
+            a.cost += 100000 + c / 16;
         }
-        totalCells += j.cells;
         // segment stream capacity: every grid reserves its worst case (3 + traces * (1 + 4 * (nH + nV + 6)) ints)
         long long cap = 0;
         if (j.grids.size() == 1 && j.grids[0].kind == GRID_GLOBAL) {
@@ -1624,18 +1669,47 @@ void Engine::upload(std::vector<Job*>& jobs) {
         }
         cap *= std::max(1, j.outScale);
         if (cap > (1LL << 30)) cap = 1LL << 30;
+        a.cap = cap;
+    });
+    long long maxRowCk = 0, maxColCk = 0, maxBox = 1, ckBytes = 0;
+    long long maxRowCkNP = 0, maxColCkNP = 0, persistTotal = 0;   // NP: grids without a persistent block
+    size_t totalStrips = 0;
+    int maxNH = 1, maxNV = 1, maxCapH = 1, maxCapV = 1, maxStrips = 1, maxLocalNH = 1, maxLocalNV = 1;
+    size_t nTasks = 0;
+    std::vector<long long> cost(nJobs, 0);
+    int64_t totalCells = 0;
+    for (size_t k = 0; k < nJobs; ++k) {
+        const JobAgg& a = agg[k];
+        JobDev& d = I.jobsDev[k];
+        if (a.missingColTab) throw std::runtime_error("unicycler_b200: banded chain grid without host-planned column table");
+        if (a.persist > 0 && persistTotal > 0) {
+            GridDesc* out = hGrids + d.gridBegin;
+            for (int q = 0; q < d.gridCount; ++q)
+                if (out[q].persistOff >= 0) out[q].persistOff += persistTotal;
+        }
+        persistTotal += a.persist;
+        nTasks += a.tasks; totalStrips += a.strips; ckBytes += a.ckBytes;
+        maxRowCk = std::max(maxRowCk, a.maxRowCk); maxColCk = std::max(maxColCk, a.maxColCk);
+        maxRowCkNP = std::max(maxRowCkNP, a.maxRowCkNP); maxColCkNP = std::max(maxColCkNP, a.maxColCkNP);
+        maxBox = std::max(maxBox, a.maxBox); maxStrips = std::max(maxStrips, a.maxStrips);
+        maxNH = std::max(maxNH, a.maxNH); maxNV = std::max(maxNV, a.maxNV);
+        maxCapH = std::max(maxCapH, a.maxCapH); maxCapV = std::max(maxCapV, a.maxCapV);
+        maxLocalNH = std::max(maxLocalNH, a.maxLocalNH); maxLocalNV = std::max(maxLocalNV, a.maxLocalNV);
+        cost[k] = a.cost;
+        totalCells += jobs[k]->cells;
         d.outOff = (long long)outOff;
-        d.outCap = (int)cap;
-        outOff += (size_t)cap;
+        d.outCap = (int)a.cap;
+        outOff += (size_t)a.cap;
     }
     I.seqBytes = off;
     I.outInts = outOff;
+    tU[1] = wallMs();
     // persistent blocks only if they fit comfortably (otherwise big grids are traced back in line from the arena)
     size_t freeB0 = 0, totalB0 = 0;
     CUDA_CHECK(cudaMemGetInfo(&freeB0, &totalB0));
     const bool usePersist = persistTotal > 0 && (size_t)persistTotal <= (freeB0 + I.capPersist) / 3 && !getenv("UNICYCLER_B200_NO_PERSIST");
     if (usePersist) { maxRowCk = maxRowCkNP; maxColCk = maxColCkNP; }
-    else for (GridDesc& gg : I.gridsAll) gg.persistOff = -1;
+    else for (size_t q = 0; q < I.nGrids; ++q) hGrids[q].persistOff = -1;
     // arena layout of one control agent
     size_t o = 0;
     auto place = [&](long long& field, size_t bytes) { field = (long long)o; o += alignUp(bytes, 256); };
@@ -1668,17 +1742,13 @@ void Engine::upload(std::vector<Job*>& jobs) {
     const size_t maxTokens = totalStrips + nTasks + 64;
     I.ringBytes = offTok + 2 * maxTokens * sizeof(int);
     // mini arenas: init row / column of the largest LOCAL grid, for every control-capable warp
-    int maxLocalNH = 1, maxLocalNV = 1;
-    for (const GridDesc& gd : I.gridsAll) {
-        GridGeom g = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
-        if (localPlan(g).local) { maxLocalNH = std::max(maxLocalNH, gd.nH); maxLocalNV = std::max(maxLocalNV, gd.nV); }
-    }
     const size_t miniInitCol = alignUp((size_t)(maxLocalNH + 2) * sizeof(DCell), 256);
     const size_t miniStride = miniInitCol + alignUp((size_t)(maxLocalNV + 2) * sizeof(DCell), 256);
-    size_t fixed = nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + I.seqBytes + I.outInts * 4 +
+    size_t fixed = nJobs * sizeof(JobDev) + I.nGrids * sizeof(GridDesc) + I.seqBytes + I.outInts * 4 +
                    I.ringBytes + (usePersist ? (size_t)persistTotal : 0) + (64u << 20);
     size_t budget = (freeB + I.capScratch > fixed) ? (size_t)((freeB + I.capScratch - fixed) * 0.9) : 0;
     long long byMem = (long long)(budget / (size_t)L.total);
+    tU[2] = wallMs();
     // pass-1 work list: long chains are cut into speculative segments (runSegment); a segment starts at a gap
     // rectangle that follows an anchor, where an exact seed makes the guessed initialisation cell likely
     std::vector<int> jobOrder(nJobs);
@@ -1737,26 +1807,28 @@ void Engine::upload(std::vector<Job*>& jobs) {
     int nSlots = (int)std::min<long long>(std::min<long long>((long long)nEntries, (long long)NCTRL * I.numSMs),
                                           std::max<long long>(byMem, 0));
     if (nSlots < 1) throw std::runtime_error("unicycler_b200: not enough device memory for one DP scratch arena");
+    tU[3] = wallMs();
     I.growDev(I.dJobs, I.capJobs, nJobs * sizeof(JobDev));
-    I.growDev(I.dGrids, I.capGrids, I.gridsAll.size() * sizeof(GridDesc) + 16);
+    I.growDev(I.dGrids, I.capGrids, I.nGrids * sizeof(GridDesc) + 16);
     I.growDev(I.dSeq, I.capSeq, I.seqBytes + 64);
     I.growDev(I.dOut, I.capOut, I.outInts * sizeof(int) + 64);
     I.growDev(I.dJobOut, I.capJobOut, nJobs * sizeof(JobOut));
     I.growDev(I.dOrder, I.capOrder, nEntries * sizeof(int));
-    I.growDev(I.dColTab, I.capColTab, I.colTabAll.size() * sizeof(ColInfo) + 64);
+    I.growDev(I.dColTab, I.capColTab, I.nColTab * sizeof(ColInfo) + 64);
     I.growDev(I.dScratch, I.capScratch, (size_t)L.total * nSlots);
     I.growDev(I.dRing, I.capRing, I.ringBytes);
     I.growDev(I.dRecs, I.capRecs, (nRecs + 1) * sizeof(GridRec));
     I.growDev(I.dMini, I.capMini, miniStride * (size_t)NCTRL * I.numSMs);
     if (usePersist) I.growDev(I.dPersist, I.capPersist, (size_t)persistTotal + 256);
     I.growHost(I.hOut, I.capHOut, I.outInts * sizeof(int) + 64);
+    tU[4] = wallMs();
     CUDA_CHECK(cudaEventRecord(I.ev[0], I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dSeq, I.hSeq, I.seqBytes, cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dJobs, I.jobsDev.data(), nJobs * sizeof(JobDev), cudaMemcpyHostToDevice, I.stream));
-    CUDA_CHECK(cudaMemcpyAsync(I.dGrids, I.gridsAll.data(), I.gridsAll.size() * sizeof(GridDesc), cudaMemcpyHostToDevice, I.stream));
+    CUDA_CHECK(cudaMemcpyAsync(I.dGrids, I.hGrids, I.nGrids * sizeof(GridDesc), cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dOrder, I.order.data(), nEntries * sizeof(int), cudaMemcpyHostToDevice, I.stream));
-    if (!I.colTabAll.empty())
-        CUDA_CHECK(cudaMemcpyAsync(I.dColTab, I.colTabAll.data(), I.colTabAll.size() * sizeof(ColInfo), cudaMemcpyHostToDevice, I.stream));
+    if (I.nColTab > 0)
+        CUDA_CHECK(cudaMemcpyAsync(I.dColTab, I.hColTab, I.nColTab * sizeof(ColInfo), cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaEventRecord(I.ev[1], I.stream));
     KParams& kp = I.kp;
     kp.jobs = (const JobDev*)I.dJobs; kp.grids = (const GridDesc*)I.dGrids; kp.seq = (const uint8_t*)I.dSeq;
@@ -1780,10 +1852,15 @@ void Engine::upload(std::vector<Job*>& jobs) {
     CUDA_CHECK(cudaMemcpyToSymbolAsync(cP, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, I.stream));
     I.stats = EngineStats();
     I.stats.cells = totalCells;
-    I.stats.h2dBytes = (int64_t)(I.seqBytes + nJobs * sizeof(JobDev) + I.gridsAll.size() * sizeof(GridDesc) + nJobs * sizeof(int) +
-                                 I.colTabAll.size() * sizeof(ColInfo));
+    I.stats.h2dBytes = (int64_t)(I.seqBytes + nJobs * sizeof(JobDev) + I.nGrids * sizeof(GridDesc) + nJobs * sizeof(int) +
+                                 I.nColTab * sizeof(ColInfo));
     I.stats.ctas = I.numSMs;
     I.stats.traceBytes = ckBytes;
+    if (getenv("UNICYCLER_B200_PROFILE")) {
+        tU[5] = wallMs();
+        fprintf(stderr, "[ub200 upload] staging=%.2f layout=%.2f split=%.2f grow=%.2f copies=%.2f ms (seq %zu B, grids %zu, colTab %zu)\n",
+                tU[1] - tU[0], tU[2] - tU[1], tU[3] - tU[2], tU[4] - tU[3], tU[5] - tU[4], I.seqBytes, I.nGrids, I.nColTab);
+    }
 }
 
 void Engine::launch() {
@@ -1884,7 +1961,9 @@ void Engine::fetch(std::vector<Job*>& jobs) {
     }
     I.stats.d2hBytes = (int64_t)(nJobs * sizeof(JobOut));
     for (size_t k = 0; k < nJobs; ++k) I.stats.d2hBytes += 4LL * std::max(0, std::min(I.jobOut[k].outLen, I.jobsDev[k].outCap));
-    for (size_t k = 0; k < nJobs; ++k) {
+    const double tParse0 = wallMs();
+    engineParallelFor((int)nJobs, [&](int kk) {
+        const size_t k = (size_t)kk;
         Job& j = *jobs[k];
         const JobDev& d = I.jobsDev[k];
         const JobOut& jo = I.jobOut[k];
@@ -1892,7 +1971,7 @@ void Engine::fetch(std::vector<Job*>& jobs) {
         r.status = jo.status;
         r.score = jo.score;
         r.gridTraces.assign(j.grids.size(), {});
-        if (jo.status != JOB_OK) continue;
+        if (jo.status != JOB_OK) return;
         const int* p = hOut + d.outOff;
         int pos = 0;
         // a big grid's candidates arrive as separate records: (grid, first candidate) -> order of arrival
@@ -1925,11 +2004,8 @@ void Engine::fetch(std::vector<Job*>& jobs) {
             auto& dst = r.gridTraces.at((size_t)part.first.first);
             for (auto& t : part.second) dst.push_back(std::move(t));
         }
-    }
-}
-
-static double wallMs() {
-    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    });
+    if (getenv("UNICYCLER_B200_PROFILE")) fprintf(stderr, "[ub200 fetch] parse=%.2f ms\n", wallMs() - tParse0);
 }
 
 void Engine::run(std::vector<Job*>& jobs) {
