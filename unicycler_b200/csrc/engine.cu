@@ -488,8 +488,8 @@ __device__ __forceinline__ bool plantCrossing(const GridCtx& G, int hInit, int v
 // One candidate of a banded-chain grid (seeds/banded_chain_alignment_traceback.h:233-355).
 // Warp-uniform: every lane of the control warp executes it; lane 0 writes.
 // REPLAY (pass 2): the crossing cell was planted by pass 1; `insertedIn` is its verdict.
-template <bool REPLAY>
-__device__ __forceinline__ void chainTracebackOne(const GridCtx& G, TraceWalker& w, OutStream& out, int startPos,
+template <bool REPLAY, typename Walker>
+__device__ __forceinline__ void chainTracebackOne(const GridCtx& G, Walker& w, OutStream& out, int startPos,
                                                   bool insertedIn, int& nPlanted, int& nTraces, int& status) {
     const bool affine = G.affine;
     const bool prefer = affine && G.kind == GRID_CHAIN_FINAL;
@@ -501,7 +501,7 @@ __device__ __forceinline__ void chainTracebackOne(const GridCtx& G, TraceWalker&
     out.put(0);
     w.nSegs = 0;
     uint32_t tv = w.tvHere();
-    uint32_t last = TraceWalker::initialDirection(tv, prefer);
+    uint32_t last = Walker::initialDirection(tv, prefer);
     Coord c = w.makeCoord(G.hNext, G.vNext);
     if (G.kind == GRID_CHAIN_FINAL) {
         if (c.currRow != nV) w.record(nH, c.currRow, nV - c.currRow, T_V);
@@ -610,6 +610,44 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& Gin, uint8_t* win,
         for (int k = 0; k < nCand && status == JOB_OK; ++k)
             chainTracebackOne<true>(G, w, out, rec->cand[k], (rec->inserted >> k) & 1, nPlanted, nTraces, status);
     }
+    out.patch(cntPos, nTraces);
+    out.patch(cntPos + 2, out.len - pos);
+    if (out.overflow && status == JOB_OK) status = JOB_OUT_OVERFLOW;
+    __syncwarp();
+    r.status = status; r.nPlanted = nPlanted;
+    r.tiles = w.tilesComputed; r.tileCycles = w.tileCycles;
+    return r;
+}
+
+// Pass 2 of a big chain grid: the traceback of ONE candidate (tied maximum) as its own record.  A lean copy of
+// tracebackGrid for the walker of task grids (trace tiles recomputed from the checkpoints); idle control warps
+// recompute the tiles ahead of the walk (tile helpers).
+__device__ __noinline__ TbResult tracebackBigCand(const GridCtx& Gin, uint8_t* win, int jobIdx, int* outBuf, int outCap, int gi,
+                                                  int h0, int v0, const GridRec* rec, int candSel, int segTag) {
+    const GridCtx& G = *toShared(&Gin);
+    const int lane = threadIdx.x & 31;
+    TbResult r;
+    r.status = JOB_OK; r.nPlanted = 0; r.pad0 = r.pad1 = 0; r.tiles = 0; r.tileCycles = 0;
+    const int reserved = recordBound(G, 1);
+    const int pos = reserveOut(jobIdx, outCap, reserved);
+    if (pos < 0) { r.status = JOB_OUT_OVERFLOW; return r; }
+    OutStream out;
+    out.buf = outBuf; out.cap = pos + reserved; out.len = pos; out.overflow = false;
+    out.h0 = h0; out.v0 = v0; out.lane = lane;
+    int status = JOB_OK, nPlanted = 0, nTraces = 0;
+    out.put(gi);
+    const int cntPos = out.len;
+    out.put(0);
+    out.put(reserved);
+    out.put(0);
+    out.put(candSel);
+    out.put(segTag);
+    TraceWalkerT<true> w(G, out, win);
+    const int cwIdx = (int)(threadIdx.x >> 5) - (NWARPS - NCTRL);
+    if (cP.tileSlots != nullptr && cwIdx >= 0)
+        w.enableHelp(cP.tileSlots + (size_t)(blockIdx.x * NCTRL + cwIdx) * TILE_SLOTS * TILE_SLOT_BYTES, jobIdx, gi);
+    chainTracebackOne<true>(G, w, out, rec->cand[candSel], (rec->inserted >> candSel) & 1, nPlanted, nTraces, status);
+    w.drainHelp();
     out.patch(cntPos, nTraces);
     out.patch(cntPos + 2, out.len - pos);
     if (out.overflow && status == JOB_OK) status = JOB_OUT_OVERFLOW;
@@ -882,7 +920,15 @@ __device__ __forceinline__ void runClaimedItem(TaskDesc* t, int taskId, int item
 
 // Claims and runs one item of the oldest open task, critical-path board first.  Returns false when no
 // item is available.
-__device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask, bool* sawOpen = nullptr) {
+// A control warp that polls for work counts as an idle tile helper until it commits to something long.
+__device__ __forceinline__ void leaveIdle(int* idleFlag) {
+    if (idleFlag != nullptr && *idleFlag) {
+        if ((threadIdx.x & 31) == 0) atomicSub(&cP.cb->idleHelpers, 1);
+        *idleFlag = 0;
+    }
+}
+
+__device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask, bool* sawOpen = nullptr, int* idleFlag = nullptr) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     int item = -1, taskId = -1, open = 0;
@@ -911,6 +957,7 @@ __device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask, bool* sawO
     item = __shfl_sync(FULLMASK, item, 0);
     if (sawOpen) *sawOpen = __shfl_sync(FULLMASK, open, 0) != 0;
     if (item < 0) return false;
+    leaveIdle(idleFlag);
     taskId = __shfl_sync(FULLMASK, taskId, 0);
     runClaimedItem(&P.ring[taskId], taskId, item, wctx, wTask);
     return true;
@@ -974,7 +1021,9 @@ __device__ __forceinline__ int ownerOf(const JobState& js, int gi) {
 // ---------------------------------------------------------------------------------------
 // pass 2: one recorded grid, start to end, on any control-capable warp
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void runPass2Grid(int jobIdx, int item, GridCtx& Gin, uint8_t* win, uint8_t* mini) {
+// Returns false when the item is left to the big-item ring (one candidate of a big grid reached through the job's
+// ordinary item counter).
+__device__ __noinline__ bool runPass2Grid(int jobIdx, int item, GridCtx& Gin, uint8_t* win, uint8_t* mini, bool fromBigRing) {
     GridCtx& G = *toShared(&Gin);
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
@@ -983,18 +1032,25 @@ __device__ __noinline__ void runPass2Grid(int jobIdx, int item, GridCtx& Gin, ui
     const int owner = ownerOf(P.jobState[jobIdx], gi);
     const GridRec* rec = &P.gridRecs[jb.recBase + (long long)owner * jb.gridCount + gi];
     const int state = rec->state;
-    if (state == 0) return;                                   // done in line by pass 1
-    if (state == 1 && ksel != 0) return;                       // small grid: item 0 walks every candidate
-    if (state == 2 && ksel >= rec->nCand) return;              // big grid: one candidate per item
+    if (state == 0) return true;                               // done in line by pass 1
+    if (state == 1 && ksel != 0) return true;                   // small grid: item 0 walks every candidate
+    if (state == 2 && ksel >= rec->nCand) return true;          // big grid: one candidate per item
+    if (state == 2 && !fromBigRing) return false;
     const GridDesc gd = P.grids[jb.gridBegin + gi];
     if (state == 2) {
         // checkpoints, init row and column live in the grid's persistent block
         setupGrid(G, jb, gd, nullptr);
-        const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, rec->nCand,
-                                          DCell{0, 0, 0}, rec, ksel, owner);
+        const long long tw0 = clock64();
+        const TbResult tb = tracebackBigCand(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, rec, ksel, owner);
         if (tb.status != JOB_OK && lane == 0) atomicMax(&P.jobState[jobIdx].status, tb.status);
+        if (lane == 0) {
+            atomicAdd(&gDbg[16], (unsigned long long)tb.tiles);
+            atomicAdd(&gDbg[17], (unsigned long long)tb.tileCycles);
+            atomicAdd(&gDbg[18], (unsigned long long)(clock64() - tw0));
+            atomicAdd(&gDbg[19], 1ull);
+        }
         __syncwarp();
-        return;
+        return true;
     }
     setupGrid(G, jb, gd, nullptr);
     if (lane == 0) {  // only the init row / column are needed (this warp's mini arena)
@@ -1024,6 +1080,7 @@ __device__ __noinline__ void runPass2Grid(int jobIdx, int item, GridCtx& Gin, ui
                                       DCell{0, 0, 0}, rec, -1, owner);
     if (tb.status != JOB_OK && lane == 0) atomicMax(&P.jobState[jobIdx].status, tb.status);
     __syncwarp();
+    return true;
 }
 
 // Marks the job complete (all passes done): final status; the records of the segment stream (reserved at their
@@ -1040,26 +1097,56 @@ __device__ __noinline__ void finalizeJob(int jobIdx) {
     if (st == JOB_OK && st2 != JOB_OK) st = st2;
     int dst = 0;
     if (st == JOB_OK && end <= cap) {
+        // the resolved chain (which segment owns which grids), one entry per lane
+        const JobState* js = &P.jobState[jobIdx];
+        const int nOwner = __ldcg(&js->nOwner);
+        const int oSeg = (lane <= MAXSEG) ? __ldcg(&js->ownerSeg[lane]) : 0;
+        const int oFrom = (lane <= MAXSEG) ? __ldcg(&js->ownerFrom[lane]) : 0;
         int src = 0;
-        while (src < end) {
-            const int reserved = __ldcg(&buf[src + 2]);
-            const int used = __ldcg(&buf[src + 3]);
-            if (reserved < 6 || used < 6 || used > reserved) { st = JOB_REF_UB; break; }  // a record was never completed
-            // records written by a speculative segment outside the range it finally owns are dropped
-            if (ownerOf(P.jobState[jobIdx], __ldcg(&buf[src])) != __ldcg(&buf[src + 5])) { src += reserved; continue; }
-            if (dst != src) {
-                for (int k = 0; k < used; k += 32) {
-                    int v = 0;
-                    if (k + lane < used) v = __ldcg(&buf[src + k + lane]);
-                    __syncwarp();
-                    if (k + lane < used) buf[dst + k + lane] = v;
-                    __syncwarp();
+        while (src < end && st == JOB_OK) {
+            // headers of up to 32 records (one dependent load each); lane r remembers record r of the batch
+            int mySrc = 0, myUsed = 0, n = 0;
+            while (n < 32 && src < end) {
+                const int hdr = (lane < 8 && src + lane < end) ? __ldcg(&buf[src + lane]) : 0;
+                const int gi = __shfl_sync(FULLMASK, hdr, 0);
+                const int reserved = __shfl_sync(FULLMASK, hdr, 2), used = __shfl_sync(FULLMASK, hdr, 3);
+                const int tag = __shfl_sync(FULLMASK, hdr, 5);
+                if (reserved < 6 || used < 6 || used > reserved) { st = JOB_REF_UB; break; }  // a record was never completed
+                // records written by a speculative segment outside the range it finally owns are dropped
+                const unsigned m = __ballot_sync(FULLMASK, lane < nOwner && (lane == 0 || gi >= oFrom));
+                const int owner = __shfl_sync(FULLMASK, oSeg, m ? 31 - __clz((int)m) : 0);
+                if (owner == tag) {
+                    if (lane == n) { mySrc = src; myUsed = used; }
+                    ++n;
                 }
+                src += reserved;
             }
-            __syncwarp();
-            if (lane == 0) buf[dst + 2] = used;
-            dst += used;
-            src += reserved;
+            if (st != JOB_OK) break;
+            for (int r = 0; r < n; ++r) {
+                const int s0 = __shfl_sync(FULLMASK, mySrc, r), used = __shfl_sync(FULLMASK, myUsed, r);
+                if (dst != s0) {
+                    // moved towards the front (dst < src) in chunks of 256 ints: all loads of a chunk are in flight
+                    // together and complete before its first store (the regions may overlap)
+                    for (int k = 0; k < used; k += 256) {
+                        int v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int q = k + u * 32 + lane;
+                            v[u] = (q < used) ? __ldcg(&buf[s0 + q]) : 0;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int q = k + u * 32 + lane;
+                            if (q < used) buf[dst + q] = v[u];
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) buf[dst + 2] = used;
+                dst += used;
+            }
         }
     }
     __syncwarp();
@@ -1074,8 +1161,112 @@ __device__ __noinline__ void finalizeJob(int jobIdx) {
     __syncwarp();
 }
 
+// Tile helper: pops one tile request, recomputes the 64 x 64 trace tile from the grid's checkpoints into this
+// warp's window and hands it to the asking warp's slot.  helpKey caches which grid G currently describes.
+__device__ __noinline__ bool tryRunTileReq(GridCtx& Gin, uint8_t* win, int& helpKey) {
+    GridCtx& G = *toShared(&Gin);
+    const KParams& P = cP;
+    const int lane = threadIdx.x & 31;
+    int got = 0, job = 0, gi = 0, tile = 0, expect = 0;
+    unsigned long long slotAddr = 0;
+    if (lane == 0) {
+        for (int tries = 0; tries < 4 && got == 0; ++tries) {
+            const int h = ldRelaxed(&P.cb->tileHead);
+            const int tl = ldRelaxed(&P.cb->tileTail);
+            if (h >= tl) break;
+            if (atomicCAS(&P.cb->tileHead, h, h + 1) != h) continue;
+            TileReq* e = &P.tileRing[h & (TILE_RING_CAP - 1)];
+            const int turn = h / TILE_RING_CAP;
+            while (ldRelaxed(&e->seq) != 2 * turn + 1) __nanosleep(32);
+            __threadfence();
+            job = __ldcg(&e->job); gi = __ldcg(&e->gi); tile = __ldcg(&e->tile); expect = __ldcg(&e->expect);
+            slotAddr = __ldcg(&e->slot);
+            const unsigned posted = (unsigned)__ldcg(&e->pad);
+            __threadfence();
+            stRelease(&e->seq, 2 * turn + 2);
+            // claim the slot (the asking warp may have cancelled the request or moved on)
+            got = (atomicCAS(reinterpret_cast<int*>(slotAddr), expect, expect + 1) == expect) ? 1 : 2;
+            if (got == 1) { atomicAdd(&gDbg[21], 1ull); atomicAdd(&gDbg[22], (unsigned long long)((unsigned)globalTimerNs() - posted)); }
+            else atomicAdd(&gDbg[23], 1ull);
+        }
+    }
+    got = __shfl_sync(FULLMASK, got, 0);
+    if (got == 0) return false;
+    if (got == 2) return true;   // a stale request: poll again at once
+    job = __shfl_sync(FULLMASK, job, 0); gi = __shfl_sync(FULLMASK, gi, 0);
+    tile = __shfl_sync(FULLMASK, tile, 0); expect = __shfl_sync(FULLMASK, expect, 0);
+    slotAddr = __shfl_sync(FULLMASK, slotAddr, 0);
+    uint8_t* slot = reinterpret_cast<uint8_t*>(slotAddr);
+    const int key = job * 65536 + gi;   // (chains have far fewer than 65536 grids)
+    if (key != helpKey) {
+        const JobDev& jb = P.jobs[job];
+        const GridDesc gd = P.grids[jb.gridBegin + gi];
+        setupGrid(G, jb, gd, nullptr);
+        helpKey = key;
+    }
+    const GridGeom& g = G.g;
+    const int tb = tile >> 16, tc = tile & 0xffff;
+    const int iLast = imin(tb * CKR + CKR, g.nV);
+    const int jLast = imin(tc * CKW + CKW, stripJhi(g, tb, CKR));
+    const int4 t = computeTileFn(G, win, iLast, jLast);
+    const int4* src = reinterpret_cast<const int4*>(toShared(win));
+    int4* dst = reinterpret_cast<int4*>(slot + 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) __stcg(dst + k * 32 + lane, src[k * 32 + lane]);
+    if (lane == 0) __stcg(reinterpret_cast<int4*>(slot + 16), t);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) stRelease(reinterpret_cast<int*>(slot), expect + 2);
+    __syncwarp();
+    return true;
+}
+
+// Claims and runs one big-grid candidate of pass 2 (the longest items: they start before the small grids).
+__device__ __noinline__ bool tryRunBig(GridCtx& G, uint8_t* win, uint8_t* mini, int* idleFlag) {
+    const KParams& P = cP;
+    const int lane = threadIdx.x & 31;
+    int t = -1, item = 0;
+    if (lane == 0) {
+        for (int tries = 0; tries < 4; ++tries) {
+            const int h = ldRelaxed(&P.cb->bigHead);
+            const int tl = ldRelaxed(&P.cb->bigTail);
+            if (h >= tl || h >= P.maxBig) break;
+            if (atomicCAS(&P.cb->bigHead, h, h + 1) != h) continue;
+            int x = 0;
+            while ((x = ldRelaxed(&P.bigRing[h].x)) == 0) __nanosleep(32);
+            __threadfence();
+            t = x - 1;
+            item = __ldcg(&P.bigRing[h].y);
+            break;
+        }
+    }
+    t = __shfl_sync(FULLMASK, t, 0);
+    if (t < 0) return false;
+    item = __shfl_sync(FULLMASK, item, 0);
+    leaveIdle(idleFlag);
+    P2Entry* e = &P.p2ring[t];
+    const int jobIdx = e->jobIdx;
+    const unsigned long long tItem0 = globalTimerNs();
+    runPass2Grid(jobIdx, item, G, win, mini, true);
+    if (lane == 0) {
+        JobOut* jo = &P.jobOut[jobIdx];
+        const unsigned long long tItem1 = globalTimerNs();
+        atomicMax(reinterpret_cast<unsigned long long*>(&jo->tP2Start), tItem0 - P.cb->t0);
+        const unsigned long long old = atomicMax(reinterpret_cast<unsigned long long*>(&jo->p2MaxNs), tItem1 - tItem0);
+        if (tItem1 - tItem0 > old) jo->p2MaxItem = item;
+        atomicAdd(reinterpret_cast<unsigned long long*>(&jo->p2SumNs), tItem1 - tItem0);
+    }
+    __threadfence();
+    __syncwarp();
+    int d = 0;
+    if (lane == 0) d = atomicAdd(&e->doneItems, 1) + 1;
+    d = __shfl_sync(FULLMASK, d, 0);
+    if (d == e->nItems) finalizeJob(jobIdx);
+    return true;
+}
+
 // Claims and runs one pass-2 grid.  Returns false when none is available.
-__device__ __noinline__ bool tryRunPass2(GridCtx& G, uint8_t* win, uint8_t* mini) {
+__device__ __noinline__ bool tryRunPass2(GridCtx& G, uint8_t* win, uint8_t* mini, int* idleFlag = nullptr) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     int h = 0, item = -1;
@@ -1097,10 +1288,20 @@ __device__ __noinline__ bool tryRunPass2(GridCtx& G, uint8_t* win, uint8_t* mini
     }
     item = __shfl_sync(FULLMASK, item, 0);
     if (item < 0) return false;
+    leaveIdle(idleFlag);
     h = __shfl_sync(FULLMASK, h, 0);
     P2Entry* e = &P.p2ring[h];
     const int jobIdx = e->jobIdx;
-    runPass2Grid(jobIdx, item, G, win, mini);
+    const unsigned long long tItem0 = globalTimerNs();
+    if (!runPass2Grid(jobIdx, item, G, win, mini, false)) return true;   // (counted by the big-item ring)
+    if (lane == 0) {
+        JobOut* jo = &P.jobOut[jobIdx];
+        const unsigned long long tItem1 = globalTimerNs();
+        atomicMax(reinterpret_cast<unsigned long long*>(&jo->tP2Start), tItem0 - P.cb->t0);
+        const unsigned long long old = atomicMax(reinterpret_cast<unsigned long long*>(&jo->p2MaxNs), tItem1 - tItem0);
+        if (tItem1 - tItem0 > old) jo->p2MaxItem = item;
+        atomicAdd(reinterpret_cast<unsigned long long*>(&jo->p2SumNs), tItem1 - tItem0);
+    }
     __threadfence();
     __syncwarp();
     int d = 0;
@@ -1182,13 +1383,32 @@ __device__ __noinline__ void finalizeSpine(int jobIdx) {
     __syncwarp();
     if (status == JOB_OK && jb.gridCount > 1) {
         // hand the recorded grids to pass 2 (grids done in line are skipped there)
+        int t = 0;
         if (lane == 0) {
-            const int t = atomicAdd(&P.cb->p2Tail, 1);
+            t = atomicAdd(&P.cb->p2Tail, 1);
             P2Entry* e = &P.p2ring[t];
             e->jobIdx = jobIdx; e->nItems = jb.gridCount * MAXREC; e->nextItem = 0; e->doneItems = 0;
             __threadfence();
-            stRelease(&e->ready, 1);
         }
+        t = __shfl_sync(FULLMASK, t, 0);
+        __syncwarp();
+        // the candidates of the big grids go to their own ring: they are the longest items and start first
+        for (int gi = lane; gi < jb.gridCount; gi += 32) {
+            const int owner = ownerOf(*js, gi);
+            const GridRec* rec = &P.gridRecs[jb.recBase + (long long)owner * jb.gridCount + gi];
+            if (__ldcg(&rec->state) != 2) continue;
+            const int nc = __ldcg(&rec->nCand);
+            for (int k = 0; k < nc && k < MAXREC; ++k) {
+                const int pos = atomicAdd(&P.cb->bigTail, 1);
+                if (pos < P.maxBig) {
+                    P.bigRing[pos].y = gi * MAXREC + k;
+                    __threadfence();
+                    stRelease(&P.bigRing[pos].x, t + 1);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence(); stRelease(&P.p2ring[t].ready, 1); }
         __syncwarp();
     } else {
         finalizeJob(jobIdx);
@@ -1397,7 +1617,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
         if (agent >= P.nSlots) agent = -1;
     }
     bool queueEmpty = (agent < 0);
-    int idle = 0;
+    int idle = 0, amIdle = 0, helpKey = -1;
     GridCtx* cctx = (cw >= 0) ? reinterpret_cast<GridCtx*>(smem + NCTRL * WINBYTES + cw * CTX_STRIDE) : nullptr;
     uint8_t* win = (cw >= 0) ? smem + cw * WINBYTES : nullptr;
     uint8_t* mini = (cw >= 0) ? P.mini + (size_t)(cw * gridDim.x + blockIdx.x) * P.miniStride : nullptr;
@@ -1415,9 +1635,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
             queueEmpty = true;
         }
         bool sawOpen = false;
-        if (tryRunOneItem(*wctx, wTask, &sawOpen)) { idle = 0; continue; }
+        if (cw >= 0 && !amIdle) {   // from here on this control warp serves tile requests between other work
+            if (lane == 0) atomicAdd(&P.cb->idleHelpers, 1);
+            amIdle = 1;
+        }
+        if (tryRunOneItem(*wctx, wTask, &sawOpen, cw >= 0 ? &amIdle : nullptr)) { idle = 0; continue; }
         if (sawOpen) idle = 0;   // strips are about to become claimable: poll again soon
-        if (cw >= 0 && tryRunPass2(*cctx, win, mini)) { idle = 0; continue; }
+        if (cw >= 0 && tryRunBig(*cctx, win, mini, &amIdle)) { idle = 0; helpKey = -1; continue; }
+        if (cw >= 0 && tryRunTileReq(*cctx, win, helpKey)) { idle = 0; continue; }
+        if (cw >= 0 && tryRunPass2(*cctx, win, mini, &amIdle)) { idle = 0; helpKey = -1; continue; }
         int done = 0;
         if (lane == 0) done = ldRelaxed(&P.cb->jobsDone);
         done = __shfl_sync(FULLMASK, done, 0);
@@ -1468,6 +1694,7 @@ struct Engine::Impl {
     void* dRecs = nullptr; size_t capRecs = 0;   // pass-1 grid records
     void* dMini = nullptr; size_t capMini = 0;   // init row / column of pass-2 grids, one per control warp
     void* dPersist = nullptr; size_t capPersist = 0;  // persistent blocks of the big chain grids
+    void* dTileSlots = nullptr; size_t capTileSlots = 0;  // trace tiles handed from helper warps to a walking warp
     // pinned host staging
     void* hSeq = nullptr; size_t capHSeq = 0;
     void* hOut = nullptr; size_t capHOut = 0;
@@ -1525,7 +1752,7 @@ Engine::~Engine() {
     if (!impl_) return;
     cudaSetDevice(impl_->device);
     cudaFree(impl_->dJobs); cudaFree(impl_->dGrids); cudaFree(impl_->dSeq); cudaFree(impl_->dOut);
-    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dScratch); cudaFree(impl_->dRing); cudaFree(impl_->dRecs); cudaFree(impl_->dMini); cudaFree(impl_->dPersist);
+    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dScratch); cudaFree(impl_->dRing); cudaFree(impl_->dRecs); cudaFree(impl_->dMini); cudaFree(impl_->dPersist); cudaFree(impl_->dTileSlots);
     cudaFreeHost(impl_->hSeq); cudaFreeHost(impl_->hOut); cudaFreeHost(impl_->hGrids); cudaFreeHost(impl_->hColTab);
     for (auto& ev : impl_->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(impl_->stream);
@@ -1737,7 +1964,10 @@ void Engine::upload(std::vector<Job*>& jobs) {
     CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
     const size_t offRing = alignUp(sizeof(ControlBlock), 256);
     const size_t offP2 = offRing + alignUp(2 * (nTasks + 1) * sizeof(TaskDesc), 256);
-    const size_t offState = offP2 + alignUp((nJobs + 1) * sizeof(P2Entry), 256);
+    const size_t maxBig = (size_t)MAXREC * nTasks + 64;
+    const size_t offBig = offP2 + alignUp((nJobs + 1) * sizeof(P2Entry), 256);
+    const size_t offTile = offBig + alignUp(maxBig * sizeof(int2), 256);
+    const size_t offState = offTile + alignUp((size_t)TILE_RING_CAP * sizeof(TileReq), 256);
     const size_t offTok = offState + alignUp((nJobs + 1) * sizeof(JobState), 256);
     const size_t maxTokens = totalStrips + nTasks + 64;
     I.ringBytes = offTok + 2 * maxTokens * sizeof(int);
@@ -1820,6 +2050,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.growDev(I.dRecs, I.capRecs, (nRecs + 1) * sizeof(GridRec));
     I.growDev(I.dMini, I.capMini, miniStride * (size_t)NCTRL * I.numSMs);
     if (usePersist) I.growDev(I.dPersist, I.capPersist, (size_t)persistTotal + 256);
+    if (usePersist) I.growDev(I.dTileSlots, I.capTileSlots, (size_t)NCTRL * I.numSMs * TILE_SLOTS * TILE_SLOT_BYTES);
     I.growHost(I.hOut, I.capHOut, I.outInts * sizeof(int) + 64);
     tU[4] = wallMs();
     CUDA_CHECK(cudaEventRecord(I.ev[0], I.stream));
@@ -1840,6 +2071,10 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.cb = (ControlBlock*)I.dRing;
     kp.ring = (TaskDesc*)((uint8_t*)I.dRing + offRing);
     kp.p2ring = (P2Entry*)((uint8_t*)I.dRing + offP2);
+    kp.bigRing = (int2*)((uint8_t*)I.dRing + offBig);
+    kp.maxBig = (int)maxBig; kp.pad9 = 0;
+    kp.tileRing = (TileReq*)((uint8_t*)I.dRing + offTile);
+    kp.tileSlots = (usePersist && !getenv("UNICYCLER_B200_NO_TILE_HELP")) ? (uint8_t*)I.dTileSlots : nullptr;
     kp.jobState = (JobState*)((uint8_t*)I.dRing + offState);
     kp.tokRing = (int*)((uint8_t*)I.dRing + offTok);
     kp.maxTokens = (int)maxTokens; kp.pad7 = 0;
@@ -1943,9 +2178,12 @@ void Engine::fetch(std::vector<Job*>& jobs) {
         }
         fprintf(stderr, "[ub200 profile] jobs=%zu agents=%d tasks=%d cycles: setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld total=%lld maxjob=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",
                 nJobs, I.kp.nSlots, I.kp.maxTasks, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], mx, tot[6], tot[7], tot[8], tot[9], tot[10], tot[11]);
-        unsigned long long dbg[16];
+        unsigned long long dbg[24];
         if (cudaMemcpyFromSymbol(dbg, gDbg, sizeof(dbg)) == cudaSuccess) {
             fprintf(stderr, "[ub200 dbg] worker items=%llu strip-cycles=%llu (rowProg wait %llu) segDone-wait=%llu cells=%llu (cumulative)\n", dbg[14], dbg[12], dbg[13], dbg[11], dbg[15]);
+            fprintf(stderr, "[ub200 dbg] big pass-2 walks=%llu tiles=%llu tile-cycles=%llu walk-cycles=%llu (cumulative)\n", dbg[19], dbg[16], dbg[17], dbg[18]);
+            fprintf(stderr, "[ub200 dbg] tile requests posted=%llu claimed by helpers=%llu (post->claim %.1f us avg) stale pops=%llu (cumulative)\n", dbg[20], dbg[21], dbg[21] ? dbg[22] / 1e3 / dbg[21] : 0.0, dbg[23]);
+            fprintf(stderr, "[ub200 dbg] grids wider than 8000: tiles from helpers=%llu (wait cycles %llu) taken back=%llu never requested=%llu (cumulative)\n", dbg[8], dbg[9], dbg[10], dbg[11]);
             fprintf(stderr, "[ub200 dbg] unbanded trace strips=%llu total=%llu steps-cycles=%llu nsteps=%llu | banded strips=%llu total=%llu steps-cycles=%llu nsteps=%llu (cumulative)\n", dbg[3], dbg[0], dbg[1], dbg[2], dbg[7], dbg[4], dbg[5], dbg[6]);
         }
         long long maxSpine = 0, maxFinal = 0; size_t ws = 0, wf = 0;
@@ -1955,6 +2193,13 @@ void Engine::fetch(std::vector<Job*>& jobs) {
         }
         fprintf(stderr, "[ub200 timeline] last spine resolved at %.2f ms (job %zu, %d grids, %d segments), last job complete at %.2f ms (job %zu, %d grids)\n",
                 maxSpine / 1e6, ws, I.jobsDev[ws].gridCount, I.jobsDev[ws].nSeg, maxFinal / 1e6, wf, I.jobsDev[wf].gridCount);
+        {
+            const JobOut& jf = I.jobOut[wf];
+            const int it = (int)jf.p2MaxItem;
+            const GridDesc& gdd = ((const GridDesc*)I.hGrids)[I.jobsDev[wf].gridBegin + it / MAXREC];
+            fprintf(stderr, "[ub200 timeline] last job: spine resolved at %.2f ms, last pass-2 item started at %.2f ms, longest item %.2f ms (grid %d cand %d: %d x %d banded %d), items total %.2f ms\n",
+                    jf.tSpine / 1e6, jf.tP2Start / 1e6, jf.p2MaxNs / 1e6, it / MAXREC, it % MAXREC, gdd.nH, gdd.nV, (int)gdd.banded, jf.p2SumNs / 1e6);
+        }
         const long long* wp = I.jobOut[worst].prof;
         fprintf(stderr, "[ub200 profile] worst job %zu (%d grids): setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",
                 worst, I.jobsDev[worst].gridCount, wp[0], wp[1], wp[2], wp[3], wp[4], wp[6], wp[7], wp[8], wp[9], wp[10], wp[11]);

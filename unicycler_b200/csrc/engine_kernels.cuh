@@ -29,6 +29,7 @@ constexpr int NTHREADS = NWARPS * 32;
 constexpr int NCTRL = 4;                 // control-capable warps per CTA
 constexpr int MODE_TASK = 0;             // score-only strip item of a published grid (checkpoints to HBM)
 constexpr int MODE_TRACE = 1;            // full trace bytes into the shared-memory window
+constexpr int MODE_TRACEG = 3;           // the same into global memory (a tile recomputed for another warp)
 constexpr int MODE_FAST = 2;             // score-only local fill, box cells (S,H,V) into the shared-memory window
 constexpr int MAXSEG = 8;                // speculative segments of one seed chain
 constexpr int MAXREC = 8;                // candidates / planted cells a pass-1 grid record can hold
@@ -56,6 +57,7 @@ struct JobDev {
 struct JobOut {
     int status, score, outLen, pad;
     long long tSpine, tFinal;   // ns after kernel start: pass 1 resolved / job complete
+    long long tP2Start, p2MaxNs, p2MaxItem, p2SumNs;  // developer timeline: start of the last pass-2 item, longest item
     long long prof[12];  // cycles: setup+init, local fill, task wait, track, traceback, total; tiles, tile cycles,
                          // local-grid traceback cycles, tracebacks, local grids, local-grid track cycles
 };
@@ -152,12 +154,41 @@ struct TaskDesc {
     int pad0, pad1, pad2;
 };
 
-struct ControlBlock {  // zeroed before every launch
+struct ControlBlock {  // zeroed before every launch; every group of counters has its own 128-byte line
     int jobQueue, jobsDone;
-    int ringHead[2], ringTail[2];  // task boards: [0] jobs on the critical path (longest chains), [1] the rest
-    int p2Head, p2Tail;            // pass-2 board
-    int tokHead[2], tokTail[2];    // token rings: one token per strip that became claimable
     unsigned long long t0;         // %globaltimer at kernel start (developer timeline)
+    int pad0[28];
+    int ringHead[2], ringTail[2];  // task boards: [0] jobs on the critical path (longest chains), [1] the rest
+    int pad1[28];
+    int tokHead[2], tokTail[2];    // token rings: one token per strip that became claimable
+    int pad2[28];
+    int p2Head, p2Tail;            // pass-2 board
+    int bigHead, bigTail;          // pass-2 items of the big grids (served before everything else of pass 2)
+    int pad3[28];
+    int tileHead, tileTail;        // tile-request ring (trace tiles recomputed ahead of a big-grid traceback)
+    int pad4[30];
+    int idleHelpers, activeWalkers; // control warps polling for work / walking a big grid (tiles are only asked for
+                                    // while the idle ones outnumber the walkers several times)
+    int pad5[30];
+};
+
+// A traceback through a big grid asks idle control warps for the trace tiles it is about to enter (the tiles on
+// the three tile diagonals ahead of it).  One request = one 64 x 64 tile recomputed from the checkpoints into a
+// slot of the asking warp (global memory): [state | .. | int4 tile extent at +16 | 4096 trace bytes at +64].
+// state = tag * 4 + {0 posted, 1 claimed by a helper, 2 done, 3 cancelled}; the tag is the slot's generation.
+constexpr int TILE_RING_CAP = 32768;
+constexpr int TILE_SLOT_BYTES = 4096 + 64;
+constexpr int TILE_SLOTS = 32;          // one per lane of the asking warp
+constexpr int TILE_CANDS = 30;          // sample points ahead of the walk whose tiles are requested
+constexpr int TILE_HELP_MIN_EXTENT = 6000; // nH + nV of a grid whose tracebacks ask for help
+constexpr int TILE_HELPERS_PER_WALK = 6; // a walk consumes a tile in a third of the time a helper needs for three
+struct TileReq {
+    int seq;        // 2 * turn: free, 2 * turn + 1: written (turn = ring position / TILE_RING_CAP)
+    int job, gi;
+    int tile;       // (64-row block << 16) | 64-column block
+    int expect;     // the slot's state word when posted (tag * 4)
+    int pad;
+    unsigned long long slot;
 };
 
 struct KParams {
@@ -178,6 +209,10 @@ struct KParams {
     int* tokRing;      // [2][maxTokens] task id + 1 of a task with a claimable strip
     int maxTokens, pad7;
     P2Entry* p2ring;   // [nJobs]
+    int2* bigRing;     // [maxBig] (pass-2 board entry + 1, item) of one candidate of a big grid
+    int maxBig, pad9;
+    TileReq* tileRing; // [TILE_RING_CAP]
+    uint8_t* tileSlots; // [control warps][TILE_SLOTS][TILE_SLOT_BYTES]
     JobState* jobState;
     GridRec* gridRecs; // [total grids]
     uint8_t* persist;  // persistent blocks of the big grids (GridDesc::persistOff), nullptr: disabled
@@ -192,7 +227,7 @@ struct KParams {
 // Launch parameters live in constant memory (a by-reference kernel argument would be copied to the
 // local-memory stack of every warp).
 __constant__ KParams cP;
-__device__ unsigned long long gDbg[16];   // developer counters (cycles), lane 0 of control warps
+__device__ unsigned long long gDbg[24];   // developer counters (cycles), lane 0 of control warps
 
 // All per-warp working state (GridCtx slots, windows, staged codes) lives in the kernel's dynamic shared
 // memory.  Out-of-line functions receive generic pointers to it; toShared() rebases such a pointer on the
@@ -399,7 +434,7 @@ template <bool AFF, bool CT, bool BANDED, int RR, int MODE, bool CAP>
 __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K, StripState<RR>& st, int c, int lane,
                                            int cBeg, int cEnd, int i0, int bS, int bV, int hcN, int nsteps,
                                            uint8_t* win, int winPitch, int2* rowOut, int2* ckOut) {
-    constexpr bool TRACE = (MODE == MODE_TRACE);
+    constexpr bool TRACE = (MODE == MODE_TRACE || MODE == MODE_TRACEG);
     const int match = K.match, mismatch = K.mismatch, go = K.go, ge = K.ge;
     const int lo = K.lo, up = K.up;
     int capEdges = 0, hNext = 0, boxRow0 = 0, boxH = 0;
@@ -520,9 +555,9 @@ template <bool AFF, bool CT, bool BANDED, int RR, int MODE>
 __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int cEnd, bool fromCk, int nsteps,
                                       bool capture, uint8_t* winIn, int winPitch) {
     const GridCtx& G = *toShared(&Gin);
-    uint8_t* win = (MODE == MODE_TASK) ? nullptr : toShared(winIn);
+    uint8_t* win = (MODE == MODE_TASK) ? nullptr : (MODE == MODE_TRACEG ? winIn : toShared(winIn));
     constexpr int SHR = 32 * RR;
-    constexpr bool TRACE = (MODE == MODE_TRACE);
+    constexpr bool TRACE = (MODE == MODE_TRACE || MODE == MODE_TRACEG);
     constexpr bool L2ONLY = (MODE == MODE_TASK);   // worker warps read the arena through L2 only
     const int lane = threadIdx.x & 31;
     const GridGeom& g = G.g;
@@ -682,16 +717,18 @@ struct OutStream {
     }
 };
 
-template <bool AFF, bool CT>
+template <bool AFF, bool CT, int MODE>
 __device__ __forceinline__ void tileDispatch(const GridCtx& G, int s, int cBeg, int cEnd, bool fromCk, int nsteps,
                                              uint8_t* win) {
-    if (G.g.banded) runStrip<AFF, CT, true, 2, MODE_TRACE>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
-    else runStrip<AFF, CT, false, 2, MODE_TRACE>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
+    if (G.g.banded) runStrip<AFF, CT, true, 2, MODE>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
+    else runStrip<AFF, CT, false, 2, MODE>(G, s, cBeg, cEnd, fromCk, nsteps, false, win, 32);
 }
 
 // Recomputes the trace bytes of the tile that holds (i, j): rows of strip s up to the lane owning row i,
 // columns from the checkpoint left of j up to j.  Returns (strip, first column, last column, last row).
-__device__ __noinline__ int4 computeTileFn(const GridCtx& Gin, uint8_t* win, int i, int j) {
+// MODE_TRACE: into the warp's shared-memory window; MODE_TRACEG: into global memory (tile helpers).
+template <int MODE>
+__device__ __noinline__ int4 computeTileT(const GridCtx& Gin, uint8_t* win, int i, int j) {
     const GridCtx& G = *toShared(&Gin);
     const GridGeom& g = G.g;
     const int b = (i - 1) / CKR;                    // 64-row block (32 lanes x 2 rows)
@@ -703,15 +740,143 @@ __device__ __noinline__ int4 computeTileFn(const GridCtx& Gin, uint8_t* win, int
     const int laneOfI = ((i - 1) - b * CKR) / 2;
     const int nsteps = (j - cBeg + 1) + laneOfI;
     __syncwarp();
-    if (G.affine) { if (G.complete) tileDispatch<true, true>(G, b, cBeg, j, fromCk, nsteps, win); else tileDispatch<true, false>(G, b, cBeg, j, fromCk, nsteps, win); }
-    else { if (G.complete) tileDispatch<false, true>(G, b, cBeg, j, fromCk, nsteps, win); else tileDispatch<false, false>(G, b, cBeg, j, fromCk, nsteps, win); }
+    if (G.affine) { if (G.complete) tileDispatch<true, true, MODE>(G, b, cBeg, j, fromCk, nsteps, win); else tileDispatch<true, false, MODE>(G, b, cBeg, j, fromCk, nsteps, win); }
+    else { if (G.complete) tileDispatch<false, true, MODE>(G, b, cBeg, j, fromCk, nsteps, win); else tileDispatch<false, false, MODE>(G, b, cBeg, j, fromCk, nsteps, win); }
     __syncwarp();
     return make_int4(b, cBeg, j, b * CKR + (laneOfI + 1) * 2);
+}
+__device__ __forceinline__ int4 computeTileFn(const GridCtx& Gin, uint8_t* win, int i, int j) {
+    return computeTileT<MODE_TRACE>(Gin, win, i, j);
 }
 
 // Pass-1 lazy trace value of cell (i, j): derived from the (S,H,V) of its three neighbours exactly like the
 // trace fill would (same cellUpdate).  One out-of-line copy (the walker calls it from many places).
 // Bit 31 of the result: a neighbour lies outside the captured box.
+// ---- tile helpers: the asking side (a control warp walking a traceback through a big grid) ----
+struct TileFetch { int4 t; int4 hist; int myTile, myTag; };
+
+// Cancels (or waits for) the request of this lane's slot; returns true when the slot is free again.
+__device__ __forceinline__ bool releaseTileSlot(uint8_t* slots, int lane, int myTag, bool wait) {
+    int* st = reinterpret_cast<int*>(slots + (size_t)lane * TILE_SLOT_BYTES);
+    int v = atomicCAS(st, myTag * 4, myTag * 4 + 3);
+    if (v == myTag * 4 || v == myTag * 4 + 2) return true;
+    if (!wait) return false;
+    while (ldRelaxed(st) != myTag * 4 + 2) __nanosleep(64);
+    return true;
+}
+
+// The trace tile that holds (i, j): taken from a helper's slot when one was asked for it in time, recomputed by
+// this warp otherwise; then the tiles ahead on the path's diagonal are requested.  myTile / myTag: this lane's slot.
+__device__ __noinline__ TileFetch fetchTileFn(const GridCtx& Gin, uint8_t* win, int i, int j, uint8_t* slots, int job, int gi,
+                                             int myTile, int myTag, int4 hist) {
+    const GridCtx& G = *toShared(&Gin);
+    const GridGeom& g = G.g;
+    const KParams& P = cP;
+    const int lane = threadIdx.x & 31;
+    const int b = (i - 1) / CKR, cbk = (j - 1) / CKW;
+    const int id = (b << 16) | cbk;
+    TileFetch r;
+    bool have = false;
+    const unsigned match = __ballot_sync(FULLMASK, myTile == id);
+    if (match) {
+        const int s = __ffs(match) - 1;
+        const int tag = __shfl_sync(FULLMASK, myTag, s);
+        uint8_t* slot = slots + (size_t)s * TILE_SLOT_BYTES;
+        int v = 0;
+        if (lane == 0) {
+            int* st = reinterpret_cast<int*>(slot);
+            const long long w0 = clock64();
+            v = atomicCAS(st, tag * 4, tag * 4 + 3);          // not claimed yet: take it back
+            if (v == tag * 4 + 1) { while ((v = ldRelaxed(st)) != tag * 4 + 2) __nanosleep(64); }
+            __threadfence();
+            if (g.nH > 8000) {
+            if (v == tag * 4 + 2) { atomicAdd(&gDbg[8], 1ull); atomicAdd(&gDbg[9], (unsigned long long)(clock64() - w0)); }
+            else atomicAdd(&gDbg[10], 1ull);
+            }
+        }
+        v = __shfl_sync(FULLMASK, v, 0);
+        if (v == tag * 4 + 2) {
+            const int4* src = reinterpret_cast<const int4*>(slot + 64);
+            int4* dst = reinterpret_cast<int4*>(toShared(win));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[k * 32 + lane] = __ldcg(src + k * 32 + lane);
+            r.t = __ldcg(reinterpret_cast<const int4*>(slot + 16));
+            have = true;
+        }
+        if (lane == s) myTile = -1;
+        __syncwarp();
+    }
+    if (!have) r.t = computeTileFn(Gin, win, i, j);
+    if (!match && lane == 0 && g.nH > 8000) atomicAdd(&gDbg[11], 1ull);
+    // slots of tiles the (monotone) path has left behind are recycled
+    if (myTile >= 0 && ((myTile >> 16) > b || (myTile & 0xffff) > cbk)) {
+        if (releaseTileSlot(slots, lane, myTag, false)) myTile = -1;
+    }
+    // ask for the tiles ahead while idle control warps exist and the ring has room
+    int go = 0;
+    if (lane == 0)
+        go = ldRelaxed(&P.cb->idleHelpers) >= TILE_HELPERS_PER_WALK * ldRelaxed(&P.cb->activeWalkers) &&
+             ldRelaxed(&P.cb->tileTail) - ldRelaxed(&P.cb->tileHead) < 4096;
+    go = __shfl_sync(FULLMASK, go, 0);
+    if (go) {
+        // the path is extrapolated along the direction of its last two tile entries (hist); lane = sample point
+        // (48 cells apart) x {on the line, 16 cells to either side of it}
+        int di = (hist.z >= 0 ? hist.z : hist.x) - i, dj = (hist.z >= 0 ? hist.w : hist.y) - j;
+        if (hist.x < 0 || (di <= 0 && dj <= 0)) { di = 1; dj = 1; }
+        di = imax(di, 0); dj = imax(dj, 0);
+        const int m = imax(di, dj);
+        const int si = di * 48 / m, sj = dj * 48 / m;
+        int cand = -1;
+        if (lane < TILE_CANDS) {
+            const int t = lane / 3 + 1, ty = lane - (lane / 3) * 3;
+            const int pi = i - t * si + (ty == 1 ? 16 : (ty == 2 ? -16 : 0));
+            const int pj = j - t * sj + (ty == 1 ? -16 : (ty == 2 ? 16 : 0));
+            if (pi >= 1 && pj >= 1 && pi <= i && pj <= j) {
+                const int tb = (pi - 1) / CKR, tc = (pj - 1) / CKW;
+                if ((tb != b || tc != cbk) && pj >= stripJlo(g, tb, CKR) && pj <= stripJhi(g, tb, CKR)) cand = (tb << 16) | tc;
+            }
+        }
+        int pushSlot = -1, pushTag = 0;
+        for (int c = 0; c < TILE_CANDS; ++c) {
+            const int cid = __shfl_sync(FULLMASK, cand, c);
+            if (cid < 0) continue;
+            if (__ballot_sync(FULLMASK, myTile == cid)) continue;
+            const unsigned freeM = __ballot_sync(FULLMASK, myTile < 0);
+            if (!freeM) break;
+            const int s = __ffs(freeM) - 1;
+            if (lane == s) {
+                myTile = cid;
+                ++myTag;
+                __stcg(reinterpret_cast<int*>(slots + (size_t)s * TILE_SLOT_BYTES), myTag * 4);
+            }
+            const int tag = __shfl_sync(FULLMASK, myTag, s);
+            if (lane == c) { pushSlot = s; pushTag = tag; }
+        }
+        const unsigned pushM = __ballot_sync(FULLMASK, pushSlot >= 0);
+        if (pushM) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&P.cb->tileTail, __popc(pushM));
+            base = __shfl_sync(FULLMASK, base, 0);
+            __syncwarp();
+            if (pushSlot >= 0) {
+                const int pos = base + __popc(pushM & ((1u << lane) - 1u));
+                TileReq* e = &P.tileRing[pos & (TILE_RING_CAP - 1)];
+                const int turn = pos / TILE_RING_CAP;
+                while (ldRelaxed(&e->seq) != 2 * turn) __nanosleep(64);
+                e->job = job; e->gi = gi; e->tile = cand; e->expect = pushTag * 4; e->pad = (int)(unsigned)globalTimerNs();
+                atomicAdd(&gDbg[20], 1ull);
+                e->slot = (unsigned long long)(slots + (size_t)pushSlot * TILE_SLOT_BYTES);
+                __threadfence();
+                stRelease(&e->seq, 2 * turn + 1);
+            }
+        }
+        __syncwarp();
+    }
+    r.myTile = myTile; r.myTag = myTag;
+    r.hist = make_int4(i, j, hist.x, hist.y);
+    return r;
+}
+
 __device__ __forceinline__ DCell fastCellAt(const GridCtx& G, const uint8_t* win, int i, int j, bool& outOfBox) {
     const GridGeom& g = G.g;
     if (g.banded) { const int d = j - i; if (d < g.lo || d > g.up) return DCell{NEG_INF, NEG_INF, NEG_INF}; }
@@ -746,7 +911,9 @@ __device__ __noinline__ uint32_t lazyTvFn(const GridCtx& Gin, const uint8_t* win
     return tv | (oob ? 0x80000000u : 0u);
 }
 
-struct TraceWalker {
+// TILEONLY: the walker of a big (task) grid — the local-window and lazy modes are compiled out.
+template <bool TILEONLY>
+struct TraceWalkerT {
     const GridCtx& G;
     OutStream& out;
     const uint8_t* __restrict__ win;     // shared-memory trace window of this control warp
@@ -764,16 +931,44 @@ struct TraceWalker {
     bool emitOn;
     bool bad;         // undefined trace value (reference: endless loop / assert)
     long long tilesComputed, tileCycles;
+    // tile helpers (big-grid pass-2 tracebacks): this warp's slots, and this lane's slot (requested tile, generation)
+    uint8_t* hSlots;
+    int hJob, hGi, myTile, myTag;
+    int4 hHist;       // entry points (row, column) of the last two tiles: the direction the path is heading
 
-    __device__ __forceinline__ TraceWalker(const GridCtx& g, OutStream& o, uint8_t* w)
+    __device__ __forceinline__ TraceWalkerT(const GridCtx& g, OutStream& o, uint8_t* w)
         : G(g), out(o), win(toShared(w)), winW(w), g(g.g), local(g.local), rrMul(g.rrMul), rr(g.RR), rrs(g.rrs), pitch(g.pitch), localJhi(g.localJhi),
           affine(g.affine), lazy(false), outOfBox(false), tS(-1), tC0(0), tMaxRow(-1), tMaxCol(-1), pc(0), pv(0), nSegs(0), emitOn(true),
-          bad(false), tilesComputed(0), tileCycles(0) {}
+          bad(false), tilesComputed(0), tileCycles(0), hSlots(nullptr), hJob(0), hGi(0), myTile(-1), myTag(0), hHist(make_int4(-1, -1, -1, -1)) {}
+
+    __device__ __forceinline__ void enableHelp(uint8_t* slots, int job, int gi) {
+        if (g.nV / CKR >= 32767 || g.nH / CKW >= 65535) return;
+        // only the long walks are worth it: they end the kernel, and helpers are a shared resource
+        if (g.nH + g.nV < TILE_HELP_MIN_EXTENT) return;
+        hSlots = slots; hJob = job; hGi = gi; myTile = -1; hHist = make_int4(-1, -1, -1, -1);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&cP.cb->activeWalkers, 1);
+        myTag = __ldcg(reinterpret_cast<const int*>(slots + (size_t)(threadIdx.x & 31) * TILE_SLOT_BYTES)) >> 2;
+        if (myTag < 0 || myTag > (1 << 28)) myTag = 0;
+    }
+    // every outstanding request is cancelled or waited for: nothing may write into the slots after the walk
+    __device__ __forceinline__ void drainHelp() {
+        if (hSlots == nullptr) return;
+        if (myTile >= 0) { releaseTileSlot(hSlots, threadIdx.x & 31, myTag, true); myTile = -1; }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) atomicSub(&cP.cb->activeWalkers, 1);
+        hSlots = nullptr;
+    }
 
     // Recompute the trace bytes of the tile that holds (i, j) (free function: the walker must stay in registers)
     __device__ __forceinline__ void computeTile(int i, int j) {
         const long long t0 = clock64();
-        const int4 t = computeTileFn(G, winW, i, j);
+        int4 t;
+        if (hSlots != nullptr) {
+            const TileFetch f = fetchTileFn(G, winW, i, j, hSlots, hJob, hGi, myTile, myTag, hHist);
+            t = f.t; myTile = f.myTile; myTag = f.myTag; hHist = f.hist;
+        } else {
+            t = computeTileFn(G, winW, i, j);
+        }
         tS = t.x; tC0 = t.y; tMaxCol = t.z; tMaxRow = t.w;
         ++tilesComputed;
         tileCycles += clock64() - t0;
@@ -783,15 +978,17 @@ struct TraceWalker {
         const int i = pv - storageOffset(g, pc);
         const int j = pc;
         if (i <= 0 || j <= 0 || i > g.nV || j > g.nH) return 0;
-        if (lazy) {
-            const uint32_t r = lazyTvFn(G, win, i, j);
-            if (r >> 31) outOfBox = true;
-            return r & 0xffu;
-        }
-        if (local) {
-            if (j > localJhi) return 0;
-            const int q = ((i - 1) * rrMul) >> 16;
-            return win[((j - 1) * pitch + q) * rrs + ((i - 1) - q * rr)];
+        if constexpr (!TILEONLY) {
+            if (lazy) {
+                const uint32_t r = lazyTvFn(G, win, i, j);
+                if (r >> 31) outOfBox = true;
+                return r & 0xffu;
+            }
+            if (local) {
+                if (j > localJhi) return 0;
+                const int q = ((i - 1) * rrMul) >> 16;
+                return win[((j - 1) * pitch + q) * rrs + ((i - 1) - q * rr)];
+            }
         }
         const int b = (i - 1) / CKR;
         if (b != tS || j < tC0 || j > tMaxCol || i > tMaxRow) {
@@ -837,7 +1034,19 @@ struct TraceWalker {
         if (tv & T_D) {
             if (!(last & T_D)) { record(c.currCol, c.currRow, frag, last); last = T_D; frag = 0; }
             // run of diagonal steps (identical to re-entering this branch once per step)
-            do { moveD(c); tv = tvHere(); --c.currCol; --c.currRow; ++frag; } while ((tv & T_D) && !c.reachedEnd());
+            if (TILEONLY && !g.banded) {
+                // unbanded task grid: storage = matrix coordinates; the bytes of the current 64 x 64 tile are read
+                // straight from the window while the run stays inside it
+                do {
+                    --pc; --pv;
+                    const int ri = pv - 1 - tS * CKR;
+                    if (ri >= 0 && pv <= tMaxRow && pc >= tC0 && pc <= tMaxCol) tv = win[(pc - tC0) * CKR + ri];
+                    else tv = tvHere();
+                    --c.currCol; --c.currRow; ++frag;
+                } while ((tv & T_D) && !c.reachedEnd());
+            } else {
+                do { moveD(c); tv = tvHere(); --c.currCol; --c.currRow; ++frag; } while ((tv & T_D) && !c.reachedEnd());
+            }
         } else if ((tv & T_MV) && (tv & T_V)) {
             if (!(last & T_V)) { record(c.currCol, c.currRow, frag, last); last = T_V; frag = 0; }
             if (aff) {
@@ -891,5 +1100,6 @@ struct TraceWalker {
         }
     }
 };
+typedef TraceWalkerT<false> TraceWalker;
 
 }  // namespace ub200
