@@ -510,7 +510,8 @@ __device__ __forceinline__ void chainTracebackOne(const GridCtx& G, Walker& w, O
     } else {
         int frag = 0;
         w.emitOn = false;
-        while (!c.reachedEnd() && tv != T_NONE) w.doTraceback(tv, last, frag, c);
+        if (w.flatWalk()) w.walkFlat(tv, last, frag, c);
+        else while (!c.reachedEnd() && tv != T_NONE) w.doTraceback(tv, last, frag, c);
         w.emitOn = true;
         const int hInit = c.currCol - c.endCol;
         const int vInit = c.currRow - c.endRow;
@@ -654,6 +655,7 @@ __device__ __noinline__ TbResult tracebackBigCand(const GridCtx& Gin, uint8_t* w
     __syncwarp();
     r.status = status; r.nPlanted = nPlanted;
     r.tiles = w.tilesComputed; r.tileCycles = w.tileCycles;
+    r.pad0 = out.len - pos;
     return r;
 }
 
@@ -923,7 +925,8 @@ __device__ __forceinline__ void runClaimedItem(TaskDesc* t, int taskId, int item
 // A control warp that polls for work counts as an idle tile helper until it commits to something long.
 __device__ __forceinline__ void leaveIdle(int* idleFlag) {
     if (idleFlag != nullptr && *idleFlag) {
-        if ((threadIdx.x & 31) == 0) atomicSub(&cP.cb->idleHelpers, 1);
+        const bool ctrl = (int)(threadIdx.x >> 5) >= NWARPS - NCTRL;
+        if ((threadIdx.x & 31) == 0) atomicSub(ctrl ? &cP.cb->idleHelpers : &cP.cb->idleWorkers, 1);
         *idleFlag = 0;
     }
 }
@@ -987,7 +990,7 @@ __device__ __noinline__ int publishAndWait(const GridCtx& Gin, GridCtx& wctx, in
     }
     __threadfence();
     __syncwarp();
-    if (lane == 0) { stRelease(&td->ready, 1); pushToken(taskId); }
+    if (lane == 0) { atomicAdd(&P.cb->openTasks, 1); stRelease(&td->ready, 1); pushToken(taskId); }
     (void)board;
     for (;;) {
         int d = 0;
@@ -1005,7 +1008,7 @@ __device__ __noinline__ int publishAndWait(const GridCtx& Gin, GridCtx& wctx, in
         else __nanosleep(200);
     }
     // one real acquire: the captures written by the worker warps are read with ordinary (L1-cached) loads
-    if (lane == 0) (void)ldAcquire(&td->doneItems);
+    if (lane == 0) { (void)ldAcquire(&td->doneItems); atomicSub(&P.cb->openTasks, 1); }
     __syncwarp();
     return JOB_OK;
 }
@@ -1044,6 +1047,12 @@ __device__ __noinline__ bool runPass2Grid(int jobIdx, int item, GridCtx& Gin, ui
         const TbResult tb = tracebackBigCand(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, rec, ksel, owner);
         if (tb.status != JOB_OK && lane == 0) atomicMax(&P.jobState[jobIdx].status, tb.status);
         if (lane == 0) {
+            // developer timeline: remember the tile statistics of the longest walk of the job
+            JobOut* jo = &P.jobOut[jobIdx];
+            const long long dur = clock64() - tw0;
+            if (dur > (long long)__ldcg(&jo->p2MaxStart)) {
+                jo->p2MaxStart = dur; jo->p2MaxTiles = tb.tiles + ((long long)tb.pad0 << 32); jo->p2MaxTileCycles = tb.tileCycles;
+            }
             atomicAdd(&gDbg[16], (unsigned long long)tb.tiles);
             atomicAdd(&gDbg[17], (unsigned long long)tb.tileCycles);
             atomicAdd(&gDbg[18], (unsigned long long)(clock64() - tw0));
@@ -1090,6 +1099,8 @@ __device__ __noinline__ void finalizeJob(int jobIdx) {
     const int lane = threadIdx.x & 31;
     __threadfence();
     const int end = ldRelaxed(&P.jobState[jobIdx].outCursor);
+    if (lane == 0) P.jobOut[jobIdx].tFin0 = (long long)(globalTimerNs() - P.cb->t0);
+    long long nRecords = 0;
     int* buf = P.out + P.jobs[jobIdx].outOff;
     const int cap = P.jobs[jobIdx].outCap;
     const int st2 = ldRelaxed(&P.jobState[jobIdx].status);
@@ -1119,6 +1130,7 @@ __device__ __noinline__ void finalizeJob(int jobIdx) {
                     if (lane == n) { mySrc = src; myUsed = used; }
                     ++n;
                 }
+                ++nRecords;
                 src += reserved;
             }
             if (st != JOB_OK) break;
@@ -1155,6 +1167,7 @@ __device__ __noinline__ void finalizeJob(int jobIdx) {
         jo->status = st;
         jo->outLen = dst;
         jo->tFinal = (long long)(globalTimerNs() - P.cb->t0);
+        jo->finRecords = nRecords;
         __threadfence();
         atomicAdd(&P.cb->jobsDone, 1);
     }
@@ -1163,19 +1176,23 @@ __device__ __noinline__ void finalizeJob(int jobIdx) {
 
 // Tile helper: pops one tile request, recomputes the 64 x 64 trace tile from the grid's checkpoints into this
 // warp's window and hands it to the asking warp's slot.  helpKey caches which grid G currently describes.
-__device__ __noinline__ bool tryRunTileReq(GridCtx& Gin, uint8_t* win, int& helpKey) {
+__device__ __noinline__ bool tryRunTileReq(GridCtx& Gin, int& helpKey) {
     GridCtx& G = *toShared(&Gin);
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     int got = 0, job = 0, gi = 0, tile = 0, expect = 0;
     unsigned long long slotAddr = 0;
     if (lane == 0) {
-        for (int tries = 0; tries < 4 && got == 0; ++tries) {
-            const int h = ldRelaxed(&P.cb->tileHead);
-            const int tl = ldRelaxed(&P.cb->tileTail);
-            if (h >= tl) break;
-            if (atomicCAS(&P.cb->tileHead, h, h + 1) != h) continue;
-            TileReq* e = &P.tileRing[h & (TILE_RING_CAP - 1)];
+        // this warp's home ring first, then its neighbours
+        const int home = (int)(blockIdx.x * NWARPS + (threadIdx.x >> 5));
+        for (int tries = 0; tries < 8 && got == 0; ++tries) {
+            const int q = (home + tries) & (TILE_QUEUES - 1);
+            ControlBlock::TileQueue* tq = &P.cb->tq[q];
+            const int h = ldRelaxed(&tq->head);
+            const int tl = ldRelaxed(&tq->tail);
+            if (h >= tl) continue;
+            if (atomicCAS(&tq->head, h, h + 1) != h) continue;
+            TileReq* e = &P.tileRing[(size_t)q * TILE_RING_CAP + (h & (TILE_RING_CAP - 1))];
             const int turn = h / TILE_RING_CAP;
             while (ldRelaxed(&e->seq) != 2 * turn + 1) __nanosleep(32);
             __threadfence();
@@ -1208,17 +1225,42 @@ __device__ __noinline__ bool tryRunTileReq(GridCtx& Gin, uint8_t* win, int& help
     const int tb = tile >> 16, tc = tile & 0xffff;
     const int iLast = imin(tb * CKR + CKR, g.nV);
     const int jLast = imin(tc * CKW + CKW, stripJhi(g, tb, CKR));
-    const int4 t = computeTileFn(G, win, iLast, jLast);
-    const int4* src = reinterpret_cast<const int4*>(toShared(win));
-    int4* dst = reinterpret_cast<int4*>(slot + 64);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) __stcg(dst + k * 32 + lane, src[k * 32 + lane]);
+    const int4 t = computeTileT<MODE_TRACEG>(G, slot + 64, iLast, jLast);   // straight into the asking warp's slot
     if (lane == 0) __stcg(reinterpret_cast<int4*>(slot + 16), t);
     __threadfence();
     __syncwarp();
     if (lane == 0) stRelease(reinterpret_cast<int*>(slot), expect + 2);
     __syncwarp();
     return true;
+}
+
+// One candidate of a big grid goes to the big-item ring (lane 0).
+__device__ __forceinline__ void pushBig(int jobIdx, int item) {
+    const KParams& P = cP;
+    const int pos = atomicAdd(&P.cb->bigTail, 1);
+    if (pos < P.maxBig) {
+        P.bigRing[pos].y = item;
+        __threadfence();
+        stRelease(&P.bigRing[pos].x, jobIdx + 1);
+    }
+}
+
+// A pass-2 item of the job is done; the last one completes the job (all lanes; finalizeJob is a warp function).
+__device__ __forceinline__ void pass2ItemDone(int jobIdx) {
+    const KParams& P = cP;
+    const int lane = threadIdx.x & 31;
+    __threadfence();
+    __syncwarp();
+    int fin = 0;
+    if (lane == 0) {
+        JobState* js = &P.jobState[jobIdx];
+        const int d = atomicAdd(&js->p2Done, 1) + 1;
+        __threadfence();
+        const int need = ldRelaxed(&js->p2Need);
+        fin = (need > 0 && d == need) ? 1 : 0;
+    }
+    fin = __shfl_sync(FULLMASK, fin, 0);
+    if (fin) finalizeJob(jobIdx);
 }
 
 // Claims and runs one big-grid candidate of pass 2 (the longest items: they start before the small grids).
@@ -1244,8 +1286,7 @@ __device__ __noinline__ bool tryRunBig(GridCtx& G, uint8_t* win, uint8_t* mini, 
     if (t < 0) return false;
     item = __shfl_sync(FULLMASK, item, 0);
     leaveIdle(idleFlag);
-    P2Entry* e = &P.p2ring[t];
-    const int jobIdx = e->jobIdx;
+    const int jobIdx = t;
     const unsigned long long tItem0 = globalTimerNs();
     runPass2Grid(jobIdx, item, G, win, mini, true);
     if (lane == 0) {
@@ -1256,12 +1297,7 @@ __device__ __noinline__ bool tryRunBig(GridCtx& G, uint8_t* win, uint8_t* mini, 
         if (tItem1 - tItem0 > old) jo->p2MaxItem = item;
         atomicAdd(reinterpret_cast<unsigned long long*>(&jo->p2SumNs), tItem1 - tItem0);
     }
-    __threadfence();
-    __syncwarp();
-    int d = 0;
-    if (lane == 0) d = atomicAdd(&e->doneItems, 1) + 1;
-    d = __shfl_sync(FULLMASK, d, 0);
-    if (d == e->nItems) finalizeJob(jobIdx);
+    pass2ItemDone(jobIdx);
     return true;
 }
 
@@ -1302,12 +1338,7 @@ __device__ __noinline__ bool tryRunPass2(GridCtx& G, uint8_t* win, uint8_t* mini
         if (tItem1 - tItem0 > old) jo->p2MaxItem = item;
         atomicAdd(reinterpret_cast<unsigned long long*>(&jo->p2SumNs), tItem1 - tItem0);
     }
-    __threadfence();
-    __syncwarp();
-    int d = 0;
-    if (lane == 0) d = atomicAdd(&e->doneItems, 1) + 1;
-    d = __shfl_sync(FULLMASK, d, 0);
-    if (d == e->nItems) finalizeJob(jobIdx);
+    pass2ItemDone(jobIdx);
     return true;
 }
 
@@ -1383,33 +1414,29 @@ __device__ __noinline__ void finalizeSpine(int jobIdx) {
     __syncwarp();
     if (status == JOB_OK && jb.gridCount > 1) {
         // hand the recorded grids to pass 2 (grids done in line are skipped there)
-        int t = 0;
-        if (lane == 0) {
-            t = atomicAdd(&P.cb->p2Tail, 1);
-            P2Entry* e = &P.p2ring[t];
-            e->jobIdx = jobIdx; e->nItems = jb.gridCount * MAXREC; e->nextItem = 0; e->doneItems = 0;
-            __threadfence();
-        }
-        t = __shfl_sync(FULLMASK, t, 0);
+        // every (grid, candidate) pair is one item, plus one for this publication (big items of segment 0 may
+        // have finished already)
+        if (lane == 0) { stRelease(&js->p2Need, jb.gridCount * MAXREC + 1); }
         __syncwarp();
         // the candidates of the big grids go to their own ring: they are the longest items and start first
+        // (segment 0 has handed over its own ones right after their pass 1)
         for (int gi = lane; gi < jb.gridCount; gi += 32) {
             const int owner = ownerOf(*js, gi);
             const GridRec* rec = &P.gridRecs[jb.recBase + (long long)owner * jb.gridCount + gi];
-            if (__ldcg(&rec->state) != 2) continue;
+            if (__ldcg(&rec->state) != 2 || (owner == 0 && __ldcg(&rec->published))) continue;
             const int nc = __ldcg(&rec->nCand);
-            for (int k = 0; k < nc && k < MAXREC; ++k) {
-                const int pos = atomicAdd(&P.cb->bigTail, 1);
-                if (pos < P.maxBig) {
-                    P.bigRing[pos].y = gi * MAXREC + k;
-                    __threadfence();
-                    stRelease(&P.bigRing[pos].x, t + 1);
-                }
-            }
+            for (int k = 0; k < nc && k < MAXREC; ++k) pushBig(jobIdx, gi * MAXREC + k);
         }
         __syncwarp();
-        if (lane == 0) { __threadfence(); stRelease(&P.p2ring[t].ready, 1); }
+        if (lane == 0) {
+            const int t = atomicAdd(&P.cb->p2Tail, 1);
+            P2Entry* e = &P.p2ring[t];
+            e->jobIdx = jobIdx; e->nItems = jb.gridCount * MAXREC; e->nextItem = 0; e->doneItems = 0;
+            __threadfence();
+            stRelease(&e->ready, 1);
+        }
         __syncwarp();
+        pass2ItemDone(jobIdx);
     } else {
         finalizeJob(jobIdx);
     }
@@ -1551,6 +1578,13 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
                 if (lane == 0) {
                     rec->state = 2; rec->nCand = TR.nCand; rec->inserted = insertedMask;
                     for (int k = 0; k < TR.nCand; ++k) rec->cand[k] = G.cand[k];
+                    // segment 0 owns every grid it walks: the long tracebacks of its big grids start right away
+                    const int early = (seg == 0 && status == JOB_OK && jb.gridCount > 1) ? 1 : 0;
+                    rec->published = early;
+                    if (early) {
+                        __threadfence();
+                        for (int k = 0; k < TR.nCand; ++k) pushBig(jobIdx, gi * MAXREC + k);
+                    }
                 }
             } else if (status == JOB_OK) {
                 const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, TR.nCand,
@@ -1635,15 +1669,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
             queueEmpty = true;
         }
         bool sawOpen = false;
-        if (cw >= 0 && !amIdle) {   // from here on this control warp serves tile requests between other work
-            if (lane == 0) atomicAdd(&P.cb->idleHelpers, 1);
+        if (!amIdle) {   // from here on this warp serves tile requests between other work
+            if (lane == 0) atomicAdd(cw >= 0 ? &P.cb->idleHelpers : &P.cb->idleWorkers, 1);
             amIdle = 1;
         }
-        if (tryRunOneItem(*wctx, wTask, &sawOpen, cw >= 0 ? &amIdle : nullptr)) { idle = 0; continue; }
+        if (tryRunOneItem(*wctx, wTask, &sawOpen, &amIdle)) { idle = 0; helpKey = -1; continue; }
         if (sawOpen) idle = 0;   // strips are about to become claimable: poll again soon
-        if (cw >= 0 && tryRunBig(*cctx, win, mini, &amIdle)) { idle = 0; helpKey = -1; continue; }
-        if (cw >= 0 && tryRunTileReq(*cctx, win, helpKey)) { idle = 0; continue; }
-        if (cw >= 0 && tryRunPass2(*cctx, win, mini, &amIdle)) { idle = 0; helpKey = -1; continue; }
+        if (cw >= 0 && tryRunBig(*cctx, win, mini, &amIdle)) { idle = 0; continue; }
+        // (three of four worker warps help only while no big grid is being filled; the worker context then holds
+        // the helped grid)
+        int fills = 0;
+        if (cw < 0 && (warp & 3) != 0) { if (lane == 0) fills = ldRelaxed(&P.cb->openTasks); fills = __shfl_sync(FULLMASK, fills, 0); }
+        if (fills == 0 && tryRunTileReq(*wctx, helpKey)) { idle = 0; wTask = -1; continue; }
+        if (cw >= 0 && tryRunPass2(*cctx, win, mini, &amIdle)) { idle = 0; continue; }
         int done = 0;
         if (lane == 0) done = ldRelaxed(&P.cb->jobsDone);
         done = __shfl_sync(FULLMASK, done, 0);
@@ -1967,7 +2005,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     const size_t maxBig = (size_t)MAXREC * nTasks + 64;
     const size_t offBig = offP2 + alignUp((nJobs + 1) * sizeof(P2Entry), 256);
     const size_t offTile = offBig + alignUp(maxBig * sizeof(int2), 256);
-    const size_t offState = offTile + alignUp((size_t)TILE_RING_CAP * sizeof(TileReq), 256);
+    const size_t offState = offTile + alignUp((size_t)TILE_QUEUES * TILE_RING_CAP * sizeof(TileReq), 256);
     const size_t offTok = offState + alignUp((nJobs + 1) * sizeof(JobState), 256);
     const size_t maxTokens = totalStrips + nTasks + 64;
     I.ringBytes = offTok + 2 * maxTokens * sizeof(int);
@@ -2182,8 +2220,8 @@ void Engine::fetch(std::vector<Job*>& jobs) {
         if (cudaMemcpyFromSymbol(dbg, gDbg, sizeof(dbg)) == cudaSuccess) {
             fprintf(stderr, "[ub200 dbg] worker items=%llu strip-cycles=%llu (rowProg wait %llu) segDone-wait=%llu cells=%llu (cumulative)\n", dbg[14], dbg[12], dbg[13], dbg[11], dbg[15]);
             fprintf(stderr, "[ub200 dbg] big pass-2 walks=%llu tiles=%llu tile-cycles=%llu walk-cycles=%llu (cumulative)\n", dbg[19], dbg[16], dbg[17], dbg[18]);
-            fprintf(stderr, "[ub200 dbg] tile requests posted=%llu claimed by helpers=%llu (post->claim %.1f us avg) stale pops=%llu (cumulative)\n", dbg[20], dbg[21], dbg[21] ? dbg[22] / 1e3 / dbg[21] : 0.0, dbg[23]);
-            fprintf(stderr, "[ub200 dbg] grids wider than 8000: tiles from helpers=%llu (wait cycles %llu) taken back=%llu never requested=%llu (cumulative)\n", dbg[8], dbg[9], dbg[10], dbg[11]);
+            fprintf(stderr, "[ub200 dbg] tile requests claimed by helpers=%llu (post->claim %.1f us avg) stale pops=%llu (cumulative)\n", dbg[21], dbg[21] ? dbg[22] / 1e3 / dbg[21] : 0.0, dbg[23]);
+            fprintf(stderr, "[ub200 dbg] helped walks: tiles from helpers=%llu taken back=%llu (cumulative)\n", dbg[8], dbg[10]);
             fprintf(stderr, "[ub200 dbg] unbanded trace strips=%llu total=%llu steps-cycles=%llu nsteps=%llu | banded strips=%llu total=%llu steps-cycles=%llu nsteps=%llu (cumulative)\n", dbg[3], dbg[0], dbg[1], dbg[2], dbg[7], dbg[4], dbg[5], dbg[6]);
         }
         long long maxSpine = 0, maxFinal = 0; size_t ws = 0, wf = 0;
@@ -2197,8 +2235,8 @@ void Engine::fetch(std::vector<Job*>& jobs) {
             const JobOut& jf = I.jobOut[wf];
             const int it = (int)jf.p2MaxItem;
             const GridDesc& gdd = ((const GridDesc*)I.hGrids)[I.jobsDev[wf].gridBegin + it / MAXREC];
-            fprintf(stderr, "[ub200 timeline] last job: spine resolved at %.2f ms, last pass-2 item started at %.2f ms, longest item %.2f ms (grid %d cand %d: %d x %d banded %d), items total %.2f ms\n",
-                    jf.tSpine / 1e6, jf.tP2Start / 1e6, jf.p2MaxNs / 1e6, it / MAXREC, it % MAXREC, gdd.nH, gdd.nV, (int)gdd.banded, jf.p2SumNs / 1e6);
+            fprintf(stderr, "[ub200 timeline] last job: spine resolved at %.2f ms, last pass-2 item started at %.2f ms, longest item %.2f ms (grid %d cand %d: %d x %d banded %d), items total %.2f ms; longest big walk: %lld cycles, %lld tiles, %lld record ints, %lld tile cycles; stream compaction started at %.2f ms (%lld records, %d ints kept)\n",
+                    jf.tSpine / 1e6, jf.tP2Start / 1e6, jf.p2MaxNs / 1e6, it / MAXREC, it % MAXREC, gdd.nH, gdd.nV, (int)gdd.banded, jf.p2SumNs / 1e6, jf.p2MaxStart, jf.p2MaxTiles & 0xffffffffLL, jf.p2MaxTiles >> 32, jf.p2MaxTileCycles, jf.tFin0 / 1e6, jf.finRecords, jf.outLen);
         }
         const long long* wp = I.jobOut[worst].prof;
         fprintf(stderr, "[ub200 profile] worst job %zu (%d grids): setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",

@@ -57,7 +57,7 @@ struct JobDev {
 struct JobOut {
     int status, score, outLen, pad;
     long long tSpine, tFinal;   // ns after kernel start: pass 1 resolved / job complete
-    long long tP2Start, p2MaxNs, p2MaxItem, p2SumNs;  // developer timeline: start of the last pass-2 item, longest item
+    long long tP2Start, p2MaxNs, p2MaxItem, p2SumNs, p2MaxTiles, p2MaxTileCycles, p2MaxStart, tFin0, finRecords;  // developer timeline: start of the last pass-2 item, longest item
     long long prof[12];  // cycles: setup+init, local fill, task wait, track, traceback, total; tiles, tile cycles,
                          // local-grid traceback cycles, tracebacks, local grids, local-grid track cycles
 };
@@ -120,7 +120,8 @@ struct GridRec {
     int state;        // 0: done in line by pass 1; 1: small grid (pass 2 fills the trace and walks all candidates);
                       // 2: big grid with a persistent block (pass 2 walks one candidate per item)
     int nCand, inserted, nPlantedIn;
-    int relMax, pad;  // grid maximum in the writing segment's score frame
+    int relMax;       // grid maximum in the writing segment's score frame
+    int published;    // 1: the big grid's candidates were handed to pass 2 by segment 0 right after its pass 1
     int cand[MAXREC];
     PlantedCell plantedIn[MAXREC];
 };
@@ -138,6 +139,8 @@ struct JobState {     // zeroed before every launch
     int segDelta[MAXSEG];      // score of its frame minus score of the frame it merged into, at the merge cell
     int segFailStatus[MAXSEG];
     int ownerSeg[MAXSEG + 1], ownerFrom[MAXSEG + 1];
+    int p2Done;       // pass-2 items finished (the big ones may start before the chain is resolved)
+    int p2Need;       // items that make the job complete (0 until the chain is resolved)
 };
 
 struct P2Entry {      // pass-2 board entry: one job whose pass 1 is complete
@@ -154,6 +157,17 @@ struct TaskDesc {
     int pad0, pad1, pad2;
 };
 
+// A traceback through a big grid asks idle control warps for the trace tiles it is about to enter (the tiles on
+// the three tile diagonals ahead of it).  One request = one 64 x 64 tile recomputed from the checkpoints into a
+// slot of the asking warp (global memory): [state | .. | int4 tile extent at +16 | 4096 trace bytes at +64].
+// state = tag * 4 + {0 posted, 1 claimed by a helper, 2 done, 3 cancelled}; the tag is the slot's generation.
+constexpr int TILE_QUEUES = 32;          // independent request rings (pops are compare-and-swap: spread the contention)
+constexpr int TILE_RING_CAP = 2048;      // entries per ring
+constexpr int TILE_SLOT_BYTES = 4096 + 64;
+constexpr int TILE_SLOTS = 32;          // one per lane of the asking warp
+constexpr int TILE_CANDS = 21;          // sample points ahead of the walk whose tiles are requested
+constexpr int TILE_HELP_MIN_EXTENT = 6000; // nH + nV of a grid whose tracebacks ask for help
+constexpr int TILE_HELPERS_PER_WALK = 6; // a walk consumes a tile in a third of the time a helper needs for three
 struct ControlBlock {  // zeroed before every launch; every group of counters has its own 128-byte line
     int jobQueue, jobsDone;
     unsigned long long t0;         // %globaltimer at kernel start (developer timeline)
@@ -165,23 +179,14 @@ struct ControlBlock {  // zeroed before every launch; every group of counters ha
     int p2Head, p2Tail;            // pass-2 board
     int bigHead, bigTail;          // pass-2 items of the big grids (served before everything else of pass 2)
     int pad3[28];
-    int tileHead, tileTail;        // tile-request ring (trace tiles recomputed ahead of a big-grid traceback)
-    int pad4[30];
+    struct TileQueue { int head, tail; int pad[30]; } tq[TILE_QUEUES];   // tile-request rings (one line each)
     int idleHelpers, activeWalkers; // control warps polling for work / walking a big grid (tiles are only asked for
                                     // while the idle ones outnumber the walkers several times)
-    int pad5[30];
+    int idleWorkers;                // worker warps polling for work: they serve tile requests only while no big grid
+    int openTasks;                  // is being filled (openTasks == 0), the fills being the critical path of pass 1
+    int pad5[28];
 };
 
-// A traceback through a big grid asks idle control warps for the trace tiles it is about to enter (the tiles on
-// the three tile diagonals ahead of it).  One request = one 64 x 64 tile recomputed from the checkpoints into a
-// slot of the asking warp (global memory): [state | .. | int4 tile extent at +16 | 4096 trace bytes at +64].
-// state = tag * 4 + {0 posted, 1 claimed by a helper, 2 done, 3 cancelled}; the tag is the slot's generation.
-constexpr int TILE_RING_CAP = 32768;
-constexpr int TILE_SLOT_BYTES = 4096 + 64;
-constexpr int TILE_SLOTS = 32;          // one per lane of the asking warp
-constexpr int TILE_CANDS = 30;          // sample points ahead of the walk whose tiles are requested
-constexpr int TILE_HELP_MIN_EXTENT = 6000; // nH + nV of a grid whose tracebacks ask for help
-constexpr int TILE_HELPERS_PER_WALK = 6; // a walk consumes a tile in a third of the time a helper needs for three
 struct TileReq {
     int seq;        // 2 * turn: free, 2 * turn + 1: written (turn = ring position / TILE_RING_CAP)
     int job, gi;
@@ -209,7 +214,7 @@ struct KParams {
     int* tokRing;      // [2][maxTokens] task id + 1 of a task with a claimable strip
     int maxTokens, pad7;
     P2Entry* p2ring;   // [nJobs]
-    int2* bigRing;     // [maxBig] (pass-2 board entry + 1, item) of one candidate of a big grid
+    int2* bigRing;     // [maxBig] (job + 1, item) of one candidate of a big grid
     int maxBig, pad9;
     TileReq* tileRing; // [TILE_RING_CAP]
     uint8_t* tileSlots; // [control warps][TILE_SLOTS][TILE_SLOT_BYTES]
@@ -228,6 +233,12 @@ struct KParams {
 // local-memory stack of every warp).
 __constant__ KParams cP;
 __device__ unsigned long long gDbg[24];   // developer counters (cycles), lane 0 of control warps
+
+__device__ __forceinline__ uint32_t ldsU8(uint32_t sharedAddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sharedAddr) : "memory");
+    return v;
+}
 
 // All per-warp working state (GridCtx slots, windows, staged codes) lives in the kernel's dynamic shared
 // memory.  Out-of-line functions receive generic pointers to it; toShared() rebases such a pointer on the
@@ -785,14 +796,11 @@ __device__ __noinline__ TileFetch fetchTileFn(const GridCtx& Gin, uint8_t* win, 
         int v = 0;
         if (lane == 0) {
             int* st = reinterpret_cast<int*>(slot);
-            const long long w0 = clock64();
             v = atomicCAS(st, tag * 4, tag * 4 + 3);          // not claimed yet: take it back
             if (v == tag * 4 + 1) { while ((v = ldRelaxed(st)) != tag * 4 + 2) __nanosleep(64); }
             __threadfence();
-            if (g.nH > 8000) {
-            if (v == tag * 4 + 2) { atomicAdd(&gDbg[8], 1ull); atomicAdd(&gDbg[9], (unsigned long long)(clock64() - w0)); }
+            if (v == tag * 4 + 2) atomicAdd(&gDbg[8], 1ull);
             else atomicAdd(&gDbg[10], 1ull);
-            }
         }
         v = __shfl_sync(FULLMASK, v, 0);
         if (v == tag * 4 + 2) {
@@ -807,7 +815,6 @@ __device__ __noinline__ TileFetch fetchTileFn(const GridCtx& Gin, uint8_t* win, 
         __syncwarp();
     }
     if (!have) r.t = computeTileFn(Gin, win, i, j);
-    if (!match && lane == 0 && g.nH > 8000) atomicAdd(&gDbg[11], 1ull);
     // slots of tiles the (monotone) path has left behind are recycled
     if (myTile >= 0 && ((myTile >> 16) > b || (myTile & 0xffff) > cbk)) {
         if (releaseTileSlot(slots, lane, myTag, false)) myTile = -1;
@@ -815,8 +822,8 @@ __device__ __noinline__ TileFetch fetchTileFn(const GridCtx& Gin, uint8_t* win, 
     // ask for the tiles ahead while idle control warps exist and the ring has room
     int go = 0;
     if (lane == 0)
-        go = ldRelaxed(&P.cb->idleHelpers) >= TILE_HELPERS_PER_WALK * ldRelaxed(&P.cb->activeWalkers) &&
-             ldRelaxed(&P.cb->tileTail) - ldRelaxed(&P.cb->tileHead) < 4096;
+        go = ldRelaxed(&P.cb->idleHelpers) + (ldRelaxed(&P.cb->openTasks) == 0 ? ldRelaxed(&P.cb->idleWorkers) : ldRelaxed(&P.cb->idleWorkers) / 4) >=
+             TILE_HELPERS_PER_WALK * ldRelaxed(&P.cb->activeWalkers);
     go = __shfl_sync(FULLMASK, go, 0);
     if (go) {
         // the path is extrapolated along the direction of its last two tile entries (hist); lane = sample point
@@ -852,19 +859,18 @@ __device__ __noinline__ TileFetch fetchTileFn(const GridCtx& Gin, uint8_t* win, 
             const int tag = __shfl_sync(FULLMASK, myTag, s);
             if (lane == c) { pushSlot = s; pushTag = tag; }
         }
-        const unsigned pushM = __ballot_sync(FULLMASK, pushSlot >= 0);
-        if (pushM) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&P.cb->tileTail, __popc(pushM));
-            base = __shfl_sync(FULLMASK, base, 0);
-            __syncwarp();
-            if (pushSlot >= 0) {
-                const int pos = base + __popc(pushM & ((1u << lane) - 1u));
-                TileReq* e = &P.tileRing[pos & (TILE_RING_CAP - 1)];
+        __syncwarp();
+        if (pushSlot >= 0) {
+            // one request per ring, starting at a ring that rotates with the tile: helpers pop by compare-and-swap
+            const int q = (id + pushSlot * 5 + (int)blockIdx.x) & (TILE_QUEUES - 1);
+            ControlBlock::TileQueue* tq = &P.cb->tq[q];
+            {
+                // (the rings hold far more than the 32 requests a walk can have outstanding: the entry is free)
+                const int pos = atomicAdd(&tq->tail, 1);
+                TileReq* e = &P.tileRing[(size_t)q * TILE_RING_CAP + (pos & (TILE_RING_CAP - 1))];
                 const int turn = pos / TILE_RING_CAP;
                 while (ldRelaxed(&e->seq) != 2 * turn) __nanosleep(64);
                 e->job = job; e->gi = gi; e->tile = cand; e->expect = pushTag * 4; e->pad = (int)(unsigned)globalTimerNs();
-                atomicAdd(&gDbg[20], 1ull);
                 e->slot = (unsigned long long)(slots + (size_t)pushSlot * TILE_SLOT_BYTES);
                 __threadfence();
                 stRelease(&e->seq, 2 * turn + 1);
@@ -918,6 +924,7 @@ struct TraceWalkerT {
     OutStream& out;
     const uint8_t* __restrict__ win;     // shared-memory trace window of this control warp
     uint8_t* winW;
+    uint32_t winS;                       // the window's 32-bit shared-space address
     // register copies of the hot GridCtx fields (G lives in shared memory)
     const GridGeom g;
     const int local, rrMul, rr, rrs, pitch, localJhi, affine;
@@ -937,7 +944,7 @@ struct TraceWalkerT {
     int4 hHist;       // entry points (row, column) of the last two tiles: the direction the path is heading
 
     __device__ __forceinline__ TraceWalkerT(const GridCtx& g, OutStream& o, uint8_t* w)
-        : G(g), out(o), win(toShared(w)), winW(w), g(g.g), local(g.local), rrMul(g.rrMul), rr(g.RR), rrs(g.rrs), pitch(g.pitch), localJhi(g.localJhi),
+        : G(g), out(o), win(toShared(w)), winW(w), winS((uint32_t)__cvta_generic_to_shared(w)), g(g.g), local(g.local), rrMul(g.rrMul), rr(g.RR), rrs(g.rrs), pitch(g.pitch), localJhi(g.localJhi),
           affine(g.affine), lazy(false), outOfBox(false), tS(-1), tC0(0), tMaxRow(-1), tMaxCol(-1), pc(0), pv(0), nSegs(0), emitOn(true),
           bad(false), tilesComputed(0), tileCycles(0), hSlots(nullptr), hJob(0), hGi(0), myTile(-1), myTag(0), hHist(make_int4(-1, -1, -1, -1)) {}
 
@@ -975,6 +982,13 @@ struct TraceWalkerT {
     }
 
     __device__ __forceinline__ uint32_t tvHere() {
+        if constexpr (TILEONLY) {
+            // unbanded task grid (storage = matrix coordinates): a cell of the current tile is one LDS away
+            if (!g.banded && tS >= 0) {
+                const unsigned ri = (unsigned)(pv - 1 - tS * CKR), cj = (unsigned)(pc - tC0);
+                if (ri < (unsigned)(tMaxRow - tS * CKR) && cj <= (unsigned)(tMaxCol - tC0)) return ldsU8(winS + cj * CKR + ri);
+            }
+        }
         const int i = pv - storageOffset(g, pc);
         const int j = pc;
         if (i <= 0 || j <= 0 || i > g.nV || j > g.nH) return 0;
@@ -996,8 +1010,7 @@ struct TraceWalkerT {
             if (j < stripJlo(g, b, CKR) || j > stripJhi(g, b, CKR)) return 0;
             computeTile(i, j);
         }
-        const int rem = (i - 1) - b * CKR;
-        return win[((j - tC0) * 32 + (rem >> 1)) * 2 + (rem & 1)];
+        return ldsU8(winS + (uint32_t)((j - tC0) * CKR + (i - 1) - b * CKR));
     }
     __device__ __forceinline__ Coord makeCoord(int endCol, int endRow) const {  // dp_traceback_impl.h:121-141
         Coord c;
@@ -1035,14 +1048,21 @@ struct TraceWalkerT {
             if (!(last & T_D)) { record(c.currCol, c.currRow, frag, last); last = T_D; frag = 0; }
             // run of diagonal steps (identical to re-entering this branch once per step)
             if (TILEONLY && !g.banded) {
-                // unbanded task grid: storage = matrix coordinates; the bytes of the current 64 x 64 tile are read
-                // straight from the window while the run stays inside it
+                // unbanded task grid: storage = matrix coordinates.  While the run stays inside the current 64 x 64
+                // tile its bytes are read straight from the window: one LDS + test per cell.
                 do {
-                    --pc; --pv;
-                    const int ri = pv - 1 - tS * CKR;
-                    if (ri >= 0 && pv <= tMaxRow && pc >= tC0 && pc <= tMaxCol) tv = win[(pc - tC0) * CKR + ri];
-                    else tv = tvHere();
-                    --c.currCol; --c.currRow; ++frag;
+                    const int nT = imin(pv - 1 - tS * CKR, pc - tC0);
+                    if (tS >= 0 && nT > 0 && pv - 1 <= tMaxRow && pc - 1 <= tMaxCol) {
+                        const int n = imin(nT, imin(c.currCol - c.endCol, c.currRow - c.endRow));
+                        uint32_t a = winS + (uint32_t)((pc - tC0) * CKR + (pv - 1 - tS * CKR));
+                        int k = 0;
+                        do { a -= CKR + 1; tv = ldsU8(a); ++k; } while ((tv & T_D) && k < n);
+                        pc -= k; pv -= k; c.currCol -= k; c.currRow -= k; frag += k;
+                    } else {
+                        --pc; --pv;
+                        tv = tvHere();
+                        --c.currCol; --c.currRow; ++frag;
+                    }
                 } while ((tv & T_D) && !c.reachedEnd());
             } else {
                 do { moveD(c); tv = tvHere(); --c.currCol; --c.currRow; ++frag; } while ((tv & T_D) && !c.reachedEnd());
@@ -1069,6 +1089,60 @@ struct TraceWalkerT {
             if (tv != T_NONE) { bad = true; tv = T_NONE; }
         }
     }
+    __device__ __forceinline__ bool flatWalk() const { return TILEONLY && !g.banded; }
+    // The loop `while (!c.reachedEnd() && tv != T_NONE) doTraceback(tv, last, frag, c)` for an unbanded task grid
+    // (storage = matrix coordinates, c.currCol == pc, c.currRow == pv) as a flat state machine: every iteration is
+    // one move and one trace-byte read, with a single read site (one LDS while the path stays inside the tile).
+    // Same decisions, in the same order, as doTraceback (dp_traceback_impl.h:335-431).
+    __device__ __forceinline__ void walkFlat(uint32_t& tvIO, uint32_t& lastIO, int& fragIO, Coord& c) {
+        enum { ST_DISPATCH = 0, ST_DRUN, ST_VRUN, ST_HRUN, ST_ONE };
+        const bool aff = affine;
+        const int endCol = c.endCol, endRow = c.endRow;
+        int col = pc, row = pv, frag = fragIO;
+        uint32_t tv = tvIO, last = lastIO;
+        int tRowLo = tS * CKR, tRows = tMaxRow - tS * CKR, tCols = tMaxCol - tC0 + 1;
+        if (tS < 0) { tRows = 0; tCols = 0; }
+        int state = ST_DISPATCH;
+        for (;;) {
+            int dr = 0, dc = 0;
+            if (state == ST_DISPATCH) {
+                if (col <= endCol || row <= endRow || tv == T_NONE) break;
+                uint32_t dir;
+                if (tv & T_D) { dir = T_D; state = ST_DRUN; }
+                else if ((tv & T_MV) && (tv & T_V)) { dir = T_V; state = aff ? ST_VRUN : ST_ONE; dr = 1; }
+                else if ((tv & T_MV) && (tv & T_VO)) { dir = T_V; state = ST_ONE; dr = 1; }
+                else if ((tv & T_MH) && (tv & T_H)) { dir = T_H; state = aff ? ST_HRUN : ST_ONE; dc = 1; }
+                else if ((tv & T_MH) && (tv & T_HO)) { dir = T_H; state = ST_ONE; dc = 1; }
+                else { bad = true; tv = T_NONE; break; }
+                if (!(last & dir)) { record(col, row, frag, last); last = dir; frag = 0; }
+            }
+            if (state == ST_DRUN) { dr = 1; dc = 1; }
+            else if (state == ST_VRUN) {
+                dr = 1; dc = 0;
+                // while ((!(tv & T_VO) || (tv & T_V)) && row != 1) step;  then one more step
+                if (!((!(tv & T_VO) || (tv & T_V)) && row != 1)) state = ST_ONE;
+            } else if (state == ST_HRUN) {
+                dr = 0; dc = 1;
+                if (!((!(tv & T_HO) || (tv & T_H)) && col != 1)) state = ST_ONE;
+            }
+            row -= dr; col -= dc; ++frag;
+            {   // the trace byte of (row, col)
+                const unsigned ri = (unsigned)(row - 1 - tRowLo), cj = (unsigned)(col - tC0);
+                if (ri < (unsigned)tRows && cj < (unsigned)tCols) {
+                    tv = ldsU8(winS + cj * CKR + ri);
+                } else {
+                    pc = col; pv = row;
+                    tv = tvHere();
+                    tRowLo = tS * CKR; tRows = tMaxRow - tS * CKR; tCols = tMaxCol - tC0 + 1;
+                    if (tS < 0) { tRows = 0; tCols = 0; }
+                }
+            }
+            if (state == ST_ONE) state = ST_DISPATCH;
+            else if (state == ST_DRUN) { if (!((tv & T_D) && col > endCol && row > endRow)) state = ST_DISPATCH; }
+        }
+        pc = col; pv = row; c.currCol = col; c.currRow = row;
+        tvIO = tv; lastIO = last; fragIO = frag;
+    }
     __device__ static uint32_t initialDirection(uint32_t& tv, bool prefer) {  // dp_traceback_impl.h:433-461
         if (prefer) {
             if (tv & T_MV) { tv &= (T_V | T_VO | T_MV); return T_V; }
@@ -1092,7 +1166,8 @@ struct TraceWalkerT {
             if (c.currCol != nH) record(c.currCol, c.currRow, nH - c.currCol, T_H);
         }
         int frag = 0;
-        while (!c.reachedEnd() && tv != T_NONE) doTraceback(tv, last, frag, c);
+        if (TILEONLY && !g.banded) walkFlat(tv, last, frag, c);
+        else while (!c.reachedEnd() && tv != T_NONE) doTraceback(tv, last, frag, c);
         record(c.currCol, c.currRow, frag, last);
         if (head) {
             if (c.currRow != 0) record(0, 0, c.currRow, T_V);
