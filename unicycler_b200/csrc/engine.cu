@@ -563,6 +563,15 @@ __device__ __forceinline__ int recordBound(const GridCtx& G, int nTraces) {
 // cursor live in registers of this function).  rec == nullptr: pass-1 in-line grid (plants the next grid's
 // cells); otherwise the pass-2 replay of a recorded grid.
 // candSel >= 0 (pass 2 of a big grid): only that candidate, as a record of its own.
+// The finished record goes into the job's record index (finalizeJob compacts the stream from it).  Lane 0.
+__device__ __forceinline__ void commitRecord(int jobIdx, int pos, int used, int gi, int segTag) {
+    const KParams& P = cP;
+    JobState* js = &P.jobState[jobIdx];
+    const int k = atomicAdd(&js->nRecIdx, 1);
+    if (k < P.jobs[jobIdx].recIdxCap) __stcg(&P.recIdx[P.jobs[jobIdx].recIdxBase + k], make_int4(pos, used, gi, segTag));
+    else atomicMax(&js->status, JOB_OUT_OVERFLOW);   // (cannot happen with the host's bound; rerun with a larger stream)
+}
+
 __device__ __noinline__ TbResult tracebackGrid(const GridCtx& Gin, uint8_t* win, int jobIdx, int* outBuf, int outCap, int gi,
                                                int h0, int v0, int nCand, DCell maxCell, const GridRec* rec, int candSel,
                                                int segTag) {
@@ -614,6 +623,7 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& Gin, uint8_t* win,
     out.patch(cntPos, nTraces);
     out.patch(cntPos + 2, out.len - pos);
     if (out.overflow && status == JOB_OK) status = JOB_OUT_OVERFLOW;
+    if (lane == 0 && !out.overflow) commitRecord(jobIdx, pos, out.len - pos, gi, segTag);
     __syncwarp();
     r.status = status; r.nPlanted = nPlanted;
     r.tiles = w.tilesComputed; r.tileCycles = w.tileCycles;
@@ -652,6 +662,7 @@ __device__ __noinline__ TbResult tracebackBigCand(const GridCtx& Gin, uint8_t* w
     out.patch(cntPos, nTraces);
     out.patch(cntPos + 2, out.len - pos);
     if (out.overflow && status == JOB_OK) status = JOB_OUT_OVERFLOW;
+    if (lane == 0 && !out.overflow) commitRecord(jobIdx, pos, out.len - pos, gi, segTag);
     __syncwarp();
     r.status = status; r.nPlanted = nPlanted;
     r.tiles = w.tilesComputed; r.tileCycles = w.tileCycles;
@@ -1098,76 +1109,85 @@ __device__ __noinline__ void finalizeJob(int jobIdx) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     __threadfence();
-    const int end = ldRelaxed(&P.jobState[jobIdx].outCursor);
+    const JobDev& jd = P.jobs[jobIdx];
+    const JobState* js = &P.jobState[jobIdx];
+    const int end = ldRelaxed(&js->outCursor);
     if (lane == 0) P.jobOut[jobIdx].tFin0 = (long long)(globalTimerNs() - P.cb->t0);
-    long long nRecords = 0;
-    int* buf = P.out + P.jobs[jobIdx].outOff;
-    const int cap = P.jobs[jobIdx].outCap;
-    const int st2 = ldRelaxed(&P.jobState[jobIdx].status);
+    const int* buf = P.out + jd.outOff;
+    int* dstBuf = P.out2 + jd.outOff;
+    const int cap = jd.outCap;
+    const int st2 = ldRelaxed(&js->status);
     int st = __ldcg(&P.jobOut[jobIdx].status);
     if (st == JOB_OK && st2 != JOB_OK) st = st2;
     int dst = 0;
+    const int nRec = min(ldRelaxed(&js->nRecIdx), jd.recIdxCap);
     if (st == JOB_OK && end <= cap) {
         // the resolved chain (which segment owns which grids), one entry per lane
-        const JobState* js = &P.jobState[jobIdx];
         const int nOwner = __ldcg(&js->nOwner);
         const int oSeg = (lane <= MAXSEG) ? __ldcg(&js->ownerSeg[lane]) : 0;
         const int oFrom = (lane <= MAXSEG) ? __ldcg(&js->ownerFrom[lane]) : 0;
-        int src = 0;
-        while (src < end && st == JOB_OK) {
-            // headers of up to 32 records (one dependent load each); lane r remembers record r of the batch
-            int mySrc = 0, myUsed = 0, n = 0;
-            while (n < 32 && src < end) {
-                const int hdr = (lane < 8 && src + lane < end) ? __ldcg(&buf[src + lane]) : 0;
-                const int gi = __shfl_sync(FULLMASK, hdr, 0);
-                const int reserved = __shfl_sync(FULLMASK, hdr, 2), used = __shfl_sync(FULLMASK, hdr, 3);
-                const int tag = __shfl_sync(FULLMASK, hdr, 5);
-                if (reserved < 6 || used < 6 || used > reserved) { st = JOB_REF_UB; break; }  // a record was never completed
-                // records written by a speculative segment outside the range it finally owns are dropped
-                const unsigned m = __ballot_sync(FULLMASK, lane < nOwner && (lane == 0 || gi >= oFrom));
-                const int owner = __shfl_sync(FULLMASK, oSeg, m ? 31 - __clz((int)m) : 0);
-                if (owner == tag) {
-                    if (lane == n) { mySrc = src; myUsed = used; }
-                    ++n;
-                }
-                ++nRecords;
-                src += reserved;
+        const int4* idx = P.recIdx + jd.recIdxBase;
+        for (int r0 = 0; r0 < nRec; r0 += 32) {
+            // one record per lane: (position, ints used, grid, segment tag)
+            int4 e = make_int4(0, 0, 0, -1);
+            if (r0 + lane < nRec) e = __ldcg(&idx[r0 + lane]);
+            // records written by a speculative segment outside the range it finally owns are dropped
+            int owner = __shfl_sync(FULLMASK, oSeg, 0);
+            for (int t = 1; t < nOwner; ++t) {
+                const int f = __shfl_sync(FULLMASK, oFrom, t), sg = __shfl_sync(FULLMASK, oSeg, t);
+                if (e.z >= f) owner = sg;
             }
-            if (st != JOB_OK) break;
-            for (int r = 0; r < n; ++r) {
-                const int s0 = __shfl_sync(FULLMASK, mySrc, r), used = __shfl_sync(FULLMASK, myUsed, r);
-                if (dst != s0) {
-                    // moved towards the front (dst < src) in chunks of 256 ints: all loads of a chunk are in flight
-                    // together and complete before its first store (the regions may overlap)
-                    for (int k = 0; k < used; k += 256) {
-                        int v[8];
+            bool keep = (r0 + lane < nRec) && owner == e.w;
+            if (keep && (e.y < 6 || e.x < 0 || e.x + e.y > end)) { keep = false; st = JOB_REF_UB; }
+            const int used = keep ? e.y : 0;
+            int incl = used;
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int q = k + u * 32 + lane;
-                            v[u] = (q < used) ? __ldcg(&buf[s0 + q]) : 0;
-                        }
-                        __syncwarp();
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(FULLMASK, incl, d);
+                if (lane >= d) incl += y;
+            }
+            const int myDst = dst + incl - used;
+            // short records: every lane copies its own; long ones: the whole warp, one record after the other
+            if (keep && used <= 96) {
+                for (int q0 = 0; q0 < used; q0 += 8) {   // eight loads in flight per lane
+                    int v[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int q = k + u * 32 + lane;
-                            if (q < used) buf[dst + q] = v[u];
-                        }
-                        __syncwarp();
+                    for (int w = 0; w < 8; ++w) v[w] = (q0 + w < used) ? __ldcg(&buf[e.x + q0 + w]) : 0;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w)
+                        if (q0 + w < used) dstBuf[myDst + q0 + w] = (q0 + w == 2) ? used : v[w];
+                }
+            }
+            unsigned longM = __ballot_sync(FULLMASK, keep && used > 96);
+            while (longM) {
+                const int r = __ffs(longM) - 1;
+                longM &= longM - 1;
+                const int s0 = __shfl_sync(FULLMASK, e.x, r), u = __shfl_sync(FULLMASK, used, r), d0 = __shfl_sync(FULLMASK, myDst, r);
+                for (int k = 0; k < u; k += 256) {
+                    int v[8];
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        const int q = k + w * 32 + lane;
+                        v[w] = (q < u) ? __ldcg(&buf[s0 + q]) : 0;
+                    }
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        const int q = k + w * 32 + lane;
+                        if (q < u) dstBuf[d0 + q] = (q == 2) ? u : v[w];
                     }
                 }
-                __syncwarp();
-                if (lane == 0) buf[dst + 2] = used;
-                dst += used;
             }
+            dst += __shfl_sync(FULLMASK, incl, 31);
         }
+        st = __reduce_max_sync(FULLMASK, st);   // (statuses are non-negative; JOB_OK == 0)
     }
     __syncwarp();
     if (lane == 0) {
         JobOut* jo = &P.jobOut[jobIdx];
         jo->status = st;
-        jo->outLen = dst;
+        jo->outLen = (st == JOB_OK) ? dst : 0;
         jo->tFinal = (long long)(globalTimerNs() - P.cb->t0);
-        jo->finRecords = nRecords;
+        jo->finRecords = nRec;
         __threadfence();
         atomicAdd(&P.cb->jobsDone, 1);
     }
@@ -1724,6 +1744,8 @@ struct Engine::Impl {
     void* dGrids = nullptr; size_t capGrids = 0;
     void* dSeq = nullptr; size_t capSeq = 0;
     void* dOut = nullptr; size_t capOut = 0;
+    void* dOut2 = nullptr; size_t capOut2 = 0;     // compacted segment streams (copied back)
+    void* dRecIdx = nullptr; size_t capRecIdx = 0; // record index of every job
     void* dJobOut = nullptr; size_t capJobOut = 0;
     void* dOrder = nullptr; size_t capOrder = 0;
     void* dColTab = nullptr; size_t capColTab = 0;
@@ -1789,7 +1811,7 @@ Engine::Engine(int device) : impl_(new Impl) {
 Engine::~Engine() {
     if (!impl_) return;
     cudaSetDevice(impl_->device);
-    cudaFree(impl_->dJobs); cudaFree(impl_->dGrids); cudaFree(impl_->dSeq); cudaFree(impl_->dOut);
+    cudaFree(impl_->dJobs); cudaFree(impl_->dGrids); cudaFree(impl_->dSeq); cudaFree(impl_->dOut); cudaFree(impl_->dOut2); cudaFree(impl_->dRecIdx);
     cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dScratch); cudaFree(impl_->dRing); cudaFree(impl_->dRecs); cudaFree(impl_->dMini); cudaFree(impl_->dPersist); cudaFree(impl_->dTileSlots);
     cudaFreeHost(impl_->hSeq); cudaFreeHost(impl_->hOut); cudaFreeHost(impl_->hGrids); cudaFreeHost(impl_->hColTab);
     for (auto& ev : impl_->ev) cudaEventDestroy(ev);
@@ -2023,7 +2045,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     for (size_t k = 0; k < nJobs; ++k) jobOrder[k] = (int)k;
     std::stable_sort(jobOrder.begin(), jobOrder.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     const bool noSplit = getenv("UNICYCLER_B200_NO_SPLIT") != nullptr;
-    size_t nRecs = 0;
+    size_t nRecs = 0, nRecIdx = 0;
     // every work-list entry must get a control warp at kernel start (a segment waits for the ones after it), so
     // extra segments are only handed out while warps with an arena remain; longest chains first
     long long extraBudget = std::min<long long>((long long)NCTRL * I.numSMs, std::max<long long>(byMem, 0)) - (long long)nJobs;
@@ -2067,6 +2089,12 @@ void Engine::upload(std::vector<Job*>& jobs) {
         d.pad2 = 0;
         d.recBase = (long long)nRecs;
         nRecs += (size_t)nSeg * (size_t)n;
+        // record index: one record per (segment, grid) of pass 1, per small grid of pass 2, per candidate of a big grid
+        d.recIdxBase = (long long)nRecIdx;
+        d.recIdxCap = (int)std::min<long long>(((long long)(nSeg + 1) * n + (long long)MAXREC * (long long)agg[k].tasks + 8) *
+                                               std::max(1, j.outScale), 1LL << 28);
+        d.pad3 = 0;
+        nRecIdx += (size_t)d.recIdxCap;
     }
     I.order.clear();
     for (int jk : jobOrder)
@@ -2086,6 +2114,8 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.growDev(I.dScratch, I.capScratch, (size_t)L.total * nSlots);
     I.growDev(I.dRing, I.capRing, I.ringBytes);
     I.growDev(I.dRecs, I.capRecs, (nRecs + 1) * sizeof(GridRec));
+    I.growDev(I.dRecIdx, I.capRecIdx, (nRecIdx + 1) * sizeof(int4));
+    I.growDev(I.dOut2, I.capOut2, I.outInts * sizeof(int) + 64);
     I.growDev(I.dMini, I.capMini, miniStride * (size_t)NCTRL * I.numSMs);
     if (usePersist) I.growDev(I.dPersist, I.capPersist, (size_t)persistTotal + 256);
     if (usePersist) I.growDev(I.dTileSlots, I.capTileSlots, (size_t)NCTRL * I.numSMs * TILE_SLOTS * TILE_SLOT_BYTES);
@@ -2101,7 +2131,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     CUDA_CHECK(cudaEventRecord(I.ev[1], I.stream));
     KParams& kp = I.kp;
     kp.jobs = (const JobDev*)I.dJobs; kp.grids = (const GridDesc*)I.dGrids; kp.seq = (const uint8_t*)I.dSeq;
-    kp.out = (int*)I.dOut; kp.jobOut = (JobOut*)I.dJobOut; kp.order = (const int*)I.dOrder;
+    kp.out = (int*)I.dOut; kp.out2 = (int*)I.dOut2; kp.recIdx = (int4*)I.dRecIdx; kp.jobOut = (JobOut*)I.dJobOut; kp.order = (const int*)I.dOrder;
     kp.colTabPool = (const ColInfo*)I.dColTab;
     kp.nJobs = (int)nJobs; kp.nSlots = nSlots; kp.maxTasks = (int)nTasks + 1;
     kp.nEntries = (int)nEntries; kp.pad6 = 0;
@@ -2191,13 +2221,13 @@ void Engine::fetch(std::vector<Job*>& jobs) {
     }
     if (nJobs > 64 && (end <= 4 * used || nJobs > 4096)) {
         // many small jobs: one copy of everything up to the last used int beats one copy per job
-        if (end > 0) CUDA_CHECK(cudaMemcpyAsync(hOut, I.dOut, end * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+        if (end > 0) CUDA_CHECK(cudaMemcpyAsync(hOut, I.dOut2, end * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
     } else {
         for (size_t k = 0; k < nJobs; ++k) {
             const JobDev& d = I.jobsDev[k];
             int len = std::min(I.jobOut[k].outLen, d.outCap);
             if (len > 0)
-                CUDA_CHECK(cudaMemcpyAsync(hOut + d.outOff, (int*)I.dOut + d.outOff, (size_t)len * sizeof(int),
+                CUDA_CHECK(cudaMemcpyAsync(hOut + d.outOff, (int*)I.dOut2 + d.outOff, (size_t)len * sizeof(int),
                                            cudaMemcpyDeviceToHost, I.stream));
         }
     }

@@ -52,6 +52,8 @@ struct JobDev {
     int segStart[MAXSEG + 1];  // first grid of every segment; segStart[nSeg] = gridCount
     int pad2;
     long long recBase;         // GridRec index of (segment 0, grid 0); record of (p, k) = recBase + p * gridCount + k
+    long long recIdxBase;      // this job's slice of the record index (KParams::recIdx)
+    int recIdxCap, pad3;
 };
 
 struct JobOut {
@@ -139,6 +141,7 @@ struct JobState {     // zeroed before every launch
     int segDelta[MAXSEG];      // score of its frame minus score of the frame it merged into, at the merge cell
     int segFailStatus[MAXSEG];
     int ownerSeg[MAXSEG + 1], ownerFrom[MAXSEG + 1];
+    int nRecIdx;      // records committed to the job's record index
     int p2Done;       // pass-2 items finished (the big ones may start before the chain is resolved)
     int p2Need;       // items that make the job complete (0 until the chain is resolved)
 };
@@ -200,7 +203,9 @@ struct KParams {
     const JobDev* jobs;
     const GridDesc* grids;
     const uint8_t* seq;
-    int* out;
+    int* out;          // segment streams as written: records reserved at their worst-case size, by many warps
+    int* out2;         // the same streams compacted by finalizeJob (what the host copies)
+    int4* recIdx;      // (position, ints used, grid, segment tag) of every completed record, per job
     JobOut* jobOut;
     const int* order;  // pass-1 work list: jobIdx * MAXSEG + segment, longest chains first
     int nEntries, pad6;
