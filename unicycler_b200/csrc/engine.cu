@@ -2049,6 +2049,26 @@ void Engine::upload(std::vector<Job*>& jobs) {
     // every work-list entry must get a control warp at kernel start (a segment waits for the ones after it), so
     // extra segments are only handed out while warps with an arena remain; longest chains first
     long long extraBudget = std::min<long long>((long long)NCTRL * I.numSMs, std::max<long long>(byMem, 0)) - (long long)nJobs;
+    // latency model of the serial spine (cycles): ~100 k per small grid; a big rectangle is filled as a pipeline of
+    // strips, (columns/32 + 2 x strips) chunks of ~16 k cycles
+    auto gridLatency = [&](const GridDesc& gd) {
+        GridGeom gg = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
+        if (localPlan(gg).local) return 100e3;
+        return ((double)gd.nH / 32.0 + 2.0 * stripCount(gg, SH)) * 16e3 + 200e3;
+    };
+    // up to 8 segments per chain; up to MAXSEG when that leaves most control warps free (few, long chains)
+    int segCap = 8;
+    if (!noSplit) {
+        long long wanted8 = 0;
+        for (size_t k = 0; k < nJobs; ++k) {
+            const Job& j = *jobs[k];
+            if (!j.complete || j.grids.size() < 16) continue;
+            double total = 0;
+            for (const GridDesc& gd : j.grids) total += gridLatency(gd);
+            wanted8 += std::max<long long>(0, std::min<long long>(8, (long long)(total / 4e6 + 0.5)) - 1);
+        }
+        if (2 * wanted8 <= extraBudget) segCap = MAXSEG;
+    }
     for (int jk : jobOrder) {
         const size_t k = (size_t)jk;
         Job& j = *jobs[k];
@@ -2057,19 +2077,13 @@ void Engine::upload(std::vector<Job*>& jobs) {
         int nSeg = 1;
         d.segStart[0] = 0;
         if (!noSplit && j.complete && n >= 16 && extraBudget > 0) {
-            // latency model of the serial spine (cycles): ~100 k per small grid; a big rectangle is filled as a
-            // pipeline of strips, (columns/32 + 2 x strips) chunks of ~16 k cycles
             std::vector<double> gc((size_t)n);
             double total = 0;
             for (int g = 0; g < n; ++g) {
-                const GridDesc& gd = j.grids[(size_t)g];
-                GridGeom gg = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
-                double c = 100e3;
-                if (!localPlan(gg).local) c = ((double)gd.nH / 32.0 + 2.0 * stripCount(gg, SH)) * 16e3 + 200e3;
-                gc[(size_t)g] = c;
-                total += c;
+                gc[(size_t)g] = gridLatency(j.grids[(size_t)g]);
+                total += gc[(size_t)g];
             }
-            const int want = (int)std::min<long long>(std::min<long long>(MAXSEG, (long long)(total / 4e6 + 0.5)), extraBudget + 1);
+            const int want = (int)std::min<long long>(std::min<long long>(segCap, (long long)(total / 4e6 + 0.5)), extraBudget + 1);
             double acc = 0;
             int nextP = 1;
             for (int g = 1; g < n - 1 && nextP < want; ++g) {

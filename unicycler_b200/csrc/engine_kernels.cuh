@@ -31,7 +31,7 @@ constexpr int MODE_TASK = 0;             // score-only strip item of a published
 constexpr int MODE_TRACE = 1;            // full trace bytes into the shared-memory window
 constexpr int MODE_TRACEG = 3;           // the same into global memory (a tile recomputed for another warp)
 constexpr int MODE_FAST = 2;             // score-only local fill, box cells (S,H,V) into the shared-memory window
-constexpr int MAXSEG = 8;                // speculative segments of one seed chain
+constexpr int MAXSEG = 24;               // speculative segments of one seed chain
 constexpr int MAXREC = 8;                // candidates / planted cells a pass-1 grid record can hold
 constexpr unsigned FULLMASK = 0xffffffffu;
 
