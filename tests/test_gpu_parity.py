@@ -183,6 +183,21 @@ def test_in_line_path_matches_two_pass_path(ub, monkeypatch):
     assert not bad, bad[:5]
 
 
+@pytest.mark.parametrize('seg_cycles', ['2.5e6', '6e6', '40e6'])
+def test_result_does_not_depend_on_how_chains_are_cut_into_segments(ub, monkeypatch, seg_cycles):
+    """Long seed chains are walked by several warps at once from guessed initialisation cells; the guess is only
+    kept when it is proven right, so any segmentation (here: three different latency budgets per segment, from many
+    short segments to none) must give the reference's strings.  Also guards the sizing of the task boards, which a
+    grid enters once per segment that walks it."""
+    d = load_golden('semiglobal_sample.json.gz')
+    jobs = golden_chain_jobs(d)
+    monkeypatch.setenv('UNICYCLER_B200_SEG_CYCLES', seg_cycles)
+    got = ub.chain_alignment_batch(jobs, tuple(d['scheme']), jobs[0]['band'])
+    monkeypatch.delenv('UNICYCLER_B200_SEG_CYCLES')
+    bad = [(j['readName'], j['refName']) for j, g in zip(jobs, got) if mask_ms(g) != j['result']]
+    assert not bad, bad[:5]
+
+
 @pytest.mark.skipif(not os.path.isfile(REF_LIB), reason='oracle/_ref not built')
 def test_semi_global_with_ambiguous_and_lower_case_bases(ub):
     """k-mers that are not pure upper-case ACGT take the literal-string route of the k-mer index

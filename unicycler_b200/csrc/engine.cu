@@ -382,7 +382,7 @@ __device__ __noinline__ void trackChain(const GridCtx& Gin, TrackResult& res, co
     __syncwarp();
     res.maxScore = (n == 0) ? NEG_INF : best;
     res.nCand = n;
-    res.status = ub ? JOB_REF_UB : JOB_OK;
+    res.status = ub ? UB_VERDICT : JOB_OK;
 }
 
 // Tracking for the default scout (GRID_GLOBAL): first maximum in column-major visiting order with
@@ -442,11 +442,11 @@ __device__ __forceinline__ bool plantCrossing(const GridCtx& G, int hInit, int v
     DCell* cellPtr = nullptr;
     int i1, i2;
     if (vInit <= 0) {
-        if (hInit < 0 || hInit >= G.capNextH) status = JOB_REF_UB;
+        if (hInit < 0 || hInit >= G.capNextH) status = UB_VERDICT;
         else cellPtr = &G.hInitNext[hInit];
         i1 = hInit; i2 = 0;
     } else {
-        if (vInit >= G.capNextV) status = JOB_REF_UB;
+        if (vInit >= G.capNextV) status = UB_VERDICT;
         else cellPtr = &G.vInitNext[vInit];
         i1 = 0; i2 = vInit;
     }
@@ -478,7 +478,7 @@ __device__ __forceinline__ bool plantCrossing(const GridCtx& G, int hInit, int v
                 if (lane == 0) G.planted[nPlanted] = PlantedCell{i1, i2, cell};
                 ++nPlanted;
                 inserted = true;
-            } else status = JOB_REF_UB;
+            } else status = UB_VERDICT;
         }
         __syncwarp();
     }
@@ -529,7 +529,7 @@ __device__ __forceinline__ void chainTracebackOne(const GridCtx& G, Walker& w, O
             if (currCol != 0) w.record(0, 0, currCol, T_H);
         }
     }
-    if (w.bad) status = JOB_REF_UB;
+    if (w.bad) status = UB_VERDICT;
     if (w.nSegs == 0) {
         out.len = headerPos;  // empty target: not appended (traceback.h:383-385)
     } else {
@@ -608,7 +608,7 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& Gin, uint8_t* win,
             tvOverride = (int)t;
         }
         w.generic(G.affine, true, true, tvOverride);
-        if (w.bad) status = JOB_REF_UB;
+        if (w.bad) status = UB_VERDICT;
         out.patch(hdr, w.nSegs);
         nTraces = 1;
     } else if (rec == nullptr) {
@@ -690,7 +690,7 @@ __device__ __noinline__ void bigShortWalks(const GridCtx& Gin, uint8_t* win, int
         Coord c = w.makeCoord(G.hNext, G.vNext);
         int frag = 0;
         while (!c.reachedEnd() && tv != T_NONE) w.doTraceback(tv, last, frag, c);
-        if (w.bad) { status = JOB_REF_UB; break; }
+        if (w.bad) { status = UB_VERDICT; break; }
         if (plantCrossing(G, c.currCol - c.endCol, c.currRow - c.endRow, last, nPlanted, status)) insertedMask |= 1 << k;
     }
     tiles += w.tilesComputed; tileCycles += w.tileCycles;
@@ -817,7 +817,7 @@ __device__ __noinline__ bool fastShortWalks(const GridCtx& Gin, uint8_t* win, in
         if (G.affine) x = G.g.banded ? leanCrossing<true, true>(L, i, j, c) : leanCrossing<true, false>(L, i, j, c);
         else x = G.g.banded ? leanCrossing<false, true>(L, i, j, c) : leanCrossing<false, false>(L, i, j, c);
         if (x.bad & 2) return false;            // left the box (a gap run crossing the origin line)
-        if (x.bad) { status = JOB_REF_UB; break; }
+        if (x.bad) { status = UB_VERDICT; break; }
         if (debugBoth) {  // developer check: the generic walker in lazy mode must find the same crossing
             w.lazy = true; w.emitOn = false; w.outOfBox = false;
             uint32_t tv = w.tvHere();
@@ -826,7 +826,7 @@ __device__ __noinline__ bool fastShortWalks(const GridCtx& Gin, uint8_t* win, in
             int frag = 0;
             while (!c2.reachedEnd() && tv != T_NONE) w.doTraceback(tv, last, frag, c2);
             if (w.outOfBox || c2.currCol - c2.endCol != x.hInit || c2.currRow - c2.endRow != x.vInit || last != x.last) {
-                status = JOB_REF_UB; break;
+                status = UB_VERDICT; break;
             }
         }
         if (plantCrossing(G, x.hInit, x.vInit, x.last, nPlanted, status)) insertedMask |= 1 << k;
@@ -986,7 +986,7 @@ __device__ __noinline__ int publishAndWait(const GridCtx& Gin, GridCtx& wctx, in
     int t = 0;
     if (lane == 0) t = atomicAdd(&P.cb->ringTail[board], 1);
     t = __shfl_sync(FULLMASK, t, 0);
-    if (t >= P.maxTasks) return JOB_REF_UB;  // cannot happen: the host sizes the boards to the number of big grids
+    if (t >= P.maxTasks) return UB_VERDICT;  // cannot happen: the host sizes the boards to the number of publications
     const int taskId = board * P.maxTasks + t;
     TaskDesc* td = &P.ring[taskId];
     const int* src = reinterpret_cast<const int*>(&G);
@@ -1138,7 +1138,7 @@ __device__ __noinline__ void finalizeJob(int jobIdx) {
                 if (e.z >= f) owner = sg;
             }
             bool keep = (r0 + lane < nRec) && owner == e.w;
-            if (keep && (e.y < 6 || e.x < 0 || e.x + e.y > end)) { keep = false; st = JOB_REF_UB; }
+            if (keep && (e.y < 6 || e.x < 0 || e.x + e.y > end)) { keep = false; st = UB_VERDICT; }
             const int used = keep ? e.y : 0;
             int incl = used;
 #pragma unroll
@@ -2022,15 +2022,22 @@ void Engine::upload(std::vector<Job*>& jobs) {
     // number of control agents with an arena: bounded by jobs and by memory
     size_t freeB = 0, totalB = 0;
     CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
-    const size_t offRing = alignUp(sizeof(ControlBlock), 256);
-    const size_t offP2 = offRing + alignUp(2 * (nTasks + 1) * sizeof(TaskDesc), 256);
+    // control region (zeroed per launch).  A big grid is published once by every segment that walks it, so the
+    // task boards and token rings are sized by publications, not by grids.
+    size_t offRing = 0, offP2 = 0, offBig = 0, offTile = 0, offState = 0, offTok = 0, maxTokens = 0, maxPub = 0;
     const size_t maxBig = (size_t)MAXREC * nTasks + 64;
-    const size_t offBig = offP2 + alignUp((nJobs + 1) * sizeof(P2Entry), 256);
-    const size_t offTile = offBig + alignUp(maxBig * sizeof(int2), 256);
-    const size_t offState = offTile + alignUp((size_t)TILE_QUEUES * TILE_RING_CAP * sizeof(TileReq), 256);
-    const size_t offTok = offState + alignUp((nJobs + 1) * sizeof(JobState), 256);
-    const size_t maxTokens = totalStrips + nTasks + 64;
-    I.ringBytes = offTok + 2 * maxTokens * sizeof(int);
+    auto layoutRings = [&](size_t pubTasks, size_t pubStrips) {
+        maxPub = pubTasks + 1;
+        offRing = alignUp(sizeof(ControlBlock), 256);
+        offP2 = offRing + alignUp(2 * maxPub * sizeof(TaskDesc), 256);
+        offBig = offP2 + alignUp((nJobs + 1) * sizeof(P2Entry), 256);
+        offTile = offBig + alignUp(maxBig * sizeof(int2), 256);
+        offState = offTile + alignUp((size_t)TILE_QUEUES * TILE_RING_CAP * sizeof(TileReq), 256);
+        offTok = offState + alignUp((nJobs + 1) * sizeof(JobState), 256);
+        maxTokens = pubStrips + pubTasks + 64;
+        I.ringBytes = offTok + 2 * maxTokens * sizeof(int);
+    };
+    layoutRings(nTasks * 8, totalStrips * 8);   // (estimate for the memory budget; exact once the segments are known)
     // mini arenas: init row / column of the largest LOCAL grid, for every control-capable warp
     const size_t miniInitCol = alignUp((size_t)(maxLocalNH + 2) * sizeof(DCell), 256);
     const size_t miniStride = miniInitCol + alignUp((size_t)(maxLocalNV + 2) * sizeof(DCell), 256);
@@ -2056,6 +2063,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
         if (localPlan(gg).local) return 100e3;
         return ((double)gd.nH / 32.0 + 2.0 * stripCount(gg, SH)) * 16e3 + 200e3;
     };
+    const double SEG_CYCLES = getenv("UNICYCLER_B200_SEG_CYCLES") ? atof(getenv("UNICYCLER_B200_SEG_CYCLES")) : 4e6;   // spine latency worth one segment
     // up to 8 segments per chain; up to MAXSEG when that leaves most control warps free (few, long chains)
     int segCap = 8;
     if (!noSplit) {
@@ -2065,7 +2073,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
             if (!j.complete || j.grids.size() < 16) continue;
             double total = 0;
             for (const GridDesc& gd : j.grids) total += gridLatency(gd);
-            wanted8 += std::max<long long>(0, std::min<long long>(8, (long long)(total / 4e6 + 0.5)) - 1);
+            wanted8 += std::max<long long>(0, std::min<long long>(8, (long long)(total / SEG_CYCLES + 0.5)) - 1);
         }
         if (2 * wanted8 <= extraBudget) segCap = MAXSEG;
     }
@@ -2083,7 +2091,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
                 gc[(size_t)g] = gridLatency(j.grids[(size_t)g]);
                 total += gc[(size_t)g];
             }
-            const int want = (int)std::min<long long>(std::min<long long>(segCap, (long long)(total / 4e6 + 0.5)), extraBudget + 1);
+            const int want = (int)std::min<long long>(std::min<long long>(segCap, (long long)(total / SEG_CYCLES + 0.5)), extraBudget + 1);
             double acc = 0;
             int nextP = 1;
             for (int g = 1; g < n - 1 && nextP < want; ++g) {
@@ -2109,6 +2117,19 @@ void Engine::upload(std::vector<Job*>& jobs) {
                                                std::max(1, j.outScale), 1LL << 28);
         d.pad3 = 0;
         nRecIdx += (size_t)d.recIdxCap;
+    }
+    {
+        size_t pubTasks = 0, pubStrips = 0;
+        for (size_t k = 0; k < nJobs; ++k) {
+            pubTasks += (size_t)I.jobsDev[k].nSeg * agg[k].tasks;
+            pubStrips += (size_t)I.jobsDev[k].nSeg * agg[k].strips;
+        }
+        layoutRings(pubTasks, pubStrips);
+    }
+    if (getenv("UNICYCLER_B200_PROFILE")) {
+        long long segs = 0;
+        for (size_t k = 0; k < nJobs; ++k) segs += I.jobsDev[k].nSeg;
+        fprintf(stderr, "[ub200 upload] %zu jobs in %lld segments (cap %d per chain), %lld control warps left without a segment\n", nJobs, segs, segCap, extraBudget);
     }
     I.order.clear();
     for (int jk : jobOrder)
@@ -2147,7 +2168,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.jobs = (const JobDev*)I.dJobs; kp.grids = (const GridDesc*)I.dGrids; kp.seq = (const uint8_t*)I.dSeq;
     kp.out = (int*)I.dOut; kp.out2 = (int*)I.dOut2; kp.recIdx = (int4*)I.dRecIdx; kp.jobOut = (JobOut*)I.dJobOut; kp.order = (const int*)I.dOrder;
     kp.colTabPool = (const ColInfo*)I.dColTab;
-    kp.nJobs = (int)nJobs; kp.nSlots = nSlots; kp.maxTasks = (int)nTasks + 1;
+    kp.nJobs = (int)nJobs; kp.nSlots = nSlots; kp.maxTasks = (int)maxPub;
     kp.nEntries = (int)nEntries; kp.pad6 = 0;
     kp.nHiJobs = std::max(8, (int)nEntries / 8);
     kp.cb = (ControlBlock*)I.dRing;
@@ -2263,6 +2284,8 @@ void Engine::fetch(std::vector<Job*>& jobs) {
         unsigned long long dbg[24];
         if (cudaMemcpyFromSymbol(dbg, gDbg, sizeof(dbg)) == cudaSuccess) {
             fprintf(stderr, "[ub200 dbg] worker items=%llu strip-cycles=%llu (rowProg wait %llu) segDone-wait=%llu cells=%llu (cumulative)\n", dbg[14], dbg[12], dbg[13], dbg[11], dbg[15]);
+            int ubSite = 0;
+            if (cudaMemcpyFromSymbol(&ubSite, gUbSite, sizeof(int)) == cudaSuccess && ubSite) fprintf(stderr, "[ub200 dbg] first JOB_REF_UB verdict at engine.cu:%d\n", ubSite);
             fprintf(stderr, "[ub200 dbg] big pass-2 walks=%llu tiles=%llu tile-cycles=%llu walk-cycles=%llu (cumulative)\n", dbg[19], dbg[16], dbg[17], dbg[18]);
             fprintf(stderr, "[ub200 dbg] tile requests claimed by helpers=%llu (post->claim %.1f us avg) stale pops=%llu (cumulative)\n", dbg[21], dbg[21] ? dbg[22] / 1e3 / dbg[21] : 0.0, dbg[23]);
             fprintf(stderr, "[ub200 dbg] helped walks: tiles from helpers=%llu taken back=%llu (cumulative)\n", dbg[8], dbg[10]);

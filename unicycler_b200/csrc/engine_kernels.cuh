@@ -237,7 +237,10 @@ struct KParams {
 // Launch parameters live in constant memory (a by-reference kernel argument would be copied to the
 // local-memory stack of every warp).
 __constant__ KParams cP;
-__device__ unsigned long long gDbg[24];   // developer counters (cycles), lane 0 of control warps
+__device__ unsigned long long gDbg[24];
+__device__ int gUbSite;                   // developer aid: source line of the first JOB_REF_UB verdict
+__device__ __forceinline__ int markUb(int line) { atomicCAS(&gUbSite, 0, line); return 0; }
+#define UB_VERDICT (markUb(__LINE__), JOB_REF_UB)   // developer counters (cycles), lane 0 of control warps
 
 __device__ __forceinline__ uint32_t ldsU8(uint32_t sharedAddr) {
     uint32_t v;
@@ -636,7 +639,7 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
     int upProg = 0;                // cached progress of the strip above
     // the strip below becomes claimable once this one is two chunks past that strip's first column
     bool signalled = false;
-    const int signalAt = imin(cEnd, stripJlo(g, s + 1, SHR) + 63);
+    const int signalAt = imin(cEnd, stripJlo(g, s + 1, SHR) + 31);
     const int upJhi = (s > 0) ? stripJhi(g, s - 1, SHR) : 0;
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
