@@ -307,8 +307,11 @@ def main():
         raise SystemExit('e2e parity failure: %d reads differ from the reference golden output' % bad)
     barrier()
     t0 = time.perf_counter()
+    e2e_steps_ms = []
     for _ in range(args.steps):
+        t_step = time.perf_counter()
         e2e_step()
+        e2e_steps_ms.append((time.perf_counter() - t_step) * 1e3)
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     e2e_gcups = world * cells_per_rank / e2e_s / 1e9
@@ -336,7 +339,8 @@ def main():
             wall_ms_timed_region=wall_ms,
             gpu_launches=args.steps,
             e2e=dict(value=e2e_gcups, unit='GCUPS', h2d_bytes_per_step=tb2['h2d_bytes'], d2h_bytes_per_step=tb2['d2h_bytes'],
-                     ms_per_step=e2e_s * 1e3, reads_per_s=world * len(reads) / e2e_s,
+                     ms_per_step=e2e_s * 1e3, ms_per_step_median_rank0=sorted(e2e_steps_ms)[len(e2e_steps_ms) // 2],
+                     reads_per_s=world * len(reads) / e2e_s,
                      path='ub200_semiGlobalAlignmentBatch (host strings in, result strings out)'),
             roofline=dict(bound='hbm', achieved=achieved_gbs, peak=hbm_peak, unit='GB/s', frac=achieved_gbs / hbm_peak,
                           traffic=ncu_traffic(), kernel='dpAgentKernel', bytes_per_cell=1,
