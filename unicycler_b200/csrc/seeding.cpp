@@ -453,30 +453,96 @@ double getPointDensityScore(int radius, Point p, const Cloud& cloud) {
     return score;
 }
 
-Point getHighestDensityPoint(int radius, const Cloud& cloud) {
-    // Every point's score is independent; the winner is the first strictly greater score in cloud order
-    // (semi_global_align.cpp:577-589), so the scores can be computed on spare host cores and scanned in order.
-    const size_t n = cloud.pts.size();
-    std::vector<double> score(n);
+// Exact density scores of the listed points (independent of each other: spare host cores help).
+static void densityScores(int radius, const Cloud& cloud, const std::vector<uint32_t>& which, std::vector<double>& score) {
+    const size_t n = which.size();
     int helpers = 0;
     if (n >= 2048) helpers = acquireSpareHostThreads(7);
     if (helpers == 0) {
-        for (size_t i = 0; i < n; ++i) score[i] = getPointDensityScore(radius, cloud.pts[i], cloud);
+        for (size_t q = 0; q < n; ++q) score[which[q]] = getPointDensityScore(radius, cloud.pts[which[q]], cloud);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const size_t b = next.fetch_add(256);
+            if (b >= n) break;
+            const size_t e = std::min(n, b + 256);
+            for (size_t q = b; q < e; ++q) score[which[q]] = getPointDensityScore(radius, cloud.pts[which[q]], cloud);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < helpers; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    releaseSpareHostThreads(helpers);
+}
+
+Point getHighestDensityPoint(int radius, const Cloud& cloud) {
+    // The winner is the first point in cloud order whose score is strictly greater than all before it
+    // (semi_global_align.cpp:577-589).  The score of a point sums ((1+a)/(k+1) - a) over its neighbours, k = distance
+    // between the diagonals of the two points: only neighbours within 5 diagonals contribute a positive term, and the
+    // L1 ball is a square in (x+y, x-y), so an UPPER BOUND of every score comes from counting, per nearby diagonal,
+    // the points whose x+y lies within the radius.  Exact scores (the reference's neighbour order and summation) are
+    // then only computed for the points whose bound reaches the best exact score found among the top bounds.
+    const size_t n = cloud.pts.size();
+    std::vector<double> score(n, -1.0);
+    std::vector<uint32_t> all;
+    if (n < 48) {
+        all.resize(n);
+        for (size_t i = 0; i < n; ++i) all[i] = (uint32_t)i;
+        densityScores(radius, cloud, all, score);
     } else {
-        std::atomic<size_t> next(0);
-        auto work = [&]() {
-            for (;;) {
-                const size_t b = next.fetch_add(256);
-                if (b >= n) break;
-                const size_t e = std::min(n, b + 256);
-                for (size_t i = b; i < e; ++i) score[i] = getPointDensityScore(radius, cloud.pts[i], cloud);
+        const double a = 1.0 / SCORE_DISTANCE_FROM_DIAGONAL;
+        const int KMAX = 5;
+        double term[KMAX + 1];
+        for (int k = 0; k <= KMAX; ++k) term[k] = std::max(0.0, ((1.0 + a) / (k + 1.0)) - a);
+        // (diagonal, anti-diagonal, point) sorted by diagonal, then along the diagonal
+        struct DS { int d, s; uint32_t idx; };
+        std::vector<DS> ds(n);
+        for (size_t i = 0; i < n; ++i) ds[i] = DS{cloud.pts[i].x - cloud.pts[i].y, cloud.pts[i].x + cloud.pts[i].y, (uint32_t)i};
+        std::sort(ds.begin(), ds.end(), [](const DS& p, const DS& q) { return p.d != q.d ? p.d < q.d : p.s < q.s; });
+        struct Grp { int d; uint32_t b, e; };
+        std::vector<Grp> grp;
+        for (size_t i = 0; i < n;) {
+            size_t e = i;
+            while (e < n && ds[e].d == ds[i].d) ++e;
+            grp.push_back(Grp{ds[i].d, (uint32_t)i, (uint32_t)e});
+            i = e;
+        }
+        // per pair (diagonal, diagonal + k): the window [s - radius, s + radius] slides monotonically
+        std::vector<double> bound(n, 0.0);
+        for (size_t g = 0; g < grp.size(); ++g) {
+            size_t h0 = g;
+            while (h0 > 0 && grp[h0 - 1].d >= grp[g].d - KMAX) --h0;
+            for (size_t h = h0; h < grp.size() && grp[h].d <= grp[g].d + KMAX; ++h) {
+                const int k = grp[h].d - grp[g].d;
+                const double t = term[k < 0 ? -k : k];
+                if (t <= 0.0) continue;
+                uint32_t lo = grp[h].b, hi = grp[h].b;
+                for (uint32_t q = grp[g].b; q < grp[g].e; ++q) {
+                    const int sv = ds[q].s;
+                    while (lo < grp[h].e && ds[lo].s < sv - radius) ++lo;
+                    while (hi < grp[h].e && ds[hi].s <= sv + radius) ++hi;
+                    bound[ds[q].idx] += (double)(hi - lo) * t;
+                }
             }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 0; t < helpers; ++t) pool.emplace_back(work);
-        work();
-        for (auto& th : pool) th.join();
-        releaseSpareHostThreads(helpers);
+        }
+        for (size_t i = 0; i < n; ++i) bound[i] = bound[i] * (1.0 + 1e-9) + 1e-9;
+        // exact scores of the 3 largest bounds give the threshold
+        std::vector<uint32_t> byBound(n);
+        for (size_t i = 0; i < n; ++i) byBound[i] = (uint32_t)i;
+        const size_t top = std::min<size_t>(3, n);
+        std::partial_sort(byBound.begin(), byBound.begin() + (long)top, byBound.end(),
+                          [&](uint32_t x, uint32_t y) { return bound[x] > bound[y]; });
+        std::vector<uint32_t> first(byBound.begin(), byBound.begin() + (long)top);
+        densityScores(radius, cloud, first, score);
+        double threshold = 0.0;   // (scores that are not positive never win: the start value of the scan is 0)
+        for (uint32_t i : first) threshold = std::max(threshold, score[i]);
+        for (size_t i = 0; i < n; ++i)
+            if (score[i] < 0.0 && bound[i] >= threshold) all.push_back((uint32_t)i);
+        densityScores(radius, cloud, all, score);
+        if (getenv("UB200_DBG_DENSITY")) fprintf(stderr, "density: n=%zu evaluated=%zu threshold=%.2f maxbound=%.2f\n", n, all.size() + top, threshold, bound[byBound[0]]);
     }
     Point best = cloud.pts[0];
     double bestScore = 0.0;
