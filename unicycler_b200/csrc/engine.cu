@@ -2066,16 +2066,31 @@ void Engine::upload(std::vector<Job*>& jobs) {
     const double SEG_CYCLES = getenv("UNICYCLER_B200_SEG_CYCLES") ? atof(getenv("UNICYCLER_B200_SEG_CYCLES")) : 4e6;   // spine latency worth one segment
     // up to 8 segments per chain; up to MAXSEG when that leaves most control warps free (few, long chains)
     int segCap = 8;
+    std::vector<int> grant(nJobs, 1);
     if (!noSplit) {
+        std::vector<double> spineLatency(nJobs, 0.0);
         long long wanted8 = 0;
         for (size_t k = 0; k < nJobs; ++k) {
             const Job& j = *jobs[k];
             if (!j.complete || j.grids.size() < 16) continue;
             double total = 0;
             for (const GridDesc& gd : j.grids) total += gridLatency(gd);
+            spineLatency[k] = total;
             wanted8 += std::max<long long>(0, std::min<long long>(8, (long long)(total / SEG_CYCLES + 0.5)) - 1);
         }
         if (2 * wanted8 <= extraBudget) segCap = MAXSEG;
+        // the spare control warps are handed out level by level (every chain gets its 2nd segment before any gets
+        // a 3rd), longest estimated spine first
+        std::vector<int> byLatency(nJobs);
+        for (size_t k = 0; k < nJobs; ++k) byLatency[k] = (int)k;
+        std::stable_sort(byLatency.begin(), byLatency.end(), [&](int a, int b) { return spineLatency[(size_t)a] > spineLatency[(size_t)b]; });
+        long long left = extraBudget;
+        for (int level = 2; level <= segCap && left > 0; ++level)
+            for (int jk : byLatency) {
+                if (left <= 0) break;
+                const int want = (int)std::min<long long>(segCap, (long long)(spineLatency[(size_t)jk] / SEG_CYCLES + 0.5));
+                if (want >= level) { grant[(size_t)jk] = level; --left; }
+            }
     }
     for (int jk : jobOrder) {
         const size_t k = (size_t)jk;
@@ -2091,7 +2106,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
                 gc[(size_t)g] = gridLatency(j.grids[(size_t)g]);
                 total += gc[(size_t)g];
             }
-            const int want = (int)std::min<long long>(std::min<long long>(segCap, (long long)(total / SEG_CYCLES + 0.5)), extraBudget + 1);
+            const int want = (int)std::min<long long>(grant[k], extraBudget + 1);
             double acc = 0;
             int nextP = 1;
             for (int g = 1; g < n - 1 && nextP < want; ++g) {
@@ -2134,6 +2149,28 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.order.clear();
     for (int jk : jobOrder)
         for (int p = 0; p < I.jobsDev[(size_t)jk].nSeg; ++p) I.order.push_back(jk * MAXSEG + p);
+    {
+        // The strips of big grids are served by the whole GPU through two token rings; the critical-path ring (the
+        // first nHiJobs entries) goes to the segments with the most big-grid cells to fill: their spines are the
+        // longest (longest-processing-time first).  Entries without big grids keep the order by job cost.
+        std::vector<double> bigCells(I.order.size(), 0.0);
+        for (size_t e = 0; e < I.order.size(); ++e) {
+            const int jk = I.order[e] / MAXSEG, p = I.order[e] % MAXSEG;
+            const JobDev& d = I.jobsDev[(size_t)jk];
+            const Job& j = *jobs[(size_t)jk];
+            const int gEnd = (p + 1 < d.nSeg) ? d.segStart[p + 1] : d.gridCount;
+            for (int g = d.segStart[p]; g < gEnd; ++g) {
+                const GridDesc& gd = j.grids[(size_t)g];
+                if (!localPlan(makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up)).local) bigCells[e] += (double)referenceCells(gd);
+            }
+        }
+        std::vector<size_t> perm(I.order.size());
+        for (size_t e = 0; e < perm.size(); ++e) perm[e] = e;
+        std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return bigCells[a] > bigCells[b]; });
+        std::vector<int> sorted(I.order.size());
+        for (size_t e = 0; e < perm.size(); ++e) sorted[e] = I.order[perm[e]];
+        I.order.swap(sorted);
+    }
     const size_t nEntries = I.order.size();
     int nSlots = (int)std::min<long long>(std::min<long long>((long long)nEntries, (long long)NCTRL * I.numSMs),
                                           std::max<long long>(byMem, 0));
