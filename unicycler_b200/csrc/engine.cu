@@ -1035,8 +1035,7 @@ __device__ __forceinline__ int ownerOf(const JobState& js, int gi) {
 // ---------------------------------------------------------------------------------------
 // pass 2: one recorded grid, start to end, on any control-capable warp
 // ---------------------------------------------------------------------------------------
-// Returns false when the item is left to the big-item ring (one candidate of a big grid reached through the job's
-// ordinary item counter).
+// One pass-2 item: a recorded small grid (all its candidates) or, from the big-item ring, one candidate of a big grid.
 __device__ __noinline__ bool runPass2Grid(int jobIdx, int item, GridCtx& Gin, uint8_t* win, uint8_t* mini, bool fromBigRing) {
     GridCtx& G = *toShared(&Gin);
     const KParams& P = cP;
@@ -1047,9 +1046,9 @@ __device__ __noinline__ bool runPass2Grid(int jobIdx, int item, GridCtx& Gin, ui
     const GridRec* rec = &P.gridRecs[jb.recBase + (long long)owner * jb.gridCount + gi];
     const int state = rec->state;
     if (state == 0) return true;                               // done in line by pass 1
+    if (state == 2 && !fromBigRing) return true;                // big grid: its candidates are items of the big ring
     if (state == 1 && ksel != 0) return true;                   // small grid: item 0 walks every candidate
-    if (state == 2 && ksel >= rec->nCand) return true;          // big grid: one candidate per item
-    if (state == 2 && !fromBigRing) return false;
+    if (state == 2 && ksel >= rec->nCand) return true;
     const GridDesc gd = P.grids[jb.gridBegin + gi];
     if (state == 2) {
         // checkpoints, init row and column live in the grid's persistent block
@@ -1266,7 +1265,7 @@ __device__ __forceinline__ void pushBig(int jobIdx, int item) {
 }
 
 // A pass-2 item of the job is done; the last one completes the job (all lanes; finalizeJob is a warp function).
-__device__ __forceinline__ void pass2ItemDone(int jobIdx) {
+__device__ __forceinline__ void pass2ItemDone(int jobIdx, int count = 1) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
     __threadfence();
@@ -1274,7 +1273,7 @@ __device__ __forceinline__ void pass2ItemDone(int jobIdx) {
     int fin = 0;
     if (lane == 0) {
         JobState* js = &P.jobState[jobIdx];
-        const int d = atomicAdd(&js->p2Done, 1) + 1;
+        const int d = atomicAdd(&js->p2Done, count) + count;
         __threadfence();
         const int need = ldRelaxed(&js->p2Need);
         fin = (need > 0 && d == need) ? 1 : 0;
@@ -1325,7 +1324,8 @@ __device__ __noinline__ bool tryRunBig(GridCtx& G, uint8_t* win, uint8_t* mini, 
 __device__ __noinline__ bool tryRunPass2(GridCtx& G, uint8_t* win, uint8_t* mini, int* idleFlag = nullptr) {
     const KParams& P = cP;
     const int lane = threadIdx.x & 31;
-    int h = 0, item = -1;
+    constexpr int CHUNK = 4;   // grids claimed per atomic (one counter per job: every idle control warp pulls on it)
+    int h = 0, item = -1, nItems = 0;
     if (lane == 0) {
         h = ldRelaxed(&P.cb->p2Head);
         for (;;) {
@@ -1334,8 +1334,8 @@ __device__ __noinline__ bool tryRunPass2(GridCtx& G, uint8_t* win, uint8_t* mini
             if (ldRelaxed(&e->ready) == 0) break;
             const int n = e->nItems;
             if (ldVolatile(&e->nextItem) < n) {
-                const int k = atomicAdd(&e->nextItem, 1);
-                if (k < n) { item = k; break; }
+                const int k = atomicAdd(&e->nextItem, CHUNK);
+                if (k < n) { item = k; nItems = n; break; }
             }
             atomicCAS(&P.cb->p2Head, h, h + 1);
             ++h;
@@ -1344,21 +1344,25 @@ __device__ __noinline__ bool tryRunPass2(GridCtx& G, uint8_t* win, uint8_t* mini
     }
     item = __shfl_sync(FULLMASK, item, 0);
     if (item < 0) return false;
+    nItems = __shfl_sync(FULLMASK, nItems, 0);
     leaveIdle(idleFlag);
     h = __shfl_sync(FULLMASK, h, 0);
     P2Entry* e = &P.p2ring[h];
     const int jobIdx = e->jobIdx;
-    const unsigned long long tItem0 = globalTimerNs();
-    if (!runPass2Grid(jobIdx, item, G, win, mini, false)) return true;   // (counted by the big-item ring)
-    if (lane == 0) {
-        JobOut* jo = &P.jobOut[jobIdx];
-        const unsigned long long tItem1 = globalTimerNs();
-        atomicMax(reinterpret_cast<unsigned long long*>(&jo->tP2Start), tItem0 - P.cb->t0);
-        const unsigned long long old = atomicMax(reinterpret_cast<unsigned long long*>(&jo->p2MaxNs), tItem1 - tItem0);
-        if (tItem1 - tItem0 > old) jo->p2MaxItem = item;
-        atomicAdd(reinterpret_cast<unsigned long long*>(&jo->p2SumNs), tItem1 - tItem0);
+    const int last = imin(item + CHUNK, nItems);
+    for (int gi = item; gi < last; ++gi) {
+        const unsigned long long tItem0 = globalTimerNs();
+        runPass2Grid(jobIdx, gi * MAXREC, G, win, mini, false);
+        if (lane == 0) {
+            JobOut* jo = &P.jobOut[jobIdx];
+            const unsigned long long tItem1 = globalTimerNs();
+            atomicMax(reinterpret_cast<unsigned long long*>(&jo->tP2Start), tItem0 - P.cb->t0);
+            const unsigned long long old = atomicMax(reinterpret_cast<unsigned long long*>(&jo->p2MaxNs), tItem1 - tItem0);
+            if (tItem1 - tItem0 > old) jo->p2MaxItem = gi * MAXREC;
+            atomicAdd(reinterpret_cast<unsigned long long*>(&jo->p2SumNs), tItem1 - tItem0);
+        }
     }
-    pass2ItemDone(jobIdx);
+    pass2ItemDone(jobIdx, last - item);
     return true;
 }
 
@@ -1434,24 +1438,27 @@ __device__ __noinline__ void finalizeSpine(int jobIdx) {
     __syncwarp();
     if (status == JOB_OK && jb.gridCount > 1) {
         // hand the recorded grids to pass 2 (grids done in line are skipped there)
-        // every (grid, candidate) pair is one item, plus one for this publication (big items of segment 0 may
-        // have finished already)
-        if (lane == 0) { stRelease(&js->p2Need, jb.gridCount * MAXREC + 1); }
-        __syncwarp();
         // the candidates of the big grids go to their own ring: they are the longest items and start first
         // (segment 0 has handed over its own ones right after their pass 1)
+        int bigCands = 0;
         for (int gi = lane; gi < jb.gridCount; gi += 32) {
             const int owner = ownerOf(*js, gi);
             const GridRec* rec = &P.gridRecs[jb.recBase + (long long)owner * jb.gridCount + gi];
-            if (__ldcg(&rec->state) != 2 || (owner == 0 && __ldcg(&rec->published))) continue;
-            const int nc = __ldcg(&rec->nCand);
-            for (int k = 0; k < nc && k < MAXREC; ++k) pushBig(jobIdx, gi * MAXREC + k);
+            if (__ldcg(&rec->state) != 2) continue;
+            const int nc = min(__ldcg(&rec->nCand), MAXREC);
+            bigCands += nc;
+            if (owner == 0 && __ldcg(&rec->published)) continue;
+            for (int k = 0; k < nc; ++k) pushBig(jobIdx, gi * MAXREC + k);
         }
+        bigCands = __reduce_add_sync(FULLMASK, bigCands);
+        // items of the job: one per grid, one per candidate of a big grid, one for this publication (big items may
+        // have finished already: whoever brings p2Done to p2Need completes the job)
+        if (lane == 0) { __threadfence(); stRelease(&js->p2Need, jb.gridCount + bigCands + 1); }
         __syncwarp();
         if (lane == 0) {
             const int t = atomicAdd(&P.cb->p2Tail, 1);
             P2Entry* e = &P.p2ring[t];
-            e->jobIdx = jobIdx; e->nItems = jb.gridCount * MAXREC; e->nextItem = 0; e->doneItems = 0;
+            e->jobIdx = jobIdx; e->nItems = jb.gridCount; e->nextItem = 0; e->doneItems = 0;
             __threadfence();
             stRelease(&e->ready, 1);
         }
