@@ -542,7 +542,6 @@ Point getHighestDensityPoint(int radius, const Cloud& cloud) {
         for (size_t i = 0; i < n; ++i)
             if (score[i] < 0.0 && bound[i] >= threshold) all.push_back((uint32_t)i);
         densityScores(radius, cloud, all, score);
-        if (getenv("UB200_DBG_DENSITY")) fprintf(stderr, "density: n=%zu evaluated=%zu threshold=%.2f maxbound=%.2f\n", n, all.size() + top, threshold, bound[byBound[0]]);
     }
     Point best = cloud.pts[0];
     double bestScore = 0.0;
