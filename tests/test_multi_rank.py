@@ -56,7 +56,8 @@ def test_broadcast_and_all_gather_world2(tmp_path):
             empty = sharding.all_gather_strings(['x'], dist, dev)
         assert empty == ['x']
         dist.destroy_process_group()
-        print('rank', rank, 'ok')
+        sys.stdout.write('rank {} ok'.format(rank) + chr(10))
+        sys.stdout.flush()
     ''' % ROOT))
     env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29541')
     out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
