@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <queue>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -2086,18 +2087,19 @@ void Engine::upload(std::vector<Job*>& jobs) {
             wanted8 += std::max<long long>(0, std::min<long long>(8, (long long)(total / SEG_CYCLES + 0.5)) - 1);
         }
         if (2 * wanted8 <= extraBudget) segCap = MAXSEG;
-        // the spare control warps are handed out level by level (every chain gets its 2nd segment before any gets
-        // a 3rd), longest estimated spine first
-        std::vector<int> byLatency(nJobs);
-        for (size_t k = 0; k < nJobs; ++k) byLatency[k] = (int)k;
-        std::stable_sort(byLatency.begin(), byLatency.end(), [&](int a, int b) { return spineLatency[(size_t)a] > spineLatency[(size_t)b]; });
+        // the spare control warps go, one at a time, to the chain whose segments are currently the longest
+        // (minimises the longest spine), while a segment stays worth at least SEG_CYCLES / 2
+        std::priority_queue<std::pair<double, int> > heap;
+        for (size_t k = 0; k < nJobs; ++k)
+            if (spineLatency[k] >= SEG_CYCLES) heap.push(std::make_pair(spineLatency[k], (int)k));
         long long left = extraBudget;
-        for (int level = 2; level <= segCap && left > 0; ++level)
-            for (int jk : byLatency) {
-                if (left <= 0) break;
-                const int want = (int)std::min<long long>(segCap, (long long)(spineLatency[(size_t)jk] / SEG_CYCLES + 0.5));
-                if (want >= level) { grant[(size_t)jk] = level; --left; }
-            }
+        while (left > 0 && !heap.empty()) {
+            const int jk = heap.top().second;
+            heap.pop();
+            int& g = grant[(size_t)jk];
+            ++g; --left;
+            if (g < segCap && spineLatency[(size_t)jk] / (g + 1) >= SEG_CYCLES * 0.5) heap.push(std::make_pair(spineLatency[(size_t)jk] / g, jk));
+        }
     }
     for (int jk : jobOrder) {
         const size_t k = (size_t)jk;
