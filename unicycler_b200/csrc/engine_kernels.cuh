@@ -731,6 +731,13 @@ struct OutStream {
         else overflow = true;
         ++len;
     }
+    // one trace segment (four ints) with a single bounds check
+    __device__ __forceinline__ void put4(int a, int b, int c, int d) {
+        if (len + 4 <= cap) {
+            if (lane == 0) { int* p = buf + len; p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
+        } else overflow = true;
+        len += 4;
+    }
     __device__ __forceinline__ void patch(int pos, int x) {
         if (pos < cap && lane == 0) buf[pos] = x;
     }
@@ -1043,7 +1050,7 @@ struct TraceWalkerT {
         else if (tv & T_H) dir = T_H;
         else return;
         if (!emitOn) return;
-        out.put(h + out.h0); out.put(v + out.v0); out.put(len); out.put(dir);
+        out.put4(h + out.h0, v + out.v0, len, dir);
         ++nSegs;
     }
     __device__ __forceinline__ void moveH(const Coord& c) { if (c.isInBand()) { --pc; ++pv; } else --pc; }
@@ -1123,6 +1130,29 @@ struct TraceWalkerT {
                 else if ((tv & T_MH) && (tv & T_HO)) { dir = T_H; state = ST_ONE; dc = 1; }
                 else { bad = true; tv = T_NONE; break; }
                 if (!(last & dir)) { record(col, row, frag, last); last = dir; frag = 0; }
+            }
+            // runs inside the current tile: as many of the steps below as stay in the tile, one LDS each
+            {
+                const unsigned ri = (unsigned)(row - 1 - tRowLo), cj = (unsigned)(col - tC0);
+                if (state != ST_DISPATCH && state != ST_ONE && ri < (unsigned)tRows && cj < (unsigned)tCols) {
+                    uint32_t a = winS + cj * CKR + ri;
+                    int k = 0;
+                    if (state == ST_DRUN) {
+                        // here tv has T_D and the end is not reached: move while that holds
+                        const int kTile = imin((int)ri, (int)cj), kEnd = imin(col - endCol, row - endRow);
+                        if (kTile >= 1) {
+                            do { a -= CKR + 1; tv = ldsU8(a); ++k; } while ((tv & T_D) && k < kEnd && k < kTile);
+                            row -= k; col -= k; frag += k;
+                            if (!(tv & T_D) || k >= kEnd) { state = ST_DISPATCH; continue; }
+                        }
+                    } else if (state == ST_VRUN) {
+                        while (((tv & (T_VO | T_V)) != T_VO) && row - k != 1 && k < (int)ri) { a -= 1; tv = ldsU8(a); ++k; }
+                        row -= k; frag += k;
+                    } else {
+                        while (((tv & (T_HO | T_H)) != T_HO) && col - k != 1 && k < (int)cj) { a -= CKR; tv = ldsU8(a); ++k; }
+                        col -= k; frag += k;
+                    }
+                }
             }
             if (state == ST_DRUN) { dr = 1; dc = 1; }
             else if (state == ST_VRUN) {
