@@ -169,8 +169,8 @@ constexpr int TILE_RING_CAP = 2048;      // entries per ring
 constexpr int TILE_SLOT_BYTES = 4096 + 64;
 constexpr int TILE_SLOTS = 32;          // one per lane of the asking warp
 constexpr int TILE_CANDS = 21;          // sample points ahead of the walk whose tiles are requested
-constexpr int TILE_HELP_MIN_EXTENT = 6000; // nH + nV of a grid whose tracebacks ask for help
-constexpr int TILE_HELPERS_PER_WALK = 6; // a walk consumes a tile in a third of the time a helper needs for three
+constexpr int TILE_HELP_MIN_EXTENT = 9000; // nH + nV of a grid whose tracebacks ask for help
+constexpr int TILE_HELPERS_PER_WALK = 4; // a walk consumes a tile in a third of the time a helper needs for three
 struct ControlBlock {  // zeroed before every launch; every group of counters has its own 128-byte line
     int jobQueue, jobsDone;
     unsigned long long t0;         // %globaltimer at kernel start (developer timeline)
