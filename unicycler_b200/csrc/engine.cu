@@ -84,7 +84,7 @@ __device__ __noinline__ void setupGrid(GridCtx& Gin, const JobDev& jb, const Gri
         G.local = lp.local; G.RR = lp.local ? lp.RR : 8; G.rrMul = 65536 / G.RR + 1; G.rrs = lp.local ? lp.RRS : 8; G.pad2 = 0; G.pitch = lp.pitch; G.localJhi = lp.jhi;
         G.NS = lp.local ? 1 : stripCount(g, SH);
         // banded strips are short (band width + 256 columns): one item per strip; unbanded rows are cut into segments
-        G.nSeg = 1;   // one item per strip: a strip is a serial walk over its columns; strips pipeline with a two-chunk lag
+        G.nSeg = 1;   // one item per strip: a strip is a serial walk over its columns; strips pipeline with a one-chunk lag
         if (!lp.local && P.persist != nullptr && gd.persistOff >= 0) {
             // big grid with its own persistent block: [rowCk | colCk | ckBase | rowProg | segDone | initRow | initCol]
             uint8_t* pb = P.persist + gd.persistOff;
@@ -949,7 +949,7 @@ __device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask, bool* sawO
     int item = -1, taskId = -1, open = 0;
     if (lane == 0) {
         // Pop a token (critical-path ring first): it names a task that had a claimable strip.  Strips are claimed
-        // in order and only once the strip above is two chunks in (readyUpTo), so no warp parks on a far-away strip.
+        // in order and only once the strip above is one chunk in (readyUpTo), so no warp parks on a far-away strip.
         for (int board = 0; board < 2 && item < 0; ++board) {
             for (int tries = 0; tries < 8 && item < 0; ++tries) {
                 const int h = ldRelaxed(&P.cb->tokHead[board]);

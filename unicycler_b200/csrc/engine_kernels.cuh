@@ -11,9 +11,9 @@
 //     order and runs a SCORE-ONLY fill (no trace bits: ~10 instructions per cell).  Inside an item lane t
 //     owns 8 consecutive rows and walks the columns one step behind lane t-1 (anti-diagonal wavefront,
 //     cell hand-off with __shfl_up).  The row between two strips and, every CKW columns, the column state
-//     of a strip are written to HBM as CHECKPOINTS (0.16 B per cell instead of a 1 B/cell trace);
+//     of a strip (plus a row every 64 rows) are written to HBM as CHECKPOINTS (0.25 B per cell instead of 1 B/cell);
 //     release/acquire progress counters order producer and consumer items.
-//   * traceback of a big grid: the control warp RECOMPUTES the trace bytes of the 256 x CKW tile under
+//   * traceback of a big grid: the control warp RECOMPUTES the trace bytes of the 64 x 64 tile under
 //     the path from the checkpoints (bit-identical, integer arithmetic) into its shared-memory window and
 //     walks it exactly like SeqAn's TracebackCoordinator_, in SeqAn's storage coordinates (dpgeom.hpp).
 #pragma once
@@ -156,7 +156,7 @@ struct TaskDesc {
     int ready;       // release-published by the control warp
     int nextItem;    // claimed by compare-and-swap, in order
     int doneItems;   // completed items (release)
-    int readyUpTo;   // items <= readyUpTo may be claimed: strip s+1 becomes claimable once strip s is two chunks in
+    int readyUpTo;   // items <= readyUpTo may be claimed: strip s+1 becomes claimable once strip s is one chunk (32 columns) in
     int pad0, pad1, pad2;
 };
 
@@ -637,7 +637,7 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
     int2* rowOut = (MODE == MODE_TASK) ? G.rowCk + (size_t)s * (SH / CKR) * (size_t)(g.nH + 1) : nullptr;
     const int nch = (nsteps + 31) / 32;
     int upProg = 0;                // cached progress of the strip above
-    // the strip below becomes claimable once this one is two chunks past that strip's first column
+    // the strip below becomes claimable once this one is one chunk (32 columns) past that strip's first column
     bool signalled = false;
     const int signalAt = imin(cEnd, stripJlo(g, s + 1, SHR) + 31);
     const int upJhi = (s > 0) ? stripJhi(g, s - 1, SHR) : 0;
@@ -708,7 +708,7 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
 // traceback (seqan/align/dp_traceback_impl.h, seeds/banded_chain_alignment_traceback.h)
 // in SeqAn storage coordinates (col, cv).  Executed by ALL lanes of the control warp with identical
 // (warp-uniform) control flow; only lane 0 writes results.  Trace bytes come from the warp's
-// shared-memory window: the whole grid for local grids, the recomputed 256 x CKW tile otherwise.
+// shared-memory window: the whole grid for local grids, the recomputed 64 x 64 tile otherwise.
 // ---------------------------------------------------------------------------------------
 struct Coord {
     int currCol, currRow, endCol, endRow, bp1, bp2;
