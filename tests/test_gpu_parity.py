@@ -198,6 +198,20 @@ def test_result_does_not_depend_on_how_chains_are_cut_into_segments(ub, monkeypa
     assert not bad, bad[:5]
 
 
+@pytest.mark.parametrize('switch', ['UNICYCLER_B200_NO_TILE_HELP', 'UNICYCLER_B200_NO_PERSIST', 'UNICYCLER_B200_NO_SPLIT'])
+def test_scheduling_switches_do_not_change_results(ub, monkeypatch, switch):
+    """Tile helpers (other warps recompute trace tiles ahead of a long traceback), persistent checkpoint blocks
+    (big-grid tracebacks deferred to pass 2) and speculative segments only change WHEN work happens; with each of
+    them switched off the sample_data chains must still give the reference's strings."""
+    d = load_golden('semiglobal_sample.json.gz')
+    jobs = golden_chain_jobs(d)
+    monkeypatch.setenv(switch, '1')
+    got = ub.chain_alignment_batch(jobs, tuple(d['scheme']), jobs[0]['band'])
+    monkeypatch.delenv(switch)
+    bad = [(j['readName'], j['refName']) for j, g in zip(jobs, got) if mask_ms(g) != j['result']]
+    assert not bad, bad[:5]
+
+
 @pytest.mark.skipif(not os.path.isfile(REF_LIB), reason='oracle/_ref not built')
 def test_semi_global_with_ambiguous_and_lower_case_bases(ub):
     """k-mers that are not pure upper-case ACGT take the literal-string route of the k-mer index
