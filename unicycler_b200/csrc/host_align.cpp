@@ -293,45 +293,49 @@ typedef std::vector<Seg> Trace;
 inline int segEndH(const Seg& s) { return s.dir == T_V ? s.hBeg : s.hBeg + s.len; }
 inline int segEndV(const Seg& s) { return s.dir == T_H ? s.vBeg : s.vBeg + s.len; }
 
-void smoothGluePoint(Trace& path, size_t referenceSize) {
-    size_t endOld = path.size() - referenceSize;
-    size_t beginNew = endOld - 1;
-    if (path[endOld].dir == path[beginNew].dir) {
-        path[endOld].len += path[beginNew].len;
-        path.erase(path.begin() + (long)beginNew);
+// The reference keeps a trace with its LAST alignment segment first and glues a local trace in front of the global
+// one (seeds/banded_chain_alignment_impl.h, _glueTracebacks): a copy of the whole global trace per grid.  Here the
+// global traces are kept in alignment order while gluing, so a local trace is appended in O(its own length); the
+// segment arithmetic (connection test, merge of equal directions at the glue point, order of the resulting
+// traces, erasure of unconnected ones) is the reference's.
+typedef std::vector<Seg> TraceFwd;   // alignment order: first segment of the alignment first
+
+inline void appendLocal(TraceFwd& g, const Trace& local) {
+    // the glue point: the global trace's last segment and the local trace's first one (stored last)
+    size_t k = local.size();
+    if (!g.empty() && k > 0 && g.back().dir == local[k - 1].dir) {   // _smoothGluePoint
+        g.back().len += local[k - 1].len;
+        --k;
     }
+    for (; k > 0; --k) g.push_back(local[k - 1]);
 }
 
-void glueTracebacks(std::vector<Trace>& global, const std::vector<Trace>& local) {
-    if (global.empty()) { global = local; return; }
+void glueTracebacksFwd(std::vector<TraceFwd>& global, const std::vector<Trace>& local) {
+    if (global.empty()) {
+        for (const Trace& t : local) global.emplace_back(t.rbegin(), t.rend());
+        return;
+    }
     const size_t lengthGlobal = global.size();
-    size_t oldNum = lengthGlobal;
     std::vector<size_t> toErase;
     for (size_t j = 0; j < lengthGlobal; ++j) {
-        const Seg gEnd = global[j].front();
+        const Seg gEnd = global[j].back();
         const size_t numCurr = global[j].size();
-        size_t numAdded = 0;
         bool connected = false;
         for (size_t i = 0; i < local.size(); ++i) {
             const Seg& lBeg = local[i].back();
             if (segEndH(gEnd) != lBeg.hBeg || segEndV(gEnd) != lBeg.vBeg) continue;
-            Trace joined(local[i]);
-            joined.insert(joined.end(), global[j].end() - (long)numCurr, global[j].end());
             if (connected) {
-                global.push_back(joined);
-                ++numAdded;
+                // a further local trace continues the same global trace: a new trace from the old part
+                TraceFwd joined(global[j].begin(), global[j].begin() + (long)numCurr);
+                joined.back() = gEnd;
+                appendLocal(joined, local[i]);
+                global.push_back(std::move(joined));
             } else {
-                global[j].swap(joined);
+                appendLocal(global[j], local[i]);
                 connected = true;
             }
         }
-        if (!connected)
-            toErase.push_back(j);
-        else {
-            smoothGluePoint(global[j], numCurr);
-            for (size_t t = oldNum; t < oldNum + numAdded; ++t) smoothGluePoint(global[t], numCurr);
-            oldNum += numAdded;
-        }
+        if (!connected) toErase.push_back(j);
     }
     for (size_t i = toErase.size(); i > 0; --i) global.erase(global.begin() + (long)toErase[i - 1]);
 }
@@ -339,30 +343,31 @@ void glueTracebacks(std::vector<Trace>& global, const std::vector<Trace>& local)
 }  // namespace
 
 void glueChain(const std::vector<GridDesc>& grids, const JobResult& res, std::vector<Seg>& trace, bool& empty) {
-    std::vector<Trace> global;
+    std::vector<TraceFwd> global;
     for (size_t k = 0; k < grids.size(); ++k) {
         const std::vector<Trace>& local = res.gridTraces[k];
         switch (grids[k].glue) {
         case GLUE_APPEND:
-            for (const Trace& t : local) global.push_back(t);
+            for (const Trace& t : local) global.emplace_back(t.rbegin(), t.rend());
             break;
         case GLUE_ASSIGN:
-            global = local;
+            global.clear();
+            for (const Trace& t : local) global.emplace_back(t.rbegin(), t.rend());
             break;
         case GLUE_IF_NONEMPTY:
-            if (!local.empty()) glueTracebacks(global, local);
+            if (!local.empty()) glueTracebacksFwd(global, local);
             break;
         case GLUE_ALWAYS:
             if (local.empty()) {
                 // _glueTracebacks with an empty local set: every global trace is unconnected and erased
                 if (!global.empty()) global.clear();
             } else
-                glueTracebacks(global, local);
+                glueTracebacksFwd(global, local);
             break;
         }
     }
     empty = global.empty();
-    if (!empty) trace = global[0];
+    if (!empty) trace.assign(global[0].rbegin(), global[0].rend());
     else trace.clear();
 }
 
