@@ -54,8 +54,22 @@ void deleteRefSeqs(void* refSeqs);
 /* replaces include/string_functions.h:28 (src/string_functions.cpp:27-29); cpp_wrappers.py:123-133 */
 void freeCString(char* p);
 
-/* The remaining symbols cpp_wrappers.py dereferences at import (semiGlobalAlignmentExhaustive,
- * startAlignment, endAlignment, overlapAlignment, multipleSequenceAlignment, minimapAlignReads,
+/* replaces include/semi_global_align_exhaustive.h (src/semi_global_align_exhaustive.cpp:18-67); cpp_wrappers.py:61-74.
+ * Unbanded alignment with all four end gaps free; result string like fullyGlobalAlignment, "" on failure. */
+char* semiGlobalAlignmentExhaustive(char* s1, char* s2, int matchScore, int mismatchScore, int gapOpenScore,
+                                    int gapExtensionScore);
+
+/* replace include/start_end_align.h:22-24 (src/start_end_align.cpp:19-101); cpp_wrappers.py:325-357.
+ * Position in s2 where the alignment of s1 to the start / end of s2 ends / starts; -1 on failure. */
+int startAlignment(char* s1, char* s2, int matchScore, int mismatchScore, int gapOpenScore, int gapExtensionScore);
+int endAlignment(char* s1, char* s2, int matchScore, int mismatchScore, int gapOpenScore, int gapExtensionScore);
+
+/* replaces include/overlap_align.h (src/overlap_align.cpp:17-81); cpp_wrappers.py:180-200.
+ * Overlap of the end of s1 with the start of s2: "overlap1,overlap2", "-1,-1" on failure. */
+char* overlapAlignment(char* s1, char* s2, int matchScore, int mismatchScore, int gapOpenScore,
+                       int gapExtensionScore, int guessOverlap);
+
+/* The remaining symbols cpp_wrappers.py dereferences at import (multipleSequenceAlignment, minimapAlignReads,
  * minimapAlignReadsWithSettings, miniasmAssembly, simulateDepths, getRandomSequenceAlignmentErrorRates)
  * are exported as forwarders: they dlopen() the library named by UNICYCLER_B200_FORWARD_LIB (the stock
  * cpp_functions.so) and abort with a clear message if it is not set.  They are outside the hot path. */
@@ -117,7 +131,18 @@ int64_t ub200_chainCells(int readLen, int refLen, const int64_t* seeds, int nSee
  * returns the number of sub-DPs of the banded-chain alignment, -1 if the chain is unsupported. */
 int ub200_chainPlan(int readLen, int refLen, const int64_t* seeds, int nSeeds, int bandSize, int32_t* out, int cap);
 
-/* Selects the CUDA device for this process' engine (before first use).  Returns 0 on success. */
+/* The i.i.d. ACGT pairs that getRandomSequenceAlignmentScores(seqLength, n, ...) aligns when its generator is seeded
+ * with `seed` (std::mt19937 + std::uniform_int_distribution<int>(0, 3), s1 then s2 of each pair,
+ * src/random_alignments.cpp:33-40, 167-185).  s1[i] / s2[i] receive malloc()ed strings.  Lets a test feed the very
+ * same pairs to the reference's fullyGlobalAlignment. */
+int ub200_calibrationPairs(int seqLength, int n, unsigned seed, char** s1, char** s2);
+
+/* Coalescer counters: device batches run so far, and ABI requests they served (requests / batches > 1 means that
+ * concurrent per-read calls were merged into shared launches). */
+void ub200_coalescerStats(int64_t* batches, int64_t* requests);
+
+/* Selects the CUDA device for this process' engine (before first use, never while calls are in flight).
+ * Returns 0 on success, -1 when a batch is running. */
 int ub200_setDevice(int device);
 /* Integer-pipe microbenchmark (dependent-free IADD3/VIMNMX mix on all SMs): returns int32 ops/s. */
 double ub200_intPeakOpsPerSec(void);

@@ -65,6 +65,14 @@ class AbiLib(object):
         L.deleteRefSeqs.restype = None
         L.freeCString.argtypes = [ctypes.c_void_p]
         L.freeCString.restype = None
+        L.semiGlobalAlignmentExhaustive.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4
+        L.semiGlobalAlignmentExhaustive.restype = ctypes.c_void_p
+        for n in ('startAlignment', 'endAlignment'):
+            f = getattr(L, n)
+            f.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4
+            f.restype = ctypes.c_int
+        L.overlapAlignment.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 5
+        L.overlapAlignment.restype = ctypes.c_void_p
         if hasattr(L, 'minimapAlignReads'):
             L.minimapAlignReads.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int]
@@ -82,6 +90,22 @@ class AbiLib(object):
     def path(self, s1, s2, scheme, banded, band):
         m, mm, go, ge = scheme
         return self._str(self.lib.pathAlignment(s1.encode(), s2.encode(), m, mm, go, ge, banded, band))
+
+    def exhaustive(self, s1, s2, scheme):
+        m, mm, go, ge = scheme
+        return self._str(self.lib.semiGlobalAlignmentExhaustive(s1.encode(), s2.encode(), m, mm, go, ge))
+
+    def start(self, s1, s2, scheme):
+        m, mm, go, ge = scheme
+        return self.lib.startAlignment(s1.encode(), s2.encode(), m, mm, go, ge)
+
+    def end(self, s1, s2, scheme):
+        m, mm, go, ge = scheme
+        return self.lib.endAlignment(s1.encode(), s2.encode(), m, mm, go, ge)
+
+    def overlap(self, s1, s2, scheme, guess):
+        m, mm, go, ge = scheme
+        return self._str(self.lib.overlapAlignment(s1.encode(), s2.encode(), m, mm, go, ge, guess))
 
     def random_scores(self, length, n, scheme):
         m, mm, go, ge = scheme

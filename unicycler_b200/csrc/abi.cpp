@@ -8,7 +8,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <random>
@@ -23,6 +25,7 @@
 #include "../../include/unicycler_b200.h"
 #include "engine.hpp"
 #include "host_align.hpp"
+#include "hostpool.hpp"
 #include "seeding.hpp"
 
 using namespace ub200;
@@ -55,11 +58,81 @@ Engine& engine() {
     abort();
 }
 
+// Request coalescer in front of Engine::run (SURVEY.md 8b "Threading"): the reference's callers invoke the per-read
+// ABI from a pool of Python threads (unicycler_align.py:203-225).  Concurrent callers enqueue their jobs; whoever
+// finds the engine free becomes the leader, takes EVERYTHING that is pending (group commit) and runs it as one
+// device batch; callers that arrive while a batch is running form the next one.  A leader that knows other calls
+// are still in their host stage waits a short window (UNICYCLER_B200_COALESCE_US, default 300) for them.
+struct RunRequest {
+    std::vector<Job*>* jobs;
+    bool done = false;
+    std::exception_ptr err;
+};
+std::mutex g_coMu;
+std::condition_variable g_coCv;
+std::deque<RunRequest*> g_coPending;
+bool g_coRunning = false;
+std::atomic<int> g_hostStageCalls(0);   // ABI calls currently between entry and submission
+std::atomic<long long> g_coBatches(0), g_coRequests(0);
+
+struct HostStageScope {
+    HostStageScope() { g_hostStageCalls.fetch_add(1); }
+    ~HostStageScope() { leave(); }
+    void leave() { if (in) { in = false; g_hostStageCalls.fetch_sub(1); std::lock_guard<std::mutex> lk(g_coMu); g_coCv.notify_all(); } }
+    bool in = true;
+};
+
+void runCoalesced(std::vector<Job*>& jobs) {
+    if (jobs.empty()) return;
+    static const long windowUs = [] { const char* e = getenv("UNICYCLER_B200_COALESCE_US"); return e ? atol(e) : 300L; }();
+    RunRequest r;
+    r.jobs = &jobs;
+    std::unique_lock<std::mutex> lk(g_coMu);
+    g_coPending.push_back(&r);
+    g_coCv.notify_all();
+    while (!r.done) {
+        if (g_coRunning) { g_coCv.wait(lk); continue; }
+        g_coRunning = true;   // leader
+        if (windowUs > 0) {
+            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(windowUs);
+            while (g_hostStageCalls.load() > 0 && g_coCv.wait_until(lk, deadline) != std::cv_status::timeout) {}
+        }
+        std::vector<RunRequest*> batch(g_coPending.begin(), g_coPending.end());
+        g_coPending.clear();
+        lk.unlock();
+        std::exception_ptr err;
+        try {
+            if (batch.size() == 1) engine().run(*batch[0]->jobs);
+            else {
+                std::vector<Job*> all;
+                for (RunRequest* q : batch) all.insert(all.end(), q->jobs->begin(), q->jobs->end());
+                engine().run(all);
+            }
+        } catch (...) { err = std::current_exception(); }
+        g_coBatches.fetch_add(1);
+        g_coRequests.fetch_add((long long)batch.size());
+        lk.lock();
+        g_coRunning = false;
+        for (RunRequest* q : batch) { q->done = true; q->err = err; }
+        g_coCv.notify_all();
+    }
+    lk.unlock();
+    if (r.err) std::rethrow_exception(r.err);
+}
+
 char* dupString(const std::string& s) {  // cppStringToCString, src/string_functions.cpp:19-24
     char* p = (char*)malloc(s.size() + 1);
     memcpy(p, s.data(), s.size());
     p[s.size()] = '\0';
     return p;
+}
+
+// One line on stderr the first time a job is dropped because the reference's own behaviour is undefined for it.
+void noteUndefined(int status) {
+    static std::atomic<bool> said(false);
+    if (!said.exchange(true))
+        fprintf(stderr, "unicycler_b200: note: an alignment was dropped (status %d: the reference indexes out of bounds or "
+                        "throws for this input; it returns no alignment there too)\n", status);
 }
 
 long long nowMs() {
@@ -78,30 +151,8 @@ std::vector<std::string> splitString(const std::string& in, char delim) {  // sr
     return result;
 }
 
-// Runs f(i) for i in [0, n) on the host cores (the per-read host stages are independent;
-// the reference gets the same parallelism from Python threads, unicycler_align.py:203-225).
-template <typename F>
-void parallelFor(int n, F f) {
-    int threads = (int)std::thread::hardware_concurrency();
-    const char* e = getenv("UNICYCLER_B200_HOST_THREADS");
-    if (e) threads = atoi(e);
-    threads = std::max(1, std::min(threads, n));
-    if (threads == 1) {
-        g_hostBusy.fetch_add(1);
-        for (int i = 0; i < n; ++i) f(i);
-        g_hostBusy.fetch_sub(1);
-        return;
-    }
-    std::atomic<int> next(0);
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t)
-        pool.emplace_back([&]() {
-            g_hostBusy.fetch_add(1);  // a busy core: inner stages may only borrow the idle ones
-            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i);
-            g_hostBusy.fetch_sub(1);
-        });
-    for (auto& th : pool) th.join();
-}
+// Per-read host stages run on the process-wide pool (hostpool.hpp); the reference gets the same parallelism from
+// Python threads (unicycler_align.py:203-225).
 
 double nowSec() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -143,6 +194,7 @@ std::string finishPairJob(PairJob& pj, const Scoring& sc, bool path) {
     if (!pj.planned) return "";  // see DESIGN.md: empty inputs / band width < 3 are undefined in the reference
     const JobResult& r = pj.job.result;
     if (r.status == JOB_BAD_SCORE) return "";  // catch (...) -> return 0 (global_align.cpp:69-82)
+    if (r.status == JOB_REF_UB || r.status == JOB_INVALID) { noteUndefined(r.status); return ""; }
     if (r.status != JOB_OK) fatal("DP job failed with status " + std::to_string(r.status));
     if (path && r.score < -1000000) return "";  // path_align.cpp:84-85
     const std::vector<Seg>& trace = r.gridTraces[0][0];
@@ -150,6 +202,71 @@ std::string finishPairJob(PairJob& pj, const Scoring& sc, bool path) {
     scoreAlignment(trace, false, pj.H.data(), (long)pj.H.size(), pj.V.data(), (long)pj.V.size(), 0, true, true, !path,
                    sc, rec);
     return fullString(rec, "s1", "s2", nowMs() - pj.startMs);
+}
+
+// Unbanded globalAlignment(align, score, AlignConfig<top, left, right, bottom>) as one GRID_GLOBAL job
+// (semi_global_align_exhaustive.cpp:40-67, start_end_align.cpp:19-101, overlap_align.cpp:17-81).
+// AlignConfig<TTop, TLeft, TRight, TBottom>: free gaps in the first row / first column / last column / last row.
+void buildFreeEndJob(PairJob& pj, const std::string& s1, const std::string& s2, const Scoring& sc, bool top, bool left,
+                     bool right, bool bottom) {
+    pj.startMs = nowMs();
+    toDna5(s1.data(), s1.size(), pj.H);
+    toDna5(s2.data(), s2.size(), pj.V);
+    Job& j = pj.job;
+    j.H = pj.H.data(); j.lenH = (int32_t)pj.H.size();
+    j.V = pj.V.data(); j.lenV = (int32_t)pj.V.size();
+    j.match = sc.match; j.mismatch = sc.mismatch; j.gapOpen = sc.gapOpen; j.gapExtend = sc.gapExtend;
+    j.freeFirstRow = top; j.freeFirstCol = left; j.freeLastCol = right; j.freeLastRow = bottom;
+    j.complete = 0;   // SingleTrace
+    pj.planned = planGlobal((long)pj.H.size(), (long)pj.V.size(), false, 0, 0, top, left, bottom, right, j.grids);
+}
+
+// Runs the job; false when the reference's call throws / yields nothing (caught there, mapped to its failure value).
+bool runFreeEndJob(PairJob& pj) {
+    if (!pj.planned) return false;
+    std::vector<Job*> jobs{&pj.job};
+    runCoalesced(jobs);
+    const JobResult& r = pj.job.result;
+    if (r.status == JOB_BAD_SCORE) return false;
+    if (r.status == JOB_REF_UB || r.status == JOB_INVALID) { noteUndefined(r.status); return false; }
+    if (r.status != JOB_OK) fatal("DP job failed with status " + std::to_string(r.status));
+    return true;
+}
+
+// Calls f(hasBase1, hasBase2) for every alignment column in order: the two gapped rows the reference streams out of
+// the Align object (start_end_align.cpp:64-83), walked straight from the trace segments (stored last segment first).
+template <typename F>
+long forEachColumn(const std::vector<Seg>& trace, F f) {
+    long cols = 0;
+    for (size_t k = trace.size(); k > 0; --k) {
+        const Seg& s = trace[k - 1];
+        for (int t = 0; t < s.len; ++t, ++cols) f(s.dir != T_V, s.dir != T_H);
+    }
+    return cols;
+}
+
+// start_end_align.cpp:30-101
+int startEndAlignmentImpl(const char* s1, const char* s2, bool start, const Scoring& sc) {
+    HostStageScope hostStage;
+    std::string sequence1(s1), sequence2(s2);
+    const int trimSize = int(sequence1.length() * 1.5);
+    const int trimOffset = start ? 0 : std::max(0, int(sequence2.length()) - trimSize);
+    if (int(sequence2.length()) > trimSize) sequence2 = sequence2.substr((size_t)trimOffset, (size_t)trimSize);
+    PairJob pj;
+    if (start) buildFreeEndJob(pj, sequence1, sequence2, sc, false, false, true, false);
+    else buildFreeEndJob(pj, sequence1, sequence2, sc, false, true, false, false);
+    hostStage.leave();
+    if (!runFreeEndJob(pj)) return -1;
+    int seq2Pos = 0, seq2PosAtSeq1Start = -1, seq2PosAtSeq1End = -1;
+    const long cols = forEachColumn(pj.job.result.gridTraces[0][0], [&](bool b1, bool b2) {
+        if (b1) {
+            if (seq2PosAtSeq1Start == -1) seq2PosAtSeq1Start = seq2Pos;
+            seq2PosAtSeq1End = seq2Pos + 1;
+        }
+        if (b2) ++seq2Pos;
+    });
+    if (cols == 0) return -1;
+    return start ? seq2PosAtSeq1End : seq2PosAtSeq1Start + trimOffset;
 }
 
 // ------------------------------------------------------------------ chain jobs
@@ -178,9 +295,12 @@ void buildChainJob(ChainJob& cj, const char* readSeq, size_t readLen, const char
 
 // returns false when the reference produces no alignment (exception swallowed at semi_global_align.cpp:311)
 bool finishChainJob(ChainJob& cj, const Scoring& sc, std::string& out) {
-    if (!cj.planned) fatal("seed chain geometry outside the supported range (reference behaviour undefined)");
+    // Geometry the reference itself cannot align (negative grid origin, empty infix: its unsigned sizes wrap and
+    // the resulting bad_alloc is swallowed by the catch (...) at semi_global_align.cpp:297-311): no alignment.
+    if (!cj.planned) { noteUndefined(JOB_INVALID); return false; }
     const JobResult& r = cj.job.result;
     if (r.status == JOB_BAD_SCORE) return false;
+    if (r.status == JOB_REF_UB || r.status == JOB_INVALID) { noteUndefined(r.status); return false; }
     if (r.status != JOB_OK) fatal("chain DP job failed with status " + std::to_string(r.status));
     std::vector<Seg> trace;
     bool empty = true;
@@ -353,6 +473,9 @@ extern "C" {
 const char* ub200_version(void) { return "unicycler_b200 0.1 (reference ABI: Unicycler 0.5.1)"; }
 
 int ub200_setDevice(int device) {
+    // not while a batch is running or queued (the engine would be destroyed under it)
+    std::unique_lock<std::mutex> co(g_coMu);
+    if (g_coRunning || !g_coPending.empty()) return -1;
     std::lock_guard<std::mutex> lock(g_engineMu);
     if (g_engine && g_engine->device() != device) g_engine.reset();
     g_device = device;
@@ -368,10 +491,12 @@ void deleteRefSeqs(void* h) { delete (SeqMap*)h; }
 static char* pairAlignment(char* s1, char* s2, int m, int mm, int go, int ge, bool useBanding, int bandSize, bool path) {
     Scoring sc{m, mm, go, ge};
     PairJob pj;
+    HostStageScope hostStage;
     buildPairJob(pj, s1, s2, sc, useBanding, bandSize, path);
+    hostStage.leave();
     if (pj.planned) {
         std::vector<Job*> jobs{&pj.job};
-        engine().run(jobs);
+        runCoalesced(jobs);
     }
     return dupString(finishPairJob(pj, sc, path));
 }
@@ -396,7 +521,7 @@ int ub200_globalAlignmentBatch(int n, const char* const* s1, const char* const* 
     });
     for (int i = 0; i < n; ++i)
         if (pjs[(size_t)i]->planned) jobs.push_back(&pjs[(size_t)i]->job);
-    engine().run(jobs);
+    runCoalesced(jobs);
     parallelFor(n, [&](int i) { results[i] = dupString(finishPairJob(*pjs[(size_t)i], sc, path)); });
     return 0;
 }
@@ -432,7 +557,7 @@ char* getRandomSequenceAlignmentScores(int seqLength, int n, int m, int mm, int 
         std::vector<Job*> jobs;
         for (long long i = 0; i < cnt; ++i)
             if (pjs[(size_t)i]->planned) jobs.push_back(&pjs[(size_t)i]->job);
-        engine().run(jobs);
+        runCoalesced(jobs);
         std::vector<double> batchScores((size_t)cnt, 0.0);
         std::vector<char> have((size_t)cnt, 0);
         parallelFor((int)cnt, [&](int i) {
@@ -458,6 +583,25 @@ char* getRandomSequenceAlignmentScores(int seqLength, int n, int m, int mm, int 
     return dupString(std::to_string(mean) + "," + std::to_string(sd));
 }
 
+int ub200_calibrationPairs(int seqLength, int n, unsigned seed, char** s1, char** s2) {
+    std::mt19937 gen(seed);
+    std::uniform_int_distribution<int> dist(0, 3);
+    static const char bases[4] = {'A', 'C', 'G', 'T'};
+    std::string a((size_t)std::max(0, seqLength), 'A'), b(a);
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < seqLength; ++k) a[(size_t)k] = bases[dist(gen)];
+        for (int k = 0; k < seqLength; ++k) b[(size_t)k] = bases[dist(gen)];
+        s1[i] = dupString(a);
+        s2[i] = dupString(b);
+    }
+    return 0;
+}
+
+void ub200_coalescerStats(int64_t* batches, int64_t* requests) {
+    if (batches) *batches = g_coBatches.load();
+    if (requests) *requests = g_coRequests.load();
+}
+
 static void seedsFromArray(const int64_t* seeds, int nSeeds, std::vector<ChainSeed>& chain) {
     chain.resize((size_t)nSeeds);
     for (int i = 0; i < nSeeds; ++i)
@@ -473,9 +617,9 @@ char* ub200_chainAlignment(const char* readSeq, const char* refSeq, const int64_
     ChainJob cj;
     cj.readName = readName; cj.refName = refName; cj.refOffset = refOffset;
     buildChainJob(cj, readSeq, strlen(readSeq), refSeq, strlen(refSeq), chain, sc, bandSize);
-    if (!cj.planned) return dupString("!ERROR:unsupported seed chain geometry");
-    std::vector<Job*> jobs{&cj.job};
-    engine().run(jobs);
+    std::vector<Job*> jobs;
+    if (cj.planned) jobs.push_back(&cj.job);
+    runCoalesced(jobs);
     std::string out;
     if (!finishChainJob(cj, sc, out)) out = "";
     return dupString(out);
@@ -496,8 +640,7 @@ static int buildChainBatch(int n, const char* const* readSeqs, const char* const
         cj.refName = refNames ? refNames[i] : "ref";
         cj.refOffset = refOffsets ? refOffsets[i] : 0;
         buildChainJob(cj, readSeqs[i], strlen(readSeqs[i]), refSeqs[i], strlen(refSeqs[i]), chain, sc, bandSize);
-        if (!cj.planned) return -1;
-        jobs.push_back(&cj.job);
+        if (cj.planned) jobs.push_back(&cj.job);   // unplanned: no alignment, like the reference's swallowed exception
     }
     return 0;
 }
@@ -511,7 +654,7 @@ int ub200_chainAlignmentBatch(int n, const char* const* readSeqs, const char* co
     std::vector<Job*> jobs;
     if (buildChainBatch(n, readSeqs, refSeqs, seeds, seedOffsets, sc, bandSize, readNames, refNames, refOffsets, cjs, jobs))
         return -1;
-    engine().run(jobs);
+    runCoalesced(jobs);
     parallelFor(n, [&](int i) {
         std::string out;
         if (!finishChainJob(*cjs[(size_t)i], sc, out)) out = "";
@@ -592,12 +735,15 @@ char* semiGlobalAlignment(char* readName, char* readSeq, int verbosity, char* hi
                           int go, int ge, double, bool, int sensitivityLevel) {
     Scoring sc{m, mm, go, ge};
     ReadWork w;
+    HostStageScope hostStage;   // lets a coalescing leader know that this call is about to submit
     prepareRead(w, readName, readSeq, verbosity, hits, (SeqMap*)refSeqs, sc, sensitivityLevel);
     parallelFor((int)w.units.size(), [&](int k) { seedUnit(w, w.units[(size_t)k], verbosity, (SeqMap*)refSeqs, sc); });
     collectUnits(w);
     std::vector<Job*> jobs;
-    for (auto& cj : w.jobs) jobs.push_back(&cj->job);
-    engine().run(jobs);
+    for (auto& cj : w.jobs)
+        if (cj->planned) jobs.push_back(&cj->job);
+    hostStage.leave();
+    runCoalesced(jobs);
     return dupString(finishRead(w, sc));
 }
 
@@ -637,7 +783,8 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     for (int i = 0; i < n; ++i) collectUnits(*works[(size_t)i]);
     std::vector<Job*> jobs;
     for (int i = 0; i < n; ++i)
-        for (auto& cj : works[(size_t)i]->jobs) jobs.push_back(&cj->job);
+        for (auto& cj : works[(size_t)i]->jobs)
+            if (cj->planned) jobs.push_back(&cj->job);
     const double t1 = nowSec();
     if (getenv("UNICYCLER_B200_HOST_ONLY")) {  // developer aid: time the host stage without a GPU
         fprintf(stderr, "[ub200 host] reads=%d jobs=%zu prepare=%.1f ms (kmers %.1f, linetrace %.1f [fillCloud %.1f, densest point %.1f], seeds+chain %.1f thread-ms)\n", n,
@@ -646,7 +793,7 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
         for (int i = 0; i < n; ++i) results[i] = dupString("");
         return 0;
     }
-    engine().run(jobs);
+    runCoalesced(jobs);
     const double t2 = nowSec();
     parallelFor(n, [&](int k) {
         const int i = order[(size_t)k];
@@ -690,23 +837,50 @@ void ub200_lastStats(int64_t* cells, double* kernelMs, int64_t* launches, double
     if (d2hMs) *d2hMs = s.d2hMs;
 }
 
-// ---- forwarders for the symbols outside the hot path (cpp_wrappers.py:61-74,180-357)
-char* semiGlobalAlignmentExhaustive(char* a, char* b, int c, int d, int e, int f) {
-    typedef char* (*F)(char*, char*, int, int, int, int);
-    return ((F)forwardSym("semiGlobalAlignmentExhaustive"))(a, b, c, d, e, f);
+// ---- the remaining SeqAn pairwise DPs, on the same GRID_GLOBAL kernel path
+char* semiGlobalAlignmentExhaustive(char* s1, char* s2, int m, int mm, int go, int ge) {
+    // src/semi_global_align_exhaustive.cpp:40-67: AlignConfig<true,true,true,true>, ScoredAlignment(..., true, true, true)
+    Scoring sc{m, mm, go, ge};
+    HostStageScope hostStage;
+    PairJob pj;
+    buildFreeEndJob(pj, s1, s2, sc, true, true, true, true);
+    hostStage.leave();
+    if (!runFreeEndJob(pj)) return dupString("");
+    AlignmentRecord rec;
+    scoreAlignment(pj.job.result.gridTraces[0][0], false, pj.H.data(), (long)pj.H.size(), pj.V.data(), (long)pj.V.size(), 0,
+                   true, true, true, sc, rec);
+    return dupString(fullString(rec, "s1", "s2", nowMs() - pj.startMs));
 }
-char* startAlignment(char* a, char* b, int c, int d, int e, int f) {
-    typedef char* (*F)(char*, char*, int, int, int, int);
-    return ((F)forwardSym("startAlignment"))(a, b, c, d, e, f);
+int startAlignment(char* s1, char* s2, int m, int mm, int go, int ge) {  // src/start_end_align.cpp:19-21
+    return startEndAlignmentImpl(s1, s2, true, Scoring{m, mm, go, ge});
 }
-char* endAlignment(char* a, char* b, int c, int d, int e, int f) {
-    typedef char* (*F)(char*, char*, int, int, int, int);
-    return ((F)forwardSym("endAlignment"))(a, b, c, d, e, f);
+int endAlignment(char* s1, char* s2, int m, int mm, int go, int ge) {    // src/start_end_align.cpp:24-26
+    return startEndAlignmentImpl(s1, s2, false, Scoring{m, mm, go, ge});
 }
-char* overlapAlignment(char* a, char* b, int c, int d, int e, int f, int g) {
-    typedef char* (*F)(char*, char*, int, int, int, int, int);
-    return ((F)forwardSym("overlapAlignment"))(a, b, c, d, e, f, g);
+char* overlapAlignment(char* s1, char* s2, int m, int mm, int go, int ge, int guessOverlap) {
+    // src/overlap_align.cpp:17-81: suffix of s1 against prefix of s2, AlignConfig<true,false,true,false>
+    Scoring sc{m, mm, go, ge};
+    HostStageScope hostStage;
+    std::string sequence1(s1), sequence2(s2);
+    const int trimSize = int((guessOverlap + 100) * 1.5);
+    if (trimSize < int(sequence1.length())) sequence1 = sequence1.substr(sequence1.length() - (size_t)trimSize, (size_t)trimSize);
+    if (trimSize < int(sequence2.length())) sequence2 = sequence2.substr(0, (size_t)trimSize);
+    PairJob pj;
+    buildFreeEndJob(pj, sequence1, sequence2, sc, true, false, true, false);
+    hostStage.leave();
+    if (!runFreeEndJob(pj)) return dupString("-1,-1");
+    int seq1Pos = 0, seq2Pos = 0, seq1PosAtSeq2Start = -1, seq2PosAtSeq1End = -1;
+    const long cols = forEachColumn(pj.job.result.gridTraces[0][0], [&](bool b1, bool b2) {
+        if (b1) seq2PosAtSeq1End = seq2Pos + 1;
+        if (b2 && seq1PosAtSeq2Start == -1) seq1PosAtSeq2Start = seq1Pos;
+        if (b1) ++seq1Pos;
+        if (b2) ++seq2Pos;
+    });
+    if (cols == 0) return dupString("-1,-1");
+    return dupString(std::to_string(seq1Pos - seq1PosAtSeq2Start) + "," + std::to_string(seq2PosAtSeq1End));
 }
+
+// ---- forwarders for the symbols outside the hot path (cpp_wrappers.py:180-357)
 char* multipleSequenceAlignment(char** a, char** b, unsigned long c, unsigned int d, int e, int f, int g, int h) {
     typedef char* (*F)(char**, char**, unsigned long, unsigned int, int, int, int, int);
     return ((F)forwardSym("multipleSequenceAlignment"))(a, b, c, d, e, f, g, h);

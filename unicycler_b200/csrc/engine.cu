@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "engine_kernels.cuh"
+#include "hostpool.hpp"
 
 namespace ub200 {
 
@@ -1832,25 +1833,11 @@ EngineStats Engine::lastStats() const { return impl_->stats; }
 
 static size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// f(i) for i in [0, n) on a few host threads (staging and parsing are independent per job)
+// f(i) for i in [0, n) on a few threads of the process-wide host pool (staging and parsing are independent per job)
 template <typename F>
 static void engineParallelFor(int n, F f) {
-    int threads = std::min<int>(8, (int)std::thread::hardware_concurrency());
-    if (const char* e = getenv("UNICYCLER_B200_HOST_THREADS")) threads = atoi(e);
-    threads = std::max(1, std::min(threads, n / 4));
-    if (threads <= 1) { for (int i = 0; i < n; ++i) f(i); return; }
-    std::atomic<int> next(0);
-    std::exception_ptr err;
-    std::mutex errMu;
-    auto body = [&]() {
-        try { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i); }
-        catch (...) { std::lock_guard<std::mutex> lk(errMu); if (!err) err = std::current_exception(); }
-    };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; ++t) pool.emplace_back(body);
-    body();
-    for (auto& th : pool) th.join();
-    if (err) std::rethrow_exception(err);
+    if (n < 8) { for (int i = 0; i < n; ++i) f(i); return; }
+    parallelFor(n, f, 1, std::min(7, n / 4));
 }
 
 static double wallMs() {

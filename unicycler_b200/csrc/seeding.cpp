@@ -4,6 +4,7 @@
 // seeds_global_chaining.h:102-280).  The container types, hash and iteration orders are the reference's
 // on purpose: several decisions sum doubles in container order.
 #include "seeding.hpp"
+#include "hostpool.hpp"
 
 #include <atomic>
 #include <chrono>
@@ -19,28 +20,6 @@
 #include <unordered_set>
 
 namespace ub200 {
-
-// Host-core accounting shared with the per-read thread pool (abi.cpp): a stage may borrow cores that no
-// read-level task is using.
-std::atomic<int> g_hostBusy(0);
-static int hostCores() {
-    static const int n = [] {
-        const char* e = getenv("UNICYCLER_B200_HOST_THREADS");
-        int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
-        return v < 1 ? 1 : v;
-    }();
-    return n;
-}
-int acquireSpareHostThreads(int want) {
-    for (;;) {
-        int busy = g_hostBusy.load();
-        int spare = hostCores() - busy;
-        int take = spare < want ? spare : want;
-        if (take <= 0) return 0;
-        if (g_hostBusy.compare_exchange_weak(busy, busy + take)) return take;
-    }
-}
-void releaseSpareHostThreads(int n) { g_hostBusy.fetch_sub(n); }
 
 // developer timers of the host seeding stages (seconds, summed over threads)
 std::atomic<long long> g_seedProf[6];
@@ -455,27 +434,10 @@ double getPointDensityScore(int radius, Point p, const Cloud& cloud) {
 
 // Exact density scores of the listed points (independent of each other: spare host cores help).
 static void densityScores(int radius, const Cloud& cloud, const std::vector<uint32_t>& which, std::vector<double>& score) {
-    const size_t n = which.size();
-    int helpers = 0;
-    if (n >= 2048) helpers = acquireSpareHostThreads(7);
-    if (helpers == 0) {
-        for (size_t q = 0; q < n; ++q) score[which[q]] = getPointDensityScore(radius, cloud.pts[which[q]], cloud);
-        return;
-    }
-    std::atomic<size_t> next(0);
-    auto work = [&]() {
-        for (;;) {
-            const size_t b = next.fetch_add(256);
-            if (b >= n) break;
-            const size_t e = std::min(n, b + 256);
-            for (size_t q = b; q < e; ++q) score[which[q]] = getPointDensityScore(radius, cloud.pts[which[q]], cloud);
-        }
-    };
-    std::vector<std::thread> pool;
-    for (int t = 0; t < helpers; ++t) pool.emplace_back(work);
-    work();
-    for (auto& th : pool) th.join();
-    releaseSpareHostThreads(helpers);
+    const int n = (int)which.size();
+    // idle pool workers help (nested loop of the per-read task that called us)
+    parallelFor(n, [&](int q) { score[which[(size_t)q]] = getPointDensityScore(radius, cloud.pts[which[(size_t)q]], cloud); },
+                n >= 2048 ? 256 : n, 7);
 }
 
 Point getHighestDensityPoint(int radius, const Cloud& cloud) {

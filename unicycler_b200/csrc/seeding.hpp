@@ -46,12 +46,6 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
                const SensitivityParams& sp, int verbosity, const std::string& refName, int refStart, int refEnd,
                RangeSeeds& out);
 
-std::string reverseComplement(const std::string& s);
-
-// Host-core accounting: read-level tasks register themselves as busy; inner loops may borrow idle cores.
-extern std::atomic<int> g_hostBusy;
-int acquireSpareHostThreads(int want);
-void releaseSpareHostThreads(int n);
-  // src/string_functions.cpp:52-79
+std::string reverseComplement(const std::string& s);  // src/string_functions.cpp:52-79
 
 }  // namespace ub200

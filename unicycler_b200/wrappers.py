@@ -69,6 +69,18 @@ def load_library():
     L.ub200_chainCells.restype = c_int64
     L.ub200_chainPlan.argtypes = [c_int, c_int, POINTER(c_int64), c_int, c_int, POINTER(ctypes.c_int32), c_int]
     L.ub200_chainPlan.restype = c_int
+    L.semiGlobalAlignmentExhaustive.argtypes = [c_char_p, c_char_p, c_int, c_int, c_int, c_int]
+    L.semiGlobalAlignmentExhaustive.restype = c_void_p
+    for name in ('startAlignment', 'endAlignment'):
+        f = getattr(L, name)
+        f.argtypes = [c_char_p, c_char_p, c_int, c_int, c_int, c_int]
+        f.restype = c_int
+    L.overlapAlignment.argtypes = [c_char_p, c_char_p, c_int, c_int, c_int, c_int, c_int]
+    L.overlapAlignment.restype = c_void_p
+    L.ub200_calibrationPairs.argtypes = [c_int, c_int, ctypes.c_uint, POINTER(c_void_p), POINTER(c_void_p)]
+    L.ub200_calibrationPairs.restype = c_int
+    L.ub200_coalescerStats.argtypes = [POINTER(c_int64), POINTER(c_int64)]
+    L.ub200_coalescerStats.restype = None
     L.ub200_setDevice.argtypes = [c_int]
     L.ub200_setDevice.restype = c_int
     L.ub200_intPeakOpsPerSec.argtypes = []
@@ -117,6 +129,45 @@ def path_alignment(partial_seq, full_seq, scoring_scheme, use_banding, band_size
     m, mm, go, ge = _scheme(scoring_scheme)
     return _to_str(load_library().pathAlignment(partial_seq.encode(), full_seq.encode(), m, mm, go, ge, use_banding,
                                                 band_size))
+
+
+def semi_global_alignment_exhaustive(sequence_1, sequence_2, scoring_scheme):
+    """cpp_wrappers.py:69-74"""
+    m, mm, go, ge = _scheme(scoring_scheme)
+    return _to_str(load_library().semiGlobalAlignmentExhaustive(sequence_1.encode(), sequence_2.encode(), m, mm, go, ge))
+
+
+def start_seq_alignment(s_1, s_2, scoring_scheme):
+    """cpp_wrappers.py:338-341"""
+    m, mm, go, ge = _scheme(scoring_scheme)
+    return load_library().startAlignment(s_1.encode(), s_2.encode(), m, mm, go, ge)
+
+
+def end_seq_alignment(s_1, s_2, scoring_scheme):
+    """cpp_wrappers.py:354-357"""
+    m, mm, go, ge = _scheme(scoring_scheme)
+    return load_library().endAlignment(s_1.encode(), s_2.encode(), m, mm, go, ge)
+
+
+def overlap_alignment(s_1, s_2, scoring_scheme, guess_overlap):
+    """cpp_wrappers.py:195-200 -> (overlap_1, overlap_2)"""
+    m, mm, go, ge = _scheme(scoring_scheme)
+    r = _to_str(load_library().overlapAlignment(s_1.encode(), s_2.encode(), m, mm, go, ge, guess_overlap))
+    a, b = r.split(',')
+    return int(a), int(b)
+
+
+def calibration_pairs(seq_length, n, seed):
+    """The sequence pairs getRandomSequenceAlignmentScores(seq_length, n, ...) aligns under UNICYCLER_B200_SEED=seed."""
+    a, b = (c_void_p * n)(), (c_void_p * n)()
+    load_library().ub200_calibrationPairs(seq_length, n, seed, a, b)
+    return [_to_str(p) for p in a], [_to_str(p) for p in b]
+
+
+def coalescer_stats():
+    b, r = c_int64(), c_int64()
+    load_library().ub200_coalescerStats(ctypes.byref(b), ctypes.byref(r))
+    return dict(batches=b.value, requests=r.value)
 
 
 def get_random_sequence_alignment_mean_and_std_dev(seq_length, count, scoring_scheme):
