@@ -1502,6 +1502,13 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
     for (; gi < jb.gridCount; ++gi) {
         // ---- merge check: beyond the own range, do the cells I am about to plant equal what a later segment started from?
         bool merged = false;
+        // A merge into q hands grid gi to q — but q's work on gi lives in the grid's persistent checkpoint block, which
+        // every segment that walks gi shares and the LAST one to fill it keeps.  Later segments are always ahead of
+        // earlier ones (never overtaken), so the last writer of gi is the lowest-numbered segment that walks it: a
+        // segment between this one and q that has walked gi (or still may) would overwrite q's fill after the merge.
+        // Once such a segment is met without merging into it, no merge happens at gi (this warp redoes the grid and
+        // thereby becomes its last writer and owner).
+        bool blocked = false;
         for (int q = seg + 1; q < jb.nSeg && !merged; ++q) {
             if (jb.segStart[q] > gi) break;
             int prog = 0, gone = 0;
@@ -1529,8 +1536,13 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
                 const GridRec* theirs = &P.gridRecs[jb.recBase + (long long)q * jb.gridCount + gi];
                 match = plantedMatch(planted, nPlantedPrev, theirs->plantedIn, __ldcg(&theirs->nPlantedIn), delta);
             } else continue;   // q stopped before reaching this grid
-            if (match) { merged = true; syncSeg = q; syncGrid = gi; syncDelta = delta; }
+            if (match && !blocked) { merged = true; syncSeg = q; syncGrid = gi; syncDelta = delta; }
             else {
+                // q walks gi unless it has stopped exactly here (merged or failed before filling it)
+                int walks = 1;
+                if (lane == 0) walks = (ldRelaxed(&js->segStop[q]) && ldRelaxed(&js->segProgress[q]) <= gi) ? 0 : 1;
+                walks = __shfl_sync(FULLMASK, walks, 0);
+                if (walks) blocked = true;
                 // no merge here: this warp redoes grid gi itself.  Segment q may still be working on the very same
                 // grid (same persistent block, same task counters): let it finish that grid first.
                 if (lane == 0) {
@@ -1596,7 +1608,8 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
             if (lane == 0) rec->relMax = TR.maxScore;
             nPlanted = 0;
             const bool deferBig = status == JOB_OK && !G.local && P.persist != nullptr && gd.persistOff >= 0 &&
-                                  gd.kind != GRID_GLOBAL && TR.nCand <= MAXREC && nPlantedPrev <= MAXREC && P.fastEnabled;
+                                  gd.kind != GRID_GLOBAL && TR.nCand <= MAXREC && nPlantedPrev <= MAXREC && P.fastEnabled &&
+                                  !((P.pad5 & 1) && G.g.banded) && !((P.pad5 & 4) && !G.g.banded);
             if (deferBig) {
                 // big chain grid: only the crossing walks here, one pass-2 item per tied maximum
                 int insertedMask = 0;
@@ -1608,7 +1621,7 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
                     rec->state = 2; rec->nCand = TR.nCand; rec->inserted = insertedMask;
                     for (int k = 0; k < TR.nCand; ++k) rec->cand[k] = G.cand[k];
                     // segment 0 owns every grid it walks: the long tracebacks of its big grids start right away
-                    const int early = (seg == 0 && status == JOB_OK && jb.gridCount > 1) ? 1 : 0;
+                    const int early = (seg == 0 && status == JOB_OK && jb.gridCount > 1 && !(P.pad5 & 2)) ? 1 : 0;
                     rec->published = early;
                     if (early) {
                         __threadfence();
@@ -1774,7 +1787,7 @@ struct Engine::Impl {
     std::vector<int> order;
     std::vector<JobOut> jobOut;
     KParams kp;
-    size_t seqBytes = 0, outInts = 0, ringBytes = 0;
+    size_t seqBytes = 0, outInts = 0, ringBytes = 0, offState = 0;
 
     void growDev(void*& p, size_t& cap, size_t need) {
         if (need <= cap) return;
@@ -2212,12 +2225,14 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.tileRing = (TileReq*)((uint8_t*)I.dRing + offTile);
     kp.tileSlots = (usePersist && !getenv("UNICYCLER_B200_NO_TILE_HELP")) ? (uint8_t*)I.dTileSlots : nullptr;
     kp.jobState = (JobState*)((uint8_t*)I.dRing + offState);
+    I.offState = offState;
     kp.tokRing = (int*)((uint8_t*)I.dRing + offTok);
     kp.maxTokens = (int)maxTokens; kp.pad7 = 0;
     kp.gridRecs = (GridRec*)I.dRecs;
     kp.persist = usePersist ? (uint8_t*)I.dPersist : nullptr;
     kp.mini = (uint8_t*)I.dMini; kp.miniStride = (long long)miniStride; kp.miniInitCol = (long long)miniInitCol;
-    kp.fastEnabled = getenv("UNICYCLER_B200_NO_FAST") ? 0 : (getenv("UNICYCLER_B200_CHECK_FAST") ? 2 : 1); kp.pad5 = 0;
+    kp.fastEnabled = getenv("UNICYCLER_B200_NO_FAST") ? 0 : (getenv("UNICYCLER_B200_CHECK_FAST") ? 2 : 1);
+    kp.pad5 = getenv("UNICYCLER_B200_DBG") ? atoi(getenv("UNICYCLER_B200_DBG")) : 0;   // developer switches
     kp.scratch = (uint8_t*)I.dScratch; kp.scratchStride = L.total;
     kp.lay = L;
     CUDA_CHECK(cudaMemcpyToSymbolAsync(cP, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, I.stream));
@@ -2305,6 +2320,34 @@ void Engine::fetch(std::vector<Job*>& jobs) {
     if (cudaEventElapsedTime(&ms, I.ev[2], I.ev[3]) == cudaSuccess && ms > 0.0005f) I.stats.kernelMs = ms;
     if (cudaEventElapsedTime(&ms, I.ev[0], I.ev[1]) == cudaSuccess) I.stats.h2dMs = ms;
     if (cudaEventElapsedTime(&ms, I.ev[4], I.ev[5]) == cudaSuccess) I.stats.d2hMs = ms;
+    if (getenv("UNICYCLER_B200_DUMPSTATE")) {   // developer aid: how every chain was cut and resolved
+        std::vector<JobState> js(nJobs);
+        CUDA_CHECK(cudaMemcpy(js.data(), (uint8_t*)I.dRing + I.offState, nJobs * sizeof(JobState), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < nJobs; ++k) {
+            const JobDev& d = I.jobsDev[k];
+            fprintf(stderr, "[ub200 state] job %zu: %d grids, status %d/%d, outLen %d, records %d, segments:", k, d.gridCount, I.jobOut[k].status, js[k].status, I.jobOut[k].outLen, js[k].nRecIdx);
+            for (int p = 0; p < d.nSeg; ++p)
+                fprintf(stderr, " [%d: start %d claim %d prog %d sync->%d@%d delta %d]", p, d.segStart[p], js[k].segClaim[p], js[k].segProgress[p], js[k].segSyncSeg[p], js[k].segSyncGrid[p], js[k].segDelta[p]);
+            fprintf(stderr, " owners:");
+            for (int t = 0; t < js[k].nOwner; ++t) fprintf(stderr, " %d from %d", js[k].ownerSeg[t], js[k].ownerFrom[t]);
+            fprintf(stderr, "\n");
+            if (const char* ge = getenv("UNICYCLER_B200_DUMPGRID")) {
+                const int g0 = atoi(ge);
+                std::vector<GridRec> recs((size_t)d.nSeg * d.gridCount);
+                CUDA_CHECK(cudaMemcpy(recs.data(), (GridRec*)I.dRecs + d.recBase, recs.size() * sizeof(GridRec), cudaMemcpyDeviceToHost));
+                for (int gi = std::max(0, g0 - 1); gi <= std::min(d.gridCount - 1, g0 + 1); ++gi)
+                    for (int p = 0; p < d.nSeg; ++p) {
+                        const GridRec& r = recs[(size_t)p * d.gridCount + gi];
+                        fprintf(stderr, "[ub200 rec] grid %d seg %d: state %d nCand %d inserted %d relMax %d published %d nPlantedIn %d:", gi, p, r.state, r.nCand, r.inserted, r.relMax, r.published, r.nPlantedIn);
+                        for (int q = 0; q < std::min(r.nPlantedIn, (int)MAXREC); ++q)
+                            fprintf(stderr, " (%d,%d: %d %d %d)", r.plantedIn[q].i1, r.plantedIn[q].i2, r.plantedIn[q].c.s, r.plantedIn[q].c.h, r.plantedIn[q].c.v);
+                        fprintf(stderr, " cands:");
+                        for (int q = 0; q < std::min(r.nCand, (int)MAXREC); ++q) fprintf(stderr, " %d", r.cand[q]);
+                        fprintf(stderr, "\n");
+                    }
+            }
+        }
+    }
     if (getenv("UNICYCLER_B200_PROFILE")) {
         long long tot[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
         size_t worst = 0;

@@ -344,8 +344,15 @@ void glueTracebacksFwd(std::vector<TraceFwd>& global, const std::vector<Trace>& 
 
 void glueChain(const std::vector<GridDesc>& grids, const JobResult& res, std::vector<Seg>& trace, bool& empty) {
     std::vector<TraceFwd> global;
+    const bool dump = getenv("UNICYCLER_B200_DUMPTRACES") != nullptr;   // developer aid
     for (size_t k = 0; k < grids.size(); ++k) {
         const std::vector<Trace>& local = res.gridTraces[k];
+        if (dump) {
+            fprintf(stderr, "[ub200 glue] grid %zu kind %d glue %d origin (%d,%d) %dx%d banded %d: %zu local traces, %zu global before;", k, grids[k].kind, grids[k].glue, grids[k].h0, grids[k].v0, grids[k].nH, grids[k].nV, grids[k].banded, local.size(), global.size());
+            for (const Trace& t : local)
+                if (!t.empty()) fprintf(stderr, " [%zu segs: last-stored (%d,%d,len %d,dir %d) first-stored (%d,%d,len %d,dir %d)]", t.size(), t.back().hBeg, t.back().vBeg, t.back().len, t.back().dir, t.front().hBeg, t.front().vBeg, t.front().len, t.front().dir);
+            fprintf(stderr, "\n");
+        }
         switch (grids[k].glue) {
         case GLUE_APPEND:
             for (const Trace& t : local) global.emplace_back(t.rbegin(), t.rend());
