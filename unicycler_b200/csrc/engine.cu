@@ -951,7 +951,7 @@ __device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask, bool* sawO
     if (lane == 0) {
         // Pop a token (critical-path ring first): it names a task that had a claimable strip.  Strips are claimed
         // in order and only once the strip above is one chunk in (readyUpTo), so no warp parks on a far-away strip.
-        for (int board = 0; board < 2 && item < 0; ++board) {
+        for (int board = 0; board < NBOARD && item < 0; ++board) {
             for (int tries = 0; tries < 8 && item < 0; ++tries) {
                 const int h = ldRelaxed(&P.cb->tokHead[board]);
                 const int tl = ldRelaxed(&P.cb->tokTail[board]);
@@ -1595,7 +1595,7 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
                 c2 = clock64();
                 prof[1] += c2 - d1;
             } else {
-                const int st = publishAndWait(G, wctx, wTask, board);
+                const int st = publishAndWait(G, wctx, wTask, min(max(gd.pad, 0), NBOARD - 1));
                 if (st != JOB_OK) status = st;
                 c2 = clock64();
                 prof[2] += c2 - d1;
@@ -1672,10 +1672,6 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
     if (stoppedCount == jb.nSeg) finalizeSpine(jobIdx);
 }
 
-constexpr int CTX_STRIDE = (int)((sizeof(GridCtx) + 15) / 16 * 16);
-constexpr int SMEM_CTX = NCTRL * WINBYTES;
-constexpr int SMEM_FASTSEQ = SMEM_CTX + (NCTRL + NWARPS) * CTX_STRIDE;
-constexpr int SMEM_BYTES = SMEM_FASTSEQ + NCTRL * (FASTSEQ_H + FASTSEQ_V);
 
 __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
     const KParams& P = cP;
@@ -1704,7 +1700,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
             q = __shfl_sync(FULLMASK, q, 0);
             if (q < P.nEntries) {
                 const int entry = P.order[q];
-                runSegment(entry / MAXSEG, entry % MAXSEG, q < P.nHiJobs ? 0 : 1, *cctx, *wctx, wTask, win,
+                runSegment(entry / MAXSEG, entry % MAXSEG, 0, *cctx, *wctx, wTask, win,
                            P.scratch + (size_t)agent * P.scratchStride, smem + SMEM_FASTSEQ + cw * (FASTSEQ_H + FASTSEQ_V));
                 continue;
             }
@@ -1728,8 +1724,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
         if (lane == 0) done = ldRelaxed(&P.cb->jobsDone);
         done = __shfl_sync(FULLMASK, done, 0);
         if (done >= P.nJobs) break;
-        idle = min(idle + 1, 6);
-        __nanosleep(250u << idle);   // back off to 16 us while nothing is published
+        // back off to 16 us while nothing is published; while big grids are being filled a strip may become claimable
+        // any moment and its pick-up latency is on the grid's critical path: poll every microsecond then
+        int open = 0;
+        if (lane == 0) open = ldRelaxed(&P.cb->openTasks);
+        open = __shfl_sync(FULLMASK, open, 0);
+        idle = min(idle + 1, (open > 0 && (P.pad5 & 32)) ? 2 : 6);
+        __nanosleep(250u << idle);
     }
 }
 
@@ -2037,13 +2038,13 @@ void Engine::upload(std::vector<Job*>& jobs) {
     auto layoutRings = [&](size_t pubTasks, size_t pubStrips) {
         maxPub = pubTasks + 1;
         offRing = alignUp(sizeof(ControlBlock), 256);
-        offP2 = offRing + alignUp(2 * maxPub * sizeof(TaskDesc), 256);
+        offP2 = offRing + alignUp(NBOARD * maxPub * sizeof(TaskDesc), 256);
         offBig = offP2 + alignUp((nJobs + 1) * sizeof(P2Entry), 256);
         offTile = offBig + alignUp(maxBig * sizeof(int2), 256);
         offState = offTile + alignUp((size_t)TILE_QUEUES * TILE_RING_CAP * sizeof(TileReq), 256);
         offTok = offState + alignUp((nJobs + 1) * sizeof(JobState), 256);
         maxTokens = pubStrips + pubTasks + 64;
-        I.ringBytes = offTok + 2 * maxTokens * sizeof(int);
+        I.ringBytes = offTok + NBOARD * maxTokens * sizeof(int);
     };
     layoutRings(nTasks * 8, totalStrips * 8);   // (estimate for the memory budget; exact once the segments are known)
     // mini arenas: init row / column of the largest LOCAL grid, for every control-capable warp
@@ -2159,23 +2160,38 @@ void Engine::upload(std::vector<Job*>& jobs) {
     for (int jk : jobOrder)
         for (int p = 0; p < I.jobsDev[(size_t)jk].nSeg; ++p) I.order.push_back(jk * MAXSEG + p);
     {
-        // The strips of big grids are served by the whole GPU through two token rings; the critical-path ring (the
-        // first nHiJobs entries) goes to the segments with the most big-grid cells to fill: their spines are the
-        // longest (longest-processing-time first).  Entries without big grids keep the order by job cost.
-        std::vector<double> bigCells(I.order.size(), 0.0);
-        for (size_t e = 0; e < I.order.size(); ++e) {
-            const int jk = I.order[e] / MAXSEG, p = I.order[e] % MAXSEG;
-            const JobDev& d = I.jobsDev[(size_t)jk];
-            const Job& j = *jobs[(size_t)jk];
-            const int gEnd = (p + 1 < d.nSeg) ? d.segStart[p + 1] : d.gridCount;
-            for (int g = d.segStart[p]; g < gEnd; ++g) {
+        // Critical-path scheduling.  The remaining latency of a job at grid g is the serial spine still to walk (the
+        // latency model above) plus the longest traceback among the big grids still to come (~500 cycles per
+        // row + column of the walk).  Pass-1 entries are started in that order, and every big grid is published on
+        // the task board of its quartile (board 0 is served first): the strips of a grid that many serial grids still
+        // follow must not queue behind a grid that only its own traceback follows.
+        struct BigGrid { double rem; size_t job; int g; };
+        std::vector<BigGrid> bigs;
+        std::vector<double> entryRem(I.order.size(), 0.0);
+        std::vector<std::vector<double> > segRem(nJobs);
+        for (size_t k = 0; k < nJobs; ++k) {
+            const Job& j = *jobs[k];
+            const JobDev& d = I.jobsDev[k];
+            const int n = (int)j.grids.size();
+            segRem[k].assign((size_t)d.nSeg, 0.0);
+            double suffix = 0.0, tb = 0.0;
+            int p = d.nSeg - 1;
+            for (int g = n - 1; g >= 0; --g) {
                 const GridDesc& gd = j.grids[(size_t)g];
-                if (!localPlan(makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up)).local) bigCells[e] += (double)referenceCells(gd);
+                const bool big = !localPlan(makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up)).local;
+                if (big) tb = std::max(tb, 500.0 * ((double)gd.nH + gd.nV));
+                suffix += gridLatency(gd);
+                if (big) bigs.push_back(BigGrid{suffix + tb, k, g});
+                while (p >= 0 && d.segStart[p] == g) { segRem[k][(size_t)p] = suffix + tb; --p; }
             }
         }
+        std::sort(bigs.begin(), bigs.end(), [](const BigGrid& a, const BigGrid& b) { return a.rem > b.rem; });
+        for (size_t i = 0; i < bigs.size(); ++i)
+            hGrids[I.jobsDev[bigs[i].job].gridBegin + bigs[i].g].pad = (int32_t)std::min<size_t>(NBOARD - 1, i * NBOARD / bigs.size());
+        for (size_t e = 0; e < I.order.size(); ++e) entryRem[e] = segRem[(size_t)(I.order[e] / MAXSEG)][(size_t)(I.order[e] % MAXSEG)];
         std::vector<size_t> perm(I.order.size());
         for (size_t e = 0; e < perm.size(); ++e) perm[e] = e;
-        std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return bigCells[a] > bigCells[b]; });
+        std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return entryRem[a] > entryRem[b]; });
         std::vector<int> sorted(I.order.size());
         for (size_t e = 0; e < perm.size(); ++e) sorted[e] = I.order[perm[e]];
         I.order.swap(sorted);
@@ -2216,7 +2232,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.colTabPool = (const ColInfo*)I.dColTab;
     kp.nJobs = (int)nJobs; kp.nSlots = nSlots; kp.maxTasks = (int)maxPub;
     kp.nEntries = (int)nEntries; kp.pad6 = 0;
-    kp.nHiJobs = std::max(8, (int)nEntries / 8);
+    kp.nHiJobs = 0;
     kp.cb = (ControlBlock*)I.dRing;
     kp.ring = (TaskDesc*)((uint8_t*)I.dRing + offRing);
     kp.p2ring = (P2Entry*)((uint8_t*)I.dRing + offP2);
@@ -2348,6 +2364,19 @@ void Engine::fetch(std::vector<Job*>& jobs) {
             }
         }
     }
+    if (I.kp.pad5 & 16) {
+        static unsigned long long log[16384][4];
+        int n = 0;
+        if (cudaMemcpyFromSymbol(log, gStripLog, sizeof(log)) == cudaSuccess && cudaMemcpyFromSymbol(&n, gStripLogN, sizeof(int)) == cudaSuccess) {
+            n = std::min(n, 16384);
+            for (int q = 0; q < n; ++q)
+                fprintf(stderr, "[ub200 strip] task %llu strip %llu sm %llu warp %llu cols %llu claimed %.1f computing %.1f done %.1f waited %.1f us\n",
+                        log[q][0] >> 40, (log[q][0] >> 32) & 0xff, (log[q][1] >> 32) & 0xffff, log[q][1] >> 48, log[q][2] >> 32,
+                        (log[q][0] & 0xffffffffull) / 1e3, (log[q][1] & 0xffffffffull) / 1e3, (log[q][2] & 0xffffffffull) / 1e3, log[q][3] / 1.965e3);
+            n = 0;
+            cudaMemcpyToSymbol(gStripLogN, &n, sizeof(int));
+        }
+    }
     if (getenv("UNICYCLER_B200_PROFILE")) {
         long long tot[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
         size_t worst = 0;
@@ -2380,6 +2409,22 @@ void Engine::fetch(std::vector<Job*>& jobs) {
             const GridDesc& gdd = ((const GridDesc*)I.hGrids)[I.jobsDev[wf].gridBegin + it / MAXREC];
             fprintf(stderr, "[ub200 timeline] last job: spine resolved at %.2f ms, last pass-2 item started at %.2f ms, longest item %.2f ms (grid %d cand %d: %d x %d banded %d), items total %.2f ms; longest big walk: %lld cycles, %lld tiles, %lld record ints, %lld tile cycles; stream compaction started at %.2f ms (%lld records, %d ints kept)\n",
                     jf.tSpine / 1e6, jf.tP2Start / 1e6, jf.p2MaxNs / 1e6, it / MAXREC, it % MAXREC, gdd.nH, gdd.nV, (int)gdd.banded, jf.p2SumNs / 1e6, jf.p2MaxStart, jf.p2MaxTiles & 0xffffffffLL, jf.p2MaxTiles >> 32, jf.p2MaxTileCycles, jf.tFin0 / 1e6, jf.finRecords, jf.outLen);
+        }
+        {
+            std::vector<size_t> byS(nJobs);
+            for (size_t k = 0; k < nJobs; ++k) byS[k] = k;
+            std::sort(byS.begin(), byS.end(), [&](size_t a, size_t b) { return I.jobOut[a].tSpine > I.jobOut[b].tSpine; });
+            for (size_t q = 0; q < std::min<size_t>(6, nJobs); ++q) {
+                const size_t k = byS[q];
+                const long long* pp = I.jobOut[k].prof;
+                long long bigCells = 0; int nBig = 0;
+                for (int g = 0; g < I.jobsDev[k].gridCount; ++g) {
+                    const GridDesc& gd = ((const GridDesc*)I.hGrids)[I.jobsDev[k].gridBegin + g];
+                    if (!localPlan(makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up)).local) { bigCells += referenceCells(gd); ++nBig; }
+                }
+                fprintf(stderr, "[ub200 spine] job %zu: %d grids (%d big, %.3g cells) %d segs: spine %.2f ms final %.2f ms | cycles setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld total(max seg)=%lld\n",
+                        k, I.jobsDev[k].gridCount, nBig, (double)bigCells, I.jobsDev[k].nSeg, I.jobOut[k].tSpine / 1e6, I.jobOut[k].tFinal / 1e6, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5]);
+            }
         }
         const long long* wp = I.jobOut[worst].prof;
         fprintf(stderr, "[ub200 profile] worst job %zu (%d grids): setup+init=%lld localfill=%lld taskwait=%lld track=%lld traceback=%lld | tiles=%lld tilecycles=%lld localtb=%lld tracebacks=%lld localgrids=%lld localtrack=%lld\n",

@@ -52,7 +52,8 @@ struct GridDesc {
     // big grids (filled by worker items): the grid's persistent block (checkpoints, progress counters, init
     // row/column) inside the batch's persistent buffer, set by Engine::upload; -1: none (per-agent arena)
     int64_t persistOff;
-    int32_t ckTiles, pad;    // number of 256-row column-checkpoint tiles of the grid
+    int32_t ckTiles;         // number of 256-row column-checkpoint tiles of the grid
+    int32_t pad;             // big grids: task board (0 = served first), set by Engine::upload from the remaining spine latency
 };
 
 struct Seg {                 // seqan/align/dp_trace_segment.h (TraceSegment_)

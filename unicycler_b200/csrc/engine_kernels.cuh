@@ -33,6 +33,7 @@ constexpr int MODE_TRACEG = 3;           // the same into global memory (a tile 
 constexpr int MODE_FAST = 2;             // score-only local fill, box cells (S,H,V) into the shared-memory window
 constexpr int MAXSEG = 24;               // speculative segments of one seed chain
 constexpr int MAXREC = 8;                // candidates / planted cells a pass-1 grid record can hold
+constexpr int NBOARD = 4;                // task boards, served in this order: [0] holds the grids with the longest remaining spine
 constexpr unsigned FULLMASK = 0xffffffffu;
 
 struct DCell {
@@ -175,10 +176,10 @@ struct ControlBlock {  // zeroed before every launch; every group of counters ha
     int jobQueue, jobsDone;
     unsigned long long t0;         // %globaltimer at kernel start (developer timeline)
     int pad0[28];
-    int ringHead[2], ringTail[2];  // task boards: [0] jobs on the critical path (longest chains), [1] the rest
-    int pad1[28];
-    int tokHead[2], tokTail[2];    // token rings: one token per strip that became claimable
-    int pad2[28];
+    int ringHead[NBOARD], ringTail[NBOARD];  // task boards, by remaining critical path of the publishing job (GridDesc::pad)
+    int pad1[32 - 2 * NBOARD];
+    int tokHead[NBOARD], tokTail[NBOARD];    // token rings: one token per strip that became claimable
+    int pad2[32 - 2 * NBOARD];
     int p2Head, p2Tail;            // pass-2 board
     int bigHead, bigTail;          // pass-2 items of the big grids (served before everything else of pass 2)
     int pad3[28];
@@ -213,10 +214,10 @@ struct KParams {
     int nJobs;
     int nSlots;        // control agents with an arena
     int maxTasks;      // capacity of each task board
-    int nHiJobs;       // the first nHiJobs jobs of `order` publish on board 0
+    int nHiJobs;       // (unused)
     ControlBlock* cb;
-    TaskDesc* ring;    // [2][maxTasks]
-    int* tokRing;      // [2][maxTokens] task id + 1 of a task with a claimable strip
+    TaskDesc* ring;    // [NBOARD][maxTasks]
+    int* tokRing;      // [NBOARD][maxTokens] task id + 1 of a task with a claimable strip
     int maxTokens, pad7;
     P2Entry* p2ring;   // [nJobs]
     int2* bigRing;     // [maxBig] (job + 1, item) of one candidate of a big grid
@@ -238,6 +239,8 @@ struct KParams {
 // local-memory stack of every warp).
 __constant__ KParams cP;
 __device__ unsigned long long gDbg[24];
+__device__ unsigned long long gStripLog[16384][4];   // developer timeline of the strips (UNICYCLER_B200_DBG & 16)
+__device__ int gStripLogN;
 __device__ int gUbSite;                   // developer aid: source line of the first JOB_REF_UB verdict
 __device__ __forceinline__ int markUb(int line) { atomicCAS(&gUbSite, 0, line); return 0; }
 #define UB_VERDICT (markUb(__LINE__), JOB_REF_UB)   // developer counters (cycles), lane 0 of control warps
@@ -563,6 +566,94 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K
     }
 }
 
+// Dynamic shared memory of the kernel: [control windows | GridCtx slots | staged codes of the fast path | lean buffers]
+constexpr int CTX_STRIDE = (int)((sizeof(GridCtx) + 15) / 16 * 16);
+constexpr int SMEM_CTX = NCTRL * WINBYTES;
+constexpr int SMEM_FASTSEQ = SMEM_CTX + (NCTRL + NWARPS) * CTX_STRIDE;
+constexpr int SMEM_LEAN = SMEM_FASTSEQ + NCTRL * (FASTSEQ_H + FASTSEQ_V);
+constexpr int LEAN_BYTES = 512;   // per warp: boundary feed of one chunk (32 x int2) + one-hot column-base window (64 x u32)
+constexpr int SMEM_BYTES = SMEM_LEAN + NWARPS * LEAN_BYTES;
+
+// One chunk (32 wavefront steps) of the score-only strip fill in its steady state: affine gaps, unbanded, 8 rows per
+// lane, every lane active in every step (no ramp at the strip's ends, no scout captures).  Same cell values as
+// stripSteps<true,false,false,8,MODE_TASK,false>; what differs is how the step is issued:
+//   * no divergent code: row checkpoints are predicated stores through a per-lane pointer, a lane's column
+//     checkpoint (one step in 64) is four predicated 16-byte stores;
+//   * lane 0's boundary cells come from a 32-entry shared-memory feed (one broadcast LDS per step) instead of three
+//     indexed shuffles, the column's base code from a shared-memory window of one-hot masks (one LDS) instead of a
+//     shuffle + shift + multiply;
+//   * the loop-carried dependency is ONE op per cell: with e = max(H, D) known off the chain,
+//     V(i+1) = max(S(i) + go, V(i) + ge) = max(V(i) + max(go, ge), e(i) + go) because S(i) = max(V(i), e(i)).
+// colBase = first column of the chunk (lane t works on column colBase + kk - t in step kk).
+// CAPROW: the strip holds the grid's last row and the scouts track it (final / global matrices): lane capLane also
+// stores (S,H,V) of its row capR into lastRow[column] every step.  Lanes below the matrix compute on padding (their
+// base mask is empty); nothing they produce is ever read.
+template <bool CAPROW>
+__device__ __forceinline__ void leanChunk(const StepConsts& K, StripState<8>& st, int lane, uint32_t leanOff,
+                                          const uint8_t* seqH, int colBase, int bS, int bV, int2* rowOut, int2* ckTile,
+                                          int capLane, int capR, DCell* lastRow) {
+    int2* bnd = reinterpret_cast<int2*>(gSmem + leanOff);
+    uint32_t* hcw = reinterpret_cast<uint32_t*>(gSmem + leanOff + 256);
+    // stage: boundary (S,V) of columns colBase..colBase+31, one-hot masks of columns colBase-31..colBase+31
+    bnd[lane] = make_int2(bS, bV);
+    hcw[lane] = (1u << seqH[colBase - 32 + lane]) * 0x01010101u;            // column colBase - 31 + lane
+    if (lane < 31) hcw[32 + lane] = (1u << seqH[colBase + lane]) * 0x01010101u;   // column colBase + 1 + lane
+    __syncwarp();
+    const int match = K.match, mismatch = K.mismatch, go = K.go, ge = K.ge;
+    const int g = max(go, ge);
+    const int j0 = colBase - lane;                       // this lane's column in step 0
+    const int kkHit = (-j0) & (CKW - 1);                 // step in which the lane reaches a checkpoint column (< 32: in this chunk)
+    int2* ckPtr = ckTile + (size_t)((j0 + kkHit) / CKW) * SH + lane * 8;
+    int2* rowPtr = rowOut + (size_t)(lane >> 3) * (size_t)(K.nH + 1) + j0;
+    const bool rowLane = (lane & 7) == 7;
+    const uint32_t* hp = hcw + (31 - lane);
+    const uint32_t vm0 = st.vm[0], vm1 = st.vm[1];
+    int pubS = st.pubS, pubV = st.pubV, prevUpS = st.prevUpS;
+    uint32_t hr = 0;
+#pragma unroll 1   // (the kernel's warps run very different code: a small loop body stays in the instruction cache)
+    for (int kk = 0; kk < 32; ++kk) {
+        int inS = __shfl_up_sync(FULLMASK, pubS, 1);
+        int inV = __shfl_up_sync(FULLMASK, pubV, 1);
+        const int2 b = bnd[kk];
+        if (lane == 0) { inS = b.x; inV = b.y; }
+        hr = hp[kk];
+        const uint32_t eq0 = vm0 & hr, eq1 = vm1 & hr;
+        int Sd = prevUpS;
+        int vv = __viaddmax_s32(inS, go, inV + ge);      // V of the lane's first row
+        int ns = 0, capV = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t eqw = (r < 4) ? eq0 : eq1;
+            const int sub = (eqw & (0xffu << (8 * (r & 3)))) ? match : mismatch;
+            const int hh = __viaddmax_s32(st.Sl[r], go, st.Hl[r] + ge);
+            const int e = __viaddmax_s32(Sd, sub, hh);   // max(D, H)
+            ns = max(vv, e);
+            if (CAPROW && r == capR) capV = vv;
+            Sd = st.Sl[r];
+            st.Sl[r] = ns; st.Hl[r] = hh;
+            if (r < 7) vv = __viaddmax_s32(vv, g, e + go);   // V of the next row
+        }
+        prevUpS = inS;
+        pubS = ns; pubV = vv;
+        if (rowLane) __stcg(&rowPtr[kk], make_int2(ns, vv));
+        if (CAPROW && lane == capLane) {
+            int cs = st.Sl[0], ch = st.Hl[0];
+#pragma unroll
+            for (int r = 1; r < 8; ++r)
+                if (r == capR) { cs = st.Sl[r]; ch = st.Hl[r]; }
+            lastRow[j0 + kk] = DCell{cs, ch, capV};
+        }
+        if (kk == kkHit) {
+#pragma unroll
+            for (int r = 0; r < 8; r += 2)
+                __stcg(reinterpret_cast<int4*>(ckPtr + r), make_int4(st.Sl[r], st.Hl[r], st.Sl[r + 1], st.Hl[r + 1]));
+        }
+    }
+    st.pubS = pubS; st.pubV = pubV; st.prevUpS = prevUpS;
+    st.curHc = __ffs((int)(hr & 0xffu)) - 1;
+    __syncwarp();
+}
+
 // Runs columns cBeg..cEnd of strip s (rows s*32*RR+1 ...).  fromCk: the lane state left of cBeg comes
 // from the column checkpoint at cBeg-1 (a multiple of CKW) instead of the grid's first column.
 // nsteps <= (cEnd-cBeg+1)+31 limits the wavefront (partial tile recompute).
@@ -582,6 +673,14 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
     const GridGeom& g = G.g;
     const long long dbg0 = clock64();
     long long dbgSteps = 0, dbgWait = 0;
+    bool stripLog = MODE == MODE_TASK && (cP.pad5 & 16);
+    int logIdx = 0;
+    unsigned long long logT0 = 0, logT1 = 0;
+    if (stripLog) {
+        if (lane == 0) { logIdx = atomicAdd(&gStripLogN, 1); logT0 = globalTimerNs() - cP.cb->t0; }
+        logIdx = __shfl_sync(FULLMASK, logIdx, 0);
+        if (logIdx >= 16384) stripLog = false;
+    }
     StripState<RR> st;
     const int i0 = s * SHR + lane * RR + 1;
     const int jlo = stripJlo(g, s, SHR);
@@ -637,9 +736,11 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
     int2* rowOut = (MODE == MODE_TASK) ? G.rowCk + (size_t)s * (SH / CKR) * (size_t)(g.nH + 1) : nullptr;
     const int nch = (nsteps + 31) / 32;
     int upProg = 0;                // cached progress of the strip above
-    // the strip below becomes claimable once this one is one chunk (32 columns) past that strip's first column
+    // The strip below becomes claimable the moment this one starts computing (its first wait for the strip above is
+    // over): the warp that claims it copies the grid context and loads its first column while this strip walks its
+    // first two chunks, then waits for them.  At most one claimed strip per grid is waiting at any time, and a claimed
+    // strip only ever waits for strips claimed earlier (no deadlock among the persistent warps).
     bool signalled = false;
-    const int signalAt = imin(cEnd, stripJlo(g, s + 1, SHR) + 31);
     const int upJhi = (s > 0) ? stripJhi(g, s - 1, SHR) : 0;
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
@@ -658,6 +759,15 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
                 upProg = __shfl_sync(FULLMASK, upProg, 0);
             }
         }
+        if (MODE == MODE_TASK && !signalled && ((cP.pad5 & 64) || c >= 2 || c == nch - 1)) {
+            signalled = true;
+            if (stripLog && lane == 0) logT1 = globalTimerNs() - cP.cb->t0;
+            if (lane == 31) {
+                atomicMax(G.readyUpTo, s + 1);
+                __threadfence();
+                if (s + 1 < G.NS) pushToken(G.taskId);
+            }
+        }
         int bS = NEG_INF, bV = NEG_INF, hcN = 0;
         if (jj <= cEnd) { hcN = G.seqH[jj - 1]; upBoundary<BANDED, L2ONLY>(G, s, SHR, jj, bS, bV); }
         bool cap = false;
@@ -668,7 +778,23 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
             else cap = (jmaxChunk >= G.hNext) && ((s + 1) * SHR >= G.boxRow0);
         }
         const long long dbg1 = clock64();
-        if (cap)
+        bool lean = false;
+        if constexpr (MODE == MODE_TASK && AFF && !BANDED && RR == 8) {
+            // steady state: every lane active in all 32 steps, below-matrix lanes excluded, nothing to capture
+            const bool full = c >= 1 && cBeg + 32 * c + 31 <= cEnd && 32 * c + 31 < nsteps && !(cP.pad5 & 8);
+            const uint32_t leanOff = (uint32_t)(SMEM_LEAN + (threadIdx.x >> 5) * LEAN_BYTES);
+            if (full && !cap) {
+                lean = true;
+                leanChunk<false>(K, st, lane, leanOff, G.seqH, cBeg + 32 * c, bS, bV, rowOut, ckTile, 0, 0, nullptr);
+            } else if (full && capture && G.capEdges && cBeg + 32 * c + 31 < g.nH) {
+                // last strip of a final / global matrix, away from the last column: only the last row is captured
+                lean = true;
+                const int rl = g.nV - (s * SHR + 1);   // row nV inside the strip: lane rl / 8, row rl % 8
+                leanChunk<true>(K, st, lane, leanOff, G.seqH, cBeg + 32 * c, bS, bV, rowOut, ckTile, rl >> 3, rl & 7, G.lastRow);
+            }
+        }
+        if (lean) {}
+        else if (cap)
             stripSteps<AFF, CT, BANDED, RR, MODE, true>(G, K, st, c, lane, cBeg, cEnd, i0, bS, bV, hcN, nsteps, win,
                                                          winPitch, rowOut, ckTile);
         else
@@ -678,16 +804,17 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
         if (MODE == MODE_TASK) {
             // lane 31 has finished every column <= cBeg + 32c + 31 - 31 (and cEnd after the last chunk)
             const int done = imin(cEnd, cBeg + 32 * c + imin(31, nsteps - 1 - 32 * c) - 31);
-            if (lane == 31 && done >= cBeg) {
-                stRelease(&G.rowProg[s], done);
-                if (!signalled && done >= signalAt) {
-                    atomicMax(G.readyUpTo, s + 1);
-                    __threadfence();
-                    if (s + 1 < G.NS) pushToken(G.taskId);
-                    signalled = true;
-                }
-            }
+            if (lane == 31 && done >= cBeg) stRelease(&G.rowProg[s], done);
         }
+    }
+    if (stripLog && lane == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        gStripLog[logIdx][0] = logT0 | ((unsigned long long)s << 48) | ((unsigned long long)(G.taskId & 0xffff) << 32 << 0) * 0ull;
+        gStripLog[logIdx][0] = (logT0 & 0xffffffffull) | ((unsigned long long)s << 32) | ((unsigned long long)(G.taskId & 0xffffff) << 40);
+        gStripLog[logIdx][1] = (logT1 & 0xffffffffull) | ((unsigned long long)smid << 32) | ((unsigned long long)(threadIdx.x >> 5) << 48);
+        gStripLog[logIdx][2] = ((globalTimerNs() - cP.cb->t0) & 0xffffffffull) | ((unsigned long long)(cEnd - cBeg + 1) << 32);
+        gStripLog[logIdx][3] = (unsigned long long)dbgWait | ((unsigned long long)(unsigned)dbgSteps << 40) * 0ull;
     }
     if (MODE == MODE_TASK && lane == 0) {
         atomicAdd(&gDbg[12], (unsigned long long)(clock64() - dbg0));
