@@ -37,19 +37,23 @@ namespace {
 
 int g_device = -1;
 std::mutex g_engineMu;
-std::unique_ptr<Engine> g_engine;
+// Two engines per process (same device, own buffers and stream): a batch call runs its reads as two chunks so that the
+// host stages of one chunk overlap the kernel of the other.  Everything else uses engine 0.
+std::unique_ptr<Engine> g_engine[2];
+std::atomic<bool> g_lastCallUsedBoth(false);   // the last call was a chunked batch: its counters are in g_batchStats
+EngineStats g_batchStats;
 
-Engine& engine() {
+Engine& engine(int slot = 0) {
     std::lock_guard<std::mutex> lock(g_engineMu);
-    if (!g_engine) {
+    if (!g_engine[slot]) {
         int dev = g_device;
         if (dev < 0) {
             const char* e = getenv("UNICYCLER_B200_DEVICE");
             if (e) dev = atoi(e);
         }
-        g_engine.reset(new Engine(dev));
+        g_engine[slot].reset(new Engine(dev));
     }
-    return *g_engine;
+    return *g_engine[slot];
 }
 
 [[noreturn]] void fatal(const std::string& msg) {
@@ -101,6 +105,7 @@ void runCoalesced(std::vector<Job*>& jobs) {
         g_coPending.clear();
         lk.unlock();
         std::exception_ptr err;
+        g_lastCallUsedBoth = false;
         try {
             if (batch.size() == 1) engine().run(*batch[0]->jobs);
             else {
@@ -459,6 +464,8 @@ void* forwardSym(const char* name) {
     return sym;
 }
 
+void addStats(EngineStats& s, const EngineStats& t);
+
 // device-resident bench state
 struct ChainBench {
     std::vector<std::unique_ptr<ChainJob> > jobs;
@@ -477,7 +484,8 @@ int ub200_setDevice(int device) {
     std::unique_lock<std::mutex> co(g_coMu);
     if (g_coRunning || !g_coPending.empty()) return -1;
     std::lock_guard<std::mutex> lock(g_engineMu);
-    if (g_engine && g_engine->device() != device) g_engine.reset();
+    for (auto& e : g_engine)
+        if (e && e->device() != device) e.reset();
     g_device = device;
     return 0;
 }
@@ -682,8 +690,18 @@ double ub200_chainBenchRun(void) {
 
 double ub200_chainBenchRunSteps(int steps) { return engine().launchTimed(steps); }
 
+}  // extern "C"
+namespace {
+void addStats(EngineStats& s, const EngineStats& t) {
+    s.kernelMs += t.kernelMs; s.h2dMs += t.h2dMs; s.d2hMs += t.d2hMs; s.cells += t.cells; s.launches += t.launches;
+    s.traceBytes += t.traceBytes; s.h2dBytes += t.h2dBytes; s.d2hBytes += t.d2hBytes; s.ctas = t.ctas;
+}
+EngineStats lastCallStats() { return g_lastCallUsedBoth ? g_batchStats : engine().lastStats(); }
+}  // namespace
+extern "C" {
+
 void ub200_lastTransferBytes(int64_t* h2d, int64_t* d2h, int64_t* traceBytes, int* ctas) {
-    EngineStats s = engine().lastStats();
+    EngineStats s = lastCallStats();
     if (h2d) *h2d = s.h2dBytes;
     if (d2h) *d2h = s.d2hBytes;
     if (traceBytes) *traceBytes = s.traceBytes;
@@ -753,55 +771,96 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     Scoring sc{m, mm, go, ge};
     const double t0 = nowSec();
     std::vector<std::unique_ptr<ReadWork> > works((size_t)n);
-    // host seeding + planning: one read per task, largest reads first
+    // largest reads first: their chains have the longest spines
     std::vector<int> order((size_t)n);
     for (int i = 0; i < n; ++i) order[(size_t)i] = i;
     std::vector<size_t> len((size_t)n);
     for (int i = 0; i < n; ++i) len[(size_t)i] = strlen(readSeqs[i]);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[(size_t)a] > len[(size_t)b]; });
-    // stage A: per read — ranges and k-mer indexes
-    parallelFor(n, [&](int k) {
-        const int i = order[(size_t)k];
-        works[(size_t)i].reset(new ReadWork());
-        prepareRead(*works[(size_t)i], readNames[i], readSeqs[i], 0, hits[i], (SeqMap*)refSeqs, sc, sensitivityLevel);
-    });
-    // stage B: per (read, reference range) — seeding and planning, most expensive units first
-    std::vector<std::pair<int, int> > unitList;
-    for (int i = 0; i < n; ++i)
-        for (size_t u = 0; u < works[(size_t)i]->units.size(); ++u) unitList.emplace_back(i, (int)u);
-    std::stable_sort(unitList.begin(), unitList.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
-        const RangeUnit& ua = works[(size_t)a.first]->units[(size_t)a.second];
-        const RangeUnit& ub = works[(size_t)b.first]->units[(size_t)b.second];
-        const double ca = (double)len[(size_t)a.first] * (ua.refEnd - ua.refStart);
-        const double cb = (double)len[(size_t)b.first] * (ub.refEnd - ub.refStart);
-        return ca > cb;
-    });
-    parallelFor((int)unitList.size(), [&](int k) {
-        ReadWork& w = *works[(size_t)unitList[(size_t)k].first];
-        seedUnit(w, w.units[(size_t)unitList[(size_t)k].second], 0, (SeqMap*)refSeqs, sc);
-    });
-    for (int i = 0; i < n; ++i) collectUnits(*works[(size_t)i]);
-    std::vector<Job*> jobs;
-    for (int i = 0; i < n; ++i)
-        for (auto& cj : works[(size_t)i]->jobs)
-            if (cj->planned) jobs.push_back(&cj->job);
-    const double t1 = nowSec();
+
+    // Host seeding + planning of the reads order[k0 .. k1): one task per read (ranges, k-mer index), then one task per
+    // (read, reference range), most expensive first.  Returns the chunk's device jobs.
+    auto seedChunk = [&](int k0, int k1, std::vector<Job*>& jobs) {
+        parallelFor(k1 - k0, [&](int k) {
+            const int i = order[(size_t)(k0 + k)];
+            works[(size_t)i].reset(new ReadWork());
+            prepareRead(*works[(size_t)i], readNames[i], readSeqs[i], 0, hits[i], (SeqMap*)refSeqs, sc, sensitivityLevel);
+        });
+        std::vector<std::pair<int, int> > unitList;
+        for (int k = k0; k < k1; ++k) {
+            const int i = order[(size_t)k];
+            for (size_t u = 0; u < works[(size_t)i]->units.size(); ++u) unitList.emplace_back(i, (int)u);
+        }
+        std::stable_sort(unitList.begin(), unitList.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+            const RangeUnit& ua = works[(size_t)a.first]->units[(size_t)a.second];
+            const RangeUnit& ub = works[(size_t)b.first]->units[(size_t)b.second];
+            const double ca = (double)len[(size_t)a.first] * (ua.refEnd - ua.refStart);
+            const double cb = (double)len[(size_t)b.first] * (ub.refEnd - ub.refStart);
+            return ca > cb;
+        });
+        parallelFor((int)unitList.size(), [&](int k) {
+            ReadWork& w = *works[(size_t)unitList[(size_t)k].first];
+            seedUnit(w, w.units[(size_t)unitList[(size_t)k].second], 0, (SeqMap*)refSeqs, sc);
+        });
+        jobs.clear();
+        for (int k = k0; k < k1; ++k) {
+            ReadWork& w = *works[(size_t)order[(size_t)k]];
+            collectUnits(w);
+            for (auto& cj : w.jobs)
+                if (cj->planned) jobs.push_back(&cj->job);
+        }
+    };
+    auto finishChunk = [&](int k0, int k1) {
+        parallelFor(k1 - k0, [&](int k) {
+            const int i = order[(size_t)(k0 + k)];
+            results[i] = dupString(finishRead(*works[(size_t)i], sc));
+        });
+    };
+
     if (getenv("UNICYCLER_B200_HOST_ONLY")) {  // developer aid: time the host stage without a GPU
+        std::vector<Job*> jobs;
+        seedChunk(0, n, jobs);
         fprintf(stderr, "[ub200 host] reads=%d jobs=%zu prepare=%.1f ms (kmers %.1f, linetrace %.1f [fillCloud %.1f, densest point %.1f], seeds+chain %.1f thread-ms)\n", n,
-                jobs.size(), (t1 - t0) * 1e3, g_seedProf[0] / 1e6, g_seedProf[1] / 1e6, g_seedProf[3] / 1e6, g_seedProf[4] / 1e6, g_seedProf[2] / 1e6);
+                jobs.size(), (nowSec() - t0) * 1e3, g_seedProf[0] / 1e6, g_seedProf[1] / 1e6, g_seedProf[3] / 1e6, g_seedProf[4] / 1e6, g_seedProf[2] / 1e6);
         for (int q = 0; q < 6; ++q) g_seedProf[q] = 0;
         for (int i = 0; i < n; ++i) results[i] = dupString("");
         return 0;
     }
-    runCoalesced(jobs);
-    const double t2 = nowSec();
-    parallelFor(n, [&](int k) {
-        const int i = order[(size_t)k];
-        results[i] = dupString(finishRead(*works[(size_t)i], sc));
-    });
+
+    // Small batches are latency bound on the device (the spines of the longest chains): one launch.  Large batches
+    // are cut into chunks that alternate between two engines, so that seeding chunk k and formatting chunk k-2 overlap
+    // the kernel of chunk k-1:   host  [seed 0][seed 1][fmt 0 .. seed 2][fmt 1 .. seed 3] ...
+    //                            GPU          [kernel 0][kernel 1 .....][kernel 2 ......] ...
+    int chunk = n;
+    if (const char* e = getenv("UNICYCLER_B200_CHUNK_READS")) chunk = std::max(1, atoi(e));
+    else if (n >= 256) chunk = std::min(1024, std::max(64, n / 8));
+    const int nChunks = (n + chunk - 1) / chunk;
+    std::vector<std::vector<Job*> > jobs((size_t)nChunks);
+    auto lo = [&](int k) { return k * chunk; };
+    auto hi = [&](int k) { return std::min(n, (k + 1) * chunk); };
+    double seedMs = 0.0;
+    EngineStats batchStats;
+    for (int k = 0; k < nChunks; ++k) {
+        const double ts = nowSec();
+        seedChunk(lo(k), hi(k), jobs[(size_t)k]);
+        seedMs += (nowSec() - ts) * 1e3;
+        if (k >= 2) {   // the engine of chunk k is the one chunk k-2 used
+            engine(k & 1).end(jobs[(size_t)(k - 2)]);
+            addStats(batchStats, engine(k & 1).lastStats());
+            finishChunk(lo(k - 2), hi(k - 2));
+        }
+        engine(k & 1).begin(jobs[(size_t)k]);
+    }
+    for (int k = std::max(0, nChunks - 2); k < nChunks; ++k) {
+        engine(k & 1).end(jobs[(size_t)k]);
+        addStats(batchStats, engine(k & 1).lastStats());
+        finishChunk(lo(k), hi(k));
+    }
+    g_batchStats = batchStats;
+    g_lastCallUsedBoth = true;
     if (getenv("UNICYCLER_B200_PROFILE"))
-        fprintf(stderr, "[ub200 host] reads=%d jobs=%zu prepare=%.1f ms engine=%.1f ms finish=%.1f ms\n", n, jobs.size(),
-                (t1 - t0) * 1e3, (t2 - t1) * 1e3, (nowSec() - t2) * 1e3);
+        fprintf(stderr, "[ub200 host] reads=%d in %d chunk(s) of %d: seeding %.1f ms (host), total %.1f ms\n", n, nChunks, chunk, seedMs,
+                (nowSec() - t0) * 1e3);
     return 0;
 }
 
@@ -829,7 +888,7 @@ char* ub200_seedChains(const char* readSeq, const char* trimmedRefSeq, int sensi
 double ub200_intPeakOpsPerSec(void) { return measureIntPeak(engine().device()); }
 
 void ub200_lastStats(int64_t* cells, double* kernelMs, int64_t* launches, double* h2dMs, double* d2hMs) {
-    EngineStats s = engine().lastStats();
+    EngineStats s = lastCallStats();
     if (cells) *cells = s.cells;
     if (kernelMs) *kernelMs = s.kernelMs;
     if (launches) *launches = s.launches;

@@ -1789,6 +1789,7 @@ struct Engine::Impl {
     std::vector<JobOut> jobOut;
     KParams kp;
     size_t seqBytes = 0, outInts = 0, ringBytes = 0, offState = 0;
+    double tBegin = 0.0, tUploaded = 0.0;
 
     void growDev(void*& p, size_t& cap, size_t need) {
         if (need <= cap) return;
@@ -1804,10 +1805,35 @@ struct Engine::Impl {
         CUDA_CHECK(cudaMallocHost(&p, ncap));
         cap = ncap;
     }
-    void launchOnce() {
+    bool cooperative = false;
+    // The launch parameters live in ONE __constant__ symbol (cP) per process and the kernel takes every SM, so the
+    // (parameter copy, kernel) pairs of all engines on a device are chained with an event: an engine may stage and
+    // upload its batch while another engine's kernel runs, its own kernel starts when that one has finished.
+    // startEvent (optional) is recorded right before the kernel, i.e. after the wait.
+    void launchOnce(cudaEvent_t startEvent = nullptr) {
+        static std::mutex chainMu;
+        static cudaEvent_t lastKernel[64] = {};
         CUDA_CHECK(cudaMemsetAsync(dRing, 0, ringBytes, stream));
         CUDA_CHECK(cudaMemsetAsync(dJobOut, 0, (size_t)kp.nJobs * sizeof(JobOut), stream));
-        dpAgentKernel<<<numSMs, NTHREADS, SMEM_BYTES, stream>>>();
+        std::lock_guard<std::mutex> chain(chainMu);
+        cudaEvent_t& last = lastKernel[device & 63];
+        if (last == nullptr) CUDA_CHECK(cudaEventCreateWithFlags(&last, cudaEventDisableTiming));
+        else CUDA_CHECK(cudaStreamWaitEvent(stream, last, 0));
+        CUDA_CHECK(cudaMemcpyToSymbolAsync(cP, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, stream));
+        if (startEvent) CUDA_CHECK(cudaEventRecord(startEvent, stream));
+        launchKernel();
+        CUDA_CHECK(cudaEventRecord(last, stream));
+    }
+    void launchKernel() {
+        // The CTAs of this persistent kernel wait for each other (strip progress, token rings, job counters): all of
+        // them must be resident at once.  A cooperative launch makes the driver guarantee that (it fails loudly under
+        // MPS / a smaller partition instead of hanging); Engine::Engine has checked that one CTA fits an SM.
+        if (cooperative) {
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)dpAgentKernel, dim3((unsigned)numSMs), dim3(NTHREADS), nullptr,
+                                                   (size_t)SMEM_BYTES, stream));
+        } else {
+            dpAgentKernel<<<numSMs, NTHREADS, SMEM_BYTES, stream>>>();
+        }
     }
 };
 
@@ -1827,6 +1853,13 @@ Engine::Engine(int device) : impl_(new Impl) {
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     impl_->numSMs = prop.multiProcessorCount;
     CUDA_CHECK(cudaFuncSetAttribute(dpAgentKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int ctasPerSM = 0, coop = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, dpAgentKernel, NTHREADS, (size_t)SMEM_BYTES));
+    if (ctasPerSM < 1)
+        throw std::runtime_error("unicycler_b200: the DP kernel does not fit this device (one CTA of " + std::to_string(NTHREADS) +
+                                 " threads with " + std::to_string(SMEM_BYTES) + " B of shared memory per SM is required)");
+    CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    impl_->cooperative = coop != 0 && !getenv("UNICYCLER_B200_NO_COOP");
     CUDA_CHECK(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking));
     for (auto& ev : impl_->ev) CUDA_CHECK(cudaEventCreate(&ev));
 }
@@ -2251,7 +2284,6 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.pad5 = getenv("UNICYCLER_B200_DBG") ? atoi(getenv("UNICYCLER_B200_DBG")) : 0;   // developer switches
     kp.scratch = (uint8_t*)I.dScratch; kp.scratchStride = L.total;
     kp.lay = L;
-    CUDA_CHECK(cudaMemcpyToSymbolAsync(cP, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, I.stream));
     I.stats = EngineStats();
     I.stats.cells = totalCells;
     I.stats.h2dBytes = (int64_t)(I.seqBytes + nJobs * sizeof(JobDev) + I.nGrids * sizeof(GridDesc) + nJobs * sizeof(int) +
@@ -2269,8 +2301,7 @@ void Engine::launch() {
     Impl& I = *impl_;
     CUDA_CHECK(cudaSetDevice(I.device));
     if (I.kp.nJobs == 0) return;
-    CUDA_CHECK(cudaEventRecord(I.ev[2], I.stream));
-    I.launchOnce();
+    I.launchOnce(I.ev[2]);
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventRecord(I.ev[3], I.stream));
     I.stats.launches += 1;
@@ -2479,18 +2510,30 @@ void Engine::fetch(std::vector<Job*>& jobs) {
     if (getenv("UNICYCLER_B200_PROFILE")) fprintf(stderr, "[ub200 fetch] parse=%.2f ms\n", wallMs() - tParse0);
 }
 
-void Engine::run(std::vector<Job*>& jobs) {
-    std::lock_guard<std::mutex> lock(impl_->mu);
+void Engine::begin(std::vector<Job*>& jobs) {
+    impl_->mu.lock();
+    try {
+        if (jobs.empty()) return;
+        impl_->tBegin = wallMs();
+        upload(jobs);
+        impl_->tUploaded = wallMs();
+        launch();
+    } catch (...) {
+        impl_->mu.unlock();
+        throw;
+    }
+}
+
+void Engine::end(std::vector<Job*>& jobs) {
+    struct Unlock { std::mutex& m; ~Unlock() { m.unlock(); } } unlock{impl_->mu};
     if (jobs.empty()) return;
-    const double t0 = wallMs();
-    upload(jobs);
-    const double t1 = wallMs();
-    launch();
+    CUDA_CHECK(cudaSetDevice(impl_->device));
     CUDA_CHECK(cudaStreamSynchronize(impl_->stream));
     const double t2 = wallMs();
     fetch(jobs);
     if (getenv("UNICYCLER_B200_PROFILE"))
-        fprintf(stderr, "[ub200 engine] upload=%.1f ms kernel(sync)=%.1f ms fetch=%.1f ms\n", t1 - t0, t2 - t1, wallMs() - t2);
+        fprintf(stderr, "[ub200 engine] upload=%.1f ms kernel(sync)=%.1f ms fetch=%.1f ms\n", impl_->tUploaded - impl_->tBegin,
+                t2 - impl_->tUploaded, wallMs() - t2);
     // jobs whose segment stream overflowed (many tied tracebacks) are rerun with a larger stream
     for (int attempt = 0; attempt < 3; ++attempt) {
         std::vector<Job*> again;
@@ -2499,8 +2542,14 @@ void Engine::run(std::vector<Job*>& jobs) {
         if (again.empty()) break;
         upload(again);
         launch();
+        CUDA_CHECK(cudaStreamSynchronize(impl_->stream));
         fetch(again);
     }
+}
+
+void Engine::run(std::vector<Job*>& jobs) {
+    begin(jobs);
+    end(jobs);
 }
 
 }  // namespace ub200

@@ -113,6 +113,12 @@ public:
     ~Engine();
     // Runs all jobs to completion (results in job.result).  Thread-safe (serialised).
     void run(std::vector<Job*>& jobs);
+    // The same in two halves, so that a caller can overlap host work (seeding the next chunk, formatting the previous
+    // one) with the kernel: begin() stages, uploads and launches and returns at once; end() waits for the kernel,
+    // fetches the results and reruns jobs whose output stream overflowed.  The engine stays locked between the two
+    // calls (same thread).
+    void begin(std::vector<Job*>& jobs);
+    void end(std::vector<Job*>& jobs);
     EngineStats lastStats() const;
     int device() const;
     // Device-resident benchmark mode: upload()+plan once, then launch() repeatedly with

@@ -17,6 +17,7 @@
 #include <map>
 #include <numeric>
 #include <set>
+#include <unordered_map>
 #include <unordered_set>
 
 namespace ub200 {
@@ -595,11 +596,6 @@ PointSet lineTracing(const PointVector& common, PointSet& usedPoints, const Clou
 }
 
 // ------------------------------------------------------------------ seeds (SeqAn Seed<Simple>, Unordered SeedSet)
-struct LessBeginDiagonal {
-    bool operator()(const ChainSeed& a, const ChainSeed& b) const { return (a.beginH - a.beginV) < (b.beginH - b.beginV); }
-};
-typedef std::multiset<ChainSeed, LessBeginDiagonal> SeedMultiSet;
-
 // seeds_combination.h:102-124 (Merge): b right of / overlapping a, diagonals at most maxDiag apart
 bool combineable(const ChainSeed& a, const ChainSeed& b, unsigned maxDiag) {
     if (b.beginH < a.beginH || b.beginV < a.beginV) return false;
@@ -618,29 +614,83 @@ void mergeInto(ChainSeed& seed, const ChainSeed& other) {  // seeds_combination.
     seed.upperDiag = std::max(seed.upperDiag, other.upperDiag);
 }
 
-bool addSeedMerge(SeedMultiSet& set, const ChainSeed& seed, unsigned maxDiag) {  // seed_set_unordered.h:248-343
-    for (SeedMultiSet::iterator it = set.begin(); it != set.end(); ++it) {
-        if (combineable(*it, seed, maxDiag)) {
-            ChainSeed left = *it;
-            mergeInto(left, seed);
-            set.erase(it);
-            set.insert(left);
-            return true;
-        } else if (combineable(seed, *it, maxDiag)) {
-            ChainSeed left = seed;
-            mergeInto(left, *it);
-            set.erase(it);
-            set.insert(left);
-            return true;
+// SeqAn's SeedSet<Simple, Unordered> is a std::multiset ordered by begin diagonal (equal keys keep insertion order),
+// and addSeed(set, seed, maxDiag, Merge()) walks it from the start and merges the new seed into the FIRST element it
+// can be combined with, in either direction (seeds_seed_set_unordered.h:248-343) — a linear scan per seed, quadratic
+// per point set (15 ms of the 32 ms a 20 kb read costs on the host).  Same elements, same order, same choice here,
+// without the scan: an element that can combine with the new seed has its END diagonal within maxDiag of the seed's
+// begin diagonal (element left of the seed) or its BEGIN diagonal within maxDiag of the seed's end diagonal (seed left
+// of the element), so only the elements filed under those 2 * (2 * maxDiag + 1) diagonals are tested, and the one that
+// comes first in the multiset's order (begin diagonal, then insertion sequence) wins.
+class SeedSet {
+public:
+    SeedSet() { byBegin_.reserve(256); byEnd_.reserve(256); }
+    bool addMerge(const ChainSeed& seed, unsigned maxDiag) {
+        const long bd = seed.beginH - seed.beginV, ed = seed.endH - seed.endV;
+        int best = -1;
+        auto consider = [&](int id) {
+            if (best < 0 || before(id, best)) best = id;
+        };
+        for (long d = bd - (long)maxDiag; d <= bd + (long)maxDiag; ++d) {
+            auto it = byEnd_.find(d);
+            if (it == byEnd_.end()) continue;
+            for (int id : it->second)
+                if (combineable(nodes_[(size_t)id].s, seed, maxDiag)) consider(id);
         }
+        for (long d = ed - (long)maxDiag; d <= ed + (long)maxDiag; ++d) {
+            auto it = byBegin_.find(d);
+            if (it == byBegin_.end()) continue;
+            for (int id : it->second)
+                if (combineable(seed, nodes_[(size_t)id].s, maxDiag)) consider(id);
+        }
+        if (best < 0) return false;
+        ChainSeed merged = nodes_[(size_t)best].s;   // (the merge is symmetric: min of the begins, max of the ends)
+        mergeInto(merged, seed);
+        erase(best);
+        insert(merged);
+        return true;
     }
-    return false;
-}
+    void insert(const ChainSeed& s) {
+        const int id = (int)nodes_.size();
+        nodes_.push_back(Node{s, true});
+        byBegin_[s.beginH - s.beginV].push_back(id);
+        byEnd_[s.endH - s.endV].push_back(id);
+    }
+    // the elements in the multiset's iteration order
+    std::vector<ChainSeed> ordered() const {
+        std::vector<int> ids;
+        for (size_t i = 0; i < nodes_.size(); ++i)
+            if (nodes_[i].alive) ids.push_back((int)i);
+        std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return beginDiag(a) < beginDiag(b); });
+        std::vector<ChainSeed> out;
+        out.reserve(ids.size());
+        for (int id : ids) out.push_back(nodes_[(size_t)id].s);
+        return out;
+    }
+
+private:
+    struct Node { ChainSeed s; bool alive; };
+    long beginDiag(int id) const { return nodes_[(size_t)id].s.beginH - nodes_[(size_t)id].s.beginV; }
+    // ids grow with the insertion sequence (a merged seed is erased and re-inserted: it moves behind its equals)
+    bool before(int a, int b) const {
+        const long da = beginDiag(a), db = beginDiag(b);
+        return da < db || (da == db && a < b);
+    }
+    void erase(int id) {
+        Node& n = nodes_[(size_t)id];
+        n.alive = false;
+        drop(byBegin_[n.s.beginH - n.s.beginV], id);
+        drop(byEnd_[n.s.endH - n.s.endV], id);
+    }
+    static void drop(std::vector<int>& v, int id) { v.erase(std::find(v.begin(), v.end(), id)); }
+    std::vector<Node> nodes_;
+    std::unordered_map<long, std::vector<int> > byBegin_, byEnd_;
+};
 
 // seeds_global_chaining.h:102-280 (Gusfield sparse chaining, maximising the summed seed sizes)
-void chainSeedsGlobally(std::vector<ChainSeed>& target, const SeedMultiSet& seedSet) {
+void chainSeedsGlobally(std::vector<ChainSeed>& target, const SeedSet& seedSet) {
     typedef unsigned long TPos;
-    std::vector<ChainSeed> seeds(seedSet.begin(), seedSet.end());
+    const std::vector<ChainSeed> seeds = seedSet.ordered();
     struct IntervalPoint {
         TPos pos; bool isBegin; unsigned idx;
         bool operator<(const IntervalPoint& o) const {
@@ -661,8 +711,9 @@ void chainSeedsGlobally(std::vector<ChainSeed>& target, const SeedMultiSet& seed
     };
     const unsigned NONE = std::numeric_limits<unsigned>::max();
     std::vector<IntervalPoint> points;
-    std::map<unsigned, TPos> quality;
-    std::map<unsigned, unsigned> predecessor;
+    points.reserve(2 * seeds.size());
+    std::vector<TPos> quality(seeds.size());          // (the reference keeps these two in std::map keyed by seed index)
+    std::vector<unsigned> predecessor(seeds.size());
     for (unsigned i = 0; i < seeds.size(); ++i) {
         quality[i] = (TPos)std::max(seeds[i].endH - seeds[i].beginH, seeds[i].endV - seeds[i].beginV);
         predecessor[i] = NONE;
@@ -793,10 +844,10 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
         pts.reserve(good.size());
         for (const Point& p : good) pts.push_back(p);
         std::sort(pts.begin(), pts.end());
-        SeedMultiSet seedSet;
+        SeedSet seedSet;
         for (const Point& p : pts) {
             ChainSeed s{(long)p.x, (long)p.y, (long)p.x + kSize, (long)p.y + kSize, (long)p.x - (long)p.y, (long)p.x - (long)p.y};
-            if (!addSeedMerge(seedSet, s, 2)) seedSet.insert(s);
+            if (!seedSet.addMerge(s, 2)) seedSet.insert(s);
         }
         std::vector<ChainSeed> chain;
         chainSeedsGlobally(chain, seedSet);
