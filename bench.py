@@ -1,20 +1,31 @@
 #!/usr/bin/env python3
-"""Benchmark of the long-read alignment hot path (BASELINE.json metric: GCUPS / reads per second).
+"""Benchmark of the long-read alignment hot path (BASELINE.json metric: GCUPS / reads per second, % of the integer
+roofline, next to the reference C++ library on the host cores).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--no-extra] [--no-cpu-baseline]
 
-Workload (BASELINE.json configs[1]): sample_data/long_reads_low_depth (30 long reads, 261,649 bp) aligned
-semi-globally to sample_data/reference.fasta (3 replicons), scheme 3,-6,-5,-2, sensitivity 0 — 171
-bandedChainAlignment jobs, 23,019 sub-DPs, 8.222e9 DP cells (reference cell definition).
-The inputs (reads, references, the reference minimap's hit strings) are the committed fixture
-tests/golden/semiglobal_sample.json.gz.  One "step" aligns the whole read set once.
+Headline workload (BASELINE.json configs[1]): sample_data/long_reads_low_depth (30 long reads, 261,649 bp) aligned
+semi-globally to sample_data/reference.fasta (3 replicons), scheme 3,-6,-5,-2, sensitivity 0 — 171 bandedChainAlignment
+jobs, 23,019 sub-DPs, 8.222e9 DP cells (reference cell definition).  Inputs (reads, references, the
+reference minimap's hit strings) are the committed fixture tests/golden/semiglobal_sample.json.gz.  One "step" aligns
+the read set once.
 
-  value  GCUPS with inputs resident in HBM: K back-to-back launches of the DP kernel, CUDA events on the
-         launching stream (weak scaling: every rank aligns one copy of the read set; cells of all ranks ÷ max time).
-  e2e    the same metric through the reference-facing C ABI with HOST buffers (semiGlobalAlignment batch call:
-         host seeding + planning, H2D, kernel, D2H, trace gluing, CIGAR formatting [+ result all-gather for N>1]).
+  value     GCUPS with inputs resident in HBM: K back-to-back launches of the DP kernel, CUDA events on the launching
+            stream.
+  e2e       the same metric through the reference-facing C ABI with HOST buffers (ub200_semiGlobalAlignmentBatch: host
+            seeding + planning, H2D, kernel, D2H, trace gluing, CIGAR formatting [+ result gather for N > 1]).
+  roofline  the binding bound of this path: integer max-plus ALU work (17 int32 ops per affine cell)
+            against the measured int32 rate (ub200_intPeakOpsPerSec); roofline_hbm is the secondary (non-binding) bound.
+  N > 1     one process per GPU.  The read set is N copies of the 30 reads presented as ONE set of 30 N reads, cut
+            across the ranks by estimated DP cost (sharding.partition_by_cost); every rank aligns its own shard and the
+            result strings are gathered on rank 0 with exact sizes and checked there: weak scaling, no collective in
+            the data path.
+  configs   (N = 1, unless --no-extra) the other BASELINE configurations as bounded side measurements, each with its
+            parity gate and the reference library timed beside it: bridge path scoring (configs[2]), the calibration
+            sweep (configs[3]) and a slice of the synthetic 10 Mbp / 20 kb-read workload (configs[4]; for N > 1 the
+            slice is sharded over the ranks: strong scaling).
   --impl reference  times the UNMODIFIED reference C++ library (oracle/_ref, built from /root/reference by
-         oracle/Makefile.ref) on the host cores on a bounded sample of the same reads (rank 0 only).
+            oracle/Makefile.ref) on all host cores on the full read set (rank 0 only).
 """
 import argparse
 import json
@@ -22,7 +33,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -31,7 +41,8 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
 
 SCHEME = (3, -6, -5, -2)
-OPS_PER_CELL_AFFINE = 17  # SURVEY.md §8d: algorithmic int32 ops per affine cell update
+OPS_PER_CELL_AFFINE = 17  # SURVEY.md 8d: algorithmic int32 ops per affine cell update
+METRIC = 'GCUPS (DP cell updates per second, semi-global long-read alignment)'
 WORKLOAD = ('sample_data long_reads_low_depth (30 reads) vs reference.fasta (3 replicons): semi-global, '
             'scheme 3,-6,-5,-2, sensitivity 0; 171 banded-chain alignments, 23019 sub-DPs')
 
@@ -91,7 +102,7 @@ class ClockSampler(object):
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one dpAgentKernel launch on this workload, taken from the
+    """dram__bytes_read.sum + dram__bytes_write.sum of one dpAgentKernel launch on the headline workload, from the
     committed ncu capture summary (profiles/ncu_sample_latest.json); None if no capture is recorded."""
     try:
         d = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_sample_latest.json')))
@@ -107,25 +118,25 @@ def measured_peaks():
         return None
 
 
+def thread_map(fn, items, threads):
+    if threads <= 1 or len(items) <= 1:
+        return [fn(x) for x in items]
+    from multiprocessing.dummy import Pool as ThreadPool
+    pool = ThreadPool(min(threads, len(items)))
+    out = pool.map(fn, items)
+    pool.close()
+    return out
+
+
 def cpu_reference_run(reads, refs, threads, expected=None):
     """Unmodified reference library on the host cores (Python threads; ctypes releases the GIL, exactly how
     unicycler_align.py:203-225 drives it).  Returns wall seconds."""
-    from multiprocessing.dummy import Pool as ThreadPool
     from oracle_lib import REF_LIB, mask_semi_global
     from refdriver import AbiLib
     lib = AbiLib(REF_LIB)
     h = lib.new_refs(refs)
-
-    def one(r):
-        return lib.semi_global(r[0], r[1], r[2], h, SCHEME)
-
     t0 = time.perf_counter()
-    if threads == 1:
-        outs = [one(r) for r in reads]
-    else:
-        pool = ThreadPool(threads)
-        outs = pool.map(one, reads)
-        pool.close()
+    outs = thread_map(lambda r: lib.semi_global(r[0], r[1], r[2], h, SCHEME), reads, threads)
     dt = time.perf_counter() - t0
     lib.delete_refs(h)
     if expected is not None:
@@ -136,73 +147,236 @@ def cpu_reference_run(reads, refs, threads, expected=None):
 
 def cpu_port_run(jobs, threads):
     """Fallback when oracle/_ref did not travel: the oracle port (scalar C++) on the chain jobs."""
-    from multiprocessing.dummy import Pool as ThreadPool
     from oracle_lib import Oracle
     orc = Oracle()
-
-    def one(j):
-        return orc.chain(j['readSeq'], j['refSeq'], j['seeds'], SCHEME, j['band'], j['readName'], j['refName'], j['refOffset'])
-
     t0 = time.perf_counter()
-    pool = ThreadPool(threads)
-    pool.map(one, jobs)
-    pool.close()
+    thread_map(lambda j: orc.chain(j['readSeq'], j['refSeq'], j['seeds'], SCHEME, j['band'], j['readName'], j['refName'],
+                                   j['refOffset']), jobs, threads)
     return time.perf_counter() - t0
 
 
-def bounded_sample(reads, jobs, cells_per_job, budget_cells):
-    """First reads (file order) whose summed DP cells stay within budget_cells (at least one read)."""
-    per_read = {}
-    for j, c in zip(jobs, cells_per_job):
-        per_read[j['readName'][:-1]] = per_read.get(j['readName'][:-1], 0) + c
-    chosen, total = [], 0
-    for r in sorted(reads, key=lambda r: per_read.get(r[0], 0)):
-        c = per_read.get(r[0], 0)
-        if chosen and total + c > budget_cells:
-            break
-        chosen.append(r)
-        total += c
-    return chosen, total
+def headline_cpu_baseline(d, jobs, reads, cells):
+    """The reference on ALL reads of the workload with every host core (longest reads first so that the pool drains
+    evenly); ~10 s on the 16-core box."""
+    from oracle_lib import REF_LIB
+    threads = os.cpu_count() or 1
+    use = max(1, min(threads, len(reads)))
+    ordered = sorted(reads, key=lambda r: -len(r[1]))
+    if os.path.isfile(REF_LIB):
+        dt, kind = cpu_reference_run(ordered, d['refs'], use, d['expected']), 'reference'
+    else:
+        dt, kind = cpu_port_run(jobs, use), 'port'
+    return dict(value=cells / dt / 1e9, unit='GCUPS', cores=use, kind=kind,
+                sample='all %d reads, %.4g DP cells, %.1f s' % (len(reads), cells, dt)), dt
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
     import unicycler_b200 as ub
-    from oracle_lib import REF_LIB
     d, jobs, reads = load_workload()
-    cells_per_job = [ub.chain_cells(len(j['readSeq']), len(j['refSeq']), j['seeds'], j['band'])[0] for j in jobs]
-    threads = os.cpu_count() or 1
-    # ~0.04 GCUPS per thread (BASELINE.md): keep one step around 10-20 s
-    budget = int(0.04e9 * min(threads, 30) * 12)
-    sample, cells = bounded_sample(reads, jobs, cells_per_job, budget)
-    use_threads = max(1, min(threads, len(sample)))
-    kind = 'reference' if os.path.isfile(REF_LIB) else 'port'
-    names = set(r[0] for r in sample)
-    sample_jobs = [j for j in jobs if j['readName'][:-1] in names]
-
-    def step():
-        if kind == 'reference':
-            return cpu_reference_run(sample, d['refs'], use_threads)
-        return cpu_port_run(sample_jobs, use_threads)
-
-    for _ in range(min(args.warmup, 1)):
-        step()
-    times = [step() for _ in range(args.steps)]
+    cells = sum(ub.chain_cells(len(j['readSeq']), len(j['refSeq']), j['seeds'], j['band'])[0] for j in jobs)
+    times = []
+    base = None
+    for it in range(min(args.warmup, 1) + args.steps):
+        base, dt = headline_cpu_baseline(d, jobs, reads, cells)
+        if it >= min(args.warmup, 1):
+            times.append(dt)
     dt = sum(times) / len(times)
     gcups = cells / dt / 1e9
-    line = dict(metric='GCUPS (DP cell updates per second, semi-global long-read alignment)', value=gcups, unit='GCUPS',
-                impl='reference', n_gpus=args.gpus, steps=args.steps, warmup=min(args.warmup, 1),
-                ms_per_step=dt * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='int32',
-                data='sample_data fixture (tests/golden/semiglobal_sample.json.gz)',
-                config=dict(workload=WORKLOAD, sample='%d of %d reads (smallest first), %.3g DP cells per step' %
-                            (len(sample), len(reads), cells)),
-                reads_per_s=len(sample) / dt,
-                cpu_baseline=dict(value=gcups, unit='GCUPS', cores=use_threads, kind=kind,
-                                  sample='%d of %d reads, %.3g cells' % (len(sample), len(reads), cells)),
+    base['value'] = gcups
+    line = dict(metric=METRIC, value=gcups, unit='GCUPS', impl='reference', n_gpus=args.gpus, steps=args.steps,
+                warmup=min(args.warmup, 1), ms_per_step=dt * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='int32', data='sample_data fixture (tests/golden/semiglobal_sample.json.gz)',
+                config=dict(workload=WORKLOAD, sample='all %d reads, %.4g DP cells per step' % (len(reads), cells)),
+                reads_per_s=len(reads) / dt, cpu_baseline=base,
                 e2e=dict(value=gcups, unit='GCUPS', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# side measurements: BASELINE configs[2], [3], [4]
+# ---------------------------------------------------------------------------------------------------------------------
+
+def config3_bridge(ub, int_peak, threads):
+    """Bridge path scoring: every (s1, s2, band, entry point) the reference's path_finding sent through the seam on
+    test/test_assembly_graph.gfa (tests/golden/bridge_tuples.json.gz), as device batches."""
+    from oracle_lib import REF_LIB, load_golden, mask_ms
+    d = load_golden('bridge_tuples.json.gz')
+    strings, sc = d['strings'], tuple(d['scheme'])
+    groups = {}
+    for r in d['recorded']:
+        groups.setdefault((r['fn'], r['banded'], r['band']), []).append(r)
+
+    def step(check):
+        cells, kernel_ms, bad = 0, 0.0, 0
+        for (fn, banded, band), rs in groups.items():
+            f = ub.fully_global_alignment_batch if fn == 'global' else ub.path_alignment_batch
+            out = f([strings[r['s1']] for r in rs], [strings[r['s2']] for r in rs], sc, banded, band)
+            st = ub.last_stats()
+            cells += st['cells']
+            kernel_ms += st['kernel_ms']
+            if check:
+                bad += sum(1 for r, o in zip(rs, out) if mask_ms(o) != r['result'])
+        return cells, kernel_ms, bad
+
+    cells, _, bad = step(True)
+    if bad:
+        raise SystemExit('config 3 parity failure: %d alignments differ from the reference' % bad)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        cells, kernel_ms, _ = step(False)
+    dt = (time.perf_counter() - t0) / reps
+    n = len(d['recorded'])
+    out = dict(workload='bridge path scoring on test/test_assembly_graph.gfa (SURVEY.md 8c substitute): %d alignments '
+                        '(fullyGlobalAlignment band 1000, pathAlignment band 1000/500), up to 5.4 kb' % n,
+               pairs_per_s=n / dt, gcups_e2e=cells / dt / 1e9, gcups_kernel=cells / (kernel_ms * 1e-3) / 1e9,
+               ms_per_step=dt * 1e3, cells=cells, parity='%d/%d byte-identical to the reference' % (n, n),
+               int_roofline_frac=cells * OPS_PER_CELL_AFFINE / (kernel_ms * 1e-3) / int_peak)
+    if os.path.isfile(REF_LIB):
+        from refdriver import AbiLib
+        lib = AbiLib(REF_LIB)
+
+        def one(r):
+            f = lib.fully_global if r['fn'] == 'global' else lib.path
+            return f(strings[r['s1']], strings[r['s2']], sc, r['banded'], r['band'])
+        t0 = time.perf_counter()
+        thread_map(one, d['recorded'], threads)
+        cdt = time.perf_counter() - t0
+        out['cpu_baseline'] = dict(pairs_per_s=n / cdt, gcups=cells / cdt / 1e9, cores=min(threads, n), kind='reference',
+                                   sample='all %d alignments, %.1f s' % (n, cdt))
+    return out
+
+
+def config4_calibration(ub, int_peak, threads):
+    """Calibration sweep (getRandomSequenceAlignmentScores): L = 1 k ... 50 k with the pair count bounded to ~4e10 cells
+    per length (BASELINE names 10 k trials; the rate does not depend on the trial count once the GPU is full), plus the
+    production point (100, 25 000).  Parity of this path is pinned pair by pair in tests/test_gpu_parity_r2.py."""
+    from oracle_lib import REF_LIB
+    os.environ['UNICYCLER_B200_SEED'] = '42'
+    points = []
+    for L, n in ((100, 25000), (1000, 40000), (2000, 10000), (5000, 1600), (10000, 400), (20000, 100), (50000, 16)):
+        if L == 100:
+            ub.get_random_sequence_alignment_mean_and_std_dev(L, 2000, SCHEME)   # warm the buffers
+        t0 = time.perf_counter()
+        mean, sd = ub.get_random_sequence_alignment_mean_and_std_dev(L, n, SCHEME)
+        dt = time.perf_counter() - t0
+        st = ub.last_stats()
+        cells = n * (L + 1) * (L + 1)
+        points.append(dict(length=L, trials=n, mean=mean, sd=sd, cells=cells, seconds=dt, gcups_e2e=cells / dt / 1e9,
+                           gcups_kernel=(st['cells'] / (st['kernel_ms'] * 1e-3) / 1e9) if st['kernel_ms'] > 0 else None,
+                           int_roofline_frac=(st['cells'] * OPS_PER_CELL_AFFINE / (st['kernel_ms'] * 1e-3) / int_peak)
+                           if st['kernel_ms'] > 0 else None))
+    out = dict(workload='random-sequence score calibration, unbanded global alignment of i.i.d. ACGT pairs, seed 42',
+               points=points,
+               note='gcups_kernel / int_roofline_frac are those of the LAST device batch of the point')
+    if os.path.isfile(REF_LIB):
+        from refdriver import AbiLib
+        lib = AbiLib(REF_LIB)
+        base = []
+        for L, n in ((100, 2000), (1000, 4 * threads), (5000, threads)):
+            per = max(1, n // threads)
+            t0 = time.perf_counter()
+            thread_map(lambda _: lib.random_scores(L, per, SCHEME), list(range(threads)), threads)
+            cdt = time.perf_counter() - t0
+            cells = per * threads * (L + 1) * (L + 1)
+            base.append(dict(length=L, trials=per * threads, gcups=cells / cdt / 1e9, seconds=cdt))
+        out['cpu_baseline'] = dict(kind='reference', cores=threads, points=base)
+    return out
+
+
+def synth_reads(ref_len, n_reads, read_len, seed):
+    """BASELINE configs[4]: uniform random reference, reads = random windows (both strands, length +-10 %) with 5 %
+    substitutions, 5 % deletions, 5 % insertions; hit strings from the ground truth."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    ref = np.frombuffer(b'ACGT', dtype=np.uint8)[rng.randint(0, 4, size=ref_len)]
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b'ACGT', b'TGCA'):
+        comp[a] = b
+    bases = np.frombuffer(b'ACGT', dtype=np.uint8)
+    reads = []
+    for k in range(n_reads):
+        L = int(read_len * rng.uniform(0.9, 1.1))
+        start = int(rng.randint(0, ref_len - L))
+        frag = ref[start:start + L]
+        strand = '+' if rng.rand() < 0.5 else '-'
+        if strand == '-':
+            frag = comp[frag[::-1]]
+        u = rng.rand(L)
+        sub = u < 0.05
+        keep = ~((u >= 0.05) & (u < 0.10))
+        ins = (u >= 0.10) & (u < 0.15)
+        f = frag.copy()
+        f[sub] = bases[rng.randint(0, 4, size=int(sub.sum()))]
+        # an insertion follows its base: build the output with np.repeat (count 2 where an insertion happens)
+        counts = np.where(keep, 1, 0) + np.where(ins, 1, 0)
+        out = np.repeat(f, counts)
+        # the second copy of an inserted position becomes a random base
+        pos = np.cumsum(counts) - 1
+        ins_pos = pos[ins]
+        out[ins_pos] = bases[rng.randint(0, 4, size=len(ins_pos))]
+        seq = out.tobytes().decode()
+        reads.append(('read%d' % k, seq, '0,%d,%s,ref,%d,%d' % (len(seq), strand, start, start + L)))
+    return ref.tobytes().decode(), reads
+
+
+def config5_synthetic(ub, int_peak, threads, n_reads, dist=None, device=None, rank=0, world=1):
+    """A slice of the synthetic long-read workload; for world > 1 the reads are cut across the ranks by length
+    (strong scaling) and the results are gathered on rank 0."""
+    from oracle_lib import REF_LIB, mask_semi_global
+    from unicycler_b200 import sharding
+    ref, reads = synth_reads(10000000, n_reads, 20000, 2)
+    a, b = sharding.partition_by_cost([len(r[1]) for r in reads], world)[rank]
+    mine = reads[a:b]
+    h = ub.new_ref_seqs()
+    ub.add_ref_seq(h, 'ref', ref)
+    args = ([r[0] for r in mine], [r[1] for r in mine], [r[2] for r in mine], h, SCHEME, 0)
+    ub.semi_global_alignment_batch(*[x[:8] if isinstance(x, list) else x for x in args])   # warm-up
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    out = ub.semi_global_alignment_batch(*args)
+    st = ub.last_stats()
+    if dist is not None:
+        out = sharding.gather_strings(out, dist, device)
+        import torch
+        t = torch.tensor([time.perf_counter() - t0, float(st['cells']), st['kernel_ms']], dtype=torch.float64, device=device)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt, cells, kernel_ms = float(tmax[0].item()), float(t[1].item()), float(tmax[2].item())
+    else:
+        dt, cells, kernel_ms = time.perf_counter() - t0, float(st['cells']), st['kernel_ms']
+    ub.delete_ref_seqs(h)
+    if rank != 0:
+        return None
+    res = dict(workload='synthetic: random 10 Mbp reference, %d reads x 20 kb (+-10 %%), 15 %% errors, hits from the ground '
+                        'truth; reads cut over %d GPU(s)' % (n_reads, world),
+               reads_per_s=n_reads / dt, gcups_e2e=cells / dt / 1e9, seconds=dt, cells=cells, alignments=sum(len(o.split(';')) - 1 for o in out),
+               kernel_ms_max_rank=kernel_ms, host_threads_per_rank=max(1, (os.cpu_count() or 1) // max(1, world)),
+               note='host seeding (k-mers, line tracing, chaining) is %.0f %% of the time of this workload: it is host bound'
+                    % (100.0 * max(0.0, 1.0 - kernel_ms * 1e-3 / dt)))
+    if os.path.isfile(REF_LIB):
+        from refdriver import AbiLib
+        lib = AbiLib(REF_LIB)
+        hr = lib.new_refs([('ref', ref)])
+        sample = reads[:max(threads, 8)]
+        t0 = time.perf_counter()
+        want = thread_map(lambda r: lib.semi_global(r[0], r[1], r[2], hr, SCHEME), sample, threads)
+        cdt = time.perf_counter() - t0
+        lib.delete_refs(hr)
+        bad = sum(1 for w, o in zip(want, out[:len(sample)]) if mask_semi_global(w) != mask_semi_global(o))
+        if bad:
+            raise SystemExit('config 5 parity failure: %d of %d reads differ from the reference' % (bad, len(sample)))
+        res['parity'] = '%d/%d sampled reads byte-identical to the reference' % (len(sample), len(sample))
+        res['cpu_baseline'] = dict(reads_per_s=len(sample) / cdt, cores=min(threads, len(sample)), kind='reference',
+                                   sample='%d reads, %.1f s' % (len(sample), cdt))
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 
 def main():
     ap = argparse.ArgumentParser()
@@ -211,6 +385,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the side measurements of configs 3-5')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -222,7 +397,7 @@ def main():
 
     import torch
     import unicycler_b200 as ub
-    from oracle_lib import mask_semi_global
+    from oracle_lib import mask_ms, mask_semi_global
     from unicycler_b200 import sharding
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: the product has no CPU path')
@@ -248,22 +423,38 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     d, jobs, reads = load_workload()
-    # reference set: replicated on every GPU; rank 0 broadcasts it once over NCCL (setup, not timed)
     refs = d['refs'] if rank == 0 or dist is None else None
-    if dist is not None:
+    if dist is not None:   # reference set: rank 0 broadcasts it once over NCCL (set-up, not timed)
         refs = sharding.broadcast_references(refs, dist, device)
     cells_per_job = [ub.chain_cells(len(j['readSeq']), len(j['refSeq']), j['seeds'], j['band'])[0] for j in jobs]
-    cells_per_rank = sum(cells_per_job)
+    jobs_of_read, cells_of_read = {}, {}
+    for j, c in zip(jobs, cells_per_job):
+        jobs_of_read.setdefault(j['readName'][:-1], []).append(j)
+        cells_of_read[j['readName'][:-1]] = cells_of_read.get(j['readName'][:-1], 0) + c
+    cells_one_copy = sum(cells_per_job)
+
+    # the read set of this run: `world` copies of the 30 reads as one set, cut across the ranks by DP cost
+    all_reads = [(c, r) for c in range(world) for r in reads]
+    a, b = sharding.partition_by_cost([cells_of_read[r[0]] for _, r in all_reads], world)[rank]
+    my_reads = all_reads[a:b]
+    my_jobs = [j for _, r in my_reads for j in jobs_of_read[r[0]]]
+    my_cells = sum(cells_of_read[r[0]] for _, r in my_reads)
+    total_cells = cells_one_copy * world
 
     # ---------------- device-resident arm (value): K launches of the DP kernel on resident inputs
-    bench = ub.ChainBench(jobs, SCHEME, jobs[0]['band'])
+    bench = ub.ChainBench(my_jobs, SCHEME, jobs[0]['band'])
     tb = ub.transfer_bytes()
     for _ in range(args.warmup):
         bench.run_steps(1)
-    # parity gate on the very data that is timed
-    res = bench.finish(True)
-    from oracle_lib import mask_ms
+    res = bench.finish(True)   # parity gate on the very data that is timed
 
     def anonymous(j):
         # the resident-bench entry point carries no names/offsets: compare coordinates, scores and CIGAR
@@ -274,37 +465,41 @@ def main():
         f[4], f[5] = str(int(f[4]) - j['refOffset']), str(int(f[5]) - j['refOffset'])
         return ','.join(f)
 
-    bad = sum(1 for j, g in zip(jobs, res) if mask_ms(g) != anonymous(j))
+    bad = sum(1 for j, g in zip(my_jobs, res) if mask_ms(g) != anonymous(j))
     if bad:
-        raise SystemExit('parity failure: %d of %d alignments differ from the reference golden output' % (bad, len(jobs)))
+        raise SystemExit('parity failure: %d of %d alignments differ from the reference golden output' % (bad, len(my_jobs)))
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_wall0 = time.perf_counter()
     total_ms = bench.run_steps(args.steps)
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
-    ms_per_step = max_over_ranks(total_ms / args.steps)
-    gcups = world * cells_per_rank / (ms_per_step * 1e-3) / 1e9
+    my_ms = total_ms / args.steps
+    ms_per_step = max_over_ranks(my_ms)
+    gcups = total_cells / (ms_per_step * 1e-3) / 1e9
+    launches = args.steps
 
     # ---------------- end-to-end arm through the C ABI with host buffers
     h = ub.new_ref_seqs()
     for name, seq in refs:
         ub.add_ref_seq(h, name, seq)
-    names = [r[0] for r in reads]
-    seqs = [r[1] for r in reads]
-    hits = [r[2] for r in reads]
+    names = ['%s_c%d' % (r[0], c) if world > 1 else r[0] for c, r in my_reads]
+    seqs = [r[1] for _, r in my_reads]
+    hits = [r[2] for _, r in my_reads]
 
     def e2e_step():
         out = ub.semi_global_alignment_batch(names, seqs, hits, h, SCHEME, 0)
         if dist is not None:
-            out = sharding.all_gather_strings(out, dist, device)
+            out = sharding.gather_strings(out, dist, device)
         return out
 
     for _ in range(max(1, args.warmup)):
         out = e2e_step()
-    bad = sum(1 for r, o in zip(reads, out[:len(reads)]) if mask_semi_global(o) != d['expected'][r[0]])
-    if bad:
-        raise SystemExit('e2e parity failure: %d reads differ from the reference golden output' % bad)
+    if rank == 0:
+        want = [d['expected'][r[0]] for _, r in all_reads]
+        bad = sum(1 for w, o in zip(want, out) if mask_semi_global(o) != w) + abs(len(want) - len(out))
+        if bad:
+            raise SystemExit('e2e parity failure: %d reads differ from the reference golden output' % bad)
     barrier()
     t0 = time.perf_counter()
     e2e_steps_ms = []
@@ -312,63 +507,75 @@ def main():
         t_step = time.perf_counter()
         e2e_step()
         e2e_steps_ms.append((time.perf_counter() - t_step) * 1e3)
+        launches += ub.last_stats()['launches']
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    e2e_gcups = world * cells_per_rank / e2e_s / 1e9
+    e2e_gcups = total_cells / e2e_s / 1e9
     tb2 = ub.transfer_bytes()
+    h2d = sum_over_ranks(float(tb2['h2d_bytes']))
+    d2h = sum_over_ranks(float(tb2['d2h_bytes']))
     clocks = sampler.stop() if sampler else None
     ub.delete_ref_seqs(h)
+    min_cells, max_cells = -max_over_ranks(-float(my_cells)), max_over_ranks(float(my_cells))
 
+    line = None
     if rank == 0:
         peaks = measured_peaks()
         hbm_peak = peaks['hbm_gbs'] if peaks else 6650.0
         int_peak = ub.int_peak_ops_per_sec()
         kernel_s = ms_per_step * 1e-3
-        achieved_gbs = cells_per_rank * 1.0 / kernel_s / 1e9  # algorithmic 1 B of trace per DP cell
+        per_gpu_cells = total_cells / world
+        achieved_ops = per_gpu_cells * OPS_PER_CELL_AFFINE / kernel_s
+        achieved_gbs = per_gpu_cells * 1.0 / kernel_s / 1e9   # algorithmic 1 B of trace per DP cell
         line = dict(
-            metric='GCUPS (DP cell updates per second, semi-global long-read alignment)', value=gcups, unit='GCUPS',
-            n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
-            scaling='weak', vs_baseline=None, dtype='int32',
-            data='sample_data fixture (tests/golden/semiglobal_sample.json.gz); every rank aligns one copy',
-            config=dict(workload=WORKLOAD, cells_per_gpu_per_step=cells_per_rank, jobs_per_gpu=len(jobs),
-                        reads_per_gpu=len(reads), resident_ctas=tb['ctas'],
+            metric=METRIC, value=gcups, unit='GCUPS', n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='int32',
+            data=('sample_data fixture (tests/golden/semiglobal_sample.json.gz)' +
+                  ('; %d copies as one read set of %d reads, cut across the ranks by DP cost' % (world, len(all_reads))
+                   if world > 1 else '')),
+            config=dict(workload=WORKLOAD, cells_per_step=total_cells, reads_per_step=len(all_reads),
+                        shard_cells_min_max=[min_cells, max_cells], resident_ctas=tb['ctas'],
                         l2=('per-step working set: %.2f GB of row/column checkpoints written and re-read plus the '
                             'reference/read windows, > 126 MB L2 (no explicit flush needed)' % (tb['trace_bytes'] / 1e9)),
-                        parallelism='reads sharded over %d GPU(s); replicated reference; no data-path collective' % world),
-            reads_per_s=world * len(reads) / kernel_s,
-            wall_ms_timed_region=wall_ms,
-            gpu_launches=args.steps,
-            e2e=dict(value=e2e_gcups, unit='GCUPS', h2d_bytes_per_step=tb2['h2d_bytes'], d2h_bytes_per_step=tb2['d2h_bytes'],
-                     ms_per_step=e2e_s * 1e3, ms_per_step_median_rank0=sorted(e2e_steps_ms)[len(e2e_steps_ms) // 2],
-                     reads_per_s=world * len(reads) / e2e_s,
-                     path='ub200_semiGlobalAlignmentBatch (host strings in, result strings out)'),
-            roofline=dict(bound='hbm', achieved=achieved_gbs, peak=hbm_peak, unit='GB/s', frac=achieved_gbs / hbm_peak,
-                          traffic=ncu_traffic(), kernel='dpAgentKernel', bytes_per_cell=1,
-                          peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
-                          note=('integer max-plus kernel: the binding roofline is int_roofline. Algorithmic bytes follow '
-                                'SURVEY.md 8(d) (1 B of trace per DP cell); the kernel itself writes only %.3f B/cell of '
-                                'score checkpoints and recomputes trace bytes along the traceback path'
-                                % (tb['trace_bytes'] / float(cells_per_rank)))),
-            int_roofline=dict(achieved_ops_per_s=cells_per_rank * OPS_PER_CELL_AFFINE / kernel_s, peak_ops_per_s=int_peak,
-                              frac=cells_per_rank * OPS_PER_CELL_AFFINE / kernel_s / int_peak if int_peak else None,
-                              ops_per_cell=OPS_PER_CELL_AFFINE, peak_source='ub200_intPeakOpsPerSec microbenchmark (IADD3/VIMNMX/IMAD mix, all SMs)'),
+                        parallelism=('reads sharded over %d GPU(s) by estimated DP cost; every job carries its own reference '
+                                     'window; results gathered on rank 0 with exact sizes; no data-path collective' % world)),
+            reads_per_s=len(all_reads) / kernel_s, wall_ms_timed_region=wall_ms, gpu_launches=int(launches),
+            e2e=dict(value=e2e_gcups, unit='GCUPS', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_s * 1e3,
+                     ms_per_step_median_rank0=sorted(e2e_steps_ms)[len(e2e_steps_ms) // 2],
+                     reads_per_s=len(all_reads) / e2e_s,
+                     path='ub200_semiGlobalAlignmentBatch (host strings in, result strings out)' +
+                          (' + exact-size result gather on rank 0' if world > 1 else '')),
+            roofline=dict(bound='int32-alu', achieved=achieved_ops / 1e12, peak=int_peak / 1e12, unit='Tint32-op/s',
+                          frac=achieved_ops / int_peak, traffic=ncu_traffic(), kernel='dpAgentKernel',
+                          ops_per_cell=OPS_PER_CELL_AFFINE,
+                          peak_source='ub200_intPeakOpsPerSec: IADD3/VIMNMX/IMAD chains on all SMs, measured at start-up '
+                                      '(MEASURED_PEAKS.json holds no integer peak); nominal 148 SM x 128 lanes x 1.965 GHz = 37.2',
+                          note='integer max-plus path: no tensor-core or HBM bound applies; traffic = ncu DRAM bytes of one launch'),
+            roofline_hbm=dict(bound='hbm', achieved=achieved_gbs, peak=hbm_peak, unit='GB/s', frac=achieved_gbs / hbm_peak,
+                              bytes_per_cell=1,
+                              peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
+                              note=('secondary, non-binding bound: algorithmic bytes follow SURVEY.md 8(d) (1 B of trace per DP '
+                                    'cell); the kernel itself writes %.3f B/cell of score checkpoints and recomputes trace '
+                                    'bytes along the traceback path' % (tb['trace_bytes'] / float(max(1, my_cells))))),
             clocks=clocks)
         if world == 1 and not args.no_cpu_baseline:
-            from oracle_lib import REF_LIB
-            threads = os.cpu_count() or 1
-            budget = int(0.04e9 * min(threads, 30) * 12)
-            sample, cells = bounded_sample(reads, jobs, cells_per_job, budget)
-            use_threads = max(1, min(threads, len(sample)))
-            if os.path.isfile(REF_LIB):
-                dt = cpu_reference_run(sample, d['refs'], use_threads, d['expected'])
-                kind = 'reference'
-            else:
-                nm = set(r[0] for r in sample)
-                dt = cpu_port_run([j for j in jobs if j['readName'][:-1] in nm], use_threads)
-                kind = 'port'
-            line['cpu_baseline'] = dict(value=cells / dt / 1e9, unit='GCUPS', cores=use_threads, kind=kind,
-                                        sample='%d of %d reads (smallest first), %.3g DP cells, %.1f s' %
-                                        (len(sample), len(reads), cells, dt))
+            line['cpu_baseline'], _ = headline_cpu_baseline(d, jobs, reads, cells_one_copy)
+    # ---------------- side measurements
+    if not args.no_extra:
+        threads = os.cpu_count() or 1
+        int_peak = ub.int_peak_ops_per_sec() if rank == 0 else 1.0
+        extra = {}
+        if world == 1:
+            extra['config3_bridge_path_scoring'] = config3_bridge(ub, int_peak, threads)
+            extra['config4_calibration_sweep'] = config4_calibration(ub, int_peak, threads)
+            extra['config5_synthetic_slice'] = config5_synthetic(ub, int_peak, threads, 512)
+        else:
+            r5 = config5_synthetic(ub, int_peak, threads, 1024, dist, device, rank, world)
+            if rank == 0:
+                extra['config5_synthetic_slice'] = r5
+        if rank == 0:
+            line['configs'] = extra
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -183,3 +183,16 @@ def test_free_end_gap_entry_points_vs_reference_library(ub):
         assert ub.end_seq_alignment(a, b, SCHEME) == ref.end(a, b, SCHEME)
         g = rng.randint(0, 300)
         assert '%d,%d' % ub.overlap_alignment(a, b, SCHEME, g) == ref.overlap(a, b, SCHEME, g)
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_LIB), reason='oracle/_ref not built')
+def test_unbanded_pair_with_more_than_2_31_cells_vs_reference_library(ub):
+    """The calibration sweep of BASELINE configs[3] goes to 50 kb: (47 001)^2 cells do not fit 32-bit matrix positions
+    (the reference uses size_t).  One such pair of the calibration's own generator against the reference library
+    (~35 s on one host core)."""
+    from refdriver import AbiLib
+    ref = AbiLib(REF_LIB)
+    a, b = ub.calibration_pairs(47000, 1, 11)
+    got = ub.fully_global_alignment(a[0], b[0], SCHEME, False, 0)
+    want = ref.fully_global(a[0], b[0], SCHEME, False, 0)
+    assert mask_ms(got) == mask_ms(want)

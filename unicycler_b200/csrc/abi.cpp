@@ -37,23 +37,52 @@ namespace {
 
 int g_device = -1;
 std::mutex g_engineMu;
-// Two engines per process (same device, own buffers and stream): a batch call runs its reads as two chunks so that the
-// host stages of one chunk overlap the kernel of the other.  Everything else uses engine 0.
-std::unique_ptr<Engine> g_engine[2];
+// Engines of this process: two per device (own buffers and stream each), so that a chunked batch call can overlap
+// the host stages of one chunk with the kernel of another.  The device list is UNICYCLER_B200_DEVICES ("0,1,2,3" or
+// "all"; default: the one device selected by ub200_setDevice / UNICYCLER_B200_DEVICE / the current device): with
+// several devices the chunks of a batch call go round the devices, one host thread drives them all (jobs are
+// independent and carry their own reference window, so nothing is replicated or exchanged between the GPUs).
+// Everything that is not a chunked batch uses engine 0.
+std::vector<std::unique_ptr<Engine> > g_engines;
+std::vector<int> g_deviceList;
 std::atomic<bool> g_lastCallUsedBoth(false);   // the last call was a chunked batch: its counters are in g_batchStats
 EngineStats g_batchStats;
 
+void resolveDevices() {   // under g_engineMu
+    if (!g_deviceList.empty()) return;
+    const char* e = getenv("UNICYCLER_B200_DEVICES");
+    if (e && g_device < 0) {
+        std::string v(e);
+        if (v == "all") {
+            const int n = Engine::deviceCount();
+            for (int d = 0; d < n; ++d) g_deviceList.push_back(d);
+        } else {
+            std::stringstream ss(v);
+            std::string tok;
+            while (getline(ss, tok, ',')) if (!tok.empty()) g_deviceList.push_back(atoi(tok.c_str()));
+        }
+    }
+    if (g_deviceList.empty()) {
+        int dev = g_device;
+        if (dev < 0) { const char* d = getenv("UNICYCLER_B200_DEVICE"); if (d) dev = atoi(d); }
+        g_deviceList.push_back(dev);
+    }
+    g_engines.resize(2 * g_deviceList.size());
+}
+
+int engineCount() {
+    std::lock_guard<std::mutex> lock(g_engineMu);
+    resolveDevices();
+    return (int)g_engines.size();
+}
+
 Engine& engine(int slot = 0) {
     std::lock_guard<std::mutex> lock(g_engineMu);
-    if (!g_engine[slot]) {
-        int dev = g_device;
-        if (dev < 0) {
-            const char* e = getenv("UNICYCLER_B200_DEVICE");
-            if (e) dev = atoi(e);
-        }
-        g_engine[slot].reset(new Engine(dev));
-    }
-    return *g_engine[slot];
+    resolveDevices();
+    // slot k: device k % D, buffer set k / D (consecutive chunks of a batch go to different devices)
+    const size_t D = g_deviceList.size();
+    if (!g_engines[(size_t)slot]) g_engines[(size_t)slot].reset(new Engine(g_deviceList[(size_t)slot % D]));
+    return *g_engines[(size_t)slot];
 }
 
 [[noreturn]] void fatal(const std::string& msg) {
@@ -484,8 +513,8 @@ int ub200_setDevice(int device) {
     std::unique_lock<std::mutex> co(g_coMu);
     if (g_coRunning || !g_coPending.empty()) return -1;
     std::lock_guard<std::mutex> lock(g_engineMu);
-    for (auto& e : g_engine)
-        if (e && e->device() != device) e.reset();
+    g_engines.clear();
+    g_deviceList.clear();
     g_device = device;
     return 0;
 }
@@ -544,9 +573,9 @@ char* getRandomSequenceAlignmentScores(int seqLength, int n, int m, int mm, int 
     std::uniform_int_distribution<int> dist(0, 3);
     static const char bases[4] = {'A', 'C', 'G', 'T'};
     std::vector<double> scores;
-    // batches bounded by trace memory: ~2^31 cells per batch
+    // device batches bounded by checkpoint memory (0.25 B per cell): ~1.6e11 cells, i.e. ~40 GB, per batch
     const long long cellsPerPair = (long long)(seqLength + 1) * (seqLength + 1);
-    long long perBatch = std::max(1LL, std::min<long long>(n, (1LL << 32) / std::max(1LL, cellsPerPair)));
+    long long perBatch = std::max(1LL, std::min<long long>(n, 160000000000LL / std::max(1LL, cellsPerPair)));
     perBatch = std::min(perBatch, 65536LL);
     for (long long done = 0; done < n; done += perBatch) {
         const long long cnt = std::min<long long>(perBatch, n - done);
@@ -840,20 +869,21 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     auto hi = [&](int k) { return std::min(n, (k + 1) * chunk); };
     double seedMs = 0.0;
     EngineStats batchStats;
+    const int E = engineCount();   // two per device
     for (int k = 0; k < nChunks; ++k) {
         const double ts = nowSec();
         seedChunk(lo(k), hi(k), jobs[(size_t)k]);
         seedMs += (nowSec() - ts) * 1e3;
-        if (k >= 2) {   // the engine of chunk k is the one chunk k-2 used
-            engine(k & 1).end(jobs[(size_t)(k - 2)]);
-            addStats(batchStats, engine(k & 1).lastStats());
-            finishChunk(lo(k - 2), hi(k - 2));
+        if (k >= E) {   // the engine of chunk k is the one chunk k-E used
+            engine(k % E).end(jobs[(size_t)(k - E)]);
+            addStats(batchStats, engine(k % E).lastStats());
+            finishChunk(lo(k - E), hi(k - E));
         }
-        engine(k & 1).begin(jobs[(size_t)k]);
+        engine(k % E).begin(jobs[(size_t)k]);
     }
-    for (int k = std::max(0, nChunks - 2); k < nChunks; ++k) {
-        engine(k & 1).end(jobs[(size_t)k]);
-        addStats(batchStats, engine(k & 1).lastStats());
+    for (int k = std::max(0, nChunks - E); k < nChunks; ++k) {
+        engine(k % E).end(jobs[(size_t)k]);
+        addStats(batchStats, engine(k % E).lastStats());
         finishChunk(lo(k), hi(k));
     }
     g_batchStats = batchStats;

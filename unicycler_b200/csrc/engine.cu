@@ -427,7 +427,8 @@ __device__ __noinline__ void trackGlobal(const GridCtx& Gin, TrackResult& res) {
         res.maxScore = best;
         res.nCand = 1;
         res.maxCell = trackedCell(G, i, j);
-        if (lane == 0) G.cand[0] = j * g.dimV + i + storageOffset(g, j);
+        // (column, storage row) as two ints: column * dimV overflows 32 bits from ~46 k x 46 k cells on
+        if (lane == 0) { G.cand[0] = j; G.cand[1] = i + storageOffset(g, j); }
     }
     res.status = JOB_OK;
     __syncwarp();
@@ -599,8 +600,7 @@ __device__ __noinline__ TbResult tracebackGrid(const GridCtx& Gin, uint8_t* win,
     int nTraces = 0;
     TraceWalker w(G, out, win);
     if (G.kind == GRID_GLOBAL) {
-        const int pos0 = G.cand[0];
-        w.pc = pos0 / G.g.dimV; w.pv = pos0 % G.g.dimV;
+        w.pc = G.cand[0]; w.pv = G.cand[1];
         const int hdr = out.len; out.put(0);
         int tvOverride = -1;
         if (!G.complete && G.affine) {  // _correctTraceValue
@@ -1876,6 +1876,10 @@ Engine::~Engine() {
 }
 
 int Engine::device() const { return impl_->device; }
+int Engine::deviceCount() {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 EngineStats Engine::lastStats() const { return impl_->stats; }
 
 static size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -121,6 +121,7 @@ public:
     void end(std::vector<Job*>& jobs);
     EngineStats lastStats() const;
     int device() const;
+    static int deviceCount();   // CUDA devices visible to the process (0 when there is none)
     // Device-resident benchmark mode: upload()+plan once, then launch() repeatedly with
     // inputs already in HBM; fetch() copies results back.
     void upload(std::vector<Job*>& jobs);

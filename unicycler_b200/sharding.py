@@ -1,6 +1,5 @@
 """Multi-GPU plumbing for the alignment path: one process per GPU (torch.distributed), reads partitioned across
-ranks by estimated DP cost, reference set broadcast once, variable-length result strings gathered to every
-rank.  No collective sits inside the DP: every (read, reference range) job is independent."""
+ranks by estimated DP cost, reference set broadcast once, variable-length result strings gathered with exact sizes.  No collective sits inside the DP: every (read, reference range) job is independent."""
 import numpy as np
 
 
@@ -51,25 +50,57 @@ def broadcast_references(refs, dist, device, src=0):
     return out
 
 
-def all_gather_strings(strings, dist, device):
-    """Gathers each rank's list of result strings to every rank (lengths first, then one padded byte tensor),
-    preserving rank order.  Returns the concatenated list."""
+def gather_strings(strings, dist, device, dst=0):
+    """Gathers each rank's list of result strings on rank `dst` in rank order (None elsewhere) with exact sizes: one
+    all-gather of the byte counts, then one grouped send/recv of exactly those bytes (ncclSend/ncclRecv inside one
+    group on the GPU box, gloo in the CPU tests).  Results end on the host of the gathering rank anyway, so nothing
+    is padded and nothing is sent to ranks that do not need it."""
     import torch
-    world = dist.get_world_size()
+    world, rank = dist.get_world_size(), dist.get_rank()
     blob = '\x1e'.join(strings).encode()
     local = torch.tensor([len(blob), len(strings)], dtype=torch.int64, device=device)
     sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(sizes, local)
-    maxlen = max(int(s[0].item()) for s in sizes)
-    buf = torch.zeros(max(1, maxlen), dtype=torch.uint8, device=device)
-    if blob:
-        buf[:len(blob)] = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).to(device)
-    bufs = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(bufs, buf)
+    sizes = [(int(s[0].item()), int(s[1].item())) for s in sizes]
+    ops, bufs = [], {}
+    if rank == dst:
+        for r, (n, cnt) in enumerate(sizes):
+            if r != dst and n > 0:
+                bufs[r] = torch.empty(n, dtype=torch.uint8, device=device)
+                ops.append(dist.P2POp(dist.irecv, bufs[r], r))
+    elif blob:
+        mine = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).to(device)
+        ops.append(dist.P2POp(dist.isend, mine, dst))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if rank != dst:
+        return None
     out = []
-    for s, b in zip(sizes, bufs):
-        n, cnt = int(s[0].item()), int(s[1].item())
+    for r, (n, cnt) in enumerate(sizes):
         if cnt == 0:
             continue
-        out.extend(bytes(b[:n].cpu().numpy().tobytes()).decode().split('\x1e'))
+        data = blob if r == dst else bytes(bufs[r].cpu().numpy().tobytes())
+        out.extend(data.decode().split('\x1e'))
     return out
+
+
+def all_gather_strings(strings, dist, device):
+    """Every rank gets the concatenated list (rank order): gather on rank 0 with exact sizes, then one broadcast of
+    the packed bytes."""
+    import torch
+    rank = dist.get_rank()
+    merged = gather_strings(strings, dist, device, dst=0)
+    blob = '\x1e'.join(merged).encode() if rank == 0 else b''
+    meta = torch.tensor([len(blob), len(merged) if rank == 0 else 0], dtype=torch.int64, device=device)
+    dist.broadcast(meta, src=0)
+    n, cnt = int(meta[0].item()), int(meta[1].item())
+    if cnt == 0:
+        return []
+    if rank == 0:
+        buf = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).to(device)
+    else:
+        buf = torch.empty(n, dtype=torch.uint8, device=device)
+    if n > 0:
+        dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().numpy().tobytes()).decode().split('\x1e') if n > 0 else [''] * cnt
