@@ -376,6 +376,47 @@ def config5_synthetic(ub, int_peak, threads, n_reads, dist=None, device=None, ra
     return res
 
 
+def dropin_e2e(ub, cells, threads=8):
+    """Second end-to-end figure: NO call-site change at all — the reference's own unicycler_align.
+    semi_global_align_long_reads (thread pool of 8 Python threads, per-read C ABI) with libunicycler_b200.so installed as
+    unicycler/cpp_functions.so (tests/dropin_align_harness.py; the staged reference package travels in oracle/_ref)."""
+    import shutil
+    from oracle_lib import REF_LIB, load_golden
+    pydist = os.path.join(ROOT, 'oracle', '_ref', 'pydist')
+    if not (os.path.isdir(pydist) and os.path.isfile(REF_LIB)):
+        return dict(unavailable='oracle/_ref/pydist (staged reference Python package) not present')
+    work = tempfile.mkdtemp(prefix='ub200_dropin_')
+    try:
+        shutil.copytree(pydist, os.path.join(work, 'pkg'))
+        shutil.copy(ub.LIB_PATH, os.path.join(work, 'pkg', 'unicycler', 'cpp_functions.so'))
+        env = dict(os.environ, UNICYCLER_B200_FORWARD_LIB=REF_LIB, PYTHONWARNINGS='ignore')
+        out = os.path.join(work, 'align.json')
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'dropin_align_harness.py'), os.path.join(work, 'pkg'), out,
+                            str(threads), '4'], cwd=os.path.join(work, 'pkg'), env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, timeout=1200)
+        if r.returncode != 0:
+            raise SystemExit('drop-in driver failed: ' + r.stdout.decode()[-1500:])
+        got = json.load(open(out))
+        want = load_golden('dropin_align_sample.json.gz')
+        if got['reads'] != want['reads']:
+            raise SystemExit('drop-in parity failure: the alignments kept by the reference driver differ')
+        runs = sorted(got['times'][1:], key=lambda t: t[1])
+        loop, in_c = runs[len(runs) // 2][1], runs[len(runs) // 2][2]
+        return dict(value=cells / loop / 1e9, unit='GCUPS', ms_per_step=loop * 1e3, python_threads=threads,
+                    ms_inside_library=in_c * 1e3,
+                    note=('%.0f %% of the loop no thread is inside the library: the reference\'s Python (Alignment objects, '
+                          'tally_up_score_and_errors, under the GIL) is the rest' % (100.0 * max(0.0, 1.0 - in_c / loop))),
+                    reads_per_s=len(got['reads']) / loop,
+                    path='unmodified unicycler_align.semi_global_align_long_reads -> per-read semiGlobalAlignment (request '
+                         'coalescer); alignment loop only (minimap and file loading excluded)',
+                    parity='alignments kept per read identical to the reference library under the same driver',
+                    reference_same_driver_s=want.get('reference_seconds_8_threads'),
+                    reference_same_driver_note='reference library under the same driver with 8 threads, measured once in '
+                                               'the build container (8 cores) when the golden file was made')
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 
 def main():
@@ -560,6 +601,8 @@ def main():
             clocks=clocks)
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'], _ = headline_cpu_baseline(d, jobs, reads, cells_one_copy)
+        if world == 1 and not args.no_extra:
+            line['e2e_dropin'] = dropin_e2e(ub, cells_one_copy)
     # ---------------- side measurements
     if not args.no_extra:
         threads = os.cpu_count() or 1

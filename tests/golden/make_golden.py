@@ -25,6 +25,8 @@ Outputs (all gzip-compressed JSON):
                              path_finding.get_best_paths_for_seq on test/test_assembly_graph.gfa with synthetic read
                              consensus sequences (tests/dropin_bridge_harness.py): chosen paths and every
                              (s1, s2, band, entry point) that crossed the seam with the reference's result.
+  dropin_align_sample.json.gz  what unicycler_align.semi_global_align_long_reads (the reference's Python driver, thread
+                             pool of 8) keeps for every sample_data read with the reference library underneath.
   semiglobal_<set>.json.gz   for the reference's semi-global fixtures (test/test_semi_global_alignment*.{fasta,fastq}
                              and sample_data): references, reads, the minimap hit strings the reference's own
                              minimap produces, the expected semiGlobalAlignment output per read, and — from a
@@ -404,6 +406,21 @@ def make_bridge():
     write_json_gz('bridge_tuples.json.gz', dict(scheme=list(SCHEME), strings=table, recorded=rec, bridges=d['bridges']))
 
 
+def make_dropin_align():
+    """The reference's own driver (unicycler_align.semi_global_align_long_reads, 8 threads) on the sample_data fixture
+    with the UNMODIFIED reference library: the alignments it keeps per read (tests/dropin_align_harness.py)."""
+    import shutil
+    work = '/tmp/_golden_dropin_align'
+    shutil.rmtree(work, ignore_errors=True)
+    shutil.copytree(os.path.join(ROOT, 'oracle', '_ref', 'pydist'), work)
+    shutil.copy(REF_LIB, os.path.join(work, 'unicycler', 'cpp_functions.so'))
+    out = os.path.join(work, 'align.json')
+    subprocess.check_call([sys.executable, '-W', 'ignore', os.path.join(ROOT, 'tests', 'dropin_align_harness.py'), work, out, '8'],
+                          cwd=work)
+    d = json.load(open(out))
+    write_json_gz('dropin_align_sample.json.gz', dict(reads=d['reads'], reference_seconds_8_threads=d['times'][0][1]))
+
+
 def main():
     if not os.path.exists(REF_LIB):
         subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle'), 'ref'])
@@ -413,6 +430,8 @@ def main():
         make_global_path(ref_lib)
     if 'bridge' in which:
         make_bridge()
+    if 'dropin_align' in which:
+        make_dropin_align()
     for name, fn in (('freeend', make_freeend), ('pairs_large', make_pairs_large), ('calibration', make_calibration),
                      ('synth5', make_synth5), ('sensitivity', make_sensitivity)):
         if name in which:

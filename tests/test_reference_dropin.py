@@ -69,6 +69,23 @@ def test_bridge_path_scoring_through_reference_python(ub, tmp_path, mode):
         assert a['result'] == b['result']
 
 
+@needs_ref
+@pytest.mark.gpu
+def test_reference_alignment_driver_with_thread_pool(ub, tmp_path):
+    """unicycler_align.semi_global_align_long_reads, unmodified, with 8 Python threads on the sample_data reads: the
+    per-read ABI behind the request coalescer.  Same alignments kept, same coordinates, scores and CIGARs as with the
+    reference library (tests/golden/dropin_align_sample.json.gz)."""
+    work, env = _stage(tmp_path, ub)
+    out = os.path.join(work, 'align.json')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'dropin_align_harness.py'), work, out, '8'],
+                       cwd=work, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1500)
+    assert r.returncode == 0, r.stdout.decode()[-3000:]
+    got = json.load(open(out))
+    want = load_golden('dropin_align_sample.json.gz')
+    assert got['reads'] == want['reads']
+    assert sum(len(v) for v in got['reads'].values()) >= 30
+
+
 @pytest.mark.gpu
 def test_bridge_tuples_golden_batch(ub):
     """The alignments of the bridge run as device batches (config-3 benchmark input)."""
