@@ -47,6 +47,19 @@ WORKLOAD = ('sample_data long_reads_low_depth (30 reads) vs reference.fasta (3 r
             'scheme 3,-6,-5,-2, sensitivity 0; 171 banded-chain alignments, 23019 sub-DPs')
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of this run, on the real stdout."""
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def load_workload():
     from oracle_lib import golden_chain_jobs, load_golden
     d = load_golden('semiglobal_sample.json.gz')
@@ -191,7 +204,7 @@ def run_reference_arm(args, rank):
                 config=dict(workload=WORKLOAD, sample='all %d reads, %.4g DP cells per step' % (len(reads), cells)),
                 reads_per_s=len(reads) / dt, cpu_baseline=base,
                 e2e=dict(value=gcups, unit='GCUPS', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -431,6 +444,11 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    # stdout carries exactly ONE JSON line: everything libraries print there (NCCL's version banner ...) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == 'reference':
         run_reference_arm(args, rank)
@@ -619,7 +637,7 @@ def main():
         if rank == 0:
             line['configs'] = extra
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -137,6 +137,14 @@ int ub200_chainPlan(int readLen, int refLen, const int64_t* seeds, int nSeeds, i
  * same pairs to the reference's fullyGlobalAlignment. */
 int ub200_calibrationPairs(int seqLength, int n, unsigned seed, char** s1, char** s2);
 
+/* the tallies Alignment.tally_up_score_and_errors (unicycler/alignment.py:142-216) derives from a
+ * CIGAR by walking it base by base in Python.  readSeq = the read as aligned (reverse-complemented for '-'), refSeq =
+ * the whole reference.  Returns "matches,mismatches,insertions,deletions,rawScore,alignmentLength,percentIdentity,
+ * scaledScore" (malloc()ed; doubles printed with 17 significant digits), "" if only soft clips remain. */
+char* ub200_alignmentTallies(const char* readSeq, const char* refSeq, int readStartPos, int refStartPos,
+                             const char* cigar, int matchScore, int mismatchScore, int gapOpenScore,
+                             int gapExtensionScore);
+
 /* Coalescer counters: device batches run so far, and ABI requests they served (requests / batches > 1 means that
  * concurrent per-read calls were merged into shared launches). */
 void ub200_coalescerStats(int64_t* batches, int64_t* requests);

@@ -147,3 +147,50 @@ def test_start_end_alignment_return_int(ub):
     assert 'int startAlignment(' in header and 'int endAlignment(' in header
     lib = ctypes.CDLL(ub.LIB_PATH)
     assert lib.startAlignment and lib.endAlignment
+
+
+@needs_ref
+def test_alignment_tallies_match_the_reference_python(ub, tmp_path):
+    """ub200_alignmentTallies against Alignment.tally_up_score_and_errors of the reference's own
+    alignment.py (run in a subprocess inside the staged package) on every golden alignment of two fixtures.  No GPU."""
+    work = str(tmp_path / 'ref_pkg')
+    shutil.copytree(PYDIST, work)
+    shutil.copy(REF_LIB, os.path.join(work, 'unicycler', 'cpp_functions.so'))
+    code = r'''
+import gzip, json, sys
+sys.path.insert(0, sys.argv[1])
+import unicycler.alignment, unicycler.read_ref
+scheme = unicycler.alignment.AlignmentScoringScheme('3,-6,-5,-2')
+out = []
+for name in ('small', 'sample'):
+    d = json.load(gzip.open(sys.argv[2] + '/semiglobal_%s.json.gz' % name, 'rt'))
+    refs = {n: unicycler.read_ref.Reference(n, s) for n, s in d['refs']}
+    for rn, seq, _ in d['reads']:
+        read = unicycler.read_ref.Read(rn, seq, 'I' * len(seq))
+        for k, s in enumerate(d['expected'].get(rn, '').split(';')[:-1]):
+            a = unicycler.alignment.Alignment(seqan_output=s, read=read, reference_dict=refs, scoring_scheme=scheme)
+            out.append([name, rn, k, a.match_count, a.mismatch_count, a.insertion_count, a.deletion_count,
+                        a.raw_score, a.alignment_length, repr(a.percent_identity), repr(a.scaled_score), a.edit_distance])
+json.dump(out, open(sys.argv[3], 'w'))
+'''
+    res = os.path.join(work, 'tallies.json')
+    r = subprocess.run([sys.executable, '-W', 'ignore', '-c', code, work, os.path.join(ROOT, 'tests', 'golden'), res],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    want = json.load(open(res))
+    from oracle_lib import revcomp
+    data = {}
+    for name in ('small', 'sample'):
+        d = load_golden('semiglobal_%s.json.gz' % name)
+        data[name] = (dict(d['refs']), {r[0]: r[1] for r in d['reads']}, d)
+    n = 0
+    for name, rn, k, mc, mmc, ic, dc, raw, alen, ident, scaled, edit in want:
+        refs, reads, d = data[name]
+        s = d['expected'][rn].split(';')[k].split(',', 9)
+        read_seq = reads[rn] if s[1] == '+' else revcomp(reads[rn])
+        t = ub.alignment_tallies(read_seq, refs[s[0]], int(s[2]), int(s[4]), s[9], (3, -6, -5, -2))
+        assert (t['match_count'], t['mismatch_count'], t['insertion_count'], t['deletion_count'], t['raw_score'],
+                t['alignment_length'], t['edit_distance']) == (mc, mmc, ic, dc, raw, alen, edit), (name, rn)
+        assert repr(t['percent_identity']) == ident and repr(t['scaled_score']) == scaled, (name, rn)
+        n += 1
+    assert n >= 40

@@ -634,6 +634,52 @@ int ub200_calibrationPairs(int seqLength, int n, unsigned seed, char** s1, char*
     return 0;
 }
 
+// SURVEY.md 8(f)4 — Alignment.tally_up_score_and_errors (unicycler/alignment.py:142-216) walks every CIGAR base by base
+// in Python under the GIL; this is the same walk on the host in C++.  readSeq is the read as aligned (already reverse-
+// complemented for '-' alignments), refSeq the whole reference sequence; positions as in the result string.
+// Returns "matches,mismatches,insertions,deletions,rawScore,alignmentLength,percentIdentity,scaledScore" (doubles with 17
+// significant digits: they round-trip), or "" when nothing but soft clips is left (the Python returns early there).
+char* ub200_alignmentTallies(const char* readSeq, const char* refSeq, int readStartPos, int refStartPos, const char* cigar,
+                             int m, int mm, int go, int ge) {
+    const long readLen = (long)strlen(readSeq), refLen = (long)strlen(refSeq);
+    std::vector<std::pair<long, char> > parts;
+    for (const char* p = cigar; *p;) {
+        char* end = nullptr;
+        const long n = strtol(p, &end, 10);
+        if (end == p || !*end) break;
+        parts.emplace_back(n, *end);
+        p = end + 1;
+    }
+    if (!parts.empty() && parts.front().second == 'S') parts.erase(parts.begin());
+    if (!parts.empty() && parts.back().second == 'S') parts.pop_back();
+    if (parts.empty()) return dupString("");
+    long matches = 0, mismatches = 0, insertions = 0, deletions = 0, raw = 0, alignI = 0;
+    long readI = readStartPos, refI = refStartPos;
+    for (const auto& part : parts) {
+        const long n = part.first;
+        long score = 0;
+        if (part.second == 'I') { score = go + (n - 1) * ge; insertions += n; readI += n; }
+        else if (part.second == 'D') { score = go + (n - 1) * ge; deletions += n; refI += n; }
+        else {
+            for (long k = 0; k < n; ++k) {
+                if (readI >= readLen || refI >= refLen) break;
+                if (readSeq[readI] == refSeq[refI]) { ++matches; score += m; }
+                else { ++mismatches; score += mm; }
+                ++readI; ++refI;
+            }
+        }
+        raw += score;
+        alignI += n;
+    }
+    const double identity = 100.0 * (double)matches / (double)alignI;
+    const long perfect = (long)m * alignI, worst = (long)mm * alignI;
+    const double scaled = 100.0 * (double)(raw - worst) / (double)(perfect - worst);
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%ld,%ld,%ld,%ld,%ld,%ld,%.17g,%.17g", matches, mismatches, insertions, deletions, raw, alignI,
+             identity, scaled);
+    return dupString(buf);
+}
+
 void ub200_coalescerStats(int64_t* batches, int64_t* requests) {
     if (batches) *batches = g_coBatches.load();
     if (requests) *requests = g_coRequests.load();

@@ -654,6 +654,60 @@ __device__ __forceinline__ void leanChunk(const StepConsts& K, StripState<8>& st
     __syncwarp();
 }
 
+// One chunk of a trace-tile recompute (64-row block, 2 rows per lane, affine gaps, unbanded): the trace bytes of the
+// tile under a traceback path, recomputed from the checkpoints.  Same values and bytes as
+// stripSteps<true,CT,false,2,MODE,false>; issued like leanChunk: boundary cells and one-hot column masks come from
+// shared memory, and a lane outside the tile in a step (the wavefront's ramps: most of a 64-column tile) is masked
+// with selects instead of a divergent branch.  win: column cBeg at offset 0, 32 two-byte slots per column.
+template <bool CT, bool GLOBALWIN>
+__device__ __forceinline__ void leanTileChunk(const StepConsts& K, StripState<2>& st, int lane, uint32_t leanOff,
+                                              const uint8_t* seqH, int cBeg, int cEnd, int c, int i0, int bS, int bV,
+                                              int nsteps, uint8_t* win) {
+    int2* bnd = reinterpret_cast<int2*>(gSmem + leanOff);
+    uint32_t* hcw = reinterpret_cast<uint32_t*>(gSmem + leanOff + 256);
+    const int colBase = cBeg + 32 * c;
+    bnd[lane] = make_int2(bS, bV);
+    {   // one-hot masks of columns colBase-31 .. colBase+31 (those outside [cBeg, cEnd] are never used)
+        const int j1 = colBase - 31 + lane, j2 = colBase + 1 + lane;
+        hcw[lane] = (j1 >= cBeg && j1 <= cEnd) ? (1u << seqH[j1 - 1]) * 0x01010101u : 0u;
+        if (lane < 31) hcw[32 + lane] = (j2 <= cEnd) ? (1u << seqH[j2 - 1]) * 0x01010101u : 0u;
+    }
+    __syncwarp();
+    const int match = K.match, mismatch = K.mismatch, go = K.go, ge = K.ge;
+    const uint32_t* hp = hcw + (31 - lane);
+    const uint32_t vm0 = st.vm[0];
+    const bool rowsInside = i0 <= K.nV;   // lanes below the matrix stay idle
+    int pubS = st.pubS, pubV = st.pubV, prevUpS = st.prevUpS, S0 = st.Sl[0], S1 = st.Sl[1], H0 = st.Hl[0], H1 = st.Hl[1];
+    uint32_t hr = 0, hrLast = 0;
+    uint16_t* wp = reinterpret_cast<uint16_t*>(win) + (size_t)(colBase - lane - cBeg) * 32 + lane;   // slot of step 0
+    const int kEnd = imin(32, nsteps - 32 * c);
+#pragma unroll 1
+    for (int kk = 0; kk < kEnd; ++kk) {
+        int inS = __shfl_up_sync(FULLMASK, pubS, 1);
+        int inV = __shfl_up_sync(FULLMASK, pubV, 1);
+        const int2 b = bnd[kk];
+        if (lane == 0) { inS = b.x; inV = b.y; }
+        hr = hp[kk];
+        const int j = colBase + kk - lane;
+        const bool act = rowsInside && (32 * c + kk >= lane) && (j <= cEnd);
+        const uint32_t eq = vm0 & hr;
+        int s0, h0, v0, s1, h1, v1;
+        const uint32_t t0 = cellUpdate<true, CT, false>(s0, h0, v0, S0, H0, inS, inV, prevUpS, (eq & 0xffu) ? match : mismatch, go, ge, 0);
+        const uint32_t t1 = cellUpdate<true, CT, false>(s1, h1, v1, S1, H1, s0, v0, S0, (eq & 0xff00u) ? match : mismatch, go, ge, 0);
+        if (act) {
+            *wp = (uint16_t)(t0 | (t1 << 8));   // (win is based on the shared array or a global slot: the caller rebased it)
+            hrLast = hr;
+        }
+        S0 = act ? s0 : S0; H0 = act ? h0 : H0; S1 = act ? s1 : S1; H1 = act ? h1 : H1;
+        prevUpS = act ? inS : prevUpS;
+        pubS = act ? s1 : pubS; pubV = act ? v1 : pubV;
+        wp += 32;
+    }
+    st.pubS = pubS; st.pubV = pubV; st.prevUpS = prevUpS; st.Sl[0] = S0; st.Sl[1] = S1; st.Hl[0] = H0; st.Hl[1] = H1;
+    if (hrLast) st.curHc = __ffs((int)(hrLast & 0xffu)) - 1;
+    __syncwarp();
+}
+
 // Runs columns cBeg..cEnd of strip s (rows s*32*RR+1 ...).  fromCk: the lane state left of cBeg comes
 // from the column checkpoint at cBeg-1 (a multiple of CKW) instead of the grid's first column.
 // nsteps <= (cEnd-cBeg+1)+31 limits the wavefront (partial tile recompute).
@@ -791,6 +845,13 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
                 lean = true;
                 const int rl = g.nV - (s * SHR + 1);   // row nV inside the strip: lane rl / 8, row rl % 8
                 leanChunk<true>(K, st, lane, leanOff, G.seqH, cBeg + 32 * c, bS, bV, rowOut, ckTile, rl >> 3, rl & 7, G.lastRow);
+            }
+        }
+        if constexpr ((MODE == MODE_TRACE || MODE == MODE_TRACEG) && AFF && !BANDED && RR == 2) {
+            if (!capture && winPitch == 32 && !(cP.pad5 & 8)) {
+                lean = true;
+                leanTileChunk<CT, MODE == MODE_TRACEG>(K, st, lane, (uint32_t)(SMEM_LEAN + (threadIdx.x >> 5) * LEAN_BYTES), G.seqH,
+                                                       cBeg, cEnd, c, i0, bS, bV, nsteps, win);
             }
         }
         if (lean) {}

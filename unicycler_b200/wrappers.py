@@ -79,6 +79,8 @@ def load_library():
     L.overlapAlignment.restype = c_void_p
     L.ub200_calibrationPairs.argtypes = [c_int, c_int, ctypes.c_uint, POINTER(c_void_p), POINTER(c_void_p)]
     L.ub200_calibrationPairs.restype = c_int
+    L.ub200_alignmentTallies.argtypes = [c_char_p, c_char_p, c_int, c_int, c_char_p, c_int, c_int, c_int, c_int]
+    L.ub200_alignmentTallies.restype = c_void_p
     L.ub200_coalescerStats.argtypes = [POINTER(c_int64), POINTER(c_int64)]
     L.ub200_coalescerStats.restype = None
     L.ub200_setDevice.argtypes = [c_int]
@@ -162,6 +164,22 @@ def calibration_pairs(seq_length, n, seed):
     a, b = (c_void_p * n)(), (c_void_p * n)()
     load_library().ub200_calibrationPairs(seq_length, n, seed, a, b)
     return [_to_str(p) for p in a], [_to_str(p) for p in b]
+
+
+def alignment_tallies(read_seq_as_aligned, ref_seq, read_start_pos, ref_start_pos, cigar, scoring_scheme):
+    """The tallies of Alignment.tally_up_score_and_errors (alignment.py:142-216) computed by the library: dict with
+    match_count, mismatch_count, insertion_count, deletion_count, raw_score, alignment_length, percent_identity,
+    scaled_score, edit_distance; None when only soft clips remain."""
+    m, mm, go, ge = _scheme(scoring_scheme)
+    r = _to_str(load_library().ub200_alignmentTallies(read_seq_as_aligned.encode(), ref_seq.encode(), read_start_pos,
+                                                      ref_start_pos, cigar.encode(), m, mm, go, ge))
+    if not r:
+        return None
+    f = r.split(',')
+    d = dict(match_count=int(f[0]), mismatch_count=int(f[1]), insertion_count=int(f[2]), deletion_count=int(f[3]),
+             raw_score=int(f[4]), alignment_length=int(f[5]), percent_identity=float(f[6]), scaled_score=float(f[7]))
+    d['edit_distance'] = d['mismatch_count'] + d['insertion_count'] + d['deletion_count']
+    return d
 
 
 def coalescer_stats():
