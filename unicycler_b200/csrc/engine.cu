@@ -907,6 +907,9 @@ __device__ __noinline__ void runItem(const GridCtx& Gin, int item) {
     const int nsteps = (cEnd - cBeg + 1) + 31;
     if (G.affine) {
         if (g.banded) runStrip<true, false, true, 8, MODE_TASK>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
+        // a flat grid (one strip of at most 64 / 128 rows) is one serial walk over its columns: fewer rows per lane
+        else if (g.nV <= 64 && !(cP.pad5 & 128)) runStrip<true, false, false, 2, MODE_TASK>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
+        else if (g.nV <= 128 && !(cP.pad5 & 128)) runStrip<true, false, false, 4, MODE_TASK>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
         else runStrip<true, false, false, 8, MODE_TASK>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
     } else {
         if (g.banded) runStrip<false, false, true, 8, MODE_TASK>(G, s, cBeg, cEnd, fromCk, nsteps, true, nullptr, 0);
@@ -1637,6 +1640,12 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
             }
             prof[3] += c3 - c2; prof[4] += clock64() - c3;
         }
+        if (P.pad6 == jobIdx + 1 && seg == 0 && gi < 4096 && lane == 0) {
+            const unsigned long long t0 = P.cb->t0, now = globalTimerNs() - t0;
+            const unsigned long long cyc = (unsigned long long)(clock64() - c0);
+            gGridLog[gi][0] = now; gGridLog[gi][1] = cyc; gGridLog[gi][2] = (unsigned long long)(c2 - c1);
+            gGridLog[gi][3] = (unsigned long long)(G.local ? 0 : 1) | ((unsigned long long)(done ? 1 : 0) << 1);
+        }
         __syncwarp();
         // the next grid's record carries the cells that initialise it (pass 2 and merge checks read them)
         if (gi + 1 < jb.gridCount) {
@@ -1690,6 +1699,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
     }
     bool queueEmpty = (agent < 0);
     int idle = 0, amIdle = 0, helpKey = -1;
+    unsigned pollRng = (blockIdx.x * NWARPS + warp) * 2654435761u + 12345u;
     GridCtx* cctx = (cw >= 0) ? reinterpret_cast<GridCtx*>(smem + NCTRL * WINBYTES + cw * CTX_STRIDE) : nullptr;
     uint8_t* win = (cw >= 0) ? smem + cw * WINBYTES : nullptr;
     uint8_t* mini = (cw >= 0) ? P.mini + (size_t)(cw * gridDim.x + blockIdx.x) * P.miniStride : nullptr;
@@ -1730,7 +1740,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
         if (lane == 0) open = ldRelaxed(&P.cb->openTasks);
         open = __shfl_sync(FULLMASK, open, 0);
         idle = min(idle + 1, (open > 0 && (P.pad5 & 32)) ? 2 : 6);
-        __nanosleep(250u << idle);
+        // jittered: warps that went idle together would otherwise wake together, every 16 us — a strip that becomes
+        // claimable in between waited for that instant instead of for the next of ~2000 independent polls
+        pollRng = pollRng * 1664525u + 1013904223u;
+        const unsigned base = 250u << idle;
+        __nanosleep(base / 2 + (pollRng >> 8) % base);
     }
 }
 
@@ -2268,7 +2282,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.out = (int*)I.dOut; kp.out2 = (int*)I.dOut2; kp.recIdx = (int4*)I.dRecIdx; kp.jobOut = (JobOut*)I.dJobOut; kp.order = (const int*)I.dOrder;
     kp.colTabPool = (const ColInfo*)I.dColTab;
     kp.nJobs = (int)nJobs; kp.nSlots = nSlots; kp.maxTasks = (int)maxPub;
-    kp.nEntries = (int)nEntries; kp.pad6 = 0;
+    kp.nEntries = (int)nEntries; kp.pad6 = getenv("UNICYCLER_B200_TRACEJOB") ? atoi(getenv("UNICYCLER_B200_TRACEJOB")) + 1 : 0;
     kp.nHiJobs = 0;
     kp.cb = (ControlBlock*)I.dRing;
     kp.ring = (TaskDesc*)((uint8_t*)I.dRing + offRing);
@@ -2371,6 +2385,17 @@ void Engine::fetch(std::vector<Job*>& jobs) {
     if (cudaEventElapsedTime(&ms, I.ev[2], I.ev[3]) == cudaSuccess && ms > 0.0005f) I.stats.kernelMs = ms;
     if (cudaEventElapsedTime(&ms, I.ev[0], I.ev[1]) == cudaSuccess) I.stats.h2dMs = ms;
     if (cudaEventElapsedTime(&ms, I.ev[4], I.ev[5]) == cudaSuccess) I.stats.d2hMs = ms;
+    if (I.kp.pad6 > 0 && (size_t)I.kp.pad6 <= nJobs) {   // developer aid: the spine of one job, grid by grid
+        static unsigned long long log[4096][4];
+        const JobDev& d = I.jobsDev[(size_t)I.kp.pad6 - 1];
+        if (cudaMemcpyFromSymbol(log, gGridLog, sizeof(log)) == cudaSuccess)
+            for (int g = 0; g < std::min(d.gridCount, 4096); ++g) {
+                const GridDesc& gd = ((const GridDesc*)I.hGrids)[d.gridBegin + g];
+                fprintf(stderr, "[ub200 grid] job %d grid %d (%d x %d banded %d kind %d board %d): done at %.1f us, took %.1f us (fill/wait %.1f us) %s%s\n",
+                        I.kp.pad6 - 1, g, gd.nH, gd.nV, (int)gd.banded, gd.kind, gd.pad, log[g][0] / 1e3, log[g][1] / 1.965e3, log[g][2] / 1.965e3,
+                        (log[g][3] & 1) ? "BIG" : "local", (log[g][3] & 2) ? " fast" : "");
+            }
+    }
     if (getenv("UNICYCLER_B200_DUMPSTATE")) {   // developer aid: how every chain was cut and resolved
         std::vector<JobState> js(nJobs);
         CUDA_CHECK(cudaMemcpy(js.data(), (uint8_t*)I.dRing + I.offState, nJobs * sizeof(JobState), cudaMemcpyDeviceToHost));

@@ -241,6 +241,7 @@ __constant__ KParams cP;
 __device__ unsigned long long gDbg[24];
 __device__ unsigned long long gStripLog[16384][4];   // developer timeline of the strips (UNICYCLER_B200_DBG & 16)
 __device__ int gStripLogN;
+__device__ unsigned long long gGridLog[4096][4];   // developer timeline of one job's spine (UNICYCLER_B200_TRACEJOB)
 __device__ int gUbSite;                   // developer aid: source line of the first JOB_REF_UB verdict
 __device__ __forceinline__ int markUb(int line) { atomicCAS(&gUbSite, 0, line); return 0; }
 #define UB_VERDICT (markUb(__LINE__), JOB_REF_UB)   // developer counters (cycles), lane 0 of control warps
@@ -517,7 +518,8 @@ __device__ __forceinline__ void stripSteps(const GridCtx& G, const StepConsts& K
                 else if constexpr (RR == 2) *reinterpret_cast<uint16_t*>(p) = (uint16_t)tw[0];
                 else *reinterpret_cast<uint32_t*>(p) = tw[0];
             } else if constexpr (MODE == MODE_TASK) {
-                if ((lane & 7) == 7) __stcg(&rowOut[(size_t)(lane >> 3) * (size_t)(K.nH + 1) + j], make_int2(Su, Vu));
+                constexpr int LPB = (RR == 2 || RR == 4 || RR == 8) ? CKR / RR : 8;   // lanes per 64-row checkpoint block
+                if ((lane & (LPB - 1)) == LPB - 1) __stcg(&rowOut[(size_t)(lane / LPB) * (size_t)(K.nH + 1) + j], make_int2(Su, Vu));
                 if ((j & (CKW - 1)) == 0) {
                     int2* ck = ckOut + (size_t)(j / CKW) * SH + lane * RR;
 #pragma unroll
@@ -585,31 +587,40 @@ constexpr int SMEM_BYTES = SMEM_LEAN + NWARPS * LEAN_BYTES;
 //   * the loop-carried dependency is ONE op per cell: with e = max(H, D) known off the chain,
 //     V(i+1) = max(S(i) + go, V(i) + ge) = max(V(i) + max(go, ge), e(i) + go) because S(i) = max(V(i), e(i)).
 // colBase = first column of the chunk (lane t works on column colBase + kk - t in step kk).
+// RR rows per lane: 8 for the 256-row strips; 2 or 4 for flat grids of at most 64 / 128 rows (one strip), whose
+// fill is one long serial walk over the columns — the step is then a quarter / half as long.
 // CAPROW: the strip holds the grid's last row and the scouts track it (final / global matrices): lane capLane also
 // stores (S,H,V) of its row capR into lastRow[column] every step.  Lanes below the matrix compute on padding (their
 // base mask is empty); nothing they produce is ever read.
-template <bool CAPROW>
-__device__ __forceinline__ void leanChunk(const StepConsts& K, StripState<8>& st, int lane, uint32_t leanOff,
+// RAMP: the strip's first chunk — lane t joins the wavefront in step t; until then its state is held with selects.
+template <int RR, bool CAPROW, bool RAMP>
+__device__ __forceinline__ void leanChunk(const StepConsts& K, StripState<RR>& st, int lane, uint32_t leanOff,
                                           const uint8_t* seqH, int colBase, int bS, int bV, int2* rowOut, int2* ckTile,
                                           int capLane, int capR, DCell* lastRow) {
+    constexpr int LPB = CKR / RR;    // lanes per 64-row checkpoint block
     int2* bnd = reinterpret_cast<int2*>(gSmem + leanOff);
     uint32_t* hcw = reinterpret_cast<uint32_t*>(gSmem + leanOff + 256);
     // stage: boundary (S,V) of columns colBase..colBase+31, one-hot masks of columns colBase-31..colBase+31
     bnd[lane] = make_int2(bS, bV);
-    hcw[lane] = (1u << seqH[colBase - 32 + lane]) * 0x01010101u;            // column colBase - 31 + lane
-    if (lane < 31) hcw[32 + lane] = (1u << seqH[colBase + lane]) * 0x01010101u;   // column colBase + 1 + lane
+    {
+        const int j1 = colBase - 31 + lane;   // (< 1 only in the ramp chunk, where such columns are never used)
+        hcw[lane] = (!RAMP || j1 >= 1) ? (1u << seqH[j1 - 1]) * 0x01010101u : 0u;
+        if (lane < 31) hcw[32 + lane] = (1u << seqH[colBase + lane]) * 0x01010101u;   // column colBase + 1 + lane
+    }
     __syncwarp();
     const int match = K.match, mismatch = K.mismatch, go = K.go, ge = K.ge;
     const int g = max(go, ge);
     const int j0 = colBase - lane;                       // this lane's column in step 0
     const int kkHit = (-j0) & (CKW - 1);                 // step in which the lane reaches a checkpoint column (< 32: in this chunk)
-    int2* ckPtr = ckTile + (size_t)((j0 + kkHit) / CKW) * SH + lane * 8;
-    int2* rowPtr = rowOut + (size_t)(lane >> 3) * (size_t)(K.nH + 1) + j0;
-    const bool rowLane = (lane & 7) == 7;
+    int2* ckPtr = ckTile + (size_t)((j0 + kkHit) / CKW) * SH + lane * RR;
+    int2* rowPtr = rowOut + (size_t)(lane / LPB) * (size_t)(K.nH + 1) + j0;
+    const bool rowLane = (lane & (LPB - 1)) == LPB - 1;
     const uint32_t* hp = hcw + (31 - lane);
-    const uint32_t vm0 = st.vm[0], vm1 = st.vm[1];
+    uint32_t vm[(RR + 3) / 4];
+#pragma unroll
+    for (int w = 0; w < (RR + 3) / 4; ++w) vm[w] = st.vm[w];
     int pubS = st.pubS, pubV = st.pubV, prevUpS = st.prevUpS;
-    uint32_t hr = 0;
+    uint32_t hr = 0, hrLast = 0;
 #pragma unroll 1   // (the kernel's warps run very different code: a small loop body stays in the instruction cache)
     for (int kk = 0; kk < 32; ++kk) {
         int inS = __shfl_up_sync(FULLMASK, pubS, 1);
@@ -617,40 +628,50 @@ __device__ __forceinline__ void leanChunk(const StepConsts& K, StripState<8>& st
         const int2 b = bnd[kk];
         if (lane == 0) { inS = b.x; inV = b.y; }
         hr = hp[kk];
-        const uint32_t eq0 = vm0 & hr, eq1 = vm1 & hr;
+        const bool act = !RAMP || kk >= lane;
+        uint32_t eq[(RR + 3) / 4];
+#pragma unroll
+        for (int w = 0; w < (RR + 3) / 4; ++w) eq[w] = vm[w] & hr;
         int Sd = prevUpS;
         int vv = __viaddmax_s32(inS, go, inV + ge);      // V of the lane's first row
         int ns = 0, capV = 0;
+        int nS[RR], nH[RR];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const uint32_t eqw = (r < 4) ? eq0 : eq1;
-            const int sub = (eqw & (0xffu << (8 * (r & 3)))) ? match : mismatch;
+        for (int r = 0; r < RR; ++r) {
+            const int sub = (eq[r >> 2] & (0xffu << (8 * (r & 3)))) ? match : mismatch;
             const int hh = __viaddmax_s32(st.Sl[r], go, st.Hl[r] + ge);
             const int e = __viaddmax_s32(Sd, sub, hh);   // max(D, H)
             ns = max(vv, e);
             if (CAPROW && r == capR) capV = vv;
             Sd = st.Sl[r];
-            st.Sl[r] = ns; st.Hl[r] = hh;
-            if (r < 7) vv = __viaddmax_s32(vv, g, e + go);   // V of the next row
+            nS[r] = ns; nH[r] = hh;
+            if (r < RR - 1) vv = __viaddmax_s32(vv, g, e + go);   // V of the next row
         }
-        prevUpS = inS;
-        pubS = ns; pubV = vv;
-        if (rowLane) __stcg(&rowPtr[kk], make_int2(ns, vv));
-        if (CAPROW && lane == capLane) {
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            st.Sl[r] = (!RAMP || act) ? nS[r] : st.Sl[r];
+            st.Hl[r] = (!RAMP || act) ? nH[r] : st.Hl[r];
+        }
+        prevUpS = (!RAMP || act) ? inS : prevUpS;
+        pubS = (!RAMP || act) ? ns : pubS;
+        pubV = (!RAMP || act) ? vv : pubV;
+        if (!RAMP || act) hrLast = hr;
+        if (rowLane && act) __stcg(&rowPtr[kk], make_int2(ns, vv));
+        if (CAPROW && lane == capLane && act) {
             int cs = st.Sl[0], ch = st.Hl[0];
 #pragma unroll
-            for (int r = 1; r < 8; ++r)
+            for (int r = 1; r < RR; ++r)
                 if (r == capR) { cs = st.Sl[r]; ch = st.Hl[r]; }
             lastRow[j0 + kk] = DCell{cs, ch, capV};
         }
-        if (kk == kkHit) {
+        if (kk == kkHit && act) {
 #pragma unroll
-            for (int r = 0; r < 8; r += 2)
+            for (int r = 0; r < RR; r += 2)
                 __stcg(reinterpret_cast<int4*>(ckPtr + r), make_int4(st.Sl[r], st.Hl[r], st.Sl[r + 1], st.Hl[r + 1]));
         }
     }
     st.pubS = pubS; st.pubV = pubV; st.prevUpS = prevUpS;
-    st.curHc = __ffs((int)(hr & 0xffu)) - 1;
+    if (hrLast) st.curHc = __ffs((int)(hrLast & 0xffu)) - 1;
     __syncwarp();
 }
 
@@ -813,7 +834,7 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
                 upProg = __shfl_sync(FULLMASK, upProg, 0);
             }
         }
-        if (MODE == MODE_TASK && !signalled && ((cP.pad5 & 64) || c >= 2 || c == nch - 1)) {
+        if (MODE == MODE_TASK && !signalled && (!(cP.pad5 & 64) || c >= 2 || c == nch - 1)) {
             signalled = true;
             if (stripLog && lane == 0) logT1 = globalTimerNs() - cP.cb->t0;
             if (lane == 31) {
@@ -833,18 +854,20 @@ __device__ __noinline__ void runStrip(const GridCtx& Gin, int s, int cBeg, int c
         }
         const long long dbg1 = clock64();
         bool lean = false;
-        if constexpr (MODE == MODE_TASK && AFF && !BANDED && RR == 8) {
-            // steady state: every lane active in all 32 steps, below-matrix lanes excluded, nothing to capture
-            const bool full = c >= 1 && cBeg + 32 * c + 31 <= cEnd && 32 * c + 31 < nsteps && !(cP.pad5 & 8);
+        if constexpr (MODE == MODE_TASK && AFF && !BANDED && (RR == 8 || RR == 4 || RR == 2)) {
+            // steady state: every lane active in all 32 steps (c >= 1), or the ramp chunk (c == 0) with masked lanes
+            const bool full = cBeg + 32 * c + 31 <= cEnd && 32 * c + 31 < nsteps && !(cP.pad5 & 8) && (c >= 1 || !fromCk);
             const uint32_t leanOff = (uint32_t)(SMEM_LEAN + (threadIdx.x >> 5) * LEAN_BYTES);
-            if (full && !cap) {
+            const int rl = g.nV - (s * SHR + 1);   // row nV inside the strip: lane rl / RR, row rl % RR
+            const bool capRowOnly = capture && G.capEdges && cBeg + 32 * c + 31 < g.nH;   // last strip of a final / global
+            if (full && !cap) {                                                           // matrix, away from its last column
                 lean = true;
-                leanChunk<false>(K, st, lane, leanOff, G.seqH, cBeg + 32 * c, bS, bV, rowOut, ckTile, 0, 0, nullptr);
-            } else if (full && capture && G.capEdges && cBeg + 32 * c + 31 < g.nH) {
-                // last strip of a final / global matrix, away from the last column: only the last row is captured
+                if (c >= 1) leanChunk<RR, false, false>(K, st, lane, leanOff, G.seqH, cBeg + 32 * c, bS, bV, rowOut, ckTile, 0, 0, nullptr);
+                else leanChunk<RR, false, true>(K, st, lane, leanOff, G.seqH, cBeg, bS, bV, rowOut, ckTile, 0, 0, nullptr);
+            } else if (full && capRowOnly) {
                 lean = true;
-                const int rl = g.nV - (s * SHR + 1);   // row nV inside the strip: lane rl / 8, row rl % 8
-                leanChunk<true>(K, st, lane, leanOff, G.seqH, cBeg + 32 * c, bS, bV, rowOut, ckTile, rl >> 3, rl & 7, G.lastRow);
+                if (c >= 1) leanChunk<RR, true, false>(K, st, lane, leanOff, G.seqH, cBeg + 32 * c, bS, bV, rowOut, ckTile, rl / RR, rl % RR, G.lastRow);
+                else leanChunk<RR, true, true>(K, st, lane, leanOff, G.seqH, cBeg, bS, bV, rowOut, ckTile, rl / RR, rl % RR, G.lastRow);
             }
         }
         if constexpr ((MODE == MODE_TRACE || MODE == MODE_TRACEG) && AFF && !BANDED && RR == 2) {
