@@ -79,14 +79,46 @@ def main():
         if cur_b is not None:
             union += cur_b - cur_a
         times.append((total, t_loop[0], union))
+    # the same loop once more with the library answering from a cache: what the reference's Python alone costs
+    # (Alignment objects, tally_up_score_and_errors, SAM lines ... under the GIL)
+    cache = {}
+    orig_c = ua.semi_global_alignment
+
+    def fill(*a, **k):
+        r = orig_c(*a, **k)
+        cache[a[0]] = r
+        return r
+    ua.semi_global_alignment = fill
+    refs = unicycler.read_ref.load_references(fa)
+    read_dict, read_names, _ = unicycler.read_ref.load_long_reads(fq)
+    ua.semi_global_align_long_reads(refs, fa, read_dict, read_names, fq, threads, scheme, [None], False, 10, None, None, 0, 0, None, 0)
+    ua.semi_global_alignment = lambda *a, **k: cache[a[0]]
+    refs = unicycler.read_ref.load_references(fa)
+    read_dict, read_names, _ = unicycler.read_ref.load_long_reads(fq)
+    first = [None]
+    last = [0.0]
+    orig = ua.seqan_alignment
+
+    def timed2(*a, **k):
+        if first[0] is None:
+            first[0] = time.perf_counter()
+        r = orig(*a, **k)
+        last[0] = time.perf_counter() - first[0]
+        return r
+    ua.seqan_alignment = timed2
+    ua.semi_global_align_long_reads(refs, fa, read_dict, read_names, fq, threads, scheme, [None], False, 10, None, None, 0, 0, None, 0)
+    ua.seqan_alignment = orig
+    ua.semi_global_alignment = orig_c
+    python_only = last[0]
     res = {}
     for name in read_names:
         res[name] = sorted([a.ref.name, '-' if a.rev_comp else '+', a.read_start_pos, a.read_end_pos, a.ref_start_pos,
                             a.ref_end_pos, a.raw_score, '%.6f' % a.scaled_score, ''.join(a.cigar_parts)] for a in aligned[name].alignments)
-    json.dump(dict(threads=threads, times=times, reads=res), open(out_path, 'w'))
+    json.dump(dict(threads=threads, times=times, reads=res, python_only_s=python_only), open(out_path, 'w'))
     best = min(times, key=lambda t: t[1])
     print('reads %d, alignments kept %d, threads %d: alignment loop %.3f s (whole call %.3f s; some thread inside the C call '
-          'for %.3f s of the loop)' % (len(read_names), sum(len(v) for v in res.values()), threads, best[1], best[0], best[2]))
+          'for %.3f s of the loop); the same loop with the library answering from a cache: %.3f s' %
+          (len(read_names), sum(len(v) for v in res.values()), threads, best[1], best[0], best[2], python_only))
 
 
 if __name__ == '__main__':

@@ -2237,8 +2237,15 @@ void Engine::upload(std::vector<Job*>& jobs) {
             }
         }
         std::sort(bigs.begin(), bigs.end(), [](const BigGrid& a, const BigGrid& b) { return a.rem > b.rem; });
-        for (size_t i = 0; i < bigs.size(); ++i)
-            hGrids[I.jobsDev[bigs[i].job].gridBegin + bigs[i].g].pad = (int32_t)std::min<size_t>(NBOARD - 1, i * NBOARD / bigs.size());
+        const char* bm = getenv("UNICYCLER_B200_BOARDS");   // developer switch: how the big grids are spread over the boards
+        const int boardMode = bm ? atoi(bm) : 0;
+        for (size_t i = 0; i < bigs.size(); ++i) {
+            int32_t b = (int32_t)std::min<size_t>(NBOARD - 1, i * NBOARD / bigs.size());
+            if (boardMode == 1) b = (i * 8 < bigs.size()) ? 0 : 1;
+            else if (boardMode == 2) b = 0;
+            else if (boardMode == 3) b = (int32_t)std::min<size_t>(NBOARD - 1, i * 2 * NBOARD / bigs.size());
+            hGrids[I.jobsDev[bigs[i].job].gridBegin + bigs[i].g].pad = b;
+        }
         for (size_t e = 0; e < I.order.size(); ++e) entryRem[e] = segRem[(size_t)(I.order[e] / MAXSEG)][(size_t)(I.order[e] % MAXSEG)];
         std::vector<size_t> perm(I.order.size());
         for (size_t e = 0; e < perm.size(); ++e) perm[e] = e;
