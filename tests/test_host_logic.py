@@ -53,8 +53,16 @@ def test_seeding_matches_reference_seed_chains(ub, setname):
 def _build_cpp(name, sources):
     out = os.path.join('/tmp', name)
     subprocess.check_call(['g++', '-std=c++17', '-O2', '-I/usr/local/cuda/include', '-o', out] +
-                          [os.path.join(ROOT, s) for s in sources])
+                          [s if s.startswith('-') else os.path.join(ROOT, s) for s in sources])
     return out
+
+
+def test_host_thread_pool():
+    exe = _build_cpp('ub200_test_hostpool', ['tests/cpp/test_hostpool.cpp', 'unicycler_b200/csrc/hostpool.cpp', '-lpthread'])
+    for threads in ('1', '3', '16'):
+        out = subprocess.run([exe], env=dict(os.environ, UNICYCLER_B200_HOST_THREADS=threads), stdout=subprocess.PIPE,
+                             timeout=120)
+        assert out.returncode == 0 and b' bad 0' in out.stdout, out.stdout
 
 
 def test_storage_geometry_matches_oracle_navigator():
