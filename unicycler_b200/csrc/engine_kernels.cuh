@@ -627,7 +627,7 @@ __device__ __forceinline__ void leanChunk(const StepConsts& K, StripState<RR>& s
     for (int w = 0; w < (RR + 3) / 4; ++w) vm[w] = st.vm[w];
     int pubS = st.pubS, pubV = st.pubV, prevUpS = st.prevUpS;
     uint32_t hr = 0, hrLast = 0;
-#pragma unroll 1   // (the kernel's warps run very different code: a small loop body stays in the instruction cache)
+#pragma unroll 1   // (the kernel's warps run very different code: a small loop body stays in the instruction cache; unroll 2: no gain)
     for (int kk = 0; kk < 32; ++kk) {
         int inS = __shfl_up_sync(FULLMASK, pubS, 1);
         int inV = __shfl_up_sync(FULLMASK, pubV, 1);
