@@ -196,3 +196,59 @@ def test_unbanded_pair_with_more_than_2_31_cells_vs_reference_library(ub):
     got = ub.fully_global_alignment(a[0], b[0], SCHEME, False, 0)
     want = ref.fully_global(a[0], b[0], SCHEME, False, 0)
     assert mask_ms(got) == mask_ms(want)
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_LIB), reason='oracle/_ref not built')
+def test_gap_area_guard_vs_reference_library(ub):
+    """Two matching blocks separated by unrelated sequence: when the largest gap between chained seeds exceeds 1e8 cells
+    the reference gives up on the range (getMaxSeedChainGapArea, semi_global_align.cpp:286-291,321-347); just below and
+    above that size it aligns.  Same outcome, same strings."""
+    import random
+    from refdriver import AbiLib
+    ref_lib = AbiLib(REF_LIB)
+    rng = random.Random(5)
+
+    def rs(n):
+        return ''.join(rng.choice('ACGT') for _ in range(n))
+
+    outcomes = []
+    for gap in (9000, 10500, 12000, 15000):
+        a, b = rs(1500), rs(1500)
+        read = a + rs(gap) + b
+        ref = rs(300) + a + rs(gap) + b + rs(300)
+        hits = '0,%d,+,ref,300,%d' % (len(read), 300 + len(read))
+        h = ub.new_ref_seqs()
+        ub.add_ref_seq(h, 'ref', ref)
+        got = ub.semi_global_alignment('r', read, 0, hits, h, 3, -6, -5, -2, 0.0, False, 0)
+        ub.delete_ref_seqs(h)
+        hr = ref_lib.new_refs([('ref', ref)])
+        want = ref_lib.semi_global('r', read, hits, hr, SCHEME)
+        ref_lib.delete_refs(hr)
+        assert mask_semi_global(got) == mask_semi_global(want), gap
+        outcomes.append(len(want.split(';')) - 1)
+    assert 0 in outcomes and max(outcomes) >= 1   # the guard fired for some sizes and not for others
+
+
+def test_output_stream_overflow_is_rerun_with_a_larger_stream(tmp_path):
+    """A job whose segment stream overflows (many tied tracebacks in the reference's terms) reports JOB_OUT_OVERFLOW
+    and the engine reruns it with an eight times larger stream (Engine::end).  Forced here by starting with a thousandth
+    of the planned capacity (test hook UNICYCLER_B200_OUT_CAP_DIV, read once per process: subprocess)."""
+    import subprocess
+    import sys
+    from oracle_lib import ROOT
+    code = '''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import unicycler_b200 as ub
+from oracle_lib import golden_chain_jobs, load_golden, mask_ms
+d = load_golden("semiglobal_contained.json.gz")
+jobs = golden_chain_jobs(d)
+got = ub.chain_alignment_batch(jobs, tuple(d["scheme"]), jobs[0]["band"])
+bad = [j["readName"] for j, g in zip(jobs, got) if mask_ms(g) != j["result"]]
+assert not bad, bad
+st = ub.last_stats()
+assert st["launches"] >= 2, st      # the first launch overflowed, the rerun produced the results
+''' % (ROOT, os.path.join(ROOT, 'tests'))
+    env = dict(os.environ, UNICYCLER_B200_OUT_CAP_DIV='1000')
+    r = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]

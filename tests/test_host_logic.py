@@ -101,3 +101,21 @@ def test_chain_plan_is_consistent_with_cell_count(ub):
             else:
                 total += (nH + 1) * (nV + 1)
         assert total == cells
+
+
+def test_gap_area_guard_in_host_seeding(ub):
+    """A seed chain whose largest gap exceeds MAX_BANDED_ALIGNMENT_GAP_AREA (1e8 cells) ends the range without an
+    alignment (semi_global_align.cpp:286-291): two 1.5 kb matching blocks 10.5 kb of unrelated sequence apart."""
+    import random
+    rng = random.Random(5)
+
+    def rs(n):
+        return ''.join(rng.choice('ACGT') for _ in range(n))
+
+    sizes = {}
+    for gap in (9000, 10500):
+        a, b = rs(1500), rs(1500)
+        read = a + rs(gap) + b
+        ref = rs(300) + a + rs(gap) + b + rs(300)
+        sizes[gap] = len(ub.seed_chains(read, ref, 0))
+    assert sizes[9000] == 1 and sizes[10500] == 0, sizes

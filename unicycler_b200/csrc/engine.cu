@@ -2015,6 +2015,9 @@ void Engine::upload(std::vector<Job*>& jobs) {
             cap += 4LL * ((long long)j.lenH + j.lenV) + 1024;
         }
         cap *= std::max(1, j.outScale);
+        // test hook: start with a stream that is too small, so that the JOB_OUT_OVERFLOW rerun (Engine::end) is exercised
+        static const int capDiv = getenv("UNICYCLER_B200_OUT_CAP_DIV") ? std::max(1, atoi(getenv("UNICYCLER_B200_OUT_CAP_DIV"))) : 1;
+        if (capDiv > 1 && j.outScale <= 1) cap = std::max<long long>(64, cap / capDiv);
         if (cap > (1LL << 30)) cap = 1LL << 30;
         a.cap = cap;
     });
@@ -2576,10 +2579,15 @@ void Engine::end(std::vector<Job*>& jobs) {
         for (Job* j : jobs)
             if (j->result.status == JOB_OUT_OVERFLOW) { j->outScale *= 8; again.push_back(j); }
         if (again.empty()) break;
+        const EngineStats first = impl_->stats;   // upload() starts a new record: keep the totals of the call
         upload(again);
         launch();
         CUDA_CHECK(cudaStreamSynchronize(impl_->stream));
         fetch(again);
+        EngineStats& st = impl_->stats;
+        st.kernelMs += first.kernelMs; st.h2dMs += first.h2dMs; st.d2hMs += first.d2hMs;
+        st.launches += first.launches; st.h2dBytes += first.h2dBytes; st.d2hBytes += first.d2hBytes;
+        st.cells = first.cells; st.traceBytes = std::max(st.traceBytes, first.traceBytes);
     }
 }
 
