@@ -1640,7 +1640,7 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
             }
             prof[3] += c3 - c2; prof[4] += clock64() - c3;
         }
-        if (P.pad6 == jobIdx + 1 && seg == 0 && gi < 4096 && lane == 0) {
+        if (P.pad6 == jobIdx + 1 && gi < 4096 && lane == 0) {   // (a grid walked by two segments shows the later one)
             const unsigned long long t0 = P.cb->t0, now = globalTimerNs() - t0;
             const unsigned long long cyc = (unsigned long long)(clock64() - c0);
             gGridLog[gi][0] = now; gGridLog[gi][1] = cyc; gGridLog[gi][2] = (unsigned long long)(c2 - c1);
@@ -2484,7 +2484,8 @@ void Engine::fetch(std::vector<Job*>& jobs) {
             std::vector<size_t> byS(nJobs);
             for (size_t k = 0; k < nJobs; ++k) byS[k] = k;
             std::sort(byS.begin(), byS.end(), [&](size_t a, size_t b) { return I.jobOut[a].tSpine > I.jobOut[b].tSpine; });
-            for (size_t q = 0; q < std::min<size_t>(6, nJobs); ++q) {
+            const size_t nShow = getenv("UNICYCLER_B200_SPINES") ? (size_t)atoi(getenv("UNICYCLER_B200_SPINES")) : 6;
+            for (size_t q = 0; q < std::min<size_t>(nShow, nJobs); ++q) {
                 const size_t k = byS[q];
                 const long long* pp = I.jobOut[k].prof;
                 long long bigCells = 0; int nBig = 0;
