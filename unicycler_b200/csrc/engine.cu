@@ -954,7 +954,12 @@ __device__ __noinline__ bool tryRunOneItem(GridCtx& wctx, int& wTask, bool* sawO
     if (lane == 0) {
         // Pop a token (critical-path ring first): it names a task that had a claimable strip.  Strips are claimed
         // in order and only once the strip above is one chunk in (readyUpTo), so no warp parks on a far-away strip.
-        for (int board = 0; board < NBOARD && item < 0; ++board) {
+        // (one look at all four rings first: an idle warp's poll is two 16-byte loads when no token is waiting)
+        static_assert(NBOARD == 4, "the token counters are read as one int4 each");
+        const int4 hd = __ldcv(reinterpret_cast<const int4*>(P.cb->tokHead));
+        const int4 tls = __ldcv(reinterpret_cast<const int4*>(P.cb->tokTail));
+        const bool any = hd.x < tls.x || hd.y < tls.y || hd.z < tls.z || hd.w < tls.w;
+        for (int board = 0; any && board < NBOARD && item < 0; ++board) {
             for (int tries = 0; tries < 8 && item < 0; ++tries) {
                 const int h = ldRelaxed(&P.cb->tokHead[board]);
                 const int tl = ldRelaxed(&P.cb->tokTail[board]);
@@ -1209,13 +1214,15 @@ __device__ __noinline__ bool tryRunTileReq(GridCtx& Gin, int& helpKey) {
     if (lane == 0) {
         // this warp's home ring first, then its neighbours
         const int home = (int)(blockIdx.x * NWARPS + (threadIdx.x >> 5));
-        for (int tries = 0; tries < 8 && got == 0; ++tries) {
+        const int pending = ldRelaxed(&P.cb->tilePending);   // (an idle warp's poll is one load when nothing is posted)
+        for (int tries = 0; pending > 0 && tries < 8 && got == 0; ++tries) {
             const int q = (home + tries) & (TILE_QUEUES - 1);
             ControlBlock::TileQueue* tq = &P.cb->tq[q];
             const int h = ldRelaxed(&tq->head);
             const int tl = ldRelaxed(&tq->tail);
             if (h >= tl) continue;
             if (atomicCAS(&tq->head, h, h + 1) != h) continue;
+            atomicSub(&P.cb->tilePending, 1);
             TileReq* e = &P.tileRing[(size_t)q * TILE_RING_CAP + (h & (TILE_RING_CAP - 1))];
             const int turn = h / TILE_RING_CAP;
             while (ldRelaxed(&e->seq) != 2 * turn + 1) __nanosleep(32);
@@ -1734,16 +1741,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
         if (lane == 0) done = ldRelaxed(&P.cb->jobsDone);
         done = __shfl_sync(FULLMASK, done, 0);
         if (done >= P.nJobs) break;
-        // back off to 16 us while nothing is published; while big grids are being filled a strip may become claimable
-        // any moment and its pick-up latency is on the grid's critical path: poll every microsecond then
+        // Back-off, doubling from pad7's unit (2 us) to 128 us.  Idle warps share their schedulers with the warps that
+        // work: a poll is ~200 issue slots and a dozen L2 round trips on the hottest lines of the control block, and
+        // polling every 0.25-1 us cost the busy warps more than the pick-up latency it saved (sample_data 14.4 -> 12.6 ms,
+        // `tough` 12.6 -> 10.9 ms with the slower poll; UNICYCLER_B200_POLL_NS / _POLL_MAX for experiments).
         int open = 0;
         if (lane == 0) open = ldRelaxed(&P.cb->openTasks);
         open = __shfl_sync(FULLMASK, open, 0);
-        idle = min(idle + 1, (open > 0 && (P.pad5 & 32)) ? 2 : 6);
+        idle = min(idle + 1, (open > 0 && (P.pad5 & 32)) ? 2 : (P.pad7 >> 20));
         // jittered: warps that went idle together would otherwise wake together, every 16 us — a strip that becomes
         // claimable in between waited for that instant instead of for the next of ~2000 independent polls
         pollRng = pollRng * 1664525u + 1013904223u;
-        const unsigned base = 250u << idle;
+        const unsigned base = (unsigned)(P.pad7 & 0xfffff) << idle;
         __nanosleep(base / 2 + (pollRng >> 8) % base);
     }
 }
@@ -2304,7 +2313,8 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.jobState = (JobState*)((uint8_t*)I.dRing + offState);
     I.offState = offState;
     kp.tokRing = (int*)((uint8_t*)I.dRing + offTok);
-    kp.maxTokens = (int)maxTokens; kp.pad7 = 0;
+    kp.maxTokens = (int)maxTokens; kp.pad7 = (getenv("UNICYCLER_B200_POLL_NS") ? std::min(1 << 19, std::max(32, atoi(getenv("UNICYCLER_B200_POLL_NS")))) : 2000) |   // idle back-off unit (ns)
+              ((getenv("UNICYCLER_B200_POLL_MAX") ? std::min(10, std::max(0, atoi(getenv("UNICYCLER_B200_POLL_MAX")))) : 6) << 20);   // doublings
     kp.gridRecs = (GridRec*)I.dRecs;
     kp.persist = usePersist ? (uint8_t*)I.dPersist : nullptr;
     kp.mini = (uint8_t*)I.dMini; kp.miniStride = (long long)miniStride; kp.miniInitCol = (long long)miniInitCol;

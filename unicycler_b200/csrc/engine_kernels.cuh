@@ -188,7 +188,8 @@ struct ControlBlock {  // zeroed before every launch; every group of counters ha
                                     // while the idle ones outnumber the walkers several times)
     int idleWorkers;                // worker warps polling for work: they serve tile requests only while no big grid
     int openTasks;                  // is being filled (openTasks == 0), the fills being the critical path of pass 1
-    int pad5[28];
+    int tilePending;                // tile requests posted and not yet popped (idle warps scan the rings only when > 0)
+    int pad5[27];
 };
 
 struct TileReq {
@@ -1099,6 +1100,7 @@ __device__ __noinline__ TileFetch fetchTileFn(const GridCtx& Gin, uint8_t* win, 
             {
                 // (the rings hold far more than the 32 requests a walk can have outstanding: the entry is free)
                 const int pos = atomicAdd(&tq->tail, 1);
+                atomicAdd(&P.cb->tilePending, 1);
                 TileReq* e = &P.tileRing[(size_t)q * TILE_RING_CAP + (pos & (TILE_RING_CAP - 1))];
                 const int turn = pos / TILE_RING_CAP;
                 while (ldRelaxed(&e->seq) != 2 * turn) __nanosleep(64);

@@ -394,10 +394,23 @@ double scoreLineSegment(Point p1, Point p2, const PointSet& pointsNearLine) {
 Point shiftUp(Point p, int steps) { p.x -= steps; p.y += steps; return p; }
 Point shiftDown(Point p, int steps) { p.x += steps; p.y -= steps; return p; }
 
+// the last radius search of the line tracer on this thread (valid for one range's cloud: seedRange resets it)
+struct LastSearch { const Cloud* cloud = nullptr; Point q; PointVector pts; };
+static thread_local LastSearch g_lastSearch;
+
 Point mutateLineToBestFitPoints(Point p1, Point p2, const Cloud& cloud, PointSet& pointsNearLine, bool leftRectangle) {
     int radius = int(TRACE_LINE_STEP_DISTANCE * 1.1);
-    PointVector nearP1 = radiusSearchAroundPoint(p1, radius, cloud);
+    // p1 is the previous step's end point: when that step kept its unmutated end, the search around it has just been
+    // done (as that step's p2).  Same cloud, same query, same radius => same list in the same order.
+    LastSearch& last = g_lastSearch;
+    PointVector nearP1;
+    if (last.cloud == &cloud && last.q == p1) nearP1.swap(last.pts);
+    else nearP1 = radiusSearchAroundPoint(p1, radius, cloud);
     PointVector nearP2 = radiusSearchAroundPoint(p2, radius, cloud);
+    struct Keep {   // remember the search around the unmutated p2 for the next step
+        LastSearch& l; const Cloud* c; Point q; PointVector& v;
+        ~Keep() { l.cloud = c; l.q = q; l.pts.swap(v); }
+    } keep{last, &cloud, p2, nearP2};
     pointsNearLine.insert(nearP1.begin(), nearP1.end());
     pointsNearLine.insert(nearP2.begin(), nearP2.end());
     if (leftRectangle) return p2;
@@ -823,6 +836,7 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
     PointSet usedPoints;
     Cloud cloud;
     fillCloud(cloud, common, usedPoints);
+    g_lastSearch.cloud = nullptr;   // (a new cloud may live at the old one's address)
     std::vector<PointSet> goodPointSets;
     double bestPointScore = 0.0;
     for (int lineNum = 0; lineNum < sp.maxLineTraceCount; ++lineNum) {
