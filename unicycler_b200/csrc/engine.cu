@@ -1459,7 +1459,7 @@ __device__ __noinline__ void finalizeSpine(int jobIdx) {
             if (__ldcg(&rec->state) != 2) continue;
             const int nc = min(__ldcg(&rec->nCand), MAXREC);
             bigCands += nc;
-            if (owner == 0 && __ldcg(&rec->published)) continue;
+            if (atomicCAS(const_cast<int*>(&rec->published), 0, 1) != 0) continue;   // handed over early (confirmSegments / its own segment)
             for (int k = 0; k < nc; ++k) pushBig(jobIdx, gi * MAXREC + k);
         }
         bigCands = __reduce_add_sync(FULLMASK, bigCands);
@@ -1478,6 +1478,56 @@ __device__ __noinline__ void finalizeSpine(int jobIdx) {
         pass2ItemDone(jobIdx);
     } else {
         finalizeJob(jobIdx);
+    }
+}
+
+// Segment q is on the resolved chain from grid m on (a confirmed segment has merged into it there): append it to the
+// owner table, hand the big grids it has finished since to pass 2, and follow q's own merge if its warp has stopped
+// already.  Exactly one warp does this per segment (segConfClaim); the chain is followed in order, so the owner table
+// grows exactly as finalizeSpine will rebuild it.
+__device__ __noinline__ void confirmSegments(int jobIdx, int q, int m) {
+    const KParams& P = cP;
+    const int lane = threadIdx.x & 31;
+    const JobDev jb = P.jobs[jobIdx];
+    JobState* js = &P.jobState[jobIdx];
+    for (int guard = 0; guard < MAXSEG && q >= 0; ++guard) {
+        int won = 0;
+        if (lane == 0) won = (atomicCAS(&js->segConfClaim[q], 0, 1) == 0) ? 1 : 0;
+        won = __shfl_sync(FULLMASK, won, 0);
+        if (!won) return;
+        if (lane == 0) {
+            int n = ldRelaxed(&js->nOwner);
+            if (n == 0) { js->ownerSeg[0] = 0; js->ownerFrom[0] = 0; n = 1; }
+            js->ownerSeg[n] = q; js->ownerFrom[n] = m;
+            __threadfence();
+            stRelease(&js->nOwner, n + 1);
+            __threadfence();
+            stRelease(&js->segConfFrom1[q], m + 1);
+            __threadfence();
+        }
+        __syncwarp();
+        int prog = 0;
+        if (lane == 0) prog = ldAcquire(&js->segProgress[q]);
+        prog = __shfl_sync(FULLMASK, prog, 0);
+        GridRec* recs = &P.gridRecs[jb.recBase + (long long)q * jb.gridCount];
+        for (int gi = m + lane; gi < prog; gi += 32) {   // (q hands over the grids it finishes from now on itself)
+            GridRec* r = &recs[gi];
+            if (__ldcg(&r->state) != 2) continue;
+            if (atomicCAS(&r->published, 0, 1) != 0) continue;
+            const int nc = min(__ldcg(&r->nCand), MAXREC);
+            for (int k = 0; k < nc; ++k) pushBig(jobIdx, gi * MAXREC + k);
+        }
+        __syncwarp();
+        int nq = -1, nm = 0;
+        if (lane == 0) {
+            __threadfence();
+            if (ldAcquire(&js->segStop[q])) {
+                const int to = ldRelaxed(&js->segSyncSeg[q]);
+                if (to >= 0) { nq = to; nm = ldRelaxed(&js->segSyncGrid[q]); }
+            }
+        }
+        q = __shfl_sync(FULLMASK, nq, 0);
+        m = __shfl_sync(FULLMASK, nm, 0);
     }
 }
 
@@ -1573,7 +1623,7 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
         TrackResult TR;
         TR.maxCell = DCell{0, 0, 0};
         int nPlanted = 0;  // _nextInitializationCells.clear()
-        bool done = false;
+        bool done = false, deferredBig = false;
         const bool absoluteFrame = (seg == 0);
         // ---- fast path: score-only fill, tracking and crossing walks; trace fill + tracebacks go to pass 2
         if (G.fastOk && nPlantedPrev <= MAXREC) {
@@ -1628,16 +1678,12 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
                     bigShortWalks(G, win, TR.nCand, nPlanted, insertedMask, status, tiles, tileCycles);
                 prof[6] += tiles; prof[7] += tileCycles;
                 if (lane == 0) {
-                    rec->state = 2; rec->nCand = TR.nCand; rec->inserted = insertedMask;
+                    rec->nCand = TR.nCand; rec->inserted = insertedMask; rec->published = 0;
                     for (int k = 0; k < TR.nCand; ++k) rec->cand[k] = G.cand[k];
-                    // segment 0 owns every grid it walks: the long tracebacks of its big grids start right away
-                    const int early = (seg == 0 && status == JOB_OK && jb.gridCount > 1 && !(P.pad5 & 2)) ? 1 : 0;
-                    rec->published = early;
-                    if (early) {
-                        __threadfence();
-                        for (int k = 0; k < TR.nCand; ++k) pushBig(jobIdx, gi * MAXREC + k);
-                    }
+                    __threadfence();
+                    rec->state = 2;
                 }
+                deferredBig = true;   // (its long tracebacks start as soon as this segment is known to own the grid: below)
             } else if (status == JOB_OK) {
                 const TbResult tb = tracebackGrid(G, win, jobIdx, P.out + jb.outOff, jb.outCap, gi, gd.h0, gd.v0, TR.nCand,
                                                   TR.maxCell, nullptr, -1, seg);
@@ -1667,6 +1713,19 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
         __threadfence();
         __syncwarp();
         if (lane == 0) stRelease(&js->segProgress[seg], gi + 1);
+        // A confirmed segment (segment 0 always is) owns the grids it walks: the long tracebacks of a big grid start
+        // right away instead of when the whole chain is resolved.  (After the progress is published: the warp that
+        // confirms this segment hands over everything below the progress it reads; one of the two sees the other.)
+        if (deferredBig && jb.gridCount > 1 && !(P.pad5 & 2) && lane == 0) {
+            __threadfence();
+            const int from = (seg == 0) ? 0 : ((P.pad5 & 1024) ? -1 : ldRelaxed(&js->segConfFrom1[seg]) - 1);
+            if (from >= 0 && gi >= from && atomicCAS(&rec->published, 0, 1) == 0) {
+                __threadfence();
+                const int nc = min(rec->nCand, MAXREC);
+                for (int k = 0; k < nc; ++k) pushBig(jobIdx, gi * MAXREC + k);
+            }
+        }
+        __syncwarp();
     }
     // ---- this segment's warp stops
     if (lane == 0) {
@@ -1682,6 +1741,16 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
         stRelease(&js->segStop[seg], 1);
     }
     __syncwarp();
+    {   // a confirmed segment that merged confirms the segment it merged into (or the warp confirming this one will)
+        int cq = -1;
+        if (lane == 0 && status == JOB_OK && !cancelled && syncSeg >= 0 && !(P.pad5 & (2 | 1024))) {
+            __threadfence();
+            const int from = (seg == 0) ? 0 : ldRelaxed(&js->segConfFrom1[seg]) - 1;
+            if (from >= 0) cq = syncSeg;
+        }
+        cq = __shfl_sync(FULLMASK, cq, 0);
+        if (cq >= 0) confirmSegments(jobIdx, cq, syncGrid);
+    }
     int stoppedCount = 0;
     if (lane == 0) stoppedCount = atomicAdd(&js->segStopped, 1) + 1;
     stoppedCount = __shfl_sync(FULLMASK, stoppedCount, 0);
@@ -1728,15 +1797,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
             if (lane == 0) atomicAdd(cw >= 0 ? &P.cb->idleHelpers : &P.cb->idleWorkers, 1);
             amIdle = 1;
         }
-        if (tryRunOneItem(*wctx, wTask, &sawOpen, &amIdle)) { idle = 0; helpKey = -1; continue; }
-        if (sawOpen) idle = 0;   // strips are about to become claimable: poll again soon
-        if (cw >= 0 && tryRunBig(*cctx, win, mini, &amIdle)) { idle = 0; continue; }
-        // (three of four worker warps help only while no big grid is being filled; the worker context then holds
-        // the helped grid)
-        int fills = 0;
-        if (cw < 0 && (warp & 3) != 0) { if (lane == 0) fills = ldRelaxed(&P.cb->openTasks); fills = __shfl_sync(FULLMASK, fills, 0); }
-        if (fills == 0 && tryRunTileReq(*wctx, helpKey)) { idle = 0; wTask = -1; continue; }
-        if (cw >= 0 && tryRunPass2(*cctx, win, mini, &amIdle)) { idle = 0; continue; }
+        // One look at every queue this warp serves (three independent loads) before any of the pollers below is
+        // called: an idle poll that finds nothing costs ~40 issue slots instead of ~300 (the calls save and restore
+        // registers), on schedulers it shares with the warps that work.
+        int work = 0, walkers = 0;
+        if (lane == 0) {
+            const int4 hd = __ldcv(reinterpret_cast<const int4*>(P.cb->tokHead));
+            const int4 tl = __ldcv(reinterpret_cast<const int4*>(P.cb->tokTail));
+            const int4 st = __ldcv(reinterpret_cast<const int4*>(&P.cb->idleHelpers));   // idleHelpers, activeWalkers, openTasks, tilePending
+            work = (hd.x < tl.x) | (hd.y < tl.y) | (hd.z < tl.z) | (hd.w < tl.w) | (st.w > 0);
+            // a big traceback is walking and this warp may serve its tile requests (one every ~13 us per walk, each on
+            // the walk's critical path): keep the back-off short
+            walkers = (st.y > 0 && (cw >= 0 || (warp & 3) == 0 || st.z == 0)) ? 1 : 0;
+            if (cw >= 0) {
+                const int4 p2 = __ldcv(reinterpret_cast<const int4*>(&P.cb->p2Head));   // p2Head, p2Tail, bigHead, bigTail
+                work |= (p2.x < p2.y) | (p2.z < p2.w);
+            }
+        }
+        work = __shfl_sync(FULLMASK, work, 0);
+        walkers = __shfl_sync(FULLMASK, walkers, 0);
+        if (work) {
+            if (tryRunOneItem(*wctx, wTask, &sawOpen, &amIdle)) { idle = 0; helpKey = -1; continue; }
+            if (sawOpen) idle = 0;   // strips are about to become claimable: poll again soon
+            if (cw >= 0 && tryRunBig(*cctx, win, mini, &amIdle)) { idle = 0; continue; }
+            // (three of four worker warps help only while no big grid is being filled; the worker context then holds
+            // the helped grid)
+            int fills = 0;
+            if (cw < 0 && (warp & 3) != 0) { if (lane == 0) fills = ldRelaxed(&P.cb->openTasks); fills = __shfl_sync(FULLMASK, fills, 0); }
+            if (fills == 0 && tryRunTileReq(*wctx, helpKey)) { idle = 0; wTask = -1; continue; }
+            if (cw >= 0 && tryRunPass2(*cctx, win, mini, &amIdle)) { idle = 0; continue; }
+        }
         int done = 0;
         if (lane == 0) done = ldRelaxed(&P.cb->jobsDone);
         done = __shfl_sync(FULLMASK, done, 0);
@@ -1745,10 +1835,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
         // work: a poll is ~200 issue slots and a dozen L2 round trips on the hottest lines of the control block, and
         // polling every 0.25-1 us cost the busy warps more than the pick-up latency it saved (sample_data 14.4 -> 12.6 ms,
         // `tough` 12.6 -> 10.9 ms with the slower poll; UNICYCLER_B200_POLL_NS / _POLL_MAX for experiments).
-        int open = 0;
-        if (lane == 0) open = ldRelaxed(&P.cb->openTasks);
-        open = __shfl_sync(FULLMASK, open, 0);
-        idle = min(idle + 1, (open > 0 && (P.pad5 & 32)) ? 2 : (P.pad7 >> 20));
+        idle = min(idle + 1, walkers ? ((P.pad7 >> 24) & 15) : ((P.pad7 >> 20) & 15));
         // jittered: warps that went idle together would otherwise wake together, every 16 us — a strip that becomes
         // claimable in between waited for that instant instead of for the next of ~2000 independent polls
         pollRng = pollRng * 1664525u + 1013904223u;
@@ -2314,7 +2401,8 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.offState = offState;
     kp.tokRing = (int*)((uint8_t*)I.dRing + offTok);
     kp.maxTokens = (int)maxTokens; kp.pad7 = (getenv("UNICYCLER_B200_POLL_NS") ? std::min(1 << 19, std::max(32, atoi(getenv("UNICYCLER_B200_POLL_NS")))) : 2000) |   // idle back-off unit (ns)
-              ((getenv("UNICYCLER_B200_POLL_MAX") ? std::min(10, std::max(0, atoi(getenv("UNICYCLER_B200_POLL_MAX")))) : 6) << 20);   // doublings
+              ((getenv("UNICYCLER_B200_POLL_MAX") ? std::min(10, std::max(0, atoi(getenv("UNICYCLER_B200_POLL_MAX")))) : 6) << 20) |   // doublings
+              ((getenv("UNICYCLER_B200_POLL_WALK") ? std::min(10, std::max(0, atoi(getenv("UNICYCLER_B200_POLL_WALK")))) : 6) << 24);   // doublings while a big traceback asks for tiles (shorter was tried: worse)
     kp.gridRecs = (GridRec*)I.dRecs;
     kp.persist = usePersist ? (uint8_t*)I.dPersist : nullptr;
     kp.mini = (uint8_t*)I.dMini; kp.miniStride = (long long)miniStride; kp.miniInitCol = (long long)miniInitCol;

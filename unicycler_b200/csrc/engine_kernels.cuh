@@ -124,7 +124,7 @@ struct GridRec {
                       // 2: big grid with a persistent block (pass 2 walks one candidate per item)
     int nCand, inserted, nPlantedIn;
     int relMax;       // grid maximum in the writing segment's score frame
-    int published;    // 1: the big grid's candidates were handed to pass 2 by segment 0 right after its pass 1
+    int published;    // 1: the big grid's candidates have been handed to pass 2 (by whoever flipped it from 0)
     int cand[MAXREC];
     PlantedCell plantedIn[MAXREC];
 };
@@ -142,6 +142,10 @@ struct JobState {     // zeroed before every launch
     int segDelta[MAXSEG];      // score of its frame minus score of the frame it merged into, at the merge cell
     int segFailStatus[MAXSEG];
     int ownerSeg[MAXSEG + 1], ownerFrom[MAXSEG + 1];
+    // A segment is CONFIRMED once a confirmed segment (segment 0 is, from grid 0) has merged into it: from that grid on
+    // it is on the resolved chain, and the long tracebacks of its big grids may start before the whole chain is resolved.
+    int segConfClaim[MAXSEG];  // 1: some warp is recording the confirmation
+    int segConfFrom1[MAXSEG];  // grid from which the segment is confirmed, plus one (0: not confirmed)
     int nRecIdx;      // records committed to the job's record index
     int p2Done;       // pass-2 items finished (the big ones may start before the chain is resolved)
     int p2Need;       // items that make the job complete (0 until the chain is resolved)
@@ -184,11 +188,13 @@ struct ControlBlock {  // zeroed before every launch; every group of counters ha
     int bigHead, bigTail;          // pass-2 items of the big grids (served before everything else of pass 2)
     int pad3[28];
     struct TileQueue { int head, tail; int pad[30]; } tq[TILE_QUEUES];   // tile-request rings (one line each)
+    // (the first four are read with one 16-byte load by every idle poll)
     int idleHelpers, activeWalkers; // control warps polling for work / walking a big grid (tiles are only asked for
                                     // while the idle ones outnumber the walkers several times)
-    int idleWorkers;                // worker warps polling for work: they serve tile requests only while no big grid
-    int openTasks;                  // is being filled (openTasks == 0), the fills being the critical path of pass 1
+    int openTasks;                  // big grids being filled: worker warps serve tile requests only while it is 0 (the
+                                    // fills are the critical path of pass 1)
     int tilePending;                // tile requests posted and not yet popped (idle warps scan the rings only when > 0)
+    int idleWorkers;                // worker warps polling for work
     int pad5[27];
 };
 
