@@ -109,6 +109,16 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
  * tests to pin the seeding against golden seed chains. */
 char* ub200_seedChains(const char* readSeq, const char* trimmedRefSeq, int sensitivityLevel);
 
+/* Common k-mer points of one read strand and one window [refStart, refStart + refLen) of `ref`
+ * (src/semi_global_align.cpp:197-207 over KmerPositions, src/kmers.cpp:51-65): (x = read position, y = window
+ * position) pairs in the reference's order.  where = 0: the host join used by semiGlobalAlignment; where = 1: the
+ * device join used by ub200_semiGlobalAlignmentBatch.  Writes at most cap pairs into xy and
+ * returns the number of points (-1: no usable device). */
+int64_t ub200_commonKmers(const char* readSeq, const char* ref, int refStart, int refLen, int k, int where,
+                          int32_t* xy, int64_t cap);
+/* Counters of the device k-mer join inside the last ub200_semiGlobalAlignmentBatch call. */
+void ub200_lastJoinStats(double* kernelMs, int64_t* launches, int64_t* points, int64_t* h2dBytes, int64_t* d2hBytes);
+
 /* Counters of the last engine run on this process: DP cells (reference definition), kernel
  * milliseconds (CUDA events), launches, H2D / D2H milliseconds. */
 void ub200_lastStats(int64_t* cells, double* kernelMs, int64_t* launches, double* h2dMs, double* d2hMs);

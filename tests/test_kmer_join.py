@@ -1,0 +1,109 @@
+"""Common k-mer join: the oracle restatement against the reference's own console counts,
+the host join of the per-read entry point against the oracle (no GPU), and the device join of the batch path against
+both (-m gpu)."""
+import os
+import random
+import re
+import sys
+
+import pytest
+
+from oracle_lib import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+from kmer_join_oracle import common_kmers, reverse_complement  # noqa: E402
+
+K_OF_LEVEL = {0: 10, 1: 10, 2: 9, 3: 8}   # settings.h:17-42
+
+
+def reference_console_ranges():
+    """(read strand, window, k, count the reference printed) for every range in the verbosity-3 golden outputs."""
+    g = load_golden('semiglobal_sensitivity.json.gz')
+    cases = []
+    for setname, entries in g['sets'].items():
+        d = load_golden('semiglobal_%s.json.gz' % setname)
+        reads = {r[0]: r for r in d['reads']}
+        refs = dict(d['refs'])
+        for e in entries:
+            if e['verbosity'] < 3:
+                continue
+            console = e['expected'].split(';')[-1]
+            # "Reference ranges:" lists name+strand in the order the "Range:" blocks follow (semi_global_align.cpp:57-63, 97-131)
+            listed = re.findall(r'^    (\S+)([+-]): (\d+) - (\d+)$', console, re.M)
+            blocks = re.findall(r'^Range: (\S+): (\d+) - (\d+)\n    common (\d+)-mers: (\d+)$', console, re.M)
+            assert len(listed) == len(blocks) > 0
+            seq = reads[e['read']][1]
+            for (name, strand, s, t), (name2, s2, t2, k, count) in zip(listed, blocks):
+                assert (name, s, t) == (name2, s2, t2) and int(k) == K_OF_LEVEL[e['sensitivity']]
+                strand_seq = seq if strand == '+' else reverse_complement(seq)
+                cases.append((strand_seq, refs[name], int(s), int(t) - int(s), int(k), int(count)))
+    return cases
+
+
+def awkward_cases():
+    rng = random.Random(7)
+    def rnd(n, alphabet='ACGT'):
+        return ''.join(rng.choice(alphabet) for _ in range(n))
+    ref = rnd(3000)
+    read = ref[500:1500]
+    cases = [
+        (read, ref, 0, len(ref), 10),
+        (read, ref, 400, 1300, 8),
+        (read, ref, 400, 1300, 17),                                  # literal keys beyond 16 bases
+        (read[:300] + 'N' * 12 + read[312:], ref[:700] + 'N' * 15 + ref[715:], 0, len(ref), 10),   # N runs on both sides
+        (read[:200] + read[200:400].lower() + read[400:], ref[:800] + ref[800:900].lower() + ref[900:], 100, 2500, 9),
+        ('A' * 400 + rnd(100), rnd(50) + 'A' * 300 + rnd(50), 0, 400, 10),   # one k-mer many times on both sides
+        ('ACGT' * 100, 'ACGT' * 80, 3, 300, 10),                      # short-period repeats
+        ('ACGTACGTA', ref, 0, 500, 10),                               # read shorter than k
+        (read, ref, 10, 9, 10),                                       # window shorter than k
+        (read, ref, 10, 10, 10),                                      # window of exactly one k-mer
+        (rnd(2000, 'ACGTRYKMN'), rnd(2500, 'ACGTRYKMN'), 0, 2500, 8), # ambiguity codes as plain bytes
+    ]
+    return cases
+
+
+def test_oracle_join_matches_the_reference_console_counts():
+    cases = reference_console_ranges()
+    assert len(cases) >= 20
+    for strand_seq, ref, start, length, k, count in cases:
+        assert len(common_kmers(strand_seq, ref[start:start + length], k)) == count
+
+
+def test_host_join_matches_the_oracle(ub):
+    cases = [c[:5] for c in reference_console_ranges()[:12]] + awkward_cases()
+    for strand_seq, ref, start, length, k in cases:
+        want = common_kmers(strand_seq, ref[start:start + length], k)
+        assert ub.common_kmers(strand_seq, ref, start, length, k, on_device=False) == want
+
+
+@pytest.mark.gpu
+def test_device_join_matches_the_oracle_and_the_host_join(ub):
+    cases = [c[:5] for c in reference_console_ranges()] + awkward_cases()
+    for strand_seq, ref, start, length, k in cases:
+        want = common_kmers(strand_seq, ref[start:start + length], k)
+        got = ub.common_kmers(strand_seq, ref, start, length, k, on_device=True)
+        assert got == want, (len(got), len(want), k, start, length)
+        assert ub.common_kmers(strand_seq, ref, start, length, k, on_device=False) == want
+
+
+@pytest.mark.gpu
+def test_batch_path_joins_on_the_device_and_host_switch_gives_the_same_strings(ub, monkeypatch):
+    """The batch ABI reports the launches / points of its device join; with the developer switch that keeps the
+    host join the result strings are the same."""
+    from oracle_lib import mask_semi_global
+    d = load_golden('semiglobal_small.json.gz')
+    h = ub.new_ref_seqs()
+    for name, seq in d['refs']:
+        ub.add_ref_seq(h, name, seq)
+    reads = [r for r in d['reads'] if r[0] in d['expected']]
+    args = ([r[0] for r in reads], [r[1] for r in reads], [r[2] for r in reads], h, tuple(d['scheme']), 0)
+    out = ub.semi_global_alignment_batch(*args)
+    js = ub.last_join_stats()
+    assert js['launches'] >= 7 and js['points'] > 0 and js['kernel_ms'] > 0
+    monkeypatch.setenv('UNICYCLER_B200_HOST_KMERS', '1')
+    out_host = ub.semi_global_alignment_batch(*args)
+    assert ub.last_join_stats()['launches'] == 0
+    ub.delete_ref_seqs(h)
+    assert [mask_semi_global(o) for o in out] == [mask_semi_global(o) for o in out_host]
+    assert all(mask_semi_global(o) == d['expected'][r[0]] for r, o in zip(reads, out))

@@ -12,11 +12,12 @@ from .wrappers import (LIB_PATH, load_library, semi_global_alignment, fully_glob
                        chain_alignment, chain_alignment_batch, semi_global_alignment_batch, seed_chains,
                        last_stats, transfer_bytes, chain_cells, chain_plan, set_device, int_peak_ops_per_sec, ChainBench,
                        semi_global_alignment_exhaustive, start_seq_alignment, end_seq_alignment, overlap_alignment,
-                       calibration_pairs, coalescer_stats, alignment_tallies)
+                       calibration_pairs, coalescer_stats, alignment_tallies, common_kmers, last_join_stats)
 
 __all__ = ['LIB_PATH', 'load_library', 'semi_global_alignment', 'fully_global_alignment', 'path_alignment',
            'get_random_sequence_alignment_mean_and_std_dev', 'new_ref_seqs', 'add_ref_seq', 'delete_ref_seqs',
            'fully_global_alignment_batch', 'path_alignment_batch', 'chain_alignment', 'chain_alignment_batch',
            'semi_global_alignment_batch', 'seed_chains', 'last_stats', 'transfer_bytes', 'chain_cells', 'chain_plan', 'set_device', 'int_peak_ops_per_sec',
            'ChainBench', 'semi_global_alignment_exhaustive', 'start_seq_alignment', 'end_seq_alignment',
-           'overlap_alignment', 'calibration_pairs', 'coalescer_stats', 'alignment_tallies']
+           'overlap_alignment', 'calibration_pairs', 'coalescer_stats', 'alignment_tallies', 'common_kmers',
+           'last_join_stats']

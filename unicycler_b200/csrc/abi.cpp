@@ -26,6 +26,7 @@
 #include "engine.hpp"
 #include "host_align.hpp"
 #include "hostpool.hpp"
+#include "kmerjoin.hpp"
 #include "seeding.hpp"
 
 using namespace ub200;
@@ -84,6 +85,16 @@ Engine& engine(int slot = 0) {
     if (!g_engines[(size_t)slot]) g_engines[(size_t)slot].reset(new Engine(g_deviceList[(size_t)slot % D]));
     return *g_engines[(size_t)slot];
 }
+
+// Device k-mer join of the batch path (kmerjoin.hpp), on the first device of the list.
+std::unique_ptr<KmerJoiner> g_joiner;
+KmerJoiner& joiner() {
+    std::lock_guard<std::mutex> lock(g_engineMu);
+    resolveDevices();
+    if (!g_joiner) g_joiner.reset(new KmerJoiner(g_deviceList[0]));
+    return *g_joiner;
+}
+JoinStats g_lastJoinStats;
 
 [[noreturn]] void fatal(const std::string& msg) {
     fprintf(stderr, "unicycler_b200: fatal: %s\n", msg.c_str());
@@ -386,7 +397,7 @@ std::vector<std::pair<int, int> > simplifyRanges(std::vector<std::pair<int, int>
 
 // Host part of semiGlobalAlignment (semi_global_align.cpp:24-142): produces the chain jobs.
 void prepareRead(ReadWork& w, const char* readNameC, const char* readSeqC, int verbosity, const char* hitsC,
-                 SeqMap* refSeqs, const Scoring& sc, int sensitivityLevel) {
+                 SeqMap* refSeqs, const Scoring& sc, int sensitivityLevel, bool hostKmerIndex = true) {
     typedef std::unordered_map<std::string, std::vector<std::pair<int, int> > > RefRangeMap;
     SensitivityParams sp = sensitivityParams(sensitivityLevel);
     w.readName = readNameC;
@@ -424,10 +435,10 @@ void prepareRead(ReadWork& w, const char* readNameC, const char* readSeqC, int v
         const char strand = refName.back();
         refName.pop_back();
         if (strand == '+') {
-            if (!havePos) { buildKmerPositions(w.posSeq, sp.kSize, w.posKmers); havePos = true; }
+            if (!havePos) { if (hostKmerIndex) buildKmerPositions(w.posSeq, sp.kSize, w.posKmers); havePos = true; }
         } else if (!haveNeg) {
             w.negSeq = reverseComplement(w.posSeq);
-            buildKmerPositions(w.negSeq, sp.kSize, w.negKmers);
+            if (hostKmerIndex) buildKmerPositions(w.negSeq, sp.kSize, w.negKmers);
             haveNeg = true;
         }
         for (const auto& range : r.second) {
@@ -440,13 +451,16 @@ void prepareRead(ReadWork& w, const char* readNameC, const char* readSeqC, int v
 }
 
 // One range unit of a read: seeding + planning of its chain jobs (independent of every other unit).
-void seedUnit(ReadWork& w, RangeUnit& u, int verbosity, SeqMap* refSeqs, const Scoring& sc) {
+void seedUnit(ReadWork& w, RangeUnit& u, int verbosity, SeqMap* refSeqs, const Scoring& sc,
+              const std::vector<JoinPoint>* joined = nullptr) {
     const std::string& refSeq = refSeqs->at(u.refName);
     const std::string& readSeq = (u.strand == '+') ? w.posSeq : w.negSeq;
     const KmerPosMap& kmers = (u.strand == '+') ? w.posKmers : w.negKmers;
     std::string trimmed = refSeq.substr((size_t)u.refStart, (size_t)(u.refEnd - u.refStart));
     RangeSeeds rs;
-    seedRange(readSeq, kmers, trimmed, w.sp, verbosity, u.refName, u.refStart, u.refEnd, rs);
+    static_assert(sizeof(JoinPoint) == 2 * sizeof(int32_t), "JoinPoint is an (x, y) pair of int32");
+    seedRange(readSeq, kmers, trimmed, w.sp, verbosity, u.refName, u.refStart, u.refEnd, rs,
+              joined ? (const int32_t*)joined->data() : nullptr, joined ? joined->size() : 0);
     u.console = rs.console;
     for (const auto& chain : rs.chains) {
         std::unique_ptr<ChainJob> cj(new ChainJob());
@@ -523,7 +537,13 @@ void freeCString(char* p) { free(p); }
 
 void* newRefSeqs(void) { return new SeqMap(); }
 void addRefSeq(void* h, char* name, char* seq) { ((SeqMap*)h)->emplace(name, seq); }
-void deleteRefSeqs(void* h) { delete (SeqMap*)h; }
+void deleteRefSeqs(void* h) {
+    {   // the device join keeps resident copies keyed by the sequences' host addresses
+        std::lock_guard<std::mutex> lock(g_engineMu);
+        if (g_joiner) g_joiner->forgetReferences();
+    }
+    delete (SeqMap*)h;
+}
 
 static char* pairAlignment(char* s1, char* s2, int m, int mm, int go, int ge, bool useBanding, int bandSize, bool path) {
     Scoring sc{m, mm, go, ge};
@@ -855,11 +875,18 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
 
     // Host seeding + planning of the reads order[k0 .. k1): one task per read (ranges, k-mer index), then one task per
     // (read, reference range), most expensive first.  Returns the chunk's device jobs.
+    // Common k-mers of the whole chunk are joined on the device (kmerjoin.cu); UNICYCLER_B200_HOST_KMERS=1 keeps the
+    // host join of the per-read entry point (developer switch, same points in the same order).
+    const bool hostOnly = getenv("UNICYCLER_B200_HOST_ONLY") != nullptr;
+    const bool deviceJoin = !hostOnly && !getenv("UNICYCLER_B200_HOST_KMERS");
+    JoinStats joinStats;
+    double joinMs = 0.0;
     auto seedChunk = [&](int k0, int k1, std::vector<Job*>& jobs) {
         parallelFor(k1 - k0, [&](int k) {
             const int i = order[(size_t)(k0 + k)];
             works[(size_t)i].reset(new ReadWork());
-            prepareRead(*works[(size_t)i], readNames[i], readSeqs[i], 0, hits[i], (SeqMap*)refSeqs, sc, sensitivityLevel);
+            prepareRead(*works[(size_t)i], readNames[i], readSeqs[i], 0, hits[i], (SeqMap*)refSeqs, sc, sensitivityLevel,
+                        !deviceJoin);
         });
         std::vector<std::pair<int, int> > unitList;
         for (int k = k0; k < k1; ++k) {
@@ -873,9 +900,34 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
             const double cb = (double)len[(size_t)b.first] * (ub.refEnd - ub.refStart);
             return ca > cb;
         });
+        std::vector<std::vector<JoinPoint> > joined;
+        if (deviceJoin && !unitList.empty()) {
+            const double tj = nowSec();
+            std::vector<JoinSeq> seqs;
+            std::vector<JoinTask> tasks(unitList.size());
+            std::unordered_map<const std::string*, int> seqIndex;
+            for (size_t q = 0; q < unitList.size(); ++q) {
+                ReadWork& w = *works[(size_t)unitList[q].first];
+                const RangeUnit& u = w.units[(size_t)unitList[q].second];
+                const std::string& strandSeq = (u.strand == '+') ? w.posSeq : w.negSeq;
+                auto it = seqIndex.find(&strandSeq);
+                if (it == seqIndex.end()) {
+                    it = seqIndex.emplace(&strandSeq, (int)seqs.size()).first;
+                    seqs.push_back(JoinSeq{strandSeq.data(), (int)strandSeq.size()});
+                }
+                const std::string& refSeq = ((SeqMap*)refSeqs)->at(u.refName);
+                tasks[q] = JoinTask{it->second, refSeq.data(), refSeq.size(), u.refStart, u.refEnd - u.refStart};
+            }
+            joiner().run(seqs, tasks, works[(size_t)unitList[0].first]->sp.kSize, joined);
+            const JoinStats js = joiner().lastStats();
+            joinStats.kernelMs += js.kernelMs; joinStats.launches += js.launches; joinStats.h2dBytes += js.h2dBytes;
+            joinStats.d2hBytes += js.d2hBytes; joinStats.points += js.points; joinStats.refUploads += js.refUploads;
+            joinMs += (nowSec() - tj) * 1e3;
+        }
         parallelFor((int)unitList.size(), [&](int k) {
             ReadWork& w = *works[(size_t)unitList[(size_t)k].first];
-            seedUnit(w, w.units[(size_t)unitList[(size_t)k].second], 0, (SeqMap*)refSeqs, sc);
+            seedUnit(w, w.units[(size_t)unitList[(size_t)k].second], 0, (SeqMap*)refSeqs, sc,
+                     deviceJoin ? &joined[(size_t)k] : nullptr);
         });
         jobs.clear();
         for (int k = k0; k < k1; ++k) {
@@ -933,10 +985,14 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
         finishChunk(lo(k), hi(k));
     }
     g_batchStats = batchStats;
+    g_batchStats.launches += joinStats.launches;
+    g_batchStats.h2dBytes += joinStats.h2dBytes;
+    g_batchStats.d2hBytes += joinStats.d2hBytes;
+    g_lastJoinStats = joinStats;
     g_lastCallUsedBoth = true;
     if (getenv("UNICYCLER_B200_PROFILE"))
-        fprintf(stderr, "[ub200 host] reads=%d in %d chunk(s) of %d: seeding %.1f ms (host), total %.1f ms\n", n, nChunks, chunk, seedMs,
-                (nowSec() - t0) * 1e3);
+        fprintf(stderr, "[ub200 host] reads=%d in %d chunk(s) of %d: seeding %.1f ms (of which device k-mer join %.2f ms wall, %.3f ms kernels, %lld points), total %.1f ms\n",
+                n, nChunks, chunk, seedMs, joinMs, joinStats.kernelMs, (long long)joinStats.points, (nowSec() - t0) * 1e3);
     return 0;
 }
 
@@ -959,6 +1015,40 @@ char* ub200_seedChains(const char* readSeq, const char* trimmedRefSeq, int sensi
         out += ";";
     }
     return dupString(out);
+}
+
+// Common k-mer points of one (read strand, reference window) pair: where = 0 the host join of the per-read entry point,
+// where = 1 the device join of the batch path (the reference sequence is `ref`, the window [refStart, refStart+refLen)).
+// Writes up to cap (x, y) pairs; returns the number of points, or -1 when the device join is not available.
+int64_t ub200_commonKmers(const char* readSeq, const char* ref, int refStart, int refLen, int k, int where,
+                          int32_t* xy, int64_t cap) {
+    std::vector<int32_t> pts;
+    if (where == 0) {
+        commonKmerPoints(std::string(readSeq), std::string(ref + refStart, (size_t)refLen), k, pts);
+    } else {
+        std::vector<JoinSeq> seqs{JoinSeq{readSeq, (int)strlen(readSeq)}};
+        std::vector<JoinTask> tasks{JoinTask{0, ref, strlen(ref), refStart, refLen}};
+        std::vector<std::vector<JoinPoint> > out;
+        try {
+            joiner().run(seqs, tasks, k, out);
+        } catch (const std::exception& e) {
+            fprintf(stderr, "unicycler_b200: %s\n", e.what());
+            return -1;
+        }
+        for (const JoinPoint& p : out[0]) { pts.push_back(p.x); pts.push_back(p.y); }
+        joiner().forgetReferences();   // `ref` is caller memory that may be gone after the call
+    }
+    const int64_t n = (int64_t)pts.size() / 2;
+    for (int64_t q = 0; q < std::min(n, cap); ++q) { xy[2 * q] = pts[(size_t)(2 * q)]; xy[2 * q + 1] = pts[(size_t)(2 * q + 1)]; }
+    return n;
+}
+
+void ub200_lastJoinStats(double* kernelMs, int64_t* launches, int64_t* points, int64_t* h2dBytes, int64_t* d2hBytes) {
+    if (kernelMs) *kernelMs = g_lastJoinStats.kernelMs;
+    if (launches) *launches = g_lastJoinStats.launches;
+    if (points) *points = g_lastJoinStats.points;
+    if (h2dBytes) *h2dBytes = g_lastJoinStats.h2dBytes;
+    if (d2hBytes) *d2hBytes = g_lastJoinStats.d2hBytes;
 }
 
 double ub200_intPeakOpsPerSec(void) { return measureIntPeak(engine().device()); }

@@ -568,9 +568,12 @@ double scorePointSet(const PointSet& pointSet, const PointVector& traceDots, boo
 
 PointSet lineTracing(const PointVector& common, PointSet& usedPoints, const Cloud& cloud, int readLen, int refLen,
                      int lineNum, int verbosity, std::string& console, bool& failedLine, double& pointSetScore) {
-    Cloud startCloud;
+    // The start cloud holds the points no earlier line used: for the first line that is the range's cloud itself
+    // (same points in the same order, hence the same tree), so it is only rebuilt from the second line on.
+    Cloud rebuilt;
     const long long tA = nowNs();
-    fillCloud(startCloud, common, usedPoints);
+    if (!usedPoints.empty()) fillCloud(rebuilt, common, usedPoints);
+    const Cloud& startCloud = usedPoints.empty() ? cloud : rebuilt;
     const long long tB = nowNs();
     Point startPoint = getHighestDensityPoint(LINE_TRACING_START_POINT_SEARCH_RADIUS, startCloud);
     g_seedProf[3] += tB - tA;
@@ -791,18 +794,9 @@ long long maxSeedChainGapArea(const std::vector<ChainSeed>& chain, int readLen, 
 
 }  // namespace
 
-void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const std::string& trimmedRefSeq,
-               const SensitivityParams& sp, int verbosity, const std::string& refName, int refStart, int refEnd,
-               RangeSeeds& out) {
-    out.chains.clear();
-    const int kSize = sp.kSize;
-    const int readLen = (int)readSeq.size(), refLen = (int)trimmedRefSeq.size();
-    if (verbosity > 2)
-        out.console += "Range: " + refName + ": " + std::to_string(refStart) + " - " + std::to_string(refEnd) + "\n";
-    // common k-mers :197-207
-    const long long t0 = nowNs();
-    PointVector common;
-    if (readKmers.k != kSize) return;
+// common k-mers on the host (semi_global_align.cpp:197-207): window positions ascending, read positions ascending
+static void hostCommonKmers(const KmerPosMap& readKmers, const std::string& trimmedRefSeq, int kSize, PointVector& common) {
+    const int refLen = (int)trimmedRefSeq.size();
     if (kSize > 16) {
         const int maxI = refLen - kSize + 1;
         std::string kmer;
@@ -828,6 +822,34 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
             }
         });
     }
+}
+
+void commonKmerPoints(const std::string& readSeq, const std::string& trimmedRefSeq, int kSize, std::vector<int32_t>& xy) {
+    KmerPosMap kmers;
+    buildKmerPositions(readSeq, kSize, kmers);
+    PointVector common;
+    hostCommonKmers(kmers, trimmedRefSeq, kSize, common);
+    xy.clear();
+    xy.reserve(2 * common.size());
+    for (const Point& p : common) { xy.push_back(p.x); xy.push_back(p.y); }
+}
+
+void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const std::string& trimmedRefSeq,
+               const SensitivityParams& sp, int verbosity, const std::string& refName, int refStart, int refEnd,
+               RangeSeeds& out, const int32_t* joinedXY, size_t nJoined) {
+    out.chains.clear();
+    const int kSize = sp.kSize;
+    const int readLen = (int)readSeq.size(), refLen = (int)trimmedRefSeq.size();
+    if (verbosity > 2)
+        out.console += "Range: " + refName + ": " + std::to_string(refStart) + " - " + std::to_string(refEnd) + "\n";
+    // common k-mers :197-207
+    const long long t0 = nowNs();
+    PointVector common;
+    if (joinedXY) {   // the batch path joined the k-mers on the device (kmerjoin.cu): same points, same order
+        common.resize(nJoined);
+        for (size_t q = 0; q < nJoined; ++q) common[q] = Point(joinedXY[2 * q], joinedXY[2 * q + 1]);
+    } else if (readKmers.k != kSize) return;
+    else hostCommonKmers(readKmers, trimmedRefSeq, kSize, common);
     if (verbosity > 2)
         out.console += "    common " + std::to_string(kSize) + "-mers: " + std::to_string(common.size()) + "\n";
     if (common.empty()) return;  // the reference dereferences an empty vector here (undefined); no alignment

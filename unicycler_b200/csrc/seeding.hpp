@@ -42,9 +42,15 @@ struct RangeSeeds {
 // Everything alignReadToReferenceRange does before bandedChainAlignment (semi_global_align.cpp:197-291).
 // The returned chains stop at the first point set whose chain is empty or whose gap area exceeds
 // MAX_BANDED_ALIGNMENT_GAP_AREA, like the early returns at :286-291.
+// joinedXY != nullptr: the range's common k-mer points (x = read position, y = window position, the reference's
+// order) were already found by the device join (kmerjoin.hpp); readKmers is not used then.
 void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const std::string& trimmedRefSeq,
                const SensitivityParams& sp, int verbosity, const std::string& refName, int refStart, int refEnd,
-               RangeSeeds& out);
+               RangeSeeds& out, const int32_t* joinedXY = nullptr, size_t nJoined = 0);
+
+// The host join alone (x, y pairs in the reference's order): the per-read entry point's join, and the checker of
+// the device join in tests/.
+void commonKmerPoints(const std::string& readSeq, const std::string& trimmedRefSeq, int kSize, std::vector<int32_t>& xy);
 
 std::string reverseComplement(const std::string& s);  // src/string_functions.cpp:52-79
 

@@ -51,6 +51,11 @@ def load_library():
     L.ub200_semiGlobalAlignmentBatch.restype = c_int
     L.ub200_seedChains.argtypes = [c_char_p, c_char_p, c_int]
     L.ub200_seedChains.restype = c_void_p
+    L.ub200_commonKmers.argtypes = [c_char_p, c_char_p, c_int, c_int, c_int, c_int, POINTER(ctypes.c_int32), c_int64]
+    L.ub200_commonKmers.restype = c_int64
+    L.ub200_lastJoinStats.argtypes = [POINTER(c_double), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
+                                      POINTER(c_int64)]
+    L.ub200_lastJoinStats.restype = None
     L.ub200_lastStats.argtypes = [POINTER(c_int64), POINTER(c_double), POINTER(c_int64), POINTER(c_double),
                                   POINTER(c_double)]
     L.ub200_lastStats.restype = None
@@ -293,6 +298,31 @@ def seed_chains(read_seq, trimmed_ref_seq, sensitivity_level=0):
         body = c.split(':', 1)[1]
         chains.append([[int(x) for x in s.split(',')] for s in body.split('|')] if body else [])
     return chains
+
+
+def common_kmers(read_seq, ref_seq, ref_start, ref_len, k, on_device):
+    """Common k-mer points [(read position, window position), ...] of a read strand and the window
+    [ref_start, ref_start + ref_len) of ref_seq, in the reference's order: host join (the per-read entry point's)
+    or device join (the batch path's)."""
+    L = load_library()
+    r, f = read_seq.encode(), ref_seq.encode()
+    n = L.ub200_commonKmers(r, f, ref_start, ref_len, k, 1 if on_device else 0, None, 0)
+    if n < 0:
+        raise RuntimeError('device k-mer join unavailable')
+    buf = (ctypes.c_int32 * (2 * max(n, 1)))()
+    n2 = L.ub200_commonKmers(r, f, ref_start, ref_len, k, 1 if on_device else 0, buf, n)
+    assert n2 == n
+    return [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
+
+
+def last_join_stats():
+    """Counters of the device k-mer join inside the last semi_global_alignment_batch call."""
+    ms = c_double()
+    launches, points, h2d, d2h = c_int64(), c_int64(), c_int64(), c_int64()
+    load_library().ub200_lastJoinStats(ctypes.byref(ms), ctypes.byref(launches), ctypes.byref(points), ctypes.byref(h2d),
+                                       ctypes.byref(d2h))
+    return {'kernel_ms': ms.value, 'launches': launches.value, 'points': points.value, 'h2d_bytes': h2d.value,
+            'd2h_bytes': d2h.value}
 
 
 def last_stats():
