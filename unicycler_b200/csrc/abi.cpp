@@ -30,7 +30,7 @@
 #include "seeding.hpp"
 
 using namespace ub200;
-namespace ub200 { extern std::atomic<long long> g_seedProf[6]; }
+namespace ub200 { extern std::atomic<long long> g_seedProf[6]; extern std::atomic<long long> g_lt[10]; }
 
 typedef std::unordered_map<std::string, std::string> SeqMap;  // include/ref_seqs.h:18
 
@@ -937,11 +937,32 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
                 if (cj->planned) jobs.push_back(&cj->job);
         }
     };
+    // Formatting: one task per chain job (gluing + CIGAR of a long chain costs a millisecond: a read with six of them
+    // would otherwise be one serial task), longest chains first; then the reads' strings are put together.
     auto finishChunk = [&](int k0, int k1) {
+        std::vector<std::pair<int, int> > jobList;   // (read, job of the read)
+        for (int k = k0; k < k1; ++k) {
+            const int i = order[(size_t)k];
+            for (size_t q = 0; q < works[(size_t)i]->jobs.size(); ++q) jobList.emplace_back(i, (int)q);
+        }
+        std::stable_sort(jobList.begin(), jobList.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+            return works[(size_t)a.first]->jobs[(size_t)a.second]->job.grids.size() >
+                   works[(size_t)b.first]->jobs[(size_t)b.second]->job.grids.size();
+        });
+        std::vector<std::vector<std::string> > parts((size_t)n);
+        for (int k = k0; k < k1; ++k) parts[(size_t)order[(size_t)k]].resize(works[(size_t)order[(size_t)k]]->jobs.size());
+        parallelFor((int)jobList.size(), [&](int k) {
+            const int i = jobList[(size_t)k].first, q = jobList[(size_t)k].second;
+            std::string str;
+            if (finishChainJob(*works[(size_t)i]->jobs[(size_t)q], sc, str)) parts[(size_t)i][(size_t)q] = str + ";";
+        });
         parallelFor(k1 - k0, [&](int k) {
             const int i = order[(size_t)(k0 + k)];
-            results[i] = dupString(finishRead(*works[(size_t)i], sc));
-        });
+            std::string ret;
+            for (const std::string& part : parts[(size_t)i]) ret += part;
+            ret += works[(size_t)i]->console;
+            results[i] = dupString(ret);
+        }, 4);
     };
 
     if (getenv("UNICYCLER_B200_HOST_ONLY")) {  // developer aid: time the host stage without a GPU
@@ -950,6 +971,9 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
         fprintf(stderr, "[ub200 host] reads=%d jobs=%zu prepare=%.1f ms (kmers %.1f, linetrace %.1f [fillCloud %.1f, densest point %.1f], seeds+chain %.1f thread-ms)\n", n,
                 jobs.size(), (nowSec() - t0) * 1e3, g_seedProf[0] / 1e6, g_seedProf[1] / 1e6, g_seedProf[3] / 1e6, g_seedProf[4] / 1e6, g_seedProf[2] / 1e6);
         for (int q = 0; q < 6; ++q) g_seedProf[q] = 0;
+        fprintf(stderr, "[ub200 host] line tracer thread-ms: range tree %.1f, trace loop %.1f [searches %.1f, near set %.1f, scoring %.1f, collection %.1f], set score %.1f, used points %.1f\n",
+                g_lt[7] / 1e6, g_lt[4] / 1e6, g_lt[0] / 1e6, g_lt[1] / 1e6, g_lt[2] / 1e6, g_lt[3] / 1e6, g_lt[5] / 1e6, g_lt[6] / 1e6);
+        for (int q = 0; q < 10; ++q) g_lt[q] = 0;
         for (int i = 0; i < n; ++i) results[i] = dupString("");
         return 0;
     }
@@ -965,7 +989,7 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     std::vector<std::vector<Job*> > jobs((size_t)nChunks);
     auto lo = [&](int k) { return k * chunk; };
     auto hi = [&](int k) { return std::min(n, (k + 1) * chunk); };
-    double seedMs = 0.0;
+    double seedMs = 0.0, finishMs = 0.0;
     EngineStats batchStats;
     const int E = engineCount();   // two per device
     for (int k = 0; k < nChunks; ++k) {
@@ -975,14 +999,18 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
         if (k >= E) {   // the engine of chunk k is the one chunk k-E used
             engine(k % E).end(jobs[(size_t)(k - E)]);
             addStats(batchStats, engine(k % E).lastStats());
+            const double tf = nowSec();
             finishChunk(lo(k - E), hi(k - E));
+            finishMs += (nowSec() - tf) * 1e3;
         }
         engine(k % E).begin(jobs[(size_t)k]);
     }
     for (int k = std::max(0, nChunks - E); k < nChunks; ++k) {
         engine(k % E).end(jobs[(size_t)k]);
         addStats(batchStats, engine(k % E).lastStats());
+        const double tf = nowSec();
         finishChunk(lo(k), hi(k));
+        finishMs += (nowSec() - tf) * 1e3;
     }
     g_batchStats = batchStats;
     g_batchStats.launches += joinStats.launches;
@@ -990,9 +1018,14 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     g_batchStats.d2hBytes += joinStats.d2hBytes;
     g_lastJoinStats = joinStats;
     g_lastCallUsedBoth = true;
+    if (getenv("UNICYCLER_B200_PROFILE")) {
+        fprintf(stderr, "[ub200 host] seeding thread-ms: kmers %.1f, linetrace %.1f [start cloud %.1f, densest point %.1f], seeds+chain %.1f\n",
+                g_seedProf[0] / 1e6, g_seedProf[1] / 1e6, g_seedProf[3] / 1e6, g_seedProf[4] / 1e6, g_seedProf[2] / 1e6);
+        for (int q = 0; q < 6; ++q) g_seedProf[q] = 0;
+    }
     if (getenv("UNICYCLER_B200_PROFILE"))
-        fprintf(stderr, "[ub200 host] reads=%d in %d chunk(s) of %d: seeding %.1f ms (of which device k-mer join %.2f ms wall, %.3f ms kernels, %lld points), total %.1f ms\n",
-                n, nChunks, chunk, seedMs, joinMs, joinStats.kernelMs, (long long)joinStats.points, (nowSec() - t0) * 1e3);
+        fprintf(stderr, "[ub200 host] reads=%d in %d chunk(s) of %d: seeding %.1f ms (of which device k-mer join %.2f ms wall, %.3f ms kernels, %lld points), formatting %.1f ms, total %.1f ms\n",
+                n, nChunks, chunk, seedMs, joinMs, joinStats.kernelMs, (long long)joinStats.points, finishMs, (nowSec() - t0) * 1e3);
     return 0;
 }
 

@@ -24,6 +24,9 @@ namespace ub200 {
 
 // developer timers of the host seeding stages (seconds, summed over threads)
 std::atomic<long long> g_seedProf[6];
+// ... and of the line tracer's parts: 0 radius searches, 1 near-point set, 2 segment scoring, 3 collection, 4 whole trace loop,
+// 5 point-set score, 6 used-point bookkeeping, 7 the range's kd-tree
+std::atomic<long long> g_lt[10];
 static inline long long nowNs() {
     return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -146,7 +149,42 @@ struct Point {
 struct PointHash {  // include/semi_global_align.h:79-86
     size_t operator()(const Point& p) const { return (std::hash<int>()(p.x) ^ (std::hash<int>()(p.y) << 1)) >> 1; }
 };
-typedef std::unordered_set<Point, PointHash> PointSet;
+// The line tracer builds and drops thousands of small point sets per range; their nodes and bucket arrays come from a
+// per-thread bump arena that is rewound when a range starts (a thread seeds one range at a time, and no point set
+// outlives its range).  Only where the memory comes from changes: the hash, the bucket policy and therefore the
+// iteration order are those of the reference's std::unordered_set<Point, PointHash>.
+struct Arena {
+    std::vector<char*> blocks;
+    size_t cur = 0, used = 0;
+    static const size_t BLOCK = 1 << 20;
+    ~Arena() { for (char* b : blocks) free(b); }
+    void rewind() { cur = 0; used = 0; }
+    static size_t rounded(size_t n) { return (n + 15) & ~(size_t)15; }
+    void* alloc(size_t n) {
+        n = rounded(n);
+        if (n > BLOCK) return malloc(n);   // (not from the arena: released by deallocate)
+        if (blocks.empty()) blocks.push_back((char*)malloc(BLOCK));
+        if (used + n > BLOCK) {
+            used = 0;
+            if (++cur == blocks.size()) blocks.push_back((char*)malloc(BLOCK));
+        }
+        void* p = blocks[cur] + used;
+        used += n;
+        return p;
+    }
+};
+static thread_local Arena t_arena;
+template <typename T>
+struct ArenaAlloc {
+    typedef T value_type;
+    ArenaAlloc() {}
+    template <typename U> ArenaAlloc(const ArenaAlloc<U>&) {}
+    T* allocate(size_t n) { return (T*)t_arena.alloc(n * sizeof(T)); }
+    void deallocate(T* p, size_t n) { if (Arena::rounded(n * sizeof(T)) > Arena::BLOCK) free(p); }
+    template <typename U> bool operator==(const ArenaAlloc<U>&) const { return true; }
+    template <typename U> bool operator!=(const ArenaAlloc<U>&) const { return false; }
+};
+typedef std::unordered_set<Point, PointHash, std::equal_to<Point>, ArenaAlloc<Point> > PointSet;
 typedef std::vector<Point> PointVector;
 
 // ------------------------------------------------------------------ kd-tree (nanoflann algorithm, int L1 metric)
@@ -403,6 +441,7 @@ Point mutateLineToBestFitPoints(Point p1, Point p2, const Cloud& cloud, PointSet
     // p1 is the previous step's end point: when that step kept its unmutated end, the search around it has just been
     // done (as that step's p2).  Same cloud, same query, same radius => same list in the same order.
     LastSearch& last = g_lastSearch;
+    const long long tm0 = nowNs();
     PointVector nearP1;
     if (last.cloud == &cloud && last.q == p1) nearP1.swap(last.pts);
     else nearP1 = radiusSearchAroundPoint(p1, radius, cloud);
@@ -411,8 +450,12 @@ Point mutateLineToBestFitPoints(Point p1, Point p2, const Cloud& cloud, PointSet
         LastSearch& l; const Cloud* c; Point q; PointVector& v;
         ~Keep() { l.cloud = c; l.q = q; l.pts.swap(v); }
     } keep{last, &cloud, p2, nearP2};
+    const long long tm1 = nowNs();
     pointsNearLine.insert(nearP1.begin(), nearP1.end());
     pointsNearLine.insert(nearP2.begin(), nearP2.end());
+    const long long tm2 = nowNs();
+    g_lt[0] += tm1 - tm0; g_lt[1] += tm2 - tm1;
+    struct Sc { long long t; ~Sc() { g_lt[2] += nowNs() - t; } } scTimer{tm2};
     if (leftRectangle) return p2;
     Point p2Up = shiftUp(p2, TRACE_LINE_MUTATION_SIZE), p2Down = shiftDown(p2, TRACE_LINE_MUTATION_SIZE);
     double unmutated = scoreLineSegment(p1, p2, pointsNearLine);
@@ -581,6 +624,7 @@ PointSet lineTracing(const PointVector& common, PointSet& usedPoints, const Clou
     Point p = startPoint;
     PointVector traceDots;
     traceDots.push_back(p);
+    const long long tl0 = nowNs();
     PointVector nearby = radiusSearchAroundPoint(p, (int)TRACE_LINE_COLLECTION_DISTANCE, cloud);
     PointSet pointSet(nearby.begin(), nearby.end());
     const int directions[2] = {1, -1};
@@ -597,17 +641,24 @@ PointSet lineTracing(const PointVector& common, PointSet& usedPoints, const Clou
             PointSet pointsNearLine;
             p = mutateLineToBestFitPoints(previousP, newP, cloud, pointsNearLine, left);
             traceDots.push_back(p);
+            const long long ta0 = nowNs();
             for (const Point& q : pointsNearLine)  // addPointsNearLine :506-512
                 if (distanceToLineSegment(q, previousP, p) <= TRACE_LINE_COLLECTION_DISTANCE) pointSet.insert(q);
+            g_lt[3] += nowNs() - ta0;
             if (left) break;
         }
     }
+    const long long tl1 = nowNs();
     pointSetScore = scorePointSet(pointSet, traceDots, failedLine);
+    const long long tl2 = nowNs();
+    g_lt[4] += tl1 - tl0; g_lt[5] += tl2 - tl1;
     if (verbosity > 2) {
         console += "    line " + std::to_string(lineNum + 1) + ": " + std::to_string(pointSet.size()) + " points, " +
                    "score=" + std::to_string(pointSetScore) + " (" + (failedLine ? "bad" : "good") + ")\n";
     }
+    const long long tl3 = nowNs();
     for (const Point& q : pointSet) usedPoints.insert(q);
+    g_lt[6] += nowNs() - tl3;
     return pointSet;
 }
 
@@ -637,27 +688,42 @@ void mergeInto(ChainSeed& seed, const ChainSeed& other) {  // seeds_combination.
 // without the scan: an element that can combine with the new seed has its END diagonal within maxDiag of the seed's
 // begin diagonal (element left of the seed) or its BEGIN diagonal within maxDiag of the seed's end diagonal (seed left
 // of the element), so only the elements filed under those 2 * (2 * maxDiag + 1) diagonals are tested, and the one that
-// comes first in the multiset's order (begin diagonal, then insertion sequence) wins.
+// comes first in the multiset's order (begin diagonal, then insertion sequence) wins.  The files are arrays over the
+// range's diagonals, the elements of one diagonal linked through the nodes (no hashing).
 class SeedSet {
 public:
-    SeedSet() { byBegin_.reserve(256); byEnd_.reserve(256); }
+    // the diagonals (H - V) of every seed of the range lie in [-maxV, maxH]
+    SeedSet(long maxH, long maxV)
+        : diag0_(-maxV), headBegin_((size_t)(maxH + maxV + 1), -1), headEnd_((size_t)(maxH + maxV + 1), -1) {
+        nodes_.reserve(1024);
+    }
     bool addMerge(const ChainSeed& seed, unsigned maxDiag) {
         const long bd = seed.beginH - seed.beginV, ed = seed.endH - seed.endV;
         int best = -1;
         auto consider = [&](int id) {
             if (best < 0 || before(id, best)) best = id;
         };
-        for (long d = bd - (long)maxDiag; d <= bd + (long)maxDiag; ++d) {
-            auto it = byEnd_.find(d);
-            if (it == byEnd_.end()) continue;
-            for (int id : it->second)
-                if (combineable(nodes_[(size_t)id].s, seed, maxDiag)) consider(id);
+        // Seeds arrive with ascending beginH (the caller sorts the points): an element that ends left of this seed's
+        // begin can never be the left partner again, one that begins left of it never the right partner.  Such
+        // elements leave the files here (they stay in the set), which keeps the lists at a handful of elements.
+        const long last = (long)headBegin_.size() - 1;
+        for (long d = std::max(0L, bd - (long)maxDiag - diag0_); d <= std::min(last, bd + (long)maxDiag - diag0_); ++d) {
+            int32_t* link = &headEnd_[(size_t)d];
+            while (*link >= 0) {
+                Node& nd = nodes_[(size_t)*link];
+                if (nd.s.endH < seed.beginH) { *link = nd.nextEnd; continue; }
+                if (combineable(nd.s, seed, maxDiag)) consider(*link);
+                link = &nd.nextEnd;
+            }
         }
-        for (long d = ed - (long)maxDiag; d <= ed + (long)maxDiag; ++d) {
-            auto it = byBegin_.find(d);
-            if (it == byBegin_.end()) continue;
-            for (int id : it->second)
-                if (combineable(seed, nodes_[(size_t)id].s, maxDiag)) consider(id);
+        for (long d = std::max(0L, ed - (long)maxDiag - diag0_); d <= std::min(last, ed + (long)maxDiag - diag0_); ++d) {
+            int32_t* link = &headBegin_[(size_t)d];
+            while (*link >= 0) {
+                Node& nd = nodes_[(size_t)*link];
+                if (nd.s.beginH < seed.beginH) { *link = nd.nextBegin; continue; }
+                if (combineable(seed, nd.s, maxDiag)) consider(*link);
+                link = &nd.nextBegin;
+            }
         }
         if (best < 0) return false;
         ChainSeed merged = nodes_[(size_t)best].s;   // (the merge is symmetric: min of the begins, max of the ends)
@@ -668,9 +734,11 @@ public:
     }
     void insert(const ChainSeed& s) {
         const int id = (int)nodes_.size();
-        nodes_.push_back(Node{s, true});
-        byBegin_[s.beginH - s.beginV].push_back(id);
-        byEnd_[s.endH - s.endV].push_back(id);
+        int32_t& hb = headBegin_[slot(s.beginH - s.beginV)];
+        int32_t& he = headEnd_[slot(s.endH - s.endV)];
+        nodes_.push_back(Node{s, true, hb, he});
+        hb = id;
+        he = id;
     }
     // the elements in the multiset's iteration order
     std::vector<ChainSeed> ordered() const {
@@ -685,7 +753,10 @@ public:
     }
 
 private:
-    struct Node { ChainSeed s; bool alive; };
+    // alive elements are filed under their begin and their end diagonal (lists of a handful of elements; which one
+    // wins does not depend on their order in the list)
+    struct Node { ChainSeed s; bool alive; int32_t nextBegin, nextEnd; };
+    size_t slot(long d) const { return (size_t)(d - diag0_); }
     long beginDiag(int id) const { return nodes_[(size_t)id].s.beginH - nodes_[(size_t)id].s.beginV; }
     // ids grow with the insertion sequence (a merged seed is erased and re-inserted: it moves behind its equals)
     bool before(int a, int b) const {
@@ -695,12 +766,16 @@ private:
     void erase(int id) {
         Node& n = nodes_[(size_t)id];
         n.alive = false;
-        drop(byBegin_[n.s.beginH - n.s.beginV], id);
-        drop(byEnd_[n.s.endH - n.s.endV], id);
+        unlink(headBegin_[slot(n.s.beginH - n.s.beginV)], id, &Node::nextBegin);
+        unlink(headEnd_[slot(n.s.endH - n.s.endV)], id, &Node::nextEnd);
     }
-    static void drop(std::vector<int>& v, int id) { v.erase(std::find(v.begin(), v.end(), id)); }
+    void unlink(int32_t& head, int id, int32_t Node::*next) {
+        for (int32_t* link = &head; *link >= 0; link = &(nodes_[(size_t)*link].*next))   // (it may have left the file already)
+            if (*link == id) { *link = nodes_[(size_t)id].*next; return; }
+    }
+    long diag0_;
     std::vector<Node> nodes_;
-    std::unordered_map<long, std::vector<int> > byBegin_, byEnd_;
+    std::vector<int32_t> headBegin_, headEnd_;
 };
 
 // seeds_global_chaining.h:102-280 (Gusfield sparse chaining, maximising the summed seed sizes)
@@ -838,6 +913,7 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
                const SensitivityParams& sp, int verbosity, const std::string& refName, int refStart, int refEnd,
                RangeSeeds& out, const int32_t* joinedXY, size_t nJoined) {
     out.chains.clear();
+    t_arena.rewind();   // (every point set of the previous range on this thread is gone)
     const int kSize = sp.kSize;
     const int readLen = (int)readSeq.size(), refLen = (int)trimmedRefSeq.size();
     if (verbosity > 2)
@@ -858,6 +934,7 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
     PointSet usedPoints;
     Cloud cloud;
     fillCloud(cloud, common, usedPoints);
+    g_lt[7] += nowNs() - t1;
     g_lastSearch.cloud = nullptr;   // (a new cloud may live at the old one's address)
     std::vector<PointSet> goodPointSets;
     double bestPointScore = 0.0;
@@ -880,7 +957,7 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
         pts.reserve(good.size());
         for (const Point& p : good) pts.push_back(p);
         std::sort(pts.begin(), pts.end());
-        SeedSet seedSet;
+        SeedSet seedSet((long)readLen + kSize, (long)refLen + kSize);
         for (const Point& p : pts) {
             ChainSeed s{(long)p.x, (long)p.y, (long)p.x + kSize, (long)p.y + kSize, (long)p.x - (long)p.y, (long)p.x - (long)p.y};
             if (!seedSet.addMerge(s, 2)) seedSet.insert(s);
