@@ -881,14 +881,22 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     const bool deviceJoin = !hostOnly && !getenv("UNICYCLER_B200_HOST_KMERS");
     JoinStats joinStats;
     double joinMs = 0.0;
-    auto seedChunk = [&](int k0, int k1, std::vector<Job*>& jobs) {
+    // Per chunk: the range units in seeding order and their common k-mer points (filled one chunk ahead, see below).
+    struct ChunkSeeds {
+        std::vector<std::pair<int, int> > unitList;
+        std::vector<std::vector<JoinPoint> > joined;
+    };
+    // Stage 1 of the reads order[k0 .. k1): ranges of every read, then the k-mer join of all their units.
+    auto joinChunk = [&](int k0, int k1, ChunkSeeds& cs) {
         parallelFor(k1 - k0, [&](int k) {
             const int i = order[(size_t)(k0 + k)];
             works[(size_t)i].reset(new ReadWork());
             prepareRead(*works[(size_t)i], readNames[i], readSeqs[i], 0, hits[i], (SeqMap*)refSeqs, sc, sensitivityLevel,
                         !deviceJoin);
         });
-        std::vector<std::pair<int, int> > unitList;
+        std::vector<std::pair<int, int> >& unitList = cs.unitList;
+        unitList.clear();
+        cs.joined.clear();
         for (int k = k0; k < k1; ++k) {
             const int i = order[(size_t)k];
             for (size_t u = 0; u < works[(size_t)i]->units.size(); ++u) unitList.emplace_back(i, (int)u);
@@ -900,7 +908,6 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
             const double cb = (double)len[(size_t)b.first] * (ub.refEnd - ub.refStart);
             return ca > cb;
         });
-        std::vector<std::vector<JoinPoint> > joined;
         if (deviceJoin && !unitList.empty()) {
             const double tj = nowSec();
             std::vector<JoinSeq> seqs;
@@ -918,17 +925,22 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
                 const std::string& refSeq = ((SeqMap*)refSeqs)->at(u.refName);
                 tasks[q] = JoinTask{it->second, refSeq.data(), refSeq.size(), u.refStart, u.refEnd - u.refStart};
             }
-            joiner().run(seqs, tasks, works[(size_t)unitList[0].first]->sp.kSize, joined);
+            joiner().run(seqs, tasks, works[(size_t)unitList[0].first]->sp.kSize, cs.joined);
             const JoinStats js = joiner().lastStats();
             joinStats.kernelMs += js.kernelMs; joinStats.launches += js.launches; joinStats.h2dBytes += js.h2dBytes;
             joinStats.d2hBytes += js.d2hBytes; joinStats.points += js.points; joinStats.refUploads += js.refUploads;
             joinMs += (nowSec() - tj) * 1e3;
         }
-        parallelFor((int)unitList.size(), [&](int k) {
-            ReadWork& w = *works[(size_t)unitList[(size_t)k].first];
-            seedUnit(w, w.units[(size_t)unitList[(size_t)k].second], 0, (SeqMap*)refSeqs, sc,
-                     deviceJoin ? &joined[(size_t)k] : nullptr);
+    };
+    // Stage 2: one task per (read, reference range), most expensive first: line tracing, seeds, chain, plan.
+    // Returns the chunk's device jobs.
+    auto traceChunk = [&](int k0, int k1, ChunkSeeds& cs, std::vector<Job*>& jobs) {
+        parallelFor((int)cs.unitList.size(), [&](int k) {
+            ReadWork& w = *works[(size_t)cs.unitList[(size_t)k].first];
+            seedUnit(w, w.units[(size_t)cs.unitList[(size_t)k].second], 0, (SeqMap*)refSeqs, sc,
+                     deviceJoin ? &cs.joined[(size_t)k] : nullptr);
         });
+        cs = ChunkSeeds();
         jobs.clear();
         for (int k = k0; k < k1; ++k) {
             ReadWork& w = *works[(size_t)order[(size_t)k]];
@@ -967,7 +979,9 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
 
     if (getenv("UNICYCLER_B200_HOST_ONLY")) {  // developer aid: time the host stage without a GPU
         std::vector<Job*> jobs;
-        seedChunk(0, n, jobs);
+        ChunkSeeds cs;
+        joinChunk(0, n, cs);
+        traceChunk(0, n, cs, jobs);
         fprintf(stderr, "[ub200 host] reads=%d jobs=%zu prepare=%.1f ms (kmers %.1f, linetrace %.1f [fillCloud %.1f, densest point %.1f], seeds+chain %.1f thread-ms)\n", n,
                 jobs.size(), (nowSec() - t0) * 1e3, g_seedProf[0] / 1e6, g_seedProf[1] / 1e6, g_seedProf[3] / 1e6, g_seedProf[4] / 1e6, g_seedProf[2] / 1e6);
         for (int q = 0; q < 6; ++q) g_seedProf[q] = 0;
@@ -992,10 +1006,50 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     double seedMs = 0.0, finishMs = 0.0;
     EngineStats batchStats;
     const int E = engineCount();   // two per device
-    for (int k = 0; k < nChunks; ++k) {
+    // Pipeline over the chunks.  The line tracing of chunk k+1 runs on the host pool (started from a helper thread)
+    // while this thread stages, launches, fetches and formats around chunk k.  The DP kernel owns every SM while it
+    // runs, so the k-mer join of a chunk must not queue up behind one with the pool waiting for it: chunk k+2 is
+    // joined by this thread between staging and launching chunk k (it waits there for kernel k-1 at most, while the
+    // pool is busy tracing chunk k+1).
+    //   pool    [trace 0]         [trace 1 ...........][trace 2 ...........]
+    //   main    [join 0] [join 1] [stage 0][join 2]     [fetch+fmt 0][stage 1][join 3] ...
+    //   GPU                                [kernel 0 ....]                    [kernel 1 ....]
+    std::vector<ChunkSeeds> seeds(3);
+    struct AsyncTrace {
+        std::thread th;
+        std::exception_ptr err;
+        double ms = 0.0;
+    } tracer[2];
+    auto startTrace = [&](int k) {
+        AsyncTrace& a = tracer[k & 1];
+        a.th = std::thread([&, k] {
+            try {
+                const double ts = nowSec();
+                traceChunk(lo(k), hi(k), seeds[(size_t)(k % 3)], jobs[(size_t)k]);
+                a.ms = (nowSec() - ts) * 1e3;
+            } catch (...) {
+                a.err = std::current_exception();
+            }
+        });
+    };
+    auto waitTrace = [&](int k) {
+        AsyncTrace& a = tracer[k & 1];
+        if (a.th.joinable()) a.th.join();
+        if (a.err) std::rethrow_exception(a.err);
+        seedMs += a.ms;
+        a.ms = 0.0;
+    };
+    auto timedJoin = [&](int k) {
         const double ts = nowSec();
-        seedChunk(lo(k), hi(k), jobs[(size_t)k]);
+        joinChunk(lo(k), hi(k), seeds[(size_t)(k % 3)]);
         seedMs += (nowSec() - ts) * 1e3;
+    };
+    timedJoin(0);
+    startTrace(0);
+    if (nChunks > 1) timedJoin(1);
+    for (int k = 0; k < nChunks; ++k) {
+        waitTrace(k);
+        if (k + 1 < nChunks) startTrace(k + 1);
         if (k >= E) {   // the engine of chunk k is the one chunk k-E used
             engine(k % E).end(jobs[(size_t)(k - E)]);
             addStats(batchStats, engine(k % E).lastStats());
@@ -1003,7 +1057,9 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
             finishChunk(lo(k - E), hi(k - E));
             finishMs += (nowSec() - tf) * 1e3;
         }
-        engine(k % E).begin(jobs[(size_t)k]);
+        engine(k % E).stage(jobs[(size_t)k]);
+        if (k + 2 < nChunks) timedJoin(k + 2);
+        engine(k % E).start();
     }
     for (int k = std::max(0, nChunks - E); k < nChunks; ++k) {
         engine(k % E).end(jobs[(size_t)k]);

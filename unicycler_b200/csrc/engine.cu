@@ -1900,6 +1900,7 @@ struct Engine::Impl {
     KParams kp;
     size_t seqBytes = 0, outInts = 0, ringBytes = 0, offState = 0;
     double tBegin = 0.0, tUploaded = 0.0;
+    bool staged = false;   // stage() uploaded something that start() has to launch
 
     void growDev(void*& p, size_t& cap, size_t need) {
         if (need <= cap) return;
@@ -2648,18 +2649,32 @@ void Engine::fetch(std::vector<Job*>& jobs) {
     if (getenv("UNICYCLER_B200_PROFILE")) fprintf(stderr, "[ub200 fetch] parse=%.2f ms\n", wallMs() - tParse0);
 }
 
-void Engine::begin(std::vector<Job*>& jobs) {
+void Engine::stage(std::vector<Job*>& jobs) {
     impl_->mu.lock();
+    impl_->staged = !jobs.empty();
     try {
         if (jobs.empty()) return;
         impl_->tBegin = wallMs();
         upload(jobs);
         impl_->tUploaded = wallMs();
-        launch();
     } catch (...) {
         impl_->mu.unlock();
         throw;
     }
+}
+
+void Engine::start() {
+    try {
+        if (impl_->staged) launch();
+    } catch (...) {
+        impl_->mu.unlock();
+        throw;
+    }
+}
+
+void Engine::begin(std::vector<Job*>& jobs) {
+    stage(jobs);
+    start();
 }
 
 void Engine::end(std::vector<Job*>& jobs) {

@@ -119,6 +119,10 @@ public:
     // calls (same thread).
     void begin(std::vector<Job*>& jobs);
     void end(std::vector<Job*>& jobs);
+    // begin() in two steps: stage() locks, stages and uploads, start() launches.  A caller puts other device work
+    // (the k-mer join of the next chunk) between the two: once the persistent DP kernel is queued nothing else gets an SM.
+    void stage(std::vector<Job*>& jobs);
+    void start();
     EngineStats lastStats() const;
     int device() const;
     static int deviceCount();   // CUDA devices visible to the process (0 when there is none)
