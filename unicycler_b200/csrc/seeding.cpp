@@ -188,145 +188,115 @@ typedef std::unordered_set<Point, PointHash, std::equal_to<Point>, ArenaAlloc<Po
 typedef std::vector<Point> PointVector;
 
 // ------------------------------------------------------------------ kd-tree (nanoflann algorithm, int L1 metric)
+// Same tree, same leaf order and same search order as nanoflann's KDTreeSingleIndexAdaptor<L1_Adaptor<int,...>, ..., 2>
+// (include/nanoflann.hpp:1043-1256) built with leaf size 10 (semi_global_align.cpp:217): the ORDER in which a radius
+// search reports its matches is observable (doubles are summed in that order), so it is kept.  What is exploited:
+// with integer element / distance types the EPS of middleSplit is static_cast<int>(0.00001) == 0, so the test
+// "span > (1 - EPS) * max_span" never holds and EVERY split is on x (nanoflann.hpp:1113-1131).  The build therefore
+// only ever looks at x: it permutes one contiguous (x, index) array instead of chasing indices into the point array,
+// keeps x-intervals only, and the points are then copied in leaf order so that leaf scans are contiguous.
 class KdTree {
 public:
     explicit KdTree(const PointVector& pts) : pts_(pts), root_(-1) {}
 
     void build() {
         const size_t n = pts_.size();
-        vind_.resize(n);
-        for (size_t i = 0; i < n; ++i) vind_[i] = i;
         nodes_.clear();
         root_ = -1;
         if (n == 0) return;
-        for (int d = 0; d < 2; ++d) rootBox_[d].low = rootBox_[d].high = coord(0, d);
-        for (size_t k = 1; k < n; ++k)
-            for (int d = 0; d < 2; ++d) {
-                if (coord(k, d) < rootBox_[d].low) rootBox_[d].low = coord(k, d);
-                if (coord(k, d) > rootBox_[d].high) rootBox_[d].high = coord(k, d);
-            }
-        Interval box[2] = {rootBox_[0], rootBox_[1]};
+        ent_.resize(n);
+        for (int d = 0; d < 2; ++d) rootBox_[d].low = rootBox_[d].high = (d == 0 ? pts_[0].x : pts_[0].y);
+        for (size_t i = 0; i < n; ++i) {   // computeBoundingBox (the boxes merged back up the tree are the same extremes)
+            ent_[i] = Ent{pts_[i].x, (uint32_t)i};
+            rootBox_[0].low = std::min(rootBox_[0].low, pts_[i].x); rootBox_[0].high = std::max(rootBox_[0].high, pts_[i].x);
+            rootBox_[1].low = std::min(rootBox_[1].low, pts_[i].y); rootBox_[1].high = std::max(rootBox_[1].high, pts_[i].y);
+        }
+        nodes_.reserve(n / 4 + 8);
+        Interval box = rootBox_[0];
         root_ = divide(0, n, box);
-        rootBox_[0] = box[0];
-        rootBox_[1] = box[1];
+        leafPts_.resize(n);
+        for (size_t i = 0; i < n; ++i) leafPts_[i] = pts_[ent_[i].idx];
     }
 
-    // radiusSearch with SearchParams() defaults: eps = 0, sorted by distance (unstable std::sort)
-    void radiusSearch(const int q[2], int radius, std::vector<std::pair<size_t, int> >& out) const {
+    // radiusSearch with SearchParams() defaults: eps = 0, sorted by distance (unstable std::sort on the matches in
+    // search order: the permutation depends on the comparison results only); the matched points in that order
+    void radiusSearch(Point q, int radius, PointVector& out) const {
         out.clear();
         if (pts_.empty() || root_ < 0) return;
+        static thread_local std::vector<Match> matches;
+        matches.clear();
         int dists[2] = {0, 0};
         int distsq = 0;
+        const int qc[2] = {q.x, q.y};
         for (int d = 0; d < 2; ++d) {
-            if (q[d] < rootBox_[d].low) { dists[d] = std::abs(q[d] - rootBox_[d].low); distsq += dists[d]; }
-            if (q[d] > rootBox_[d].high) { dists[d] = std::abs(q[d] - rootBox_[d].high); distsq += dists[d]; }
+            if (qc[d] < rootBox_[d].low) { dists[d] = std::abs(qc[d] - rootBox_[d].low); distsq += dists[d]; }
+            if (qc[d] > rootBox_[d].high) { dists[d] = std::abs(qc[d] - rootBox_[d].high); distsq += dists[d]; }
         }
-        search(out, q, radius, root_, distsq, dists, 1.0f);
-        std::sort(out.begin(), out.end(),
-                  [](const std::pair<size_t, int>& a, const std::pair<size_t, int>& b) { return a.second < b.second; });
+        search(matches, q, radius, root_, distsq, dists[0]);
+        std::sort(matches.begin(), matches.end(), [](const Match& a, const Match& b) { return a.dist < b.dist; });
+        out.reserve(matches.size());
+        for (const Match& m : matches) out.push_back(m.p);
     }
 
 private:
     struct Interval { int low, high; };
+    struct Ent { int x; uint32_t idx; };
+    struct Match { int dist; Point p; };
     struct Node {
-        bool leaf;
-        size_t left, right;
-        int divfeat, divlow, divhigh;
-        int child1, child2;
+        int32_t left, right;      // leaf: range of leafPts_; inner: left = -1
+        int32_t divlow, divhigh;  // inner: largest x of the left subtree, smallest x of the right subtree
+        int32_t child1, child2;
     };
     const PointVector& pts_;
-    std::vector<size_t> vind_;
+    std::vector<Ent> ent_;
+    PointVector leafPts_;
     std::vector<Node> nodes_;
     int root_;
     Interval rootBox_[2];
     static const size_t kLeafMax = 10;  // KDTreeSingleIndexAdaptorParams(10), semi_global_align.cpp:217
 
-    int coord(size_t idx, int d) const { return d == 0 ? pts_[idx].x : pts_[idx].y; }
-
-    int divide(size_t left, size_t right, Interval box[2]) {
-        int id = (int)nodes_.size();
+    // divideTree (nanoflann.hpp:1043-1094) on x-intervals; box comes in as the parent's clipped interval and goes back
+    // as the exact interval of the subtree
+    int divide(size_t left, size_t right, Interval& box) {
+        const int id = (int)nodes_.size();
         nodes_.push_back(Node());
         if (right - left <= kLeafMax) {
-            Node nd;
-            nd.leaf = true; nd.left = left; nd.right = right; nd.child1 = nd.child2 = -1;
-            nd.divfeat = nd.divlow = nd.divhigh = 0;
-            for (int d = 0; d < 2; ++d) box[d].low = box[d].high = coord(vind_[left], d);
-            for (size_t k = left + 1; k < right; ++k)
-                for (int d = 0; d < 2; ++d) {
-                    if (box[d].low > coord(vind_[k], d)) box[d].low = coord(vind_[k], d);
-                    if (box[d].high < coord(vind_[k], d)) box[d].high = coord(vind_[k], d);
-                }
-            nodes_[(size_t)id] = nd;
-        } else {
-            size_t idx;
-            int cutfeat, cutval;
-            middleSplit(&vind_[0] + left, right - left, idx, cutfeat, cutval, box);
-            Interval lbox[2] = {box[0], box[1]};
-            lbox[cutfeat].high = cutval;
-            int c1 = divide(left, left + idx, lbox);
-            Interval rbox[2] = {box[0], box[1]};
-            rbox[cutfeat].low = cutval;
-            int c2 = divide(left + idx, right, rbox);
-            Node nd;
-            nd.leaf = false; nd.left = nd.right = 0;
-            nd.divfeat = cutfeat; nd.divlow = lbox[cutfeat].high; nd.divhigh = rbox[cutfeat].low;
-            nd.child1 = c1; nd.child2 = c2;
-            for (int d = 0; d < 2; ++d) {
-                box[d].low = std::min(lbox[d].low, rbox[d].low);
-                box[d].high = std::max(lbox[d].high, rbox[d].high);
-            }
-            nodes_[(size_t)id] = nd;
+            int mn = ent_[left].x, mx = mn;
+            for (size_t k = left + 1; k < right; ++k) { mn = std::min(mn, ent_[k].x); mx = std::max(mx, ent_[k].x); }
+            box.low = mn; box.high = mx;
+            nodes_[(size_t)id] = Node{(int32_t)left, (int32_t)right, 0, 0, -1, -1};
+            return id;
         }
-        return id;
-    }
-
-    void minMax(const size_t* ind, size_t count, int d, int& mn, int& mx) const {
-        mn = mx = coord(ind[0], d);
-        for (size_t i = 1; i < count; ++i) {
-            int v = coord(ind[i], d);
-            if (v < mn) mn = v;
-            if (v > mx) mx = v;
-        }
-    }
-
-    // With integer element/distance types the EPS of the original is static_cast<int>(0.00001) == 0, so the
-    // "span > (1-EPS)*max_span" test never holds and the cut dimension stays 0 (nanoflann.hpp:1113-1131).
-    void middleSplit(size_t* ind, size_t count, size_t& index, int& cutfeat, int& cutval, const Interval box[2]) {
-        const int EPS = static_cast<int>(0.00001);
-        int maxSpan = box[0].high - box[0].low;
-        for (int d = 1; d < 2; ++d) {
-            int span = box[d].high - box[d].low;
-            if (span > maxSpan) maxSpan = span;
-        }
-        int maxSpread = -1;
-        cutfeat = 0;
-        for (int d = 0; d < 2; ++d) {
-            int span = box[d].high - box[d].low;
-            if (span > (1 - EPS) * maxSpan) {
-                int mn, mx;
-                minMax(ind, count, d, mn, mx);
-                int spread = mx - mn;
-                if (spread > maxSpread) { cutfeat = d; maxSpread = spread; }
-            }
-        }
-        int splitVal = (box[cutfeat].low + box[cutfeat].high) / 2;
-        int mn, mx;
-        minMax(ind, count, cutfeat, mn, mx);
-        if (splitVal < mn) cutval = mn;
-        else if (splitVal > mx) cutval = mx;
-        else cutval = splitVal;
+        // middleSplit (nanoflann.hpp:1113-1160) with cutfeat == 0
+        Ent* ind = &ent_[left];
+        const size_t count = right - left;
+        const int splitVal = (box.low + box.high) / 2;
+        int mn = ind[0].x, mx = mn;
+        for (size_t i = 1; i < count; ++i) { mn = std::min(mn, ind[i].x); mx = std::max(mx, ind[i].x); }
+        const int cutval = splitVal < mn ? mn : (splitVal > mx ? mx : splitVal);
         size_t lim1, lim2;
-        planeSplit(ind, count, cutfeat, cutval, lim1, lim2);
+        planeSplit(ind, count, cutval, lim1, lim2);
+        size_t index;
         if (lim1 > count / 2) index = lim1;
         else if (lim2 < count / 2) index = lim2;
         else index = count / 2;
+        Interval lbox = box, rbox = box;
+        lbox.high = cutval;
+        const int c1 = divide(left, left + index, lbox);
+        rbox.low = cutval;
+        const int c2 = divide(left + index, right, rbox);
+        nodes_[(size_t)id] = Node{-1, 0, lbox.high, rbox.low, c1, c2};
+        box.low = std::min(lbox.low, rbox.low);
+        box.high = std::max(lbox.high, rbox.high);
+        return id;
     }
 
-    void planeSplit(size_t* ind, size_t count, int cutfeat, int cutval, size_t& lim1, size_t& lim2) {
+    // planeSplit (nanoflann.hpp:1170-1202): the same two exchange passes, on the (x, index) entries
+    static void planeSplit(Ent* ind, size_t count, int cutval, size_t& lim1, size_t& lim2) {
         size_t left = 0, right = count - 1;
         for (;;) {
-            while (left <= right && coord(ind[left], cutfeat) < cutval) ++left;
-            while (right && left <= right && coord(ind[right], cutfeat) >= cutval) --right;
+            while (left <= right && ind[left].x < cutval) ++left;
+            while (right && left <= right && ind[right].x >= cutval) --right;
             if (left > right || !right) break;
             std::swap(ind[left], ind[right]);
             ++left;
@@ -335,8 +305,8 @@ private:
         lim1 = left;
         right = count - 1;
         for (;;) {
-            while (left <= right && coord(ind[left], cutfeat) <= cutval) ++left;
-            while (right && left <= right && coord(ind[right], cutfeat) > cutval) --right;
+            while (left <= right && ind[left].x <= cutval) ++left;
+            while (right && left <= right && ind[right].x > cutval) --right;
             if (left > right || !right) break;
             std::swap(ind[left], ind[right]);
             ++left;
@@ -345,52 +315,65 @@ private:
         lim2 = left;
     }
 
-    void search(std::vector<std::pair<size_t, int> >& out, const int q[2], int radius, int nodeId, int mindistsq,
-                int dists[2], float epsError) const {
+    // searchLevel (nanoflann.hpp:1212-1256); every split is on x, so only the x entry of `dists` ever changes
+    void search(std::vector<Match>& out, Point q, int radius, int nodeId, int mindistsq, int distX) const {
         const Node& nd = nodes_[(size_t)nodeId];
-        if (nd.leaf) {
-            for (size_t i = nd.left; i < nd.right; ++i) {
-                size_t index = vind_[i];
-                int dist = std::abs(q[0] - pts_[index].x) + std::abs(q[1] - pts_[index].y);
-                if (dist < radius) out.push_back(std::make_pair(index, dist));
+        if (nd.left >= 0) {
+            for (int32_t i = nd.left; i < nd.right; ++i) {
+                const Point& p = leafPts_[(size_t)i];
+                const int dist = std::abs(q.x - p.x) + std::abs(q.y - p.y);
+                if (dist < radius) out.push_back(Match{dist, p});
             }
             return;
         }
-        int idx = nd.divfeat;
-        int val = q[idx];
-        int diff1 = val - nd.divlow, diff2 = val - nd.divhigh;
+        const int val = q.x;
+        const int diff1 = val - nd.divlow, diff2 = val - nd.divhigh;
         int best, other, cutDist;
         if (diff1 + diff2 < 0) { best = nd.child1; other = nd.child2; cutDist = std::abs(val - nd.divhigh); }
         else { best = nd.child2; other = nd.child1; cutDist = std::abs(val - nd.divlow); }
-        search(out, q, radius, best, mindistsq, dists, epsError);
-        int dst = dists[idx];
-        mindistsq = mindistsq + cutDist - dst;
-        dists[idx] = cutDist;
-        if (mindistsq * epsError <= radius) search(out, q, radius, other, mindistsq, dists, epsError);
-        dists[idx] = dst;
+        search(out, q, radius, best, mindistsq, distX);
+        mindistsq = mindistsq + cutDist - distX;
+        if (mindistsq <= radius) search(out, q, radius, other, mindistsq, cutDist);
     }
 };
 
 // ------------------------------------------------------------------ line tracing (semi_global_align.cpp:350-605,739-803)
 struct Cloud {
     PointVector pts;
+    std::vector<uint32_t> orig;   // index of every point in the range's common points (ascending)
     KdTree tree;
     Cloud() : tree(pts) {}
 };
 
 void fillCloud(Cloud& cloud, const PointVector& common, const PointSet& used) {
     cloud.pts.clear();
-    for (const Point& p : common)
-        if (used.find(p) == used.end()) cloud.pts.push_back(p);
+    cloud.orig.clear();
+    for (size_t i = 0; i < common.size(); ++i)
+        if (used.empty() || used.find(common[i]) == used.end()) { cloud.pts.push_back(common[i]); cloud.orig.push_back((uint32_t)i); }
     cloud.tree.build();
 }
 
+// The range's common points ordered by diagonal (x - y), then along the diagonal (x + y): sorted once per range, every
+// start cloud (a subset in the same relative order) filters it.
+struct DiagOrder {
+    std::vector<uint32_t> order;
+    std::vector<int32_t> pos;     // scratch: common index -> index in the current cloud, -1 = not in it
+    void build(const PointVector& common) {
+        struct Key { uint64_t key; uint32_t idx; };
+        std::vector<Key> keys(common.size());
+        for (size_t i = 0; i < common.size(); ++i) {
+            const uint32_t d = (uint32_t)(common[i].x - common[i].y + 0x40000000), sum = (uint32_t)(common[i].x + common[i].y);
+            keys[i] = Key{((uint64_t)d << 32) | sum, (uint32_t)i};
+        }
+        std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.key < b.key; });
+        order.resize(common.size());
+        for (size_t i = 0; i < common.size(); ++i) order[i] = keys[i].idx;
+    }
+};
+
 PointVector radiusSearchAroundPoint(Point point, int radius, const Cloud& cloud) {
     PointVector out;
-    std::vector<std::pair<size_t, int> > matches;
-    const int q[2] = {point.x, point.y};
-    cloud.tree.radiusSearch(q, radius, matches);
-    for (const auto& m : matches) out.push_back(cloud.pts[m.first]);
+    cloud.tree.radiusSearch(point, radius, out);
     return out;
 }
 
@@ -416,7 +399,8 @@ double distanceToLineSegment(Point p, Point l1, Point l2) {
     return sqrt(dx * dx + dy * dy);
 }
 
-double scoreLineSegment(Point p1, Point p2, const PointSet& pointsNearLine) {
+// pointsNearLine: the step's near-point set copied out once in its iteration order (the order of the sum)
+double scoreLineSegment(Point p1, Point p2, const PointVector& pointsNearLine) {
     double slope = getSlope(p1, p2);
     if (slope > 1.0) slope = 1.0 / slope;
     double slopeScore = (MAX_SLOPE_SCORE / (1.0 - MIN_ACCEPTABLE_LINE_SEGMENT_SLOPE)) * (slope - MIN_ACCEPTABLE_LINE_SEGMENT_SLOPE);
@@ -458,21 +442,23 @@ Point mutateLineToBestFitPoints(Point p1, Point p2, const Cloud& cloud, PointSet
     struct Sc { long long t; ~Sc() { g_lt[2] += nowNs() - t; } } scTimer{tm2};
     if (leftRectangle) return p2;
     Point p2Up = shiftUp(p2, TRACE_LINE_MUTATION_SIZE), p2Down = shiftDown(p2, TRACE_LINE_MUTATION_SIZE);
-    double unmutated = scoreLineSegment(p1, p2, pointsNearLine);
-    double up = scoreLineSegment(p1, p2Up, pointsNearLine);
-    double down = scoreLineSegment(p1, p2Down, pointsNearLine);
+    static thread_local PointVector flat;
+    flat.assign(pointsNearLine.begin(), pointsNearLine.end());
+    double unmutated = scoreLineSegment(p1, p2, flat);
+    double up = scoreLineSegment(p1, p2Up, flat);
+    double down = scoreLineSegment(p1, p2Down, flat);
     while (true) {
         if (unmutated >= up && unmutated >= down) break;
         else if (up > unmutated) {
             p2Down = p2; down = unmutated;
             p2 = p2Up; unmutated = up;
             p2Up = shiftUp(p2, TRACE_LINE_MUTATION_SIZE);
-            up = scoreLineSegment(p1, p2Up, pointsNearLine);
+            up = scoreLineSegment(p1, p2Up, flat);
         } else if (down > unmutated) {
             p2Up = p2; up = unmutated;
             p2 = p2Down; unmutated = down;
             p2Down = shiftDown(p2, TRACE_LINE_MUTATION_SIZE);
-            down = scoreLineSegment(p1, p2Down, pointsNearLine);
+            down = scoreLineSegment(p1, p2Down, flat);
         }
     }
     return p2;
@@ -497,7 +483,7 @@ static void densityScores(int radius, const Cloud& cloud, const std::vector<uint
                 n >= 2048 ? 256 : n, 7);
 }
 
-Point getHighestDensityPoint(int radius, const Cloud& cloud) {
+Point getHighestDensityPoint(int radius, const Cloud& cloud, const PointVector& common, DiagOrder& diag) {
     // The winner is the first point in cloud order whose score is strictly greater than all before it
     // (semi_global_align.cpp:577-589).  The score of a point sums ((1+a)/(k+1) - a) over its neighbours, k = distance
     // between the diagonals of the two points: only neighbours within 5 diagonals contribute a positive term, and the
@@ -518,9 +504,15 @@ Point getHighestDensityPoint(int radius, const Cloud& cloud) {
         for (int k = 0; k <= KMAX; ++k) term[k] = std::max(0.0, ((1.0 + a) / (k + 1.0)) - a);
         // (diagonal, anti-diagonal, point) sorted by diagonal, then along the diagonal
         struct DS { int d, s; uint32_t idx; };
-        std::vector<DS> ds(n);
-        for (size_t i = 0; i < n; ++i) ds[i] = DS{cloud.pts[i].x - cloud.pts[i].y, cloud.pts[i].x + cloud.pts[i].y, (uint32_t)i};
-        std::sort(ds.begin(), ds.end(), [](const DS& p, const DS& q) { return p.d != q.d ? p.d < q.d : p.s < q.s; });
+        std::vector<DS> ds;
+        ds.reserve(n);
+        if (diag.order.size() != common.size()) diag.build(common);
+        diag.pos.assign(common.size(), -1);
+        for (size_t i = 0; i < n; ++i) diag.pos[cloud.orig[i]] = (int32_t)i;
+        for (uint32_t o : diag.order) {
+            const int32_t i = diag.pos[o];
+            if (i >= 0) ds.push_back(DS{common[o].x - common[o].y, common[o].x + common[o].y, (uint32_t)i});
+        }
         struct Grp { int d; uint32_t b, e; };
         std::vector<Grp> grp;
         for (size_t i = 0; i < n;) {
@@ -609,7 +601,7 @@ double scorePointSet(const PointSet& pointSet, const PointVector& traceDots, boo
     return pointCount * worstSlopeScore * varianceScore;
 }
 
-PointSet lineTracing(const PointVector& common, PointSet& usedPoints, const Cloud& cloud, int readLen, int refLen,
+PointSet lineTracing(const PointVector& common, PointSet& usedPoints, const Cloud& cloud, DiagOrder& diag, int readLen, int refLen,
                      int lineNum, int verbosity, std::string& console, bool& failedLine, double& pointSetScore) {
     // The start cloud holds the points no earlier line used: for the first line that is the range's cloud itself
     // (same points in the same order, hence the same tree), so it is only rebuilt from the second line on.
@@ -618,7 +610,7 @@ PointSet lineTracing(const PointVector& common, PointSet& usedPoints, const Clou
     if (!usedPoints.empty()) fillCloud(rebuilt, common, usedPoints);
     const Cloud& startCloud = usedPoints.empty() ? cloud : rebuilt;
     const long long tB = nowNs();
-    Point startPoint = getHighestDensityPoint(LINE_TRACING_START_POINT_SEARCH_RADIUS, startCloud);
+    Point startPoint = getHighestDensityPoint(LINE_TRACING_START_POINT_SEARCH_RADIUS, startCloud, common, diag);
     g_seedProf[3] += tB - tA;
     g_seedProf[4] += nowNs() - tB;
     Point p = startPoint;
@@ -937,11 +929,12 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
     g_lt[7] += nowNs() - t1;
     g_lastSearch.cloud = nullptr;   // (a new cloud may live at the old one's address)
     std::vector<PointSet> goodPointSets;
+    DiagOrder diag;
     double bestPointScore = 0.0;
     for (int lineNum = 0; lineNum < sp.maxLineTraceCount; ++lineNum) {
         bool failedLine = false;
         double pointSetScore = 0.0;
-        PointSet pointSet = lineTracing(common, usedPoints, cloud, readLen, refLen, lineNum, verbosity, out.console,
+        PointSet pointSet = lineTracing(common, usedPoints, cloud, diag, readLen, refLen, lineNum, verbosity, out.console,
                                         failedLine, pointSetScore);
         if (pointSetScore > bestPointScore) bestPointScore = pointSetScore;
         if (!failedLine) goodPointSets.push_back(pointSet);
