@@ -550,10 +550,16 @@ def main():
     seqs = [r[1] for _, r in my_reads]
     hits = [r[2] for _, r in my_reads]
 
+    batch_ms, gather_ms = [], []
+
     def e2e_step():
+        t_a = time.perf_counter()
         out = ub.semi_global_alignment_batch(names, seqs, hits, h, SCHEME, 0)
+        t_b = time.perf_counter()
         if dist is not None:
             out = sharding.gather_strings(out, dist, device)
+        batch_ms.append((t_b - t_a) * 1e3)
+        gather_ms.append((time.perf_counter() - t_b) * 1e3)
         return out
 
     for _ in range(max(1, args.warmup)):
@@ -606,6 +612,9 @@ def main():
             device_kmer_join=ub.last_join_stats(),
             e2e=dict(value=e2e_gcups, unit='GCUPS', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_s * 1e3,
                      ms_per_step_median_rank0=sorted(e2e_steps_ms)[len(e2e_steps_ms) // 2],
+                     batch_call_ms_median_rank0=sorted(batch_ms[-args.steps:])[args.steps // 2],
+                     gather_ms_median_rank0=sorted(gather_ms[-args.steps:])[args.steps // 2],
+                     host_threads_per_rank=max(1, (os.cpu_count() or 1) // max(1, world)),
                      reads_per_s=len(all_reads) / e2e_s,
                      path='ub200_semiGlobalAlignmentBatch (host strings in, result strings out)' +
                           (' + exact-size result gather on rank 0' if world > 1 else '')),

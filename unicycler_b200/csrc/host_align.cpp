@@ -404,29 +404,39 @@ void scoreAlignment(const std::vector<Seg>& trace, bool traceEmpty, const uint8_
     long readBases = 0, refBases = 0, startPos = startImmediately ? 0 : -1, col = 0;
     if (startImmediately) { rec.readStart = 0; rec.refStart = 0; }
     bool first = true;
+    // Every column of one trace segment has the same kind (the "started" state can only change at a segment's first
+    // column), so the walk is per segment; a diagonal segment only needs its number of equal bases.
     for (size_t k = trace.size(); k > 0; --k) {
         const Seg& s = trace[k - 1];
-        for (long t = 0; t < s.len; ++t, ++col) {
-            const bool hasRead = (s.dir != T_V), hasRef = (s.dir != T_H);
-            if (hasRead) readStarted = true;
-            if (hasRef) refStarted = true;
-            if (readStarted && refStarted && !started) {
-                rec.readStart = (int)readBases; rec.refStart = (int)refBases; started = true; startPos = col;
-            }
-            int type;
-            int colScore = 0;
-            if (!hasRead) type = started ? DELETION : NOTHING;
-            else if (!hasRef) type = started ? INSERTION : CLIP;
-            else { type = MATCH; colScore = (H[h] == V[v]) ? sc.match : sc.mismatch; }
-            if (first) { cur = type; first = false; }
-            if (type == cur) { ++curLen; curScore += colScore; }
-            else {
-                types.push_back(cur); lens.push_back(curLen); runScore.push_back(curScore);
-                cur = type; curLen = 1; curScore = colScore;
-            }
-            if (hasRead) { ++readBases; ++h; }
-            if (hasRef) { ++refBases; ++v; }
+        const long L = s.len;
+        if (L <= 0) continue;
+        const bool hasRead = (s.dir != T_V), hasRef = (s.dir != T_H);
+        if (hasRead) readStarted = true;
+        if (hasRef) refStarted = true;
+        if (readStarted && refStarted && !started) {
+            rec.readStart = (int)readBases; rec.refStart = (int)refBases; started = true; startPos = col;
         }
+        int type;
+        int segScore = 0;
+        if (!hasRead) type = started ? DELETION : NOTHING;
+        else if (!hasRef) type = started ? INSERTION : CLIP;
+        else {
+            type = MATCH;
+            long equal = 0;
+            const uint8_t* a = H + h;
+            const uint8_t* b = V + v;
+            for (long t = 0; t < L; ++t) equal += (a[t] == b[t]);
+            segScore = (int)(equal * sc.match + (L - equal) * sc.mismatch);
+        }
+        if (first) { cur = type; first = false; }
+        if (type == cur) { curLen += L; curScore += segScore; }
+        else {
+            types.push_back(cur); lens.push_back(curLen); runScore.push_back(curScore);
+            cur = type; curLen = L; curScore = segScore;
+        }
+        if (hasRead) { readBases += L; h += L; }
+        if (hasRef) { refBases += L; v += L; }
+        col += L;
     }
     long endPos = total;
     rec.readEnd = (int)readBases;
@@ -434,13 +444,22 @@ void scoreAlignment(const std::vector<Seg>& trace, bool traceEmpty, const uint8_
     if (cur == INSERTION && !goToEndSeq1) { cur = CLIP; rec.readEnd -= (int)curLen; endPos -= curLen; }
     else if (cur == DELETION && !goToEndSeq2) { cur = NOTHING; rec.refEnd -= (int)curLen; endPos -= curLen; }
     types.push_back(cur); lens.push_back(curLen); runScore.push_back(curScore);
+    // (a 12 kb read at 15 % errors has ~3 600 runs: digits are written in place, no temporary strings)
+    rec.cigar.reserve(types.size() * 3 + 16);
+    auto run = [&](long len, char op) {
+        char buf[24];
+        int nd = 0;
+        do { buf[nd++] = (char)('0' + len % 10); len /= 10; } while (len > 0);
+        while (nd > 0) rec.cigar.push_back(buf[--nd]);
+        rec.cigar.push_back(op);
+    };
     for (size_t i = 0; i < types.size(); ++i) {
         const long len = lens[i];
         switch (types[i]) {
-        case DELETION: rec.cigar += std::to_string(len) + "D"; rec.rawScore += sc.gapOpen + (int)(len - 1) * sc.gapExtend; break;
-        case INSERTION: rec.cigar += std::to_string(len) + "I"; rec.rawScore += sc.gapOpen + (int)(len - 1) * sc.gapExtend; break;
-        case CLIP: rec.cigar += std::to_string(len) + "S"; break;
-        case MATCH: rec.cigar += std::to_string(len) + "M"; rec.rawScore += runScore[i]; break;
+        case DELETION: run(len, 'D'); rec.rawScore += sc.gapOpen + (int)(len - 1) * sc.gapExtend; break;
+        case INSERTION: run(len, 'I'); rec.rawScore += sc.gapOpen + (int)(len - 1) * sc.gapExtend; break;
+        case CLIP: run(len, 'S'); break;
+        case MATCH: run(len, 'M'); rec.rawScore += runScore[i]; break;
         default: break;
         }
     }
@@ -455,9 +474,14 @@ void scoreAlignment(const std::vector<Seg>& trace, bool traceEmpty, const uint8_
 std::string fullString(const AlignmentRecord& rec, const std::string& readName, const std::string& refName,
                        long long milliseconds) {
     const char* strand = (!readName.empty() && readName.back() == '-') ? "-" : "+";
-    return refName + "," + strand + "," + std::to_string(rec.readStart) + "," + std::to_string(rec.readEnd) + "," +
-           std::to_string(rec.refStart) + "," + std::to_string(rec.refEnd) + "," + std::to_string(rec.rawScore) + "," +
-           std::to_string(rec.scaledScore) + "," + std::to_string((int)milliseconds) + "," + rec.cigar;
+    std::string out;
+    out.reserve(refName.size() + rec.cigar.size() + 96);
+    out += refName; out += ','; out += strand; out += ',';
+    out += std::to_string(rec.readStart); out += ','; out += std::to_string(rec.readEnd); out += ',';
+    out += std::to_string(rec.refStart); out += ','; out += std::to_string(rec.refEnd); out += ',';
+    out += std::to_string(rec.rawScore); out += ','; out += std::to_string(rec.scaledScore); out += ',';
+    out += std::to_string((int)milliseconds); out += ','; out += rec.cigar;
+    return out;
 }
 
 }  // namespace ub200

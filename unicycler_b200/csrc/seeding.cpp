@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <thread>
 
@@ -27,6 +28,15 @@ std::atomic<long long> g_seedProf[6];
 // ... and of the line tracer's parts: 0 radius searches, 1 near-point set, 2 segment scoring, 3 collection, 4 whole trace loop,
 // 5 point-set score, 6 used-point bookkeeping, 7 the range's kd-tree
 std::atomic<long long> g_lt[10];
+// UNICYCLER_B200_MARGINS=1: per range, the smallest relative distance between the two sides of every floating-point
+// comparison that decides a result (0 density winner vs runner-up, 1 segment mutation, 2 good/bad line, 3 best line) —
+// the evidence behind DESIGN.md 4b (which decisions would survive another summation order).
+static const bool g_margins = getenv("UNICYCLER_B200_MARGINS") != nullptr;
+static thread_local double t_minMargin[4] = {1e300, 1e300, 1e300, 1e300};
+static inline void noteMargin(int k, double a, double b) {
+    const double m = std::fabs(a - b) / (std::fabs(a) + std::fabs(b) + 1e-300);
+    if (m < t_minMargin[k]) t_minMargin[k] = m;
+}
 static inline long long nowNs() {
     return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -448,6 +458,7 @@ Point mutateLineToBestFitPoints(Point p1, Point p2, const Cloud& cloud, PointSet
     double up = scoreLineSegment(p1, p2Up, flat);
     double down = scoreLineSegment(p1, p2Down, flat);
     while (true) {
+        if (g_margins) { noteMargin(1, unmutated, up); if (unmutated >= up) noteMargin(1, unmutated, down); }
         if (unmutated >= up && unmutated >= down) break;
         else if (up > unmutated) {
             p2Down = p2; down = unmutated;
@@ -558,6 +569,15 @@ Point getHighestDensityPoint(int radius, const Cloud& cloud, const PointVector& 
     double bestScore = 0.0;
     for (size_t i = 0; i < n; ++i)
         if (score[i] > bestScore) { bestScore = score[i]; best = cloud.pts[i]; }
+    if (g_margins) {
+        double second = 0.0;
+        bool seen = false;
+        for (size_t i = 0; i < n; ++i) {
+            if (score[i] == bestScore && !seen) { seen = true; continue; }
+            if (score[i] > second) second = score[i];
+        }
+        noteMargin(0, bestScore, second);
+    }
     return best;
 }
 
@@ -598,6 +618,7 @@ double scorePointSet(const PointSet& pointSet, const PointVector& traceDots, boo
     double varianceScore = variance(xPlusY) / uniformVariance;
     if (varianceScore > 1.0) varianceScore = 1.0 / varianceScore;
     failedLine = (worstSlopeScore * varianceScore) < 0.8;
+    if (g_margins) noteMargin(2, worstSlopeScore * varianceScore, 0.8);
     return pointCount * worstSlopeScore * varianceScore;
 }
 
@@ -936,6 +957,7 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
         double pointSetScore = 0.0;
         PointSet pointSet = lineTracing(common, usedPoints, cloud, diag, readLen, refLen, lineNum, verbosity, out.console,
                                         failedLine, pointSetScore);
+        if (g_margins && lineNum > 0) noteMargin(3, pointSetScore, bestPointScore);
         if (pointSetScore > bestPointScore) bestPointScore = pointSetScore;
         if (!failedLine) goodPointSets.push_back(pointSet);
         else if (pointSetScore == bestPointScore) goodPointSets.push_back(pointSet);
@@ -944,6 +966,11 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
     }
     const long long t2 = nowNs();
     g_seedProf[1] += t2 - t1;
+    if (g_margins) {
+        fprintf(stderr, "[ub200 margins] points=%zu density %.3e mutation %.3e good/bad %.3e best-line %.3e\n", common.size(),
+                t_minMargin[0], t_minMargin[1], t_minMargin[2], t_minMargin[3]);
+        for (int q = 0; q < 4; ++q) t_minMargin[q] = 1e300;
+    }
     struct Fin { long long t; ~Fin() { g_seedProf[2] += nowNs() - t; } } fin{t2};
     for (const PointSet& good : goodPointSets) {
         PointVector pts;
