@@ -974,7 +974,8 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
             for (const std::string& part : parts[(size_t)i]) ret += part;
             ret += works[(size_t)i]->console;
             results[i] = dupString(ret);
-        }, 4);
+            works[(size_t)i].reset();   // (thousands of small trace vectors per read: released here, in parallel, not by the caller's thread at return)
+        });
     };
 
     if (getenv("UNICYCLER_B200_HOST_ONLY")) {  // developer aid: time the host stage without a GPU
