@@ -462,6 +462,8 @@ void seedUnit(ReadWork& w, RangeUnit& u, int verbosity, SeqMap* refSeqs, const S
     seedRange(readSeq, kmers, trimmed, w.sp, verbosity, u.refName, u.refStart, u.refEnd, rs,
               joined ? (const int32_t*)joined->data() : nullptr, joined ? joined->size() : 0);
     u.console = rs.console;
+    const long long tb0 = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    struct TB { long long t; ~TB() { g_seedProf[5] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() - t; } } tbTimer{tb0};
     for (const auto& chain : rs.chains) {
         std::unique_ptr<ChainJob> cj(new ChainJob());
         cj->readName = w.readName + u.strand;
@@ -983,8 +985,8 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
         ChunkSeeds cs;
         joinChunk(0, n, cs);
         traceChunk(0, n, cs, jobs);
-        fprintf(stderr, "[ub200 host] reads=%d jobs=%zu prepare=%.1f ms (kmers %.1f, linetrace %.1f [fillCloud %.1f, densest point %.1f], seeds+chain %.1f thread-ms)\n", n,
-                jobs.size(), (nowSec() - t0) * 1e3, g_seedProf[0] / 1e6, g_seedProf[1] / 1e6, g_seedProf[3] / 1e6, g_seedProf[4] / 1e6, g_seedProf[2] / 1e6);
+        fprintf(stderr, "[ub200 host] reads=%d jobs=%zu prepare=%.1f ms (kmers %.1f, linetrace %.1f [fillCloud %.1f, densest point %.1f], seeds+chain %.1f, job build + plan %.1f thread-ms)\n", n,
+                jobs.size(), (nowSec() - t0) * 1e3, g_seedProf[0] / 1e6, g_seedProf[1] / 1e6, g_seedProf[3] / 1e6, g_seedProf[4] / 1e6, g_seedProf[2] / 1e6, g_seedProf[5] / 1e6);
         for (int q = 0; q < 6; ++q) g_seedProf[q] = 0;
         fprintf(stderr, "[ub200 host] line tracer thread-ms: range tree %.1f, trace loop %.1f [searches %.1f, near set %.1f, scoring %.1f, collection %.1f], set score %.1f, used points %.1f\n",
                 g_lt[7] / 1e6, g_lt[4] / 1e6, g_lt[0] / 1e6, g_lt[1] / 1e6, g_lt[2] / 1e6, g_lt[3] / 1e6, g_lt[5] / 1e6, g_lt[6] / 1e6);
