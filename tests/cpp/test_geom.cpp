@@ -67,6 +67,29 @@ int main(int argc, char** argv) {
             if (bad <= 5) fprintf(stderr, "MISMATCH nH=%d nV=%d lo=%d up=%d (cell %zu of %zu)\n", nH, nV, lo, up, k, g_cells.size());
         }
     }
-    printf("problems %ld cells %ld bad %ld\n", problems, checkedCells, bad);
+    // bandLastColumn / bandColumnsFrom (the number of column descriptors a grid needs, planned without walking)
+    // against the walker itself, exhaustively over small geometries
+    long geoms = 0;
+    for (int nH = 1; nH <= 36; ++nH)
+        for (int nV = 1; nV <= 36; ++nV)
+            for (int lo = -40; lo < 0; ++lo)
+                for (int up = 1; up <= 40; ++up) {
+                    if (lo <= -nV && up >= nH) continue;   // planned as an unbanded grid
+                    const ub200::GridGeom g = ub200::makeGeom(nH, nV, 1, lo, up);
+                    ub200::BandWalker w; w.init(g);
+                    ub200::ColInfo ci;
+                    int prev = -1;
+                    bool consecutive = true;
+                    while (w.next(ci)) { if (ci.j != prev + 1) consecutive = false; prev = ci.j; }
+                    ++geoms;
+                    bool ok = consecutive && prev == ub200::bandLastColumn(g);
+                    for (int hNext = 0; hNext <= nH && ok; ++hNext)
+                        ok = ub200::bandColumnsFrom(g, hNext) == (prev >= hNext ? prev - hNext + 1 : 0);
+                    if (!ok) {
+                        ++bad;
+                        if (bad <= 5) fprintf(stderr, "COLUMN COUNT nH=%d nV=%d lo=%d up=%d: walker ends at %d, closed form %d\n", nH, nV, lo, up, prev, ub200::bandLastColumn(g));
+                    }
+                }
+    printf("problems %ld cells %ld column-count geometries %ld bad %ld\n", problems, checkedCells, geoms, bad);
     return bad ? 1 : 0;
 }

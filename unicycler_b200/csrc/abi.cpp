@@ -335,7 +335,7 @@ void buildChainJob(ChainJob& cj, const char* readSeq, size_t readLen, const char
     j.match = sc.match; j.mismatch = sc.mismatch; j.gapOpen = sc.gapOpen; j.gapExtend = sc.gapExtend;
     j.freeFirstRow = j.freeFirstCol = j.freeLastRow = j.freeLastCol = 1;  // AlignConfig<true,true,true,true>
     j.complete = 1;  // CompleteTrace (seeds/banded_chain_alignment_profile.h:200-204)
-    cj.planned = planChain(chain, (long)cj.H.size(), (long)cj.V.size(), bandSize, j.grids, &j.colTab);
+    cj.planned = planChain(chain, (long)cj.H.size(), (long)cj.V.size(), bandSize, j.grids, &j.colTabCount);
 }
 
 // returns false when the reference produces no alignment (exception swallowed at semi_global_align.cpp:311)

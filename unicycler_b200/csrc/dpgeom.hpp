@@ -182,6 +182,15 @@ struct BandWalker {
     }
 };
 
+// The walker yields the columns 0 .. bandLastColumn(g), one after the other (checked against the walker for every
+// geometry up to 45 x 45 with bands up to +-50, tests/cpp/test_geom.cpp): the number of column descriptors a grid
+// needs right of the next grid's origin is known without walking.
+UB_HD int32_t bandLastColumn(const GridGeom& g) {
+    const int32_t hEndBottom = imax(0, imin(g.nH, g.up + g.nV) - 1);
+    return (g.nH == 1 || hEndBottom == 0) ? 0 : hEndBottom + 1;
+}
+UB_HD int32_t bandColumnsFrom(const GridGeom& g, int32_t hNext) { return imax(0, bandLastColumn(g) - imax(0, hNext) + 1); }
+
 // seeds/banded_chain_alignment_impl.h:282-377 (_determineTrackingOptions), literal.
 // chainFinal: BandedChainFinalDPMatrix; feLastRow/feLastCol: free end gaps.
 struct TrackOpts {

@@ -1758,6 +1758,23 @@ __device__ __noinline__ void runSegment(int jobIdx, int seg, int board, GridCtx&
 }
 
 
+// Column descriptors of the banded chain grids (the tracking pass reads them: forEachFlaggedCell).  One thread per grid
+// walks the grid's columns with the BandWalker the host used to run and keeps the columns right of the next grid's
+// origin: nothing of this is planned on the host or copied any more (it was 70 % of a batch's upload bytes).
+__global__ void __launch_bounds__(128) colTabKernel(const GridDesc* grids, const long long* colBase, int nGrids, ColInfo* pool) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nGrids) return;
+    const long long base = colBase[q];
+    if (base < 0) return;
+    const GridDesc gd = grids[q];
+    BandWalker w;
+    w.init(makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up));
+    ColInfo ci;
+    int n = 0;
+    while (w.next(ci))
+        if (ci.j >= gd.hNext && n < gd.nColTab) pool[base + n++] = ci;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) dpAgentKernel() {
     const KParams& P = cP;
     uint8_t* const smem = gSmem;
@@ -1892,7 +1909,8 @@ struct Engine::Impl {
     void* hSeq = nullptr; size_t capHSeq = 0;
     void* hOut = nullptr; size_t capHOut = 0;
     void* hGrids = nullptr; size_t capHGrids = 0; size_t nGrids = 0;      // GridDesc of every job, back to back
-    void* hColTab = nullptr; size_t capHColTab = 0; size_t nColTab = 0;   // host-planned column tables
+    void* hColTab = nullptr; size_t capHColTab = 0; size_t nColTab = 0;   // per grid: first column descriptor in the device pool (-1: none)
+    void* dColBase = nullptr; size_t capColBase = 0;
     // last plan
     std::vector<JobDev> jobsDev;
     std::vector<int> order;
@@ -1979,7 +1997,7 @@ Engine::~Engine() {
     if (!impl_) return;
     cudaSetDevice(impl_->device);
     cudaFree(impl_->dJobs); cudaFree(impl_->dGrids); cudaFree(impl_->dSeq); cudaFree(impl_->dOut); cudaFree(impl_->dOut2); cudaFree(impl_->dRecIdx);
-    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dScratch); cudaFree(impl_->dRing); cudaFree(impl_->dRecs); cudaFree(impl_->dMini); cudaFree(impl_->dPersist); cudaFree(impl_->dTileSlots);
+    cudaFree(impl_->dJobOut); cudaFree(impl_->dOrder); cudaFree(impl_->dColTab); cudaFree(impl_->dColBase); cudaFree(impl_->dScratch); cudaFree(impl_->dRing); cudaFree(impl_->dRecs); cudaFree(impl_->dMini); cudaFree(impl_->dPersist); cudaFree(impl_->dTileSlots);
     cudaFreeHost(impl_->hSeq); cudaFreeHost(impl_->hOut); cudaFreeHost(impl_->hGrids); cudaFreeHost(impl_->hColTab);
     for (auto& ev : impl_->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(impl_->stream);
@@ -2025,16 +2043,16 @@ void Engine::upload(std::vector<Job*>& jobs) {
         d.gridCount = (int)j.grids.size();
         nGridsAll += j.grids.size();
         d.colTabBase = (long long)nColTabAll;
-        nColTabAll += j.colTab.size();
+        nColTabAll += (size_t)j.colTabCount;
     }
     I.growHost(I.hSeq, I.capHSeq, off + 64);
     I.growHost(I.hGrids, I.capHGrids, (nGridsAll + 1) * sizeof(GridDesc));
-    I.growHost(I.hColTab, I.capHColTab, (nColTabAll + 1) * sizeof(ColInfo));
+    I.growHost(I.hColTab, I.capHColTab, (nGridsAll + 1) * sizeof(long long));
     I.nGrids = nGridsAll;
     I.nColTab = nColTabAll;
     uint8_t* hs = (uint8_t*)I.hSeq;
     GridDesc* hGrids = (GridDesc*)I.hGrids;
-    ColInfo* hColTab = (ColInfo*)I.hColTab;
+    long long* hColBase = (long long*)I.hColTab;
     ScratchLayout L;
     memset(&L, 0, sizeof(L));
     // per-job aggregates, filled by the host cores in parallel and reduced below
@@ -2056,13 +2074,13 @@ void Engine::upload(std::vector<Job*>& jobs) {
         d.match = j.match; d.mismatch = j.mismatch; d.gapOpen = j.gapOpen; d.gapExtend = j.gapExtend;
         d.fe = (j.freeFirstRow ? 1 : 0) | (j.freeFirstCol ? 2 : 0) | (j.freeLastRow ? 4 : 0) | (j.freeLastCol ? 8 : 0);
         d.complete = j.complete;
-        if (!j.colTab.empty()) memcpy(hColTab + d.colTabBase, j.colTab.data(), j.colTab.size() * sizeof(ColInfo));
         j.cells = 0;
         GridDesc* out = hGrids + d.gridBegin;
         for (size_t q = 0; q < j.grids.size(); ++q) {
             const GridDesc& gd = j.grids[q];
             GridDesc& gg = out[q];
             gg = gd;
+            hColBase[(size_t)d.gridBegin + q] = (gd.banded && gd.kind != GRID_GLOBAL && gd.nColTab > 0) ? d.colTabBase + gd.colTabOff : -1;
             const GridGeom g = makeGeom(gd.nH, gd.nV, gd.banded, gd.lo, gd.up);
             const bool local = localPlan(g).local != 0;
             if (!local) {
@@ -2128,7 +2146,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     for (size_t k = 0; k < nJobs; ++k) {
         const JobAgg& a = agg[k];
         JobDev& d = I.jobsDev[k];
-        if (a.missingColTab) throw std::runtime_error("unicycler_b200: banded chain grid without host-planned column table");
+        if (a.missingColTab) throw std::runtime_error("unicycler_b200: banded chain grid without planned column descriptors");
         if (a.persist > 0 && persistTotal > 0) {
             GridDesc* out = hGrids + d.gridBegin;
             for (int q = 0; q < d.gridCount; ++q)
@@ -2366,6 +2384,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.growDev(I.dJobOut, I.capJobOut, nJobs * sizeof(JobOut));
     I.growDev(I.dOrder, I.capOrder, nEntries * sizeof(int));
     I.growDev(I.dColTab, I.capColTab, I.nColTab * sizeof(ColInfo) + 64);
+    I.growDev(I.dColBase, I.capColBase, (I.nGrids + 1) * sizeof(long long));
     I.growDev(I.dScratch, I.capScratch, (size_t)L.total * nSlots);
     I.growDev(I.dRing, I.capRing, I.ringBytes);
     I.growDev(I.dRecs, I.capRecs, (nRecs + 1) * sizeof(GridRec));
@@ -2382,8 +2401,13 @@ void Engine::upload(std::vector<Job*>& jobs) {
     CUDA_CHECK(cudaMemcpyAsync(I.dGrids, I.hGrids, I.nGrids * sizeof(GridDesc), cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaMemcpyAsync(I.dOrder, I.order.data(), nEntries * sizeof(int), cudaMemcpyHostToDevice, I.stream));
     if (I.nColTab > 0)
-        CUDA_CHECK(cudaMemcpyAsync(I.dColTab, I.hColTab, I.nColTab * sizeof(ColInfo), cudaMemcpyHostToDevice, I.stream));
+        CUDA_CHECK(cudaMemcpyAsync(I.dColBase, I.hColTab, I.nGrids * sizeof(long long), cudaMemcpyHostToDevice, I.stream));
     CUDA_CHECK(cudaEventRecord(I.ev[1], I.stream));
+    if (I.nColTab > 0) {
+        colTabKernel<<<(unsigned)((I.nGrids + 127) / 128), 128, 0, I.stream>>>((const GridDesc*)I.dGrids, (const long long*)I.dColBase,
+                                                                             (int)I.nGrids, (ColInfo*)I.dColTab);
+        CUDA_CHECK(cudaGetLastError());
+    }
     KParams& kp = I.kp;
     kp.jobs = (const JobDev*)I.dJobs; kp.grids = (const GridDesc*)I.dGrids; kp.seq = (const uint8_t*)I.dSeq;
     kp.out = (int*)I.dOut; kp.out2 = (int*)I.dOut2; kp.recIdx = (int4*)I.dRecIdx; kp.jobOut = (JobOut*)I.dJobOut; kp.order = (const int*)I.dOrder;
@@ -2414,7 +2438,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     I.stats = EngineStats();
     I.stats.cells = totalCells;
     I.stats.h2dBytes = (int64_t)(I.seqBytes + nJobs * sizeof(JobDev) + I.nGrids * sizeof(GridDesc) + nJobs * sizeof(int) +
-                                 I.nColTab * sizeof(ColInfo));
+                                 (I.nColTab > 0 ? I.nGrids * sizeof(long long) : 0));
     I.stats.ctas = I.numSMs;
     I.stats.traceBytes = ckBytes;
     if (getenv("UNICYCLER_B200_PROFILE")) {

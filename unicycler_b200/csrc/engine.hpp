@@ -85,7 +85,7 @@ struct Job {
     int32_t freeFirstRow = 0, freeFirstCol = 0, freeLastRow = 0, freeLastCol = 0;
     int32_t complete = 0;        // CompleteTrace (chain) vs SingleTrace (global/path)
     std::vector<GridDesc> grids;
-    std::vector<ColInfo> colTab;  // pool referenced by GridDesc::colTabOff (relative to this job)
+    long long colTabCount = 0;    // column descriptors of the job's banded chain grids (GridDesc::colTabOff is relative to the job; generated on the device)
     int32_t outScale = 1;         // multiplier of the segment-stream capacity (raised when a run overflowed)
     JobResult result;
     // DP cells as the reference counts them (dimH*dimV per sub-DP)

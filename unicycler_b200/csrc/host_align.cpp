@@ -39,10 +39,10 @@ struct Planner {
     long zerosH = 0, zerosV = 0;    // pending _initiaizeBeginningOfBandedChain sizes
     bool ok = true;
     std::vector<GridDesc>& out;
-    std::vector<ColInfo>* colTab;
+    long long* colTabCount;   // running number of column descriptors of the job (the device generates them)
 
-    Planner(long h, long v, long band, std::vector<GridDesc>& o, std::vector<ColInfo>* ct)
-        : lenH(h), lenV(v), b(band), out(o), colTab(ct) {}
+    Planner(long h, long v, long band, std::vector<GridDesc>& o, long long* ct)
+        : lenH(h), lenV(v), b(band), out(o), colTabCount(ct) {}
 
     static long hShiftBegin(const ChainSeed& s) { return s.upperDiag - (s.beginH - s.beginV); }
     static long vShiftBegin(const ChainSeed& s) { return (s.beginH - s.beginV) - s.lowerDiag; }
@@ -79,16 +79,13 @@ struct Planner {
         }
         if (kind == GRID_CHAIN_FINAL && !g.banded && (hNext != 0 || vNext != 0)) ok = false;
         g.colTabOff = 0; g.nColTab = 0; g.persistOff = -1; g.ckTiles = 0; g.pad = 0;
-        if (colTab && ok && g.banded && kind != GRID_GLOBAL) {
-            // literal column walk of _computeBandedAlignment; the tracking pass needs the columns right of
-            // the next grid's origin (seeds/banded_chain_alignment_impl.h:282-377)
-            g.colTabOff = (int32_t)colTab->size();
-            BandWalker w;
-            w.init(makeGeom(g.nH, g.nV, g.banded, g.lo, g.up));
-            ColInfo ci;
-            while (w.next(ci))
-                if (ci.j >= g.hNext) colTab->push_back(ci);
-            g.nColTab = (int32_t)colTab->size() - g.colTabOff;
+        if (colTabCount && ok && g.banded && kind != GRID_GLOBAL) {
+            // the tracking pass needs the column descriptors of _computeBandedAlignment right of the next grid's
+            // origin (seeds/banded_chain_alignment_impl.h:282-377): only their number is planned here, the device
+            // walks the columns itself (engine.cu: colTabKernel)
+            g.colTabOff = (int32_t)*colTabCount;
+            g.nColTab = bandColumnsFrom(makeGeom(g.nH, g.nV, g.banded, g.lo, g.up), g.hNext);
+            *colTabCount += g.nColTab;
         }
         out.push_back(g);
     }
@@ -248,11 +245,11 @@ struct Planner {
 }  // namespace
 
 bool planChain(const std::vector<ChainSeed>& chain, long lenH, long lenV, long bandExtension,
-               std::vector<GridDesc>& grids, std::vector<ColInfo>* colTab) {
+               std::vector<GridDesc>& grids, long long* colTabCount) {
     grids.clear();
-    if (colTab) colTab->clear();
+    if (colTabCount) *colTabCount = 0;
     if (chain.empty() || lenH < 1 || lenV < 1) return false;
-    Planner p(lenH, lenV, bandExtension, grids, colTab);
+    Planner p(lenH, lenV, bandExtension, grids, colTabCount);
     p.run(chain);
     if (!p.ok) grids.clear();
     return p.ok;

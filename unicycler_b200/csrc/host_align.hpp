@@ -24,7 +24,7 @@ void toDna5(const char* s, size_t n, std::vector<uint8_t>& out);
 // (seqan/seeds/banded_chain_alignment_impl.h:1212-1296 with :737-1177).  Returns false when the chain is
 // empty (the reference returns MinValue without touching the alignment).
 bool planChain(const std::vector<ChainSeed>& chain, long lenH, long lenV, long bandExtension,
-               std::vector<GridDesc>& grids, std::vector<ColInfo>* colTab = nullptr);
+               std::vector<GridDesc>& grids, long long* colTabCount = nullptr);
 
 // One-grid plans for globalAlignment(align, score, AlignConfig<...>[, lo, up]).
 // Returns false if _isValidDPSettings would fail (seqan/align/dp_algorithm_impl.h:117-157).
