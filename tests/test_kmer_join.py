@@ -107,3 +107,31 @@ def test_batch_path_joins_on_the_device_and_host_switch_gives_the_same_strings(u
     ub.delete_ref_seqs(h)
     assert [mask_semi_global(o) for o in out] == [mask_semi_global(o) for o in out_host]
     assert all(mask_semi_global(o) == d['expected'][r[0]] for r, o in zip(reads, out))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('setname,chunk', [('sample', 4), ('sample', 7), ('small', 1), ('tough', 3)])
+def test_chunked_pipeline_gives_the_golden_strings(ub, monkeypatch, setname, chunk):
+    """The pipeline of large batch calls (line tracing of chunk k+1 on the pool while chunk k is staged / launched /
+    fetched / formatted, k-mer join two chunks ahead, engines alternating) forced onto a small set: same strings as
+    the single-launch call and as the reference."""
+    from oracle_lib import mask_semi_global
+    d = load_golden('semiglobal_%s.json.gz' % setname)
+    h = ub.new_ref_seqs()
+    for name, seq in d['refs']:
+        ub.add_ref_seq(h, name, seq)
+    reads = [r for r in d['reads'] if r[0] in d['expected']]
+    reads = reads + [('no_hits', reads[0][1], '')] if setname == 'small' else reads   # a read without minimap hits
+    args = ([r[0] for r in reads], [r[1] for r in reads], [r[2] for r in reads], h, tuple(d['scheme']), 0)
+    monkeypatch.setenv('UNICYCLER_B200_CHUNK_READS', str(chunk))
+    out = ub.semi_global_alignment_batch(*args)
+    assert ub.last_join_stats()['launches'] >= 14   # at least two chunks were joined on the device
+    monkeypatch.delenv('UNICYCLER_B200_CHUNK_READS')
+    whole = ub.semi_global_alignment_batch(*args)
+    ub.delete_ref_seqs(h)
+    assert [mask_semi_global(o) for o in out] == [mask_semi_global(o) for o in whole]
+    for r, o in zip(reads, out):
+        if r[0] in d['expected']:
+            assert mask_semi_global(o) == d['expected'][r[0]], r[0]
+        else:
+            assert o == ''

@@ -530,6 +530,7 @@ int ub200_setDevice(int device) {
     if (g_coRunning || !g_coPending.empty()) return -1;
     std::lock_guard<std::mutex> lock(g_engineMu);
     g_engines.clear();
+    g_joiner.reset();
     g_deviceList.clear();
     g_device = device;
     return 0;
