@@ -1003,6 +1003,11 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     int chunk = n;
     if (const char* e = getenv("UNICYCLER_B200_CHUNK_READS")) chunk = std::max(1, atoi(e));
     else if (n >= 256) chunk = std::min(1024, std::max(64, n / 8));
+    else if (n >= 64) {   // fewer but long reads (a rank's share of a sharded long-read set): the host stages of such a
+        size_t bases = 0;   // call take far longer than its kernels, which a four-chunk pipeline hides
+        for (int i = 0; i < n; ++i) bases += len[(size_t)i];
+        if (bases >= 1000000) chunk = std::max(32, (n + 3) / 4);
+    }
     const int nChunks = (n + chunk - 1) / chunk;
     std::vector<std::vector<Job*> > jobs((size_t)nChunks);
     auto lo = [&](int k) { return k * chunk; };
