@@ -2436,6 +2436,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     kp.scratch = (uint8_t*)I.dScratch; kp.scratchStride = L.total;
     kp.lay = L;
     I.stats = EngineStats();
+    I.stats.launches = I.nColTab > 0 ? 1 : 0;   // colTabKernel above
     I.stats.cells = totalCells;
     I.stats.h2dBytes = (int64_t)(I.seqBytes + nJobs * sizeof(JobDev) + I.nGrids * sizeof(GridDesc) + nJobs * sizeof(int) +
                                  (I.nColTab > 0 ? I.nGrids * sizeof(long long) : 0));
