@@ -135,3 +135,31 @@ def test_chunked_pipeline_gives_the_golden_strings(ub, monkeypatch, setname, chu
             assert mask_semi_global(o) == d['expected'][r[0]], r[0]
         else:
             assert o == ''
+
+
+@pytest.mark.gpu
+def test_chunked_pipeline_over_all_devices_of_the_process():
+    """UNICYCLER_B200_DEVICES=all: the chunks of one batch call go round every visible GPU (two engines each, the k-mer
+    join on the first).  Read once per process, hence the subprocess; with one GPU this is the two-engine pipeline."""
+    import subprocess
+    code = '''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import unicycler_b200 as ub
+from oracle_lib import load_golden, mask_semi_global
+for setname, chunk in (("sample", "3"), ("tough", "2")):
+    d = load_golden("semiglobal_%%s.json.gz" %% setname)
+    h = ub.new_ref_seqs()
+    for name, seq in d["refs"]:
+        ub.add_ref_seq(h, name, seq)
+    reads = [r for r in d["reads"] if r[0] in d["expected"]]
+    os.environ["UNICYCLER_B200_CHUNK_READS"] = chunk
+    out = ub.semi_global_alignment_batch([r[0] for r in reads], [r[1] for r in reads], [r[2] for r in reads], h, tuple(d["scheme"]), 0)
+    ub.delete_ref_seqs(h)
+    bad = [r[0] for r, o in zip(reads, out) if mask_semi_global(o) != d["expected"][r[0]]]
+    assert not bad, (setname, bad)
+    assert ub.last_join_stats()["launches"] >= 14
+''' % (ROOT, os.path.join(ROOT, 'tests'))
+    env = dict(os.environ, UNICYCLER_B200_DEVICES='all')
+    r = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
