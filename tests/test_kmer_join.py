@@ -163,3 +163,46 @@ for setname, chunk in (("sample", "3"), ("tough", "2")):
     env = dict(os.environ, UNICYCLER_B200_DEVICES='all')
     r = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
     assert r.returncode == 0, r.stdout.decode()[-2000:]
+
+
+@pytest.mark.gpu
+def test_concurrent_chunked_batch_calls(ub, monkeypatch):
+    """Two threads in chunked batch calls at once (each such call holds several engines between stage and end; the
+    library serialises them) while a third one makes per-read calls through the coalescer."""
+    import threading
+    from oracle_lib import mask_semi_global
+    d = load_golden('semiglobal_sample.json.gz')
+    h = ub.new_ref_seqs()
+    for name, seq in d['refs']:
+        ub.add_ref_seq(h, name, seq)
+    reads = [r for r in d['reads'] if r[0] in d['expected']][:12]
+    args = ([r[0] for r in reads], [r[1] for r in reads], [r[2] for r in reads], h, tuple(d['scheme']), 0)
+    monkeypatch.setenv('UNICYCLER_B200_CHUNK_READS', '3')
+    outs, errs = {}, []
+
+    def batch(tag):
+        try:
+            outs[tag] = ub.semi_global_alignment_batch(*args)
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    def single():
+        try:
+            m, mm, go, ge = tuple(d['scheme'])
+            outs['single'] = [ub.semi_global_alignment(r[0], r[1], 0, r[2], h, m, mm, go, ge, 0.0, False, 0) for r in reads[:4]]
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    threads = [threading.Thread(target=batch, args=('a',)), threading.Thread(target=batch, args=('b',)),
+               threading.Thread(target=single)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+        assert not t.is_alive(), 'batch calls wait for each other'
+    ub.delete_ref_seqs(h)
+    assert not errs, errs
+    want = [d['expected'][r[0]] for r in reads]
+    assert [mask_semi_global(o) for o in outs['a']] == want
+    assert [mask_semi_global(o) for o in outs['b']] == want
+    assert [mask_semi_global(o) for o in outs['single']] == want[:4]

@@ -867,6 +867,11 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
                                    const char* const* hits, void* refSeqs, int m, int mm, int go, int ge,
                                    int sensitivityLevel, char** results) {
     Scoring sc{m, mm, go, ge};
+    // One batch call at a time per process: a chunked call holds several engines at once (stage .. end), and two such
+    // calls taking them in different order would wait for each other.  Per-read calls (request coalescer) hold one
+    // engine for one launch and interleave freely.
+    static std::mutex batchMu;
+    std::lock_guard<std::mutex> batchLock(batchMu);
     const double t0 = nowSec();
     std::vector<std::unique_ptr<ReadWork> > works((size_t)n);
     // largest reads first: their chains have the longest spines
@@ -997,9 +1002,7 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     }
 
     // Small batches are latency bound on the device (the spines of the longest chains): one launch.  Large batches
-    // are cut into chunks that alternate between two engines, so that seeding chunk k and formatting chunk k-2 overlap
-    // the kernel of chunk k-1:   host  [seed 0][seed 1][fmt 0 .. seed 2][fmt 1 .. seed 3] ...
-    //                            GPU          [kernel 0][kernel 1 .....][kernel 2 ......] ...
+    // are cut into chunks that alternate between the engines and run as the pipeline below.
     int chunk = n;
     if (const char* e = getenv("UNICYCLER_B200_CHUNK_READS")) chunk = std::max(1, atoi(e));
     else if (n >= 256) chunk = std::min(1024, std::max(64, n / 8));
