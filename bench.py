@@ -612,6 +612,7 @@ def main():
             device_kmer_join=ub.last_join_stats(),
             e2e=dict(value=e2e_gcups, unit='GCUPS', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_s * 1e3,
                      ms_per_step_median_rank0=sorted(e2e_steps_ms)[len(e2e_steps_ms) // 2],
+                     ms_steps_rank0=[round(x, 2) for x in e2e_steps_ms],
                      batch_call_ms_median_rank0=sorted(batch_ms[-args.steps:])[args.steps // 2],
                      gather_ms_median_rank0=sorted(gather_ms[-args.steps:])[args.steps // 2],
                      host_threads_per_rank=max(1, (os.cpu_count() or 1) // max(1, world)),
