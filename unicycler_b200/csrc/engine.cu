@@ -1981,6 +1981,7 @@ Engine::Engine(int device) : impl_(new Impl) {
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     impl_->numSMs = prop.multiProcessorCount;
+    if (const char* e = getenv("UNICYCLER_B200_CTAS")) impl_->numSMs = std::max(1, std::min(impl_->numSMs, atoi(e)));   // developer switch: fewer CTAs
     CUDA_CHECK(cudaFuncSetAttribute(dpAgentKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int ctasPerSM = 0, coop = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, dpAgentKernel, NTHREADS, (size_t)SMEM_BYTES));
