@@ -1011,6 +1011,14 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
         for (int i = 0; i < n; ++i) bases += len[(size_t)i];
         if (bases >= 1000000) chunk = std::max(32, (n + 3) / 4);
     }
+    if (chunk == n && n >= 8 && n < 256 && !getenv("UNICYCLER_B200_CHUNK_READS")) {
+        // Few host threads (one rank of several on a box): tracing the lighter half of the reads takes longer than the
+        // kernel of the heavier half (~11 ms whatever the batch: a critical path), so two launches hide one of them.
+        // With many threads the second launch would only wait for the first (profiles/r2_summary.md, section 7).
+        size_t bases = 0;
+        for (int i = 0; i < n; ++i) bases += len[(size_t)i];
+        if (bases / (size_t)hostThreads() >= 40000) chunk = (n + 1) / 2;   // (sample_data: up to 6 threads)
+    }
     const int nChunks = (n + chunk - 1) / chunk;
     std::vector<std::vector<Job*> > jobs((size_t)nChunks);
     auto lo = [&](int k) { return k * chunk; };
