@@ -1924,8 +1924,25 @@ struct Engine::Impl {
         if (need <= cap) return;
         if (p) CUDA_CHECK(cudaFree(p));
         size_t ncap = need + need / 4 + 256;
+        allocEpoch().fetch_add(1);
         CUDA_CHECK(cudaMalloc(&p, ncap));
         cap = ncap;
+    }
+    // Free device memory as the planner sees it.  cudaMemGetInfo is a driver call that now and then takes 10-70 ms on a
+    // shared node (measured: it was the one source of slow batch calls, tools/outlier_probe.py), so it is only asked again
+    // after some engine of this process has (re)allocated device memory; in the steady state of a campaign (batches of
+    // similar shape, buffers at their working size) it is not called at all.
+    static std::atomic<int>& allocEpoch() { static std::atomic<int> e(0); return e; }
+    size_t cachedFree = 0, cachedTotal = 0;
+    int cachedEpoch = -1;
+    void memInfo(size_t& freeB, size_t& totalB) {
+        const int now = allocEpoch().load();
+        if (cachedEpoch != now) {
+            CUDA_CHECK(cudaMemGetInfo(&cachedFree, &cachedTotal));
+            cachedEpoch = now;
+        }
+        freeB = cachedFree;
+        totalB = cachedTotal;
     }
     void growHost(void*& p, size_t& cap, size_t need) {
         if (need <= cap) return;
@@ -2006,6 +2023,7 @@ Engine::~Engine() {
 }
 
 int Engine::device() const { return impl_->device; }
+void Engine::noteDeviceAllocation() { Impl::allocEpoch().fetch_add(1); }
 int Engine::deviceCount() {
     int n = 0;
     return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
@@ -2172,7 +2190,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     tU[1] = wallMs();
     // persistent blocks only if they fit comfortably (otherwise big grids are traced back in line from the arena)
     size_t freeB0 = 0, totalB0 = 0;
-    CUDA_CHECK(cudaMemGetInfo(&freeB0, &totalB0));
+    I.memInfo(freeB0, totalB0);
     const bool usePersist = persistTotal > 0 && (size_t)persistTotal <= (freeB0 + I.capPersist) / 3 && !getenv("UNICYCLER_B200_NO_PERSIST");
     if (usePersist) { maxRowCk = maxRowCkNP; maxColCk = maxColCkNP; }
     else for (size_t q = 0; q < I.nGrids; ++q) hGrids[q].persistOff = -1;
@@ -2200,7 +2218,7 @@ void Engine::upload(std::vector<Job*>& jobs) {
     L.maxRowCk = maxRowCk; L.maxColCk = maxColCk; L.maxStrips = maxStrips;
     // number of control agents with an arena: bounded by jobs and by memory
     size_t freeB = 0, totalB = 0;
-    CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
+    I.memInfo(freeB, totalB);
     // control region (zeroed per launch).  A big grid is published once by every segment that walks it, so the
     // task boards and token rings are sized by publications, not by grids.
     size_t offRing = 0, offP2 = 0, offBig = 0, offTile = 0, offState = 0, offTok = 0, maxTokens = 0, maxPub = 0;

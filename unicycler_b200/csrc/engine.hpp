@@ -126,6 +126,9 @@ public:
     EngineStats lastStats() const;
     int device() const;
     static int deviceCount();   // CUDA devices visible to the process (0 when there is none)
+    // Other device allocations of this process (k-mer join buffers, resident references) tell the engines that their
+    // cached view of the free device memory is stale.
+    static void noteDeviceAllocation();
     // Device-resident benchmark mode: upload()+plan once, then launch() repeatedly with
     // inputs already in HBM; fetch() copies results back.
     void upload(std::vector<Job*>& jobs);

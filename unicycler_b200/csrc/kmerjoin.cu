@@ -1,6 +1,7 @@
 // Device k-mer join (see kmerjoin.hpp).  sm_100a; byte / integer work, HBM- and latency-bound: coalesced
 // grid-stride passes over flat position arrays, grids sized in multiples of the SM count.
 #include "kmerjoin.hpp"
+#include "engine.hpp"
 #include "hostpool.hpp"
 
 #include <cuda_runtime.h>
@@ -221,6 +222,7 @@ struct KmerJoiner::Impl {
         if (b.p) JOIN_CUDA(cudaFree(b.p));
         b.p = nullptr; b.cap = 0;
         const size_t cap = need + need / 4 + 4096;
+        Engine::noteDeviceAllocation();
         JOIN_CUDA(cudaMalloc(&b.p, cap));
         b.cap = cap;
     }
@@ -237,6 +239,7 @@ struct KmerJoiner::Impl {
         if (it != refs.end() && it->second.second == len) return it->second.first;
         if (it != refs.end()) { cudaFree(it->second.first); refs.erase(it); }
         uint8_t* d = nullptr;
+        Engine::noteDeviceAllocation();
         JOIN_CUDA(cudaMalloc((void**)&d, len + 64));
         JOIN_CUDA(cudaMemcpyAsync(d, base, len, cudaMemcpyHostToDevice, stream));
         JOIN_CUDA(cudaStreamSynchronize(stream));   // (the source is pageable caller memory)
