@@ -41,8 +41,10 @@ HostPool::~HostPool() {
     for (auto& th : threads_) th.join();
 }
 
-void HostPool::drain(Loop& L) {
+void HostPool::drain(Loop& L, bool helper) {
     for (;;) {
+        // a helper gives way to loops that opened after this one (it comes back when they are done)
+        if (helper && newestSeq_.load(std::memory_order_relaxed) > L.seq && newerLoopWantsHelp(L.seq)) break;
         const int b = L.next.fetch_add(L.grain);
         if (b >= L.n) break;
         const int e = std::min(L.n, b + L.grain);
@@ -56,6 +58,16 @@ void HostPool::drain(Loop& L) {
     }
 }
 
+bool HostPool::newerLoopWantsHelp(unsigned long long seq) {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (size_t q = open_.size(); q > 0; --q) {
+        const auto& o = open_[q - 1];
+        if (o->seq <= seq) break;   // (open_ is in opening order)
+        if (o->next.load(std::memory_order_relaxed) < o->n && o->helpersLeft.load(std::memory_order_relaxed) > 0) return true;
+    }
+    return false;
+}
+
 void HostPool::workerMain() {
     for (;;) {
         std::shared_ptr<Loop> L;
@@ -63,7 +75,8 @@ void HostPool::workerMain() {
             std::unique_lock<std::mutex> lk(mu_);
             for (;;) {
                 if (stop_) return;
-                for (auto& o : open_) {
+                for (size_t q = open_.size(); q > 0; --q) {   // newest first
+                    auto& o = open_[q - 1];
                     if (o->next.load(std::memory_order_relaxed) >= o->n) continue;
                     if (o->helpersLeft.fetch_sub(1) <= 0) { o->helpersLeft.fetch_add(1); continue; }
                     L = o;
@@ -74,7 +87,7 @@ void HostPool::workerMain() {
             }
             L->active.fetch_add(1);
         }
-        drain(*L);
+        drain(*L, true);
         L->helpersLeft.fetch_add(1);
         if (L->active.fetch_sub(1) == 1) {
             std::lock_guard<std::mutex> lk(mu_);   // pairs with the owner's wait below
@@ -91,10 +104,12 @@ void HostPool::run(int n, const std::function<void(int)>& f, int grain, int maxH
     L->active.store(1);
     {
         std::lock_guard<std::mutex> lk(mu_);
+        L->seq = ++seqCounter_;
         open_.push_back(L);
+        newestSeq_.store(L->seq, std::memory_order_relaxed);
     }
     cv_.notify_all();
-    drain(*L);
+    drain(*L, false);
     {
         std::unique_lock<std::mutex> lk(mu_);
         open_.erase(std::find(open_.begin(), open_.end(), L));

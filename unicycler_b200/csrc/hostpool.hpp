@@ -3,7 +3,10 @@
 // (unicycler_align.py:203-225); here the library owns ONE lazily created pool, sized by
 // UNICYCLER_B200_HOST_THREADS or, by default, the machine's cores divided by LOCAL_WORLD_SIZE (one process per GPU
 // must not oversubscribe the box N-fold).  parallelFor() may be called concurrently from many threads and may be
-// nested: the caller always takes part in its own loop, pool workers help with whatever loops are open.
+// nested: the caller always takes part in its own loop, pool workers help with whatever loops are open — the NEWEST
+// loop first, and a worker leaves an older loop between two of its items when a newer one has opened: the long loop of
+// a pipeline (line tracing of the next chunk, milliseconds per item) lends its workers to the short loops of the
+// thread that drives the pipeline (result parsing, formatting, staging) instead of leaving that thread to run them alone.
 #pragma once
 #include <atomic>
 #include <condition_variable>
@@ -31,6 +34,7 @@ private:
     struct Loop {
         const std::function<void(int)>* f;
         int n, grain;
+        unsigned long long seq = 0;   // opening order
         std::atomic<int> next{0};
         std::atomic<int> active{0};   // threads currently inside the loop body
         std::atomic<int> helpersLeft{0};
@@ -39,7 +43,10 @@ private:
     };
     HostPool();
     void workerMain();
-    static void drain(Loop& L);
+    void drain(Loop& L, bool helper);
+    bool newerLoopWantsHelp(unsigned long long seq);
+    unsigned long long seqCounter_ = 0;   // under mu_
+    std::atomic<unsigned long long> newestSeq_{0};
     std::vector<std::thread> threads_;
     std::mutex mu_;
     std::condition_variable cv_;
