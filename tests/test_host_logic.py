@@ -71,6 +71,14 @@ def test_storage_geometry_matches_oracle_navigator():
     assert ' bad 0' in out, out
 
 
+def test_point_set_iterates_like_the_reference_container():
+    """pointset.hpp against std::unordered_set<Point, PointHash>: same elements in the same order after range
+    construction, range / single insertions with duplicates, and copies (doubles are summed in that order)."""
+    exe = _build_cpp('ub200_test_pointset', ['tests/cpp/test_pointset.cpp'])
+    out = subprocess.check_output([exe, '300']).decode()
+    assert ' bad 0' in out, out
+
+
 @pytest.mark.parametrize('setname', ['small', 'contained', 'tough'])
 def test_chain_planner_matches_oracle_grid_sequence(setname):
     exe = _build_cpp('ub200_test_plan', ['tests/cpp/test_plan.cpp', 'oracle/dp_oracle.cpp',

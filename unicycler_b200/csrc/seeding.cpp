@@ -5,6 +5,7 @@
 // on purpose: several decisions sum doubles in container order.
 #include "seeding.hpp"
 #include "hostpool.hpp"
+#include "pointset.hpp"
 
 #include <atomic>
 #include <chrono>
@@ -149,53 +150,10 @@ std::string reverseComplement(const std::string& s) {
 
 namespace {
 
-struct Point {
-    int x, y;
-    Point() : x(0), y(0) {}
-    Point(int px, int py) : x(px), y(py) {}
-    bool operator==(const Point& o) const { return x == o.x && y == o.y; }
-    bool operator<(const Point& o) const { return x == o.x ? y < o.y : x < o.x; }
-};
-struct PointHash {  // include/semi_global_align.h:79-86
-    size_t operator()(const Point& p) const { return (std::hash<int>()(p.x) ^ (std::hash<int>()(p.y) << 1)) >> 1; }
-};
-// The line tracer builds and drops thousands of small point sets per range; their nodes and bucket arrays come from a
-// per-thread bump arena that is rewound when a range starts (a thread seeds one range at a time, and no point set
-// outlives its range).  Only where the memory comes from changes: the hash, the bucket policy and therefore the
-// iteration order are those of the reference's std::unordered_set<Point, PointHash>.
-struct Arena {
-    std::vector<char*> blocks;
-    size_t cur = 0, used = 0;
-    static const size_t BLOCK = 1 << 20;
-    ~Arena() { for (char* b : blocks) free(b); }
-    void rewind() { cur = 0; used = 0; }
-    static size_t rounded(size_t n) { return (n + 15) & ~(size_t)15; }
-    void* alloc(size_t n) {
-        n = rounded(n);
-        if (n > BLOCK) return malloc(n);   // (not from the arena: released by deallocate)
-        if (blocks.empty()) blocks.push_back((char*)malloc(BLOCK));
-        if (used + n > BLOCK) {
-            used = 0;
-            if (++cur == blocks.size()) blocks.push_back((char*)malloc(BLOCK));
-        }
-        void* p = blocks[cur] + used;
-        used += n;
-        return p;
-    }
-};
-static thread_local Arena t_arena;
-template <typename T>
-struct ArenaAlloc {
-    typedef T value_type;
-    ArenaAlloc() {}
-    template <typename U> ArenaAlloc(const ArenaAlloc<U>&) {}
-    T* allocate(size_t n) { return (T*)t_arena.alloc(n * sizeof(T)); }
-    void deallocate(T* p, size_t n) { if (Arena::rounded(n * sizeof(T)) > Arena::BLOCK) free(p); }
-    template <typename U> bool operator==(const ArenaAlloc<U>&) const { return true; }
-    template <typename U> bool operator!=(const ArenaAlloc<U>&) const { return false; }
-};
-typedef std::unordered_set<Point, PointHash, std::equal_to<Point>, ArenaAlloc<Point> > PointSet;
-typedef std::vector<Point> PointVector;
+using seed::Point;
+using seed::PointHash;
+using seed::PointSet;      // the reference's std::unordered_set<Point, PointHash>, iteration order included (pointset.hpp)
+using seed::PointVector;
 
 // ------------------------------------------------------------------ kd-tree (nanoflann algorithm, int L1 metric)
 // Same tree, same leaf order and same search order as nanoflann's KDTreeSingleIndexAdaptor<L1_Adaptor<int,...>, ..., 2>
@@ -359,7 +317,7 @@ void fillCloud(Cloud& cloud, const PointVector& common, const PointSet& used) {
     cloud.pts.clear();
     cloud.orig.clear();
     for (size_t i = 0; i < common.size(); ++i)
-        if (used.empty() || used.find(common[i]) == used.end()) { cloud.pts.push_back(common[i]); cloud.orig.push_back((uint32_t)i); }
+        if (used.empty() || !used.contains(common[i])) { cloud.pts.push_back(common[i]); cloud.orig.push_back((uint32_t)i); }
     cloud.tree.build();
 }
 
@@ -926,7 +884,7 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
                const SensitivityParams& sp, int verbosity, const std::string& refName, int refStart, int refEnd,
                RangeSeeds& out, const int32_t* joinedXY, size_t nJoined) {
     out.chains.clear();
-    t_arena.rewind();   // (every point set of the previous range on this thread is gone)
+    seed::Arena::mine().rewind();   // (every point set of the previous range on this thread is gone)
     const int kSize = sp.kSize;
     const int readLen = (int)readSeq.size(), refLen = (int)trimmedRefSeq.size();
     if (verbosity > 2)
