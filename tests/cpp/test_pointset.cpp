@@ -7,6 +7,9 @@
 #include <unordered_set>
 #include <vector>
 
+#include <cstring>
+
+#include "../../unicycler_b200/csrc/linegeom.hpp"
 #include "../../unicycler_b200/csrc/pointset.hpp"
 
 using ub200::seed::Point;
@@ -82,6 +85,24 @@ int main(int argc, char** argv) {
         compare(r2, s2, "insertions into a copy", it);
         compare(r, s, "original after the copy grew", it);
     }
-    printf("checks %ld bad %ld\n", g_checks, g_bad);
+    // distancesToLineSegment (two points per step) against distanceToLineSegment, bit for bit
+    long distChecks = 0;
+    for (int it = 0; it < 4000; ++it) {
+        const int span = (it % 5 == 0) ? 30 : 60000;
+        Point l1((int)(rng() % span), (int)(rng() % span)), l2((int)(rng() % span), (int)(rng() % span));
+        if (it % 7 == 0) l2 = l1;                                   // degenerate segment
+        if (it % 11 == 0) l2 = Point(l1.x + 500, l1.y + 500);         // the tracer's step
+        if (it % 13 == 0) { l1 = Point(l1.x - 40000, l1.y - 40000); }   // segments may leave the rectangle (negative ends)
+        std::vector<Point> pts(rng() % 70);
+        for (auto& p : pts) p = (rng() % 4 == 0) ? (rng() % 2 ? l1 : l2) : Point((int)(rng() % span), (int)(rng() % span));
+        std::vector<double> got(pts.size() + 1, -1.0);
+        ub200::seed::distancesToLineSegment(pts.data(), pts.size(), l1, l2, got.data());
+        for (size_t i = 0; i < pts.size(); ++i) {
+            const double want = ub200::seed::distanceToLineSegment(pts[i], l1, l2);
+            ++distChecks;
+            if (memcmp(&want, &got[i], sizeof(double)) != 0) { ++g_bad; if (g_bad <= 5) fprintf(stderr, "DISTANCE differs: %.17g vs %.17g\n", want, got[i]); }
+        }
+    }
+    printf("checks %ld distances %ld bad %ld\n", g_checks, distChecks, g_bad);
     return g_bad ? 1 : 0;
 }

@@ -6,6 +6,7 @@
 #include "seeding.hpp"
 #include "hostpool.hpp"
 #include "pointset.hpp"
+#include "linegeom.hpp"
 
 #include <atomic>
 #include <chrono>
@@ -353,19 +354,11 @@ double getSlope(const Point& p1, const Point& p2) {
     return slope;
 }
 
-double distanceToLineSegment(Point p, Point l1, Point l2) {
-    double A = p.x - l1.x, B = p.y - l1.y, C = l2.x - l1.x, D = l2.y - l1.y;
-    double dot = A * C + B * D;
-    double lenSq = C * C + D * D;
-    double param = -1;
-    if (lenSq != 0) param = dot / lenSq;
-    double xx, yy;
-    if (param < 0) { xx = l1.x; yy = l1.y; }
-    else if (param > 1) { xx = l2.x; yy = l2.y; }
-    else { xx = l1.x + param * C; yy = l1.y + param * D; }
-    double dx = p.x - xx, dy = p.y - yy;
-    return sqrt(dx * dx + dy * dy);
-}
+using seed::distanceToLineSegment;   // linegeom.hpp (one point / two points at a time, bit-identical)
+
+// the near-point set of the current step in its iteration order, and scratch for the distances (per thread)
+static thread_local PointVector t_flat;
+static thread_local std::vector<double> t_dist;
 
 // pointsNearLine: the step's near-point set copied out once in its iteration order (the order of the sum)
 double scoreLineSegment(Point p1, Point p2, const PointVector& pointsNearLine) {
@@ -374,10 +367,10 @@ double scoreLineSegment(Point p1, Point p2, const PointVector& pointsNearLine) {
     double slopeScore = (MAX_SLOPE_SCORE / (1.0 - MIN_ACCEPTABLE_LINE_SEGMENT_SLOPE)) * (slope - MIN_ACCEPTABLE_LINE_SEGMENT_SLOPE);
     double maxScorePerPoint = MAX_POINTS_SCORE / TRACE_LINE_STEP_DISTANCE;
     double pointDistanceScore = 0.0;
-    for (const Point& p : pointsNearLine) {
-        double dist = distanceToLineSegment(p, p1, p2);
-        pointDistanceScore += maxScorePerPoint / (dist + 1.0);
-    }
+    const size_t n = pointsNearLine.size();
+    if (t_dist.size() < n) t_dist.resize(n);
+    seed::distancesToLineSegment(pointsNearLine.data(), n, p1, p2, t_dist.data());
+    for (size_t i = 0; i < n; ++i) pointDistanceScore += maxScorePerPoint / (t_dist[i] + 1.0);   // (summed in set order)
     return slopeScore + pointDistanceScore;
 }
 
@@ -408,10 +401,10 @@ Point mutateLineToBestFitPoints(Point p1, Point p2, const Cloud& cloud, PointSet
     const long long tm2 = nowNs();
     g_lt[0] += tm1 - tm0; g_lt[1] += tm2 - tm1;
     struct Sc { long long t; ~Sc() { g_lt[2] += nowNs() - t; } } scTimer{tm2};
+    PointVector& flat = t_flat;
+    flat.assign(pointsNearLine.begin(), pointsNearLine.end());
     if (leftRectangle) return p2;
     Point p2Up = shiftUp(p2, TRACE_LINE_MUTATION_SIZE), p2Down = shiftDown(p2, TRACE_LINE_MUTATION_SIZE);
-    static thread_local PointVector flat;
-    flat.assign(pointsNearLine.begin(), pointsNearLine.end());
     double unmutated = scoreLineSegment(p1, p2, flat);
     double up = scoreLineSegment(p1, p2Up, flat);
     double down = scoreLineSegment(p1, p2Down, flat);
@@ -613,8 +606,13 @@ PointSet lineTracing(const PointVector& common, PointSet& usedPoints, const Clou
             p = mutateLineToBestFitPoints(previousP, newP, cloud, pointsNearLine, left);
             traceDots.push_back(p);
             const long long ta0 = nowNs();
-            for (const Point& q : pointsNearLine)  // addPointsNearLine :506-512
-                if (distanceToLineSegment(q, previousP, p) <= TRACE_LINE_COLLECTION_DISTANCE) pointSet.insert(q);
+            {   // addPointsNearLine :506-512, over the step's near points in their set order (t_flat, filled by the call above)
+                const size_t nNear = t_flat.size();
+                if (t_dist.size() < nNear) t_dist.resize(nNear);
+                seed::distancesToLineSegment(t_flat.data(), nNear, previousP, p, t_dist.data());
+                for (size_t q = 0; q < nNear; ++q)
+                    if (t_dist[q] <= TRACE_LINE_COLLECTION_DISTANCE) pointSet.insert(t_flat[q]);
+            }
             g_lt[3] += nowNs() - ta0;
             if (left) break;
         }
@@ -824,6 +822,34 @@ void chainSeedsGlobally(std::vector<ChainSeed>& target, const SeedSet& seedSet) 
     std::reverse(target.begin(), target.end());
 }
 
+// std::sort(points) of the reference (by x, then y; the points of a set are distinct, so every correct sort gives the
+// same sequence): least-significant-digit radix sort on the packed (x, y) key, passes over constant digits skipped.
+void sortPoints(PointVector& pts) {
+    const size_t n = pts.size();
+    bool packable = n >= 64;
+    for (size_t i = 0; i < n && packable; ++i) packable = pts[i].x >= 0 && pts[i].y >= 0;
+    if (!packable) { std::sort(pts.begin(), pts.end()); return; }
+    static thread_local std::vector<uint64_t> a, b;
+    a.resize(n); b.resize(n);
+    uint64_t all1 = ~0ull, any1 = 0;
+    for (size_t i = 0; i < n; ++i) {
+        a[i] = ((uint64_t)(uint32_t)pts[i].x << 32) | (uint32_t)pts[i].y;
+        all1 &= a[i]; any1 |= a[i];
+    }
+    const uint64_t varying = all1 ^ any1;   // bits that differ between some two keys
+    uint64_t* src = a.data();
+    uint64_t* dst = b.data();
+    for (int shift = 0; shift < 64; shift += 11) {
+        if (((varying >> shift) & 0x7ff) == 0) continue;
+        size_t count[2049] = {0};
+        for (size_t i = 0; i < n; ++i) ++count[((src[i] >> shift) & 0x7ff) + 1];
+        for (int d = 0; d < 2048; ++d) count[d + 1] += count[d];
+        for (size_t i = 0; i < n; ++i) dst[count[(src[i] >> shift) & 0x7ff]++] = src[i];
+        std::swap(src, dst);
+    }
+    for (size_t i = 0; i < n; ++i) pts[i] = Point((int)(src[i] >> 32), (int)(uint32_t)src[i]);
+}
+
 long long maxSeedChainGapArea(const std::vector<ChainSeed>& chain, int readLen, int refLen) {  // :321-347
     int prevH = 0, prevV = 0;
     long long maxArea = 0;
@@ -934,7 +960,7 @@ void seedRange(const std::string& readSeq, const KmerPosMap& readKmers, const st
         PointVector pts;
         pts.reserve(good.size());
         for (const Point& p : good) pts.push_back(p);
-        std::sort(pts.begin(), pts.end());
+        sortPoints(pts);
         SeedSet seedSet((long)readLen + kSize, (long)refLen + kSize);
         for (const Point& p : pts) {
             ChainSeed s{(long)p.x, (long)p.y, (long)p.x + kSize, (long)p.y + kSize, (long)p.x - (long)p.y, (long)p.x - (long)p.y};
