@@ -1005,7 +1005,16 @@ int ub200_semiGlobalAlignmentBatch(int n, const char* const* readNames, const ch
     // are cut into chunks that alternate between the engines and run as the pipeline below.
     int chunk = n;
     if (const char* e = getenv("UNICYCLER_B200_CHUNK_READS")) chunk = std::max(1, atoi(e));
-    else if (n >= 256) chunk = std::min(1024, std::max(64, n / 8));
+    else if (n >= 256) {
+        // ~2.5 Mbp of reads per chunk (128 reads of 20 kb: measured optimum of the 512- and 2 048-read synthetic slices,
+        // 64 / 96 / 128 / 171 reads per chunk: 2 311 / 2 446 / 2 368 / 2 291 reads/s; 128 / 256 / 512: 2 923 / 2 795 / 2 573),
+        // at least four chunks
+        size_t bases = 0;
+        for (int i = 0; i < n; ++i) bases += len[(size_t)i];
+        const double avg = std::max(1.0, (double)bases / n);
+        chunk = (int)std::min(1024.0, std::max(64.0, 2.5e6 / avg));
+        chunk = std::max(32, std::min(chunk, (n + 3) / 4));
+    }
     else if (n >= 64) {   // fewer but long reads (a rank's share of a sharded long-read set): the host stages of such a
         size_t bases = 0;   // call take far longer than its kernels, which a four-chunk pipeline hides
         for (int i = 0; i < n; ++i) bases += len[(size_t)i];
