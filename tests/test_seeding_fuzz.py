@@ -3,8 +3,9 @@ against the reference itself: a scratch build of the reference's semi_global_ali
 chain handed to bandedChainAlignment and then SKIPS the alignment (the DP is not what is tested here), linked against
 the objects of the unmodified build (oracle/_ref).  Random references and reads of many lengths, error rates, strands,
 repeats and N runs, all four sensitivity levels; the product's seed chains (ub200_seedChains, no GPU needed) must be
-identical, chain by chain and seed by seed (48 cases by default, UB200_FUZZ_CASES=n for more: 90 cases with long
-windows at every level were run once, 8 minutes).  Runs where /root/reference and the compiled reference objects exist (the
+identical, chain by chain and seed by seed (48 cases by default; UB200_FUZZ_CASES / UB200_FUZZ_SEED for more: 90 cases
+with long windows at every level, and 120 cases with seed 777, were run once with the final code — 8 and 23 minutes, no
+difference).  Runs where /root/reference and the compiled reference objects exist (the
 build container); skipped on the GPU box."""
 import glob
 import os
